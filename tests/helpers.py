@@ -1,0 +1,201 @@
+"""Shared test helpers: golden-file reader, C-oracle loader, deterministic input streams."""
+import ctypes
+import gzip
+import hashlib
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_sign_input():
+    """tests/golden/sign_input.bin.gz -> list of (seed, pk, sig, msg); see make_golden.py."""
+    raw = gzip.open(os.path.join(ROOT, "tests", "golden", "sign_input.bin.gz")).read()
+    off, recs = 0, []
+    while off < len(raw):
+        seed, pk, sig = raw[off:off + 32], raw[off + 32:off + 64], raw[off + 64:off + 128]
+        (ml,) = struct.unpack_from("<I", raw, off + 128)
+        msg = raw[off + 132:off + 132 + ml]
+        off += 132 + ml
+        recs.append((seed, pk, sig, msg))
+    assert len(recs) == 1024
+    return recs
+
+
+class COracle:
+    """ctypes view of oracle/_build/liboracle.so (oracle/ref10_port.c)."""
+
+    def __init__(self, path):
+        L = ctypes.CDLL(path)
+        self.L = L
+        u8p = ctypes.c_char_p
+        L.oracle_init.restype = None
+        L.oracle_sha512.argtypes = [u8p, ctypes.c_size_t, u8p]
+        L.oracle_sc_reduce64.argtypes = [u8p, u8p]
+        L.oracle_sc_muladd.argtypes = [u8p, u8p, u8p, u8p]
+        L.oracle_scalar_is_canonical.argtypes = [u8p]
+        L.oracle_point_is_canonical.argtypes = [u8p]
+        L.oracle_point_decode_ok.argtypes = [u8p]
+        L.oracle_point_recode.argtypes = [u8p, u8p]
+        L.oracle_point_has_small_order.argtypes = [u8p]
+        L.oracle_mul_base.argtypes = [u8p, u8p]
+        L.oracle_mul.argtypes = [u8p, u8p, u8p]
+        L.oracle_point_add.argtypes = [u8p, u8p, u8p, ctypes.c_int]
+        L.oracle_eddsa_verify.argtypes = [u8p, u8p, ctypes.c_size_t, u8p, ctypes.c_size_t]
+        L.oracle_schnorr_verify.argtypes = [u8p, u8p, ctypes.c_size_t, u8p, ctypes.c_size_t]
+        L.oracle_pubpoly_eval.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_uint32]
+        L.oracle_vss_verify_deal.argtypes = [u8p, ctypes.c_int, ctypes.c_uint32, u8p]
+        vp = ctypes.c_void_p
+        L.oracle_mul_base_batch.argtypes = [ctypes.c_size_t, vp, vp, ctypes.c_int]
+        L.oracle_mul_batch.argtypes = [ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
+        L.oracle_eddsa_verify_batch.argtypes = [ctypes.c_size_t, vp, vp, vp, vp, vp, ctypes.c_int]
+        L.oracle_schnorr_verify_batch.argtypes = [ctypes.c_size_t, vp, vp, vp, vp, vp, ctypes.c_int]
+        L.oracle_vss_verify_batch.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
+        L.oracle_msm.argtypes = [u8p, ctypes.c_size_t, vp, vp]
+        L.oracle_init()
+
+    # ---- single-item wrappers
+    def sha512(self, m):
+        out = ctypes.create_string_buffer(64)
+        self.L.oracle_sha512(m, len(m), out)
+        return out.raw
+
+    def sc_reduce64(self, d):
+        out = ctypes.create_string_buffer(32)
+        self.L.oracle_sc_reduce64(out, d)
+        return out.raw
+
+    def sc_muladd(self, a, b, c):
+        out = ctypes.create_string_buffer(32)
+        self.L.oracle_sc_muladd(out, a, b, c)
+        return out.raw
+
+    def scalar_is_canonical(self, s):
+        return bool(self.L.oracle_scalar_is_canonical(s))
+
+    def point_is_canonical(self, s):
+        return bool(self.L.oracle_point_is_canonical(s))
+
+    def point_decode_ok(self, s):
+        return bool(self.L.oracle_point_decode_ok(s))
+
+    def point_recode(self, s):
+        out = ctypes.create_string_buffer(32)
+        return out.raw if self.L.oracle_point_recode(out, s) else None
+
+    def point_has_small_order(self, s):
+        return self.L.oracle_point_has_small_order(s)
+
+    def mul_base(self, a):
+        out = ctypes.create_string_buffer(32)
+        self.L.oracle_mul_base(out, a)
+        return out.raw
+
+    def mul(self, a, p):
+        out = ctypes.create_string_buffer(32)
+        return out.raw if self.L.oracle_mul(out, a, p) else None
+
+    def point_add(self, p, q, subtract=False):
+        out = ctypes.create_string_buffer(32)
+        return out.raw if self.L.oracle_point_add(out, p, q, int(subtract)) else None
+
+    def eddsa_verify(self, pk, msg, sig):
+        return self.L.oracle_eddsa_verify(pk, msg, len(msg), sig, len(sig))
+
+    def schnorr_verify(self, pk, msg, sig):
+        return self.L.oracle_schnorr_verify(pk, msg, len(msg), sig, len(sig))
+
+    def pubpoly_eval(self, commits, idx):
+        out = ctypes.create_string_buffer(32)
+        ok = self.L.oracle_pubpoly_eval(out, b"".join(commits), len(commits), idx)
+        return out.raw if ok else None
+
+    def vss_verify_deal(self, commits, idx, share):
+        return self.L.oracle_vss_verify_deal(b"".join(commits), len(commits), idx, share)
+
+    # ---- numpy batch wrappers (uint8 arrays, C-contiguous)
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def mul_base_batch(self, scalars, nthreads=1):
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+        out = np.empty_like(scalars)
+        self.L.oracle_mul_base_batch(scalars.shape[0], self._p(scalars), self._p(out), nthreads)
+        return out
+
+    def mul_batch(self, scalars, points, nthreads=1):
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+        points = np.ascontiguousarray(points, dtype=np.uint8)
+        out = np.empty_like(scalars)
+        self.L.oracle_mul_batch(scalars.shape[0], self._p(scalars), self._p(points), self._p(out), nthreads)
+        return out
+
+    def verify_batch(self, pk, msg, msg_off, sig, nthreads=1, schnorr=False):
+        pk = np.ascontiguousarray(pk, dtype=np.uint8)
+        sig = np.ascontiguousarray(sig, dtype=np.uint8)
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        n = pk.shape[0]
+        st = np.empty(n, dtype=np.uint8)
+        fn = self.L.oracle_schnorr_verify_batch if schnorr else self.L.oracle_eddsa_verify_batch
+        fn(n, self._p(pk), self._p(msg), self._p(msg_off), self._p(sig), self._p(st), nthreads)
+        return st
+
+    def vss_verify_batch(self, commits, idx, shares, nthreads=1):
+        commits = np.ascontiguousarray(commits, dtype=np.uint8)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        shares = np.ascontiguousarray(shares, dtype=np.uint8)
+        out = np.empty(idx.shape[0], dtype=np.uint8)
+        self.L.oracle_vss_verify_batch(self._p(commits), commits.shape[0], idx.shape[0], self._p(idx), self._p(shares), self._p(out), nthreads)
+        return out
+
+    def msm(self, scalars, points):
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint8)
+        points = np.ascontiguousarray(points, dtype=np.uint8)
+        out = ctypes.create_string_buffer(32)
+        ok = self.L.oracle_msm(out, scalars.shape[0], self._p(scalars), self._p(points))
+        return out.raw if ok else None
+
+
+_ORACLE = None
+
+
+def load_c_oracle():
+    global _ORACLE
+    if _ORACLE is None:
+        path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        src = os.path.join(ROOT, "oracle", "ref10_port.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        _ORACLE = COracle(path)
+    return _ORACLE
+
+
+L_ORDER = 2**252 + 27742317777372353535851937790883648493
+
+
+def xof_bytes(seed: str, n: int) -> bytes:
+    """Deterministic byte stream: BLAKE3-XOF of an ASCII seed — the construction behind the
+    reference's suite.xof(Some(seed)) (suite.rs:128-133, xof/blake3/xof.rs:114-125).  Falls
+    back to SHAKE-256 if the blake3 module is missing (only determinism matters here)."""
+    try:
+        import blake3
+
+        return blake3.blake3(seed.encode()).digest(length=n)
+    except ImportError:  # pragma: no cover
+        return hashlib.shake_256(seed.encode()).digest(n)
+
+
+def random_scalars(seed: str, n: int) -> np.ndarray:
+    """n scalars < L as an (n,32) uint8 array (top 4 bits masked then reduced mod L;
+    the distribution detail is irrelevant to parity)."""
+    raw = np.frombuffer(xof_bytes(seed, 32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    out = np.empty_like(raw)
+    for i in range(n):
+        v = int.from_bytes(raw[i].tobytes(), "little") % L_ORDER
+        out[i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+    return out
