@@ -1,0 +1,150 @@
+/*
+ * kyber_b200.h — C ABI of the B200-native edwards25519 hot path of teleconsys/kyber-rs.
+ *
+ * This is the drop-in boundary.  kyber-rs has no FFI of its own; the seam is
+ * its generic trait surface (src/group.rs: Scalar :22, Point :85, Group :185) that every
+ * protocol module is generic over.  A `kyber-b200-sys` crate binds exactly these symbols
+ *  and adds batch methods behind the same traits.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference/src).
+ *
+ * Conventions
+ *  - Points and scalars cross the ABI in the reference's own wire encoding: 32-byte
+ *    compressed points (Point::marshal_binary, group/edwards25519/point.rs:35-41) and
+ *    32-byte little-endian scalars (Scalar.v, scalar.rs:24).  Scalars are used as raw
+ *    integers, never reduced mod L on entry, exactly like Point::mul.
+ *  - All buffers are caller-owned.  `kb_*` functions take HOST pointers, copy in, run the
+ *    CUDA kernels, copy out and return after the device has finished.  `kb_dev_*` functions
+ *    take DEVICE pointers plus a CUDA stream (cudaStream_t as void*, NULL = default stream)
+ *    and only enqueue work; nothing is retained after return.
+ *  - Return value: KB_OK or a negative kb_err.  Per-item outcomes go to status arrays.
+ *  - There is no CPU fallback: with no usable CUDA device every call fails with
+ *    KB_ERR_CUDA.
+ *  - A context is bound to one CUDA device and is not thread-safe; use one per host thread
+ *    (the reference is single-threaded, group.rs has no shared mutable state).
+ */
+#ifndef KYBER_B200_H
+#define KYBER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kb_ctx kb_ctx;
+
+typedef enum kb_err {
+    KB_OK = 0,
+    KB_ERR_ARG = -1,   /* null pointer / bad size / bad flag */
+    KB_ERR_CUDA = -2,  /* CUDA runtime error; kb_last_error() has the text */
+    KB_ERR_NOMEM = -3,
+} kb_err;
+
+/* Per-signature outcome; mirrors SignatureError (sign/error.rs:6-25) in the order the
+ * respective verifier reports it. */
+typedef enum kb_sig_status {
+    KB_SIG_STATUS_OK = 0,
+    KB_SIG_STATUS_LENGTH = 1,            /* InvalidSignatureLength (host-side mirror only) */
+    KB_SIG_STATUS_NOT_CANONICAL = 2,     /* SignatureNotCanonical  */
+    KB_SIG_STATUS_R_NOT_CANONICAL = 3,   /* RNotCanonical          */
+    KB_SIG_STATUS_R_SMALL_ORDER = 4,     /* RSmallOrder            */
+    KB_SIG_STATUS_PK_NOT_CANONICAL = 5,  /* PublicKeyNotCanonical  */
+    KB_SIG_STATUS_PK_SMALL_ORDER = 6,    /* PublicKeySmallOrder    */
+    KB_SIG_STATUS_MARSHALLING = 7,       /* MarshallingError: "invalid Ed25519 curve point" */
+    KB_SIG_STATUS_INVALID = 8            /* InvalidSignature       */
+} kb_sig_status;
+
+/* flags for the scalar-multiplication entry points */
+#define KB_FLAG_VARTIME 1u      /* scalars are public: direct table indexing instead of the
+                                   reference's constant-time select (ge.rs:423-434,488-500) */
+#define KB_FLAG_SHARED_POINT 2u /* `points` holds ONE 32-byte point used for every scalar  */
+
+/* ---- context ---------------------------------------------------------------------- */
+int kb_ctx_create(int device, kb_ctx** out);
+void kb_ctx_destroy(kb_ctx* ctx);
+const char* kb_last_error(const kb_ctx* ctx);
+int kb_device_sm_count(const kb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t kb_launch_count(const kb_ctx* ctx);
+/* pinned host memory for callers that want full PCIe bandwidth on the kb_* copies */
+void* kb_host_alloc(size_t bytes);
+void kb_host_free(void* p);
+
+/* ---- Point::mul (group/edwards25519/point.rs:207-225) ------------------------------- */
+/* out[i] = compress(scalars[i] * B): Point::mul(s, None) -> ge_scalar_mult_base (ge.rs:442) */
+int kb_point_mul_base_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, uint8_t* out, uint32_t flags);
+/* out[i] = compress(scalars[i] * P_i): Point::mul(s, Some(p)) -> ge_scalar_mult (ge.rs:508).
+ * status[i] = 1 when points[i] fails Point::unmarshal_binary (ge.rs:124; out[i] is then zero). */
+int kb_point_mul_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, uint8_t* status, uint32_t flags);
+
+/* ---- encodings and point arithmetic ------------------------------------------------- */
+/* Point::unmarshal_binary followed by marshal_binary (ge.rs:124-179 then :112-122):
+ * out[i] = canonical re-encoding, status[i] = 1 if the input is not a curve point. */
+int kb_point_recode_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* status);
+/* Point::add / Point::sub (point.rs:179,190) on encodings; status[i] = 1 if either fails to decode */
+int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* out, uint8_t* status, int subtract);
+/* byte-level checks: bit0 = Point::is_canonical (point.rs:322, bug-compatible),
+ * bit1 = Point::has_small_order (point.rs:286), bit2 = decodes (ge.rs:124) */
+int kb_point_check_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* flags_out);
+
+/* ---- scalars -------------------------------------------------------------------------- */
+/* Scalar::set_bytes on 64-byte digests (scalar.rs:175; integer_field/integer.rs:386): LE integer mod L */
+int kb_sc_reduce64_batch(kb_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out32);
+/* sc_mul_add (scalar.rs:279): out = (a*b + c) mod L; with c = 0 this is Scalar `*`, with b = 1 Scalar `+` */
+int kb_sc_muladd_batch(kb_ctx* ctx, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out);
+/* h_i = Scalar::set_bytes(SHA-512(R_i || A_i || M_i)) (eddsa_sig.rs:195-200, schnorr_sig.rs:128-141,
+ * dss_sig.rs:312-326).  msg_off has n+1 entries; message i is msg[msg_off[i] .. msg_off[i+1]). */
+int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out32);
+
+/* ---- signatures ----------------------------------------------------------------------- */
+/* eddsa::verify_with_checks (sign/eddsa/eddsa_sig.rs:159-212); sig is n x 64 bytes */
+int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);
+/* schnorr::verify_with_checks (sign/schnorr/schnorr_sig.rs:53-110) */
+int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);
+
+/* ---- committed polynomials (share/poly.rs) -------------------------------------------- */
+/* PubPoly::eval (poly.rs:457-469) for npoly polynomials of t commitments each
+ * (commits = npoly*t encodings, coefficient-major inside a polynomial):
+ * out[k] = compress(poly[poly_id[k]].eval(idx[k])), status[k] = 1 if that polynomial holds an
+ * undecodable commitment. */
+int kb_pubpoly_eval_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, uint8_t* out, uint8_t* status);
+/* Group math of vss::pedersen Aggregator::verify_deal (share/vss/pedersen/vss.rs:899-912) and
+ * PubPoly::check (poly.rs:526-530): verdict[k] = 1 iff shares[k]*B == poly[poly_id[k]].eval(idx[k])
+ * on canonical bytes, 0 otherwise (including undecodable commitments). */
+int kb_vss_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* verdict);
+/* A whole Pedersen-DKG deal-verification round (share/dkg/pedersen/dkg.rs:513-597 x n^2):
+ * dealer d's polynomial is commits[d*t .. (d+1)*t), shares[d*n + i] is the share dealer d sent
+ * to verifier i; verdict[d*n + i] as above.  Dealers [dealer_lo, dealer_hi) only — the unit a
+ * rank owns when the round is sharded by dealer. */
+int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const uint8_t* commits, const uint8_t* shares, uint8_t* verdict);
+/* PubPoly::add (poly.rs:486-509): out[j] = a[j] + b[j] — kb_point_add_batch on t points */
+
+/* ---- multi-scalar multiplication ------------------------------------------------------ */
+/* out = compress(sum_i scalars[i] * P_i), the fold of Point::mul + Point::add (point.rs:179,207)
+ * computed with Pippenger's bucket method.  *bad_points = number of undecodable inputs (the
+ * result is then undefined).  partial128: if non-NULL, receives the UNcompressed sum as
+ * 4 x 8 LE words (X,Y,Z,T) so that per-GPU partials can be combined with kb_point_sum. */
+int kb_msm(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out32, uint8_t* partial128, uint64_t* bad_points);
+/* out = compress(sum of k uncompressed partials) — the final reduction after the NCCL gather */
+int kb_point_sum(kb_ctx* ctx, size_t k, const uint8_t* partials128, uint8_t* out32);
+
+/* ---- device-pointer variants (inputs already resident in HBM) --------------------------- */
+int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream);
+int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_out, uint32_t flags, void* stream);
+int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status, uint32_t flags, void* stream);
+int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out32, void* d_partial128, void* d_bad_points, void* stream);
+int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream);
+int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+/* Integer-multiply roofline probe: runs `iters` dependent-chain-free IMAD.WIDE.U32 per thread
+ * on every SM and returns the achieved 32x32->64 multiply-accumulates per second.
+ * kind: 0 = IMAD.WIDE.U32 (64-bit accumulate), 1 = IMAD (32-bit lo), 2 = IMAD.WIDE.U32.X carry chains,
+ * 3 = the library's own fe_mul (reported in IMAD-eq at 72 per multiplication). */
+int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KYBER_B200_H */

@@ -1,0 +1,302 @@
+"""ctypes binding of include/kyber_b200.h.  Pure plumbing: numpy (host) or torch (device)
+buffers in, kernel launches inside the library, buffers out."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkyber_b200.so")
+
+FLAG_VARTIME = 1
+FLAG_SHARED_POINT = 2
+
+# kb_sig_status -> the reference's SignatureError display strings (sign/error.rs:6-25)
+SIG_STATUS_NAMES = {
+    0: "ok",
+    1: "wrong signature length",
+    2: "signature is not canonical",
+    3: "R is not canonical",
+    4: "R has small order",
+    5: "public key is not canonical",
+    6: "public key has small order",
+    7: "marshalling error",
+    8: "signature is not valid",
+}
+
+
+class KBError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+# every symbol include/kyber_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
+    "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_add_batch", "kb_point_check_batch",
+    "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch",
+    "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_msm", "kb_point_sum",
+    "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
+    "kb_probe_imad",
+]
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen libkyber_b200.so.  Fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(path):
+        raise KBError(f"{path} not found: build it with `make -C kyber-rs_b200/csrc` (or __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(path)
+    vp, sz, u32, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+    L.kb_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.kb_ctx_destroy.argtypes = [vp]
+    L.kb_ctx_destroy.restype = None
+    L.kb_last_error.argtypes = [vp]
+    L.kb_last_error.restype = ctypes.c_char_p
+    L.kb_device_sm_count.argtypes = [vp]
+    L.kb_launch_count.argtypes = [vp]
+    L.kb_launch_count.restype = ctypes.c_uint64
+    L.kb_host_alloc.argtypes = [sz]
+    L.kb_host_alloc.restype = vp
+    L.kb_host_free.argtypes = [vp]
+    L.kb_host_free.restype = None
+    L.kb_point_mul_base_batch.argtypes = [vp, sz, vp, vp, u32]
+    L.kb_point_mul_batch.argtypes = [vp, sz, vp, vp, vp, vp, u32]
+    L.kb_point_recode_batch.argtypes = [vp, sz, vp, vp, vp]
+    L.kb_point_add_batch.argtypes = [vp, sz, vp, vp, vp, vp, i32]
+    L.kb_point_check_batch.argtypes = [vp, sz, vp, vp]
+    L.kb_sc_reduce64_batch.argtypes = [vp, sz, vp, vp]
+    L.kb_sc_muladd_batch.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.kb_challenge_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.kb_eddsa_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.kb_schnorr_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.kb_pubpoly_eval_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
+    L.kb_vss_verify_deals_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
+    L.kb_dkg_verify_round.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
+    L.kb_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.kb_point_sum.argtypes = [vp, sz, vp, vp]
+    L.kb_dev_eddsa_verify.argtypes = [vp, sz, vp, vp, vp, vp, vp, i32, vp]
+    L.kb_dev_point_mul_base.argtypes = [vp, sz, vp, vp, u32, vp]
+    L.kb_dev_point_mul.argtypes = [vp, sz, vp, vp, vp, vp, u32, vp]
+    L.kb_dev_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
+    L.kb_dev_dkg_verify_round.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
+    L.kb_dev_point_sum.argtypes = [vp, sz, vp, vp, vp]
+    L.kb_probe_imad.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    _LIB = L
+    return L
+
+
+def _u8(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def pack_messages(msgs):
+    """list of bytes -> (flat uint8 array, uint64 offsets[n+1]) as the C ABI wants them."""
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    if len(msgs):
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    flat = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy() if int(off[-1]) else np.zeros(0, dtype=np.uint8)
+    return flat, off
+
+
+class Context:
+    """One kb_ctx: one CUDA device, one host thread (the reference is single-threaded)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = ctypes.c_void_p()
+        rc = self.L.kb_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise KBError(f"kb_ctx_create(device={device}) failed with {rc}: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise KBError(f"{what} failed with {rc}: {self.L.kb_last_error(self.h).decode(errors='replace')}")
+
+    @property
+    def sm_count(self):
+        return self.L.kb_device_sm_count(self.h)
+
+    @property
+    def launches(self):
+        return int(self.L.kb_launch_count(self.h))
+
+    # ---- host-buffer API (numpy in / numpy out) ------------------------------------------
+    def point_mul_base_batch(self, scalars, flags=0):
+        s = _u8(scalars, (-1, 32))
+        out = np.empty_like(s)
+        self._check(self.L.kb_point_mul_base_batch(self.h, s.shape[0], _ptr(s), _ptr(out), flags), "kb_point_mul_base_batch")
+        return out
+
+    def point_mul_batch(self, scalars, points, flags=0):
+        s = _u8(scalars, (-1, 32))
+        p = _u8(points, (-1, 32))
+        if p.shape[0] == 1 and s.shape[0] != 1:
+            flags |= FLAG_SHARED_POINT
+        out = np.empty_like(s)
+        st = np.empty(s.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_point_mul_batch(self.h, s.shape[0], _ptr(s), _ptr(p), _ptr(out), _ptr(st), flags), "kb_point_mul_batch")
+        return out, st
+
+    def point_recode_batch(self, pts):
+        p = _u8(pts, (-1, 32))
+        out = np.empty_like(p)
+        st = np.empty(p.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_point_recode_batch(self.h, p.shape[0], _ptr(p), _ptr(out), _ptr(st)), "kb_point_recode_batch")
+        return out, st
+
+    def point_add_batch(self, p, q, subtract=False):
+        p = _u8(p, (-1, 32))
+        q = _u8(q, (-1, 32))
+        assert p.shape == q.shape
+        out = np.empty_like(p)
+        st = np.empty(p.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_point_add_batch(self.h, p.shape[0], _ptr(p), _ptr(q), _ptr(out), _ptr(st), int(subtract)), "kb_point_add_batch")
+        return out, st
+
+    def point_check_batch(self, pts):
+        p = _u8(pts, (-1, 32))
+        fl = np.empty(p.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_point_check_batch(self.h, p.shape[0], _ptr(p), _ptr(fl)), "kb_point_check_batch")
+        return fl
+
+    def sc_reduce64_batch(self, digests):
+        d = _u8(digests, (-1, 64))
+        out = np.empty((d.shape[0], 32), dtype=np.uint8)
+        self._check(self.L.kb_sc_reduce64_batch(self.h, d.shape[0], _ptr(d), _ptr(out)), "kb_sc_reduce64_batch")
+        return out
+
+    def sc_muladd_batch(self, a, b, c):
+        a, b, c = _u8(a, (-1, 32)), _u8(b, (-1, 32)), _u8(c, (-1, 32))
+        out = np.empty_like(a)
+        self._check(self.L.kb_sc_muladd_batch(self.h, a.shape[0], _ptr(a), _ptr(b), _ptr(c), _ptr(out)), "kb_sc_muladd_batch")
+        return out
+
+    def challenge_batch(self, r, a, msg, msg_off):
+        r, a = _u8(r, (-1, 32)), _u8(a, (-1, 32))
+        msg = _u8(msg)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        out = np.empty_like(r)
+        self._check(self.L.kb_challenge_batch(self.h, r.shape[0], _ptr(r), _ptr(a), _ptr(msg), _ptr(msg_off), _ptr(out)), "kb_challenge_batch")
+        return out
+
+    def verify_batch(self, pk, msg, msg_off, sig, schnorr=False):
+        pk, sig = _u8(pk, (-1, 32)), _u8(sig, (-1, 64))
+        msg = _u8(msg)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        n = pk.shape[0]
+        assert sig.shape[0] == n and msg_off.shape[0] == n + 1
+        st = np.empty(n, dtype=np.uint8)
+        fn = self.L.kb_schnorr_verify_batch if schnorr else self.L.kb_eddsa_verify_batch
+        self._check(fn(self.h, n, _ptr(pk), _ptr(msg), _ptr(msg_off), _ptr(sig), _ptr(st)), "kb_verify_batch")
+        return st
+
+    def pubpoly_eval_batch(self, commits, t, poly_id, idx):
+        c = _u8(commits, (-1, 32))
+        npoly = c.shape[0] // t
+        assert npoly * t == c.shape[0]
+        poly_id = np.ascontiguousarray(poly_id, dtype=np.uint32)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        m = idx.shape[0]
+        out = np.empty((m, 32), dtype=np.uint8)
+        st = np.empty(m, dtype=np.uint8)
+        self._check(self.L.kb_pubpoly_eval_batch(self.h, npoly, t, _ptr(c), m, _ptr(poly_id), _ptr(idx), _ptr(out), _ptr(st)), "kb_pubpoly_eval_batch")
+        return out, st
+
+    def vss_verify_deals_batch(self, commits, t, poly_id, idx, shares):
+        c = _u8(commits, (-1, 32))
+        npoly = c.shape[0] // t
+        assert npoly * t == c.shape[0]
+        poly_id = np.ascontiguousarray(poly_id, dtype=np.uint32)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        sh = _u8(shares, (-1, 32))
+        m = idx.shape[0]
+        verdict = np.empty(m, dtype=np.uint8)
+        self._check(self.L.kb_vss_verify_deals_batch(self.h, npoly, t, _ptr(c), m, _ptr(poly_id), _ptr(idx), _ptr(sh), _ptr(verdict)), "kb_vss_verify_deals_batch")
+        return verdict
+
+    def dkg_verify_round(self, n, t, commits, shares, dealer_lo=0, dealer_hi=None, verdict=None):
+        c = _u8(commits, (-1, 32))
+        sh = _u8(shares, (-1, 32))
+        ndealers = c.shape[0] // t
+        if dealer_hi is None:
+            dealer_hi = ndealers
+        if verdict is None:
+            verdict = np.zeros(ndealers * n, dtype=np.uint8)
+        self._check(self.L.kb_dkg_verify_round(self.h, n, t, dealer_lo, dealer_hi, _ptr(c), _ptr(sh), _ptr(verdict)), "kb_dkg_verify_round")
+        return verdict
+
+    def msm(self, scalars, points, want_partial=False):
+        s, p = _u8(scalars, (-1, 32)), _u8(points, (-1, 32))
+        assert s.shape == p.shape
+        out = np.empty(32, dtype=np.uint8)
+        partial = np.empty(128, dtype=np.uint8)
+        bad = np.zeros(1, dtype=np.uint64)
+        self._check(self.L.kb_msm(self.h, s.shape[0], _ptr(s), _ptr(p), _ptr(out), _ptr(partial), _ptr(bad)), "kb_msm")
+        if want_partial:
+            return out.tobytes(), partial, int(bad[0])
+        return out.tobytes(), int(bad[0])
+
+    def point_sum(self, partials):
+        p = _u8(partials, (-1, 128))
+        out = np.empty(32, dtype=np.uint8)
+        self._check(self.L.kb_point_sum(self.h, p.shape[0], _ptr(p), _ptr(out)), "kb_point_sum")
+        return out.tobytes()
+
+    def probe_imad(self, kind, iters):
+        rate, ms = ctypes.c_double(), ctypes.c_double()
+        self._check(self.L.kb_probe_imad(self.h, kind, iters, ctypes.byref(rate), ctypes.byref(ms)), "kb_probe_imad")
+        return rate.value, ms.value
+
+    # ---- device-pointer API (torch CUDA tensors; enqueues on torch's current stream) --------
+    @staticmethod
+    def _dp(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def dev_verify(self, n, pk, msg, msg_off, sig, status, schnorr=False):
+        self._check(self.L.kb_dev_eddsa_verify(self.h, n, self._dp(pk), self._dp(msg), self._dp(msg_off), self._dp(sig), self._dp(status), int(schnorr), self._stream()), "kb_dev_eddsa_verify")
+
+    def dev_point_mul_base(self, n, scalars, out, flags=0):
+        self._check(self.L.kb_dev_point_mul_base(self.h, n, self._dp(scalars), self._dp(out), flags, self._stream()), "kb_dev_point_mul_base")
+
+    def dev_point_mul(self, n, scalars, points, out, status, flags=0):
+        self._check(self.L.kb_dev_point_mul(self.h, n, self._dp(scalars), self._dp(points), self._dp(out), self._dp(status), flags, self._stream()), "kb_dev_point_mul")
+
+    def dev_msm(self, n, scalars, points, out32, partial128, bad):
+        self._check(self.L.kb_dev_msm(self.h, n, self._dp(scalars), self._dp(points), self._dp(out32), self._dp(partial128), self._dp(bad), self._stream()), "kb_dev_msm")
+
+    def dev_dkg_verify_round(self, n, t, ndealers, commits, shares, verdict):
+        self._check(self.L.kb_dev_dkg_verify_round(self.h, n, t, ndealers, self._dp(commits), self._dp(shares), self._dp(verdict), self._stream()), "kb_dev_dkg_verify_round")
+
+    def dev_point_sum(self, k, partials, out32):
+        self._check(self.L.kb_dev_point_sum(self.h, k, self._dp(partials), self._dp(out32), self._stream()), "kb_dev_point_sum")

@@ -1,0 +1,586 @@
+// capi.cu — the C ABI declared in include/kyber_b200.h.  Host code here only moves bytes
+// and launches kernels; there is deliberately no CPU implementation of any operation.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/kyber_b200.h"
+#include "kernels.cuh"
+#include "msm.cuh"
+
+#define KB_NSLOTS 28
+
+struct kb_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    ge_precomp* base_table;  // 64 x 8 entries
+    void* slot[KB_NSLOTS];
+    size_t slot_bytes[KB_NSLOTS];
+    uint64_t launches;
+    char err[256];
+};
+
+static int kb_fail(kb_ctx* ctx, cudaError_t e, const char* what)
+{
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+    return KB_ERR_CUDA;
+}
+#define KB_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return kb_fail(ctx, e_, #call);     \
+    } while (0)
+#define KB_LAUNCHED()                                              \
+    do {                                                           \
+        ctx->launches++;                                           \
+        cudaError_t e_ = cudaGetLastError();                       \
+        if (e_ != cudaSuccess) return kb_fail(ctx, e_, "launch");  \
+    } while (0)
+
+static inline unsigned kb_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// growable device scratch buffer
+static int kb_scratch(kb_ctx* ctx, int s, size_t bytes, void** out)
+{
+    if (bytes == 0) bytes = 16;
+    if (ctx->slot_bytes[s] < bytes) {
+        if (ctx->slot[s]) {
+            KB_CUDA(cudaDeviceSynchronize());  // callers' streams may still be using it
+            KB_CUDA(cudaFree(ctx->slot[s]));
+            ctx->slot[s] = nullptr;
+            ctx->slot_bytes[s] = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        KB_CUDA(cudaMalloc(&ctx->slot[s], want));
+        ctx->slot_bytes[s] = want;
+    }
+    *out = ctx->slot[s];
+    return KB_OK;
+}
+#define KB_SCRATCH(s, bytes, ptr)                                          \
+    do {                                                                   \
+        void* p_;                                                          \
+        int rc_ = kb_scratch(ctx, (s), (bytes), &p_);                      \
+        if (rc_ != KB_OK) return rc_;                                      \
+        (ptr) = reinterpret_cast<decltype(ptr)>(p_);                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// Pippenger driver (msm.cuh): chunks of <= KB_MSM_CHUNK points, partial sums chained on device
+// ------------------------------------------------------------------------------------
+static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st)
+{
+    uint32_t* acc128 = d_partial128;
+    if (!acc128) KB_SCRATCH(10, 128, acc128);
+    uint32_t* bad;
+    if (d_bad) bad = reinterpret_cast<uint32_t*>(d_bad);
+    else KB_SCRATCH(11, 8, bad);
+    KB_CUDA(cudaMemsetAsync(bad, 0, 8, st));
+    if (n == 0) {
+        kb_msm_plan pl = {0, 4, 0, 8, 0};
+        k_msm_finish<<<1, 32, 0, st>>>(pl, 1, nullptr, acc128, 1, d_out32);
+        KB_LAUNCHED();
+        return KB_OK;
+    }
+    for (size_t off = 0; off < n; off += KB_MSM_CHUNK) {
+        const size_t cn = (n - off < KB_MSM_CHUNK) ? (n - off) : KB_MSM_CHUNK;
+        kb_msm_plan pl;
+        pl.n = (uint32_t)cn;
+        pl.c = kb_msm_window_bits_host(cn);
+        pl.windows = (257 + pl.c - 1) / pl.c;
+        pl.half = 1u << (pl.c - 1);
+        pl.nb = pl.windows * pl.half;
+        const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
+        const size_t nthreads = (cn * pl.windows + KB_MSM_K - 1) / KB_MSM_K;
+        uint32_t *pts, *mags, *counts, *offsets, *cursor, *sorted, *bucket_sum, *heads, *tails, *partial;
+        uint8_t *negs, *flags;
+        KB_SCRATCH(12, 96 * cn, pts);
+        KB_SCRATCH(13, 32 * cn, mags);
+        KB_SCRATCH(14, cn, negs);
+        KB_SCRATCH(15, 4 * (size_t)pl.nb, counts);
+        KB_SCRATCH(16, 4 * ((size_t)pl.nb + 1), offsets);
+        KB_SCRATCH(17, 4 * (size_t)pl.nb, cursor);
+        KB_SCRATCH(18, 4 * cn * pl.windows, sorted);
+        KB_SCRATCH(19, 128 * (size_t)pl.nb, bucket_sum);
+        KB_SCRATCH(20, 128 * nthreads, heads);
+        KB_SCRATCH(21, 128 * nthreads, tails);
+        KB_SCRATCH(22, nthreads, flags);
+        KB_SCRATCH(23, 128 * (size_t)pl.windows * groups, partial);
+        KB_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)pl.nb, st));
+        k_msm_prepare<<<kb_blocks(cn, KB_THREADS), KB_THREADS, 0, st>>>(cn, d_points + 32 * off, d_scalars + 32 * off, pts, mags, negs, bad);
+        KB_LAUNCHED();
+        k_msm_hist<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, counts);
+        KB_LAUNCHED();
+        k_msm_scan<<<1, 1024, 0, st>>>(pl.nb, counts, offsets, cursor);
+        KB_LAUNCHED();
+        k_msm_scatter<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, negs, offsets, cursor, sorted);
+        KB_LAUNCHED();
+        k_msm_accum<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, sorted, pts, bucket_sum, heads, tails, flags);
+        KB_LAUNCHED();
+        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, bucket_sum, heads, tails, flags);
+        KB_LAUNCHED();
+        k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial);
+        KB_LAUNCHED();
+        const bool last = off + cn >= n;
+        k_msm_finish<<<1, 1024, 128 * pl.windows, st>>>(pl, groups, partial, acc128, off == 0 ? 1 : 0, last ? d_out32 : nullptr);
+        KB_LAUNCHED();
+    }
+    return KB_OK;
+}
+
+extern "C" {
+
+int kb_ctx_create(int device, kb_ctx** out)
+{
+    if (!out) return KB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return KB_ERR_CUDA;  // no CPU fallback
+    kb_ctx* ctx = (kb_ctx*)calloc(1, sizeof(kb_ctx));
+    if (!ctx) return KB_ERR_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
+    if (cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
+    k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
+    ctx->launches++;
+    cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+    cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+    cudaFuncSetAttribute(k_poly_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        cudaFree(ctx->base_table);
+        free(ctx);
+        return KB_ERR_CUDA;
+    }
+    *out = ctx;
+    return KB_OK;
+}
+
+void kb_ctx_destroy(kb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < KB_NSLOTS; s++)
+        if (ctx->slot[s]) cudaFree(ctx->slot[s]);
+    cudaFree(ctx->base_table);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+int kb_device_sm_count(const kb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t kb_launch_count(const kb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* kb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void kb_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------
+// device-pointer entry points
+// ------------------------------------------------------------------------------------
+int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_out, uint32_t flags, void* stream)
+{
+    if (!ctx || (n && (!d_scalars || !d_out))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = 64 * 8 * 96;
+    if (flags & KB_FLAG_VARTIME)
+        k_mul_base<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, (uint8_t*)d_out, ctx->base_table);
+    else
+        k_mul_base<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, (uint8_t*)d_out, ctx->base_table);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status, uint32_t flags, void* stream)
+{
+    if (!ctx || (n && (!d_scalars || !d_points || !d_out))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int shared_pt = (flags & KB_FLAG_SHARED_POINT) ? 1 : 0;
+    if (flags & KB_FLAG_VARTIME)
+        k_mul<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, (uint8_t*)d_out, (uint8_t*)d_status);
+    else
+        k_mul<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, (uint8_t*)d_out, (uint8_t*)d_status);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream)
+{
+    if (!ctx || (n && (!d_pk || !d_msg_off || !d_sig || !d_status))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (schnorr)
+        k_verify<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, (uint8_t*)d_status, ctx->base_table);
+    else
+        k_verify<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, (uint8_t*)d_status, ctx->base_table);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+// commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel
+static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_commits, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
+                       const uint8_t* d_shares, uint8_t* d_out, uint8_t* d_status, cudaStream_t st)
+{
+    uint32_t* cached;
+    uint8_t* bad;
+    const size_t nc = npoly * t;
+    KB_SCRATCH(8, nc * 128, cached);
+    KB_SCRATCH(9, nc, bad);
+    k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, st>>>(nc, d_commits, cached, bad);
+    KB_LAUNCHED();
+    const size_t smem = d_shares ? 64 * 8 * 96 : 0;
+    k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, smem, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, d_shares, d_out, d_status, ctx->base_table);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream)
+{
+    if (!ctx || !t || (n && ndealers && (!d_commits || !d_shares || !d_verdict))) return KB_ERR_ARG;
+    if (n == 0 || ndealers == 0) return KB_OK;
+    return kb_poly_run(ctx, ndealers, t, (const uint8_t*)d_commits, n * ndealers, nullptr, nullptr, n, (const uint8_t*)d_shares, (uint8_t*)d_verdict, nullptr, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------
+// host-pointer entry points: H2D, kernels, D2H, synchronise
+// ------------------------------------------------------------------------------------
+#define KB_H2D(dst, src, bytes) KB_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
+#define KB_D2H(dst, src, bytes) KB_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
+#define KB_SYNC() KB_CUDA(cudaStreamSynchronize(ctx->stream))
+#define KB_ENTER()                                  \
+    if (!ctx) return KB_ERR_ARG;                    \
+    KB_CUDA(cudaSetDevice(ctx->device))
+
+int kb_point_mul_base_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, uint8_t* out, uint32_t flags)
+{
+    KB_ENTER();
+    if (n && (!scalars || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_s, *d_o;
+    KB_SCRATCH(0, 32 * n, d_s);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_H2D(d_s, scalars, 32 * n);
+    int rc = kb_dev_point_mul_base(ctx, n, d_s, d_o, flags, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(out, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_point_mul_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, uint8_t* status, uint32_t flags)
+{
+    KB_ENTER();
+    if (n && (!scalars || !points || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    const size_t np = (flags & KB_FLAG_SHARED_POINT) ? 1 : n;
+    uint8_t *d_s, *d_p, *d_o, *d_st;
+    KB_SCRATCH(0, 32 * n, d_s);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_SCRATCH(2, 32 * np, d_p);
+    KB_SCRATCH(3, n, d_st);
+    KB_H2D(d_s, scalars, 32 * n);
+    KB_H2D(d_p, points, 32 * np);
+    int rc = kb_dev_point_mul(ctx, n, d_s, d_p, d_o, d_st, flags, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(out, d_o, 32 * n);
+    if (status) KB_D2H(status, d_st, n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_point_recode_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* status)
+{
+    KB_ENTER();
+    if (n && (!in || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_i, *d_o, *d_st;
+    KB_SCRATCH(0, 32 * n, d_i);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_SCRATCH(3, n, d_st);
+    KB_H2D(d_i, in, 32 * n);
+    k_recode<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_i, d_o, d_st);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * n);
+    if (status) KB_D2H(status, d_st, n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* out, uint8_t* status, int subtract)
+{
+    KB_ENTER();
+    if (n && (!p || !q || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_p, *d_q, *d_o, *d_st;
+    KB_SCRATCH(0, 32 * n, d_p);
+    KB_SCRATCH(2, 32 * n, d_q);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_SCRATCH(3, n, d_st);
+    KB_H2D(d_p, p, 32 * n);
+    KB_H2D(d_q, q, 32 * n);
+    k_point_add<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_p, d_q, d_o, d_st, subtract);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * n);
+    if (status) KB_D2H(status, d_st, n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_point_check_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* flags_out)
+{
+    KB_ENTER();
+    if (n && (!in || !flags_out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_i, *d_f;
+    KB_SCRATCH(0, 32 * n, d_i);
+    KB_SCRATCH(3, n, d_f);
+    KB_H2D(d_i, in, 32 * n);
+    k_point_check<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_i, d_f);
+    KB_LAUNCHED();
+    KB_D2H(flags_out, d_f, n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_sc_reduce64_batch(kb_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out32)
+{
+    KB_ENTER();
+    if (n && (!in64 || !out32)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_i, *d_o;
+    KB_SCRATCH(0, 64 * n, d_i);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_H2D(d_i, in64, 64 * n);
+    k_sc_reduce64<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_i, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out32, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_sc_muladd_batch(kb_ctx* ctx, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out)
+{
+    KB_ENTER();
+    if (n && (!a || !b || !c || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_a, *d_b, *d_c, *d_o;
+    KB_SCRATCH(0, 32 * n, d_a);
+    KB_SCRATCH(2, 32 * n, d_b);
+    KB_SCRATCH(4, 32 * n, d_c);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_H2D(d_a, a, 32 * n);
+    KB_H2D(d_b, b, 32 * n);
+    KB_H2D(d_c, c, 32 * n);
+    k_sc_muladd<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_a, d_b, d_c, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out32)
+{
+    KB_ENTER();
+    if (n && (!r32 || !a32 || !msg_off || !out32)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    const size_t mbytes = (size_t)msg_off[n];
+    if (mbytes && !msg) return KB_ERR_ARG;
+    uint8_t *d_r, *d_a, *d_m, *d_o;
+    uint64_t* d_off;
+    KB_SCRATCH(0, 32 * n, d_r);
+    KB_SCRATCH(2, 32 * n, d_a);
+    KB_SCRATCH(4, mbytes, d_m);
+    KB_SCRATCH(5, 8 * (n + 1), d_off);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_H2D(d_r, r32, 32 * n);
+    KB_H2D(d_a, a32, 32 * n);
+    if (mbytes) KB_H2D(d_m, msg, mbytes);
+    KB_H2D(d_off, msg_off, 8 * (n + 1));
+    k_challenge<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_r, d_a, d_m, d_off, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out32, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
+static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr)
+{
+    KB_ENTER();
+    if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    const size_t mbytes = (size_t)msg_off[n];
+    if (mbytes && !msg) return KB_ERR_ARG;
+    uint8_t *d_pk, *d_sig, *d_m, *d_st;
+    uint64_t* d_off;
+    KB_SCRATCH(0, 32 * n, d_pk);
+    KB_SCRATCH(2, 64 * n, d_sig);
+    KB_SCRATCH(4, mbytes, d_m);
+    KB_SCRATCH(5, 8 * (n + 1), d_off);
+    KB_SCRATCH(3, n, d_st);
+    KB_H2D(d_pk, pk, 32 * n);
+    KB_H2D(d_sig, sig, 64 * n);
+    if (mbytes) KB_H2D(d_m, msg, mbytes);
+    KB_H2D(d_off, msg_off, 8 * (n + 1));
+    int rc = kb_dev_eddsa_verify(ctx, n, d_pk, d_m, d_off, d_sig, d_st, schnorr, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(status, d_st, n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)
+{
+    return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 0);
+}
+int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)
+{
+    return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 1);
+}
+
+static int kb_poly_host(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* out,
+                        uint8_t* status)
+{
+    KB_ENTER();
+    if (!npoly || !t || !commits || (m && (!poly_id || !idx || !out))) return KB_ERR_ARG;
+    if (m == 0) return KB_OK;
+    for (size_t k = 0; k < m; k++)
+        if (poly_id[k] >= npoly) return KB_ERR_ARG;
+    uint8_t *d_c, *d_sh = nullptr, *d_o, *d_st;
+    uint32_t *d_pid, *d_idx;
+    const size_t out_bytes = shares ? m : 32 * m;
+    KB_SCRATCH(0, 32 * npoly * t, d_c);
+    KB_SCRATCH(5, 4 * m, d_pid);
+    KB_SCRATCH(6, 4 * m, d_idx);
+    KB_SCRATCH(1, out_bytes, d_o);
+    KB_SCRATCH(3, m, d_st);
+    KB_H2D(d_c, commits, 32 * npoly * t);
+    KB_H2D(d_pid, poly_id, 4 * m);
+    KB_H2D(d_idx, idx, 4 * m);
+    if (shares) {
+        KB_SCRATCH(2, 32 * m, d_sh);
+        KB_H2D(d_sh, shares, 32 * m);
+    }
+    int rc = kb_poly_run(ctx, npoly, t, d_c, m, d_pid, d_idx, 0, d_sh, d_o, d_st, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(out, d_o, out_bytes);
+    if (status && !shares) KB_D2H(status, d_st, m);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_pubpoly_eval_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, uint8_t* out, uint8_t* status)
+{
+    return kb_poly_host(ctx, npoly, t, commits, m, poly_id, idx, nullptr, out, status);
+}
+int kb_vss_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* verdict)
+{
+    if (m && !shares) return KB_ERR_ARG;
+    return kb_poly_host(ctx, npoly, t, commits, m, poly_id, idx, shares, verdict, nullptr);
+}
+int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const uint8_t* commits, const uint8_t* shares, uint8_t* verdict)
+{
+    KB_ENTER();
+    if (!t || dealer_hi < dealer_lo || !commits || !shares || !verdict) return KB_ERR_ARG;
+    const size_t nd = dealer_hi - dealer_lo;
+    if (nd == 0 || n == 0) return KB_OK;
+    uint8_t *d_c, *d_sh, *d_v;
+    KB_SCRATCH(0, 32 * nd * t, d_c);
+    KB_SCRATCH(2, 32 * nd * n, d_sh);
+    KB_SCRATCH(1, nd * n, d_v);
+    KB_H2D(d_c, commits + 32 * dealer_lo * t, 32 * nd * t);
+    KB_H2D(d_sh, shares + 32 * dealer_lo * n, 32 * nd * n);
+    int rc = kb_dev_dkg_verify_round(ctx, n, t, nd, d_c, d_sh, d_v, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(verdict + dealer_lo * n, d_v, nd * n);
+    KB_SYNC();
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// MSM
+// ------------------------------------------------------------------------------------
+int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out32, void* d_partial128, void* d_bad_points, void* stream)
+{
+    if (!ctx || (n && (!d_scalars || !d_points)) || (!d_out32 && !d_partial128)) return KB_ERR_ARG;
+    return kb_msm_run(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out32, (uint32_t*)d_partial128, (unsigned long long*)d_bad_points, (cudaStream_t)stream);
+}
+int kb_msm(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out32, uint8_t* partial128, uint64_t* bad_points)
+{
+    KB_ENTER();
+    if ((n && (!scalars || !points)) || (!out32 && !partial128)) return KB_ERR_ARG;
+    uint8_t *d_s, *d_p, *d_o;
+    KB_SCRATCH(0, 32 * n, d_s);
+    KB_SCRATCH(2, 32 * n, d_p);
+    KB_SCRATCH(1, 32 + 128 + 8, d_o);
+    if (n) {
+        KB_H2D(d_s, scalars, 32 * n);
+        KB_H2D(d_p, points, 32 * n);
+    }
+    int rc = kb_dev_msm(ctx, n, d_s, d_p, d_o, d_o + 32, d_o + 160, ctx->stream);
+    if (rc != KB_OK) return rc;
+    if (out32) KB_D2H(out32, d_o, 32);
+    if (partial128) KB_D2H(partial128, d_o + 32, 128);
+    if (bad_points) KB_D2H(bad_points, d_o + 160, 8);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream)
+{
+    if (!ctx || !d_out32 || (k && !d_partials128)) return KB_ERR_ARG;
+    k_point_sum<<<1, 32, 0, (cudaStream_t)stream>>>(k, (const uint32_t*)d_partials128, (uint8_t*)d_out32);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+int kb_point_sum(kb_ctx* ctx, size_t k, const uint8_t* partials128, uint8_t* out32)
+{
+    KB_ENTER();
+    if (!out32 || (k && !partials128)) return KB_ERR_ARG;
+    uint8_t *d_i, *d_o;
+    KB_SCRATCH(0, 128 * k, d_i);
+    KB_SCRATCH(1, 32, d_o);
+    if (k) KB_H2D(d_i, partials128, 128 * k);
+    int rc = kb_dev_point_sum(ctx, k, d_i, d_o, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(out32, d_o, 32);
+    KB_SYNC();
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// measurement
+// ------------------------------------------------------------------------------------
+int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double* elapsed_ms)
+{
+    KB_ENTER();
+    if (kind < 0 || kind > 3 || iters <= 0 || !macs_per_sec) return KB_ERR_ARG;
+    uint32_t* sink;
+    KB_SCRATCH(7, 16, sink);
+    const int threads = 256;
+    const int blocks = ctx->sm_count * 8;  // 2048 threads per SM: every SMSP has 16 warps to pick from
+    cudaEvent_t e0, e1;
+    KB_CUDA(cudaEventCreate(&e0));
+    KB_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {  // rep 0 warms up
+        KB_CUDA(cudaEventRecord(e0, ctx->stream));
+        switch (kind) {
+        case 0: k_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, sink); break;
+        case 1: k_probe<1><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, sink); break;
+        case 2: k_probe<2><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, sink); break;
+        default: k_probe<3><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, sink); break;
+        }
+        KB_LAUNCHED();
+        KB_CUDA(cudaEventRecord(e1, ctx->stream));
+        KB_CUDA(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double per_thread = (kind == 3) ? 2.0 * 72.0 : 8.0;  // MACs per loop iteration
+    const double macs = (double)blocks * threads * (double)iters * per_thread;
+    *macs_per_sec = macs / (ms * 1e-3);
+    if (elapsed_ms) *elapsed_ms = ms;
+    return KB_OK;
+}
+
+}  // extern "C"

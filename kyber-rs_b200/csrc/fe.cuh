@@ -1,0 +1,594 @@
+// fe.cuh — GF(2^255-19) arithmetic for sm_100a: 8 saturated 32-bit limbs, products built
+// from IMAD.WIDE.U32(.X) carry chains (PTX mad.lo.cc / madc.hi.cc pairs, which ptxas fuses).
+//
+// Replaces the reference's field layer src/group/edwards25519/fe.rs (10 signed 25.5-bit limbs,
+// i64 products).  Internal limb values are NOT the reference's; only what is observable
+// through fe_to_bytes / fe_is_negative / fe_is_zero has to match, and does.
+//
+// Representation invariant: an fe is any integer in [0, 2^256) congruent to the field
+// element mod p = 2^255-19 ("loosely reduced").  Every routine accepts and returns that.
+//
+// The same source compiles as plain host C++ when KB_HOST_EMU is defined; that build exists
+// ONLY so tests/ can exercise the per-thread math on a machine without a GPU.  The product
+// library never contains it (see csrc/Makefile) and has no CPU code path.
+#pragma once
+#include <stdint.h>
+
+#if defined(KB_HOST_EMU)
+#define KB_FN static inline
+#define KB_UNROLL
+#define KB_NOUNROLL
+#else
+#define KB_FN __device__ __forceinline__
+#define KB_UNROLL _Pragma("unroll")
+#define KB_NOUNROLL _Pragma("unroll 1")
+#endif
+
+struct fe {
+    uint32_t v[8];
+};
+
+// ---------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------
+
+// acc[0..7] += {a0,a1,a2,a3} * b, product k landing on the word pair (2k, 2k+1); the carry
+// out of word 7 is added to `top`.  8 PTX mads -> 4 IMAD.WIDE.U32.X.
+KB_FN void kb_cmad4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    uint64_t carry = 0;
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)a[k] * b;
+        uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + carry;
+        acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * k + 1] + (p >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+    top += (uint32_t)carry;
+#else
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#endif
+}
+
+// Same, for N = 1..3 products (used by the squaring's triangular rows).
+KB_FN void kb_cmad3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    const uint32_t a[3] = {a0, a1, a2};
+    uint64_t carry = 0;
+    for (int k = 0; k < 3; k++) {
+        uint64_t p = (uint64_t)a[k] * b;
+        uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + carry;
+        acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * k + 1] + (p >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+    top += (uint32_t)carry;
+#else
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#endif
+}
+KB_FN void kb_cmad2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    const uint32_t a[2] = {a0, a1};
+    uint64_t carry = 0;
+    for (int k = 0; k < 2; k++) {
+        uint64_t p = (uint64_t)a[k] * b;
+        uint64_t lo = (uint64_t)acc[2 * k] + (uint32_t)p + carry;
+        acc[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)acc[2 * k + 1] + (p >> 32) + (lo >> 32);
+        acc[2 * k + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+    top += (uint32_t)carry;
+#else
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(top)
+        : "r"(a0), "r"(a1), "r"(b));
+#endif
+}
+KB_FN void kb_cmad1(uint32_t* acc, uint32_t a0, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t p = (uint64_t)a0 * b;
+    uint64_t lo = (uint64_t)acc[0] + (uint32_t)p;
+    acc[0] = (uint32_t)lo;
+    uint64_t hi = (uint64_t)acc[1] + (p >> 32) + (lo >> 32);
+    acc[1] = (uint32_t)hi;
+    top += (uint32_t)(hi >> 32);
+#else
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(top)
+        : "r"(a0), "r"(b));
+#endif
+}
+
+// acc[0..15) += x[0..15) (no carry out: callers guarantee it fits)
+KB_FN void kb_acc15(uint32_t* acc, const uint32_t* x)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t c = 0;
+    for (int i = 0; i < 15; i++) {
+        c += (uint64_t)acc[i] + x[i];
+        acc[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#else
+    asm("add.cc.u32 %0, %0, %15;\n\t"
+        "addc.cc.u32 %1, %1, %16;\n\t"
+        "addc.cc.u32 %2, %2, %17;\n\t"
+        "addc.cc.u32 %3, %3, %18;\n\t"
+        "addc.cc.u32 %4, %4, %19;\n\t"
+        "addc.cc.u32 %5, %5, %20;\n\t"
+        "addc.cc.u32 %6, %6, %21;\n\t"
+        "addc.cc.u32 %7, %7, %22;\n\t"
+        "addc.cc.u32 %8, %8, %23;\n\t"
+        "addc.cc.u32 %9, %9, %24;\n\t"
+        "addc.cc.u32 %10, %10, %25;\n\t"
+        "addc.cc.u32 %11, %11, %26;\n\t"
+        "addc.cc.u32 %12, %12, %27;\n\t"
+        "addc.cc.u32 %13, %13, %28;\n\t"
+        "addc.u32 %14, %14, %29;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(x[8]), "r"(x[9]), "r"(x[10]), "r"(x[11]), "r"(x[12]), "r"(x[13]), "r"(x[14]));
+#endif
+}
+// acc[0..8) += x[0..8) (no carry out: callers guarantee it fits)
+KB_FN void kb_acc8(uint32_t* acc, const uint32_t* x)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)acc[i] + x[i];
+        acc[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#else
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+#endif
+}
+// t[0..16) <<= 1 (top bit must be clear)
+KB_FN void kb_dbl16(uint32_t* t)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t c = 0;
+    for (int i = 0; i < 16; i++) {
+        uint32_t n = t[i] >> 31;
+        t[i] = (t[i] << 1) | c;
+        c = n;
+    }
+#else
+    asm("add.cc.u32 %0, %0, %0;\n\t"
+        "addc.cc.u32 %1, %1, %1;\n\t"
+        "addc.cc.u32 %2, %2, %2;\n\t"
+        "addc.cc.u32 %3, %3, %3;\n\t"
+        "addc.cc.u32 %4, %4, %4;\n\t"
+        "addc.cc.u32 %5, %5, %5;\n\t"
+        "addc.cc.u32 %6, %6, %6;\n\t"
+        "addc.cc.u32 %7, %7, %7;\n\t"
+        "addc.cc.u32 %8, %8, %8;\n\t"
+        "addc.cc.u32 %9, %9, %9;\n\t"
+        "addc.cc.u32 %10, %10, %10;\n\t"
+        "addc.cc.u32 %11, %11, %11;\n\t"
+        "addc.cc.u32 %12, %12, %12;\n\t"
+        "addc.cc.u32 %13, %13, %13;\n\t"
+        "addc.cc.u32 %14, %14, %14;\n\t"
+        "addc.u32 %15, %15, %15;"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15]));
+#endif
+}
+// r = a + b over 8 words (each asm chain is ONE statement so the compiler cannot split it); returns the carry
+KB_FN uint32_t kb_add8(uint32_t* r, const uint32_t* a, const uint32_t* b)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a[i] + b[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+#else
+    uint32_t t[8], c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = t[i];
+    return c & 1;
+#endif
+}
+// r = a - b over 8 words; returns the borrow (0/1)
+KB_FN uint32_t kb_sub8(uint32_t* r, const uint32_t* a, const uint32_t* b)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t br = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] - b[i] - br;
+        r[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return (uint32_t)br;
+#else
+    uint32_t t[8], c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = t[i];
+    return c & 1;
+#endif
+}
+// r[0..8) += k (a 32-bit value), returns the carry out.
+KB_FN uint32_t kb_add_small(uint32_t* r, uint32_t k)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t c = k;
+    for (int i = 0; i < 8; i++) {
+        c += r[i];
+        r[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    return (uint32_t)c;
+#else
+    uint32_t c;
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "r"(k));
+    return c;
+#endif
+}
+// r[0..8) -= k, returns the borrow (0/1).
+KB_FN uint32_t kb_sub_small(uint32_t* r, uint32_t k)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t br = k;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)r[i] - br;
+        r[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return (uint32_t)br;
+#else
+    uint32_t c;
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.cc.u32 %5, %5, 0;\n\t"
+        "subc.cc.u32 %6, %6, 0;\n\t"
+        "subc.cc.u32 %7, %7, 0;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "r"(k));
+    return c & 1;
+#endif
+}
+
+// t[0..16) += a[i]^2 on word pairs (2i, 2i+1), one 16-instruction chain (8 IMAD.WIDE.U32.X).
+KB_FN void kb_sqr_acc8(uint32_t* t, const uint32_t* a)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t carry = 0;
+    for (int k = 0; k < 8; k++) {
+        uint64_t p = (uint64_t)a[k] * a[k];
+        uint64_t lo = (uint64_t)t[2 * k] + (uint32_t)p + carry;
+        t[2 * k] = (uint32_t)lo;
+        uint64_t hi = (uint64_t)t[2 * k + 1] + (p >> 32) + (lo >> 32);
+        t[2 * k + 1] = (uint32_t)hi;
+        carry = hi >> 32;
+    }
+#else
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
+          "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#endif
+}
+
+// ---------------------------------------------------------------------------------------
+// reduction of a 512-bit product: t[0..16) -> r[0..8), using 2^256 = 38 (mod p)
+// ---------------------------------------------------------------------------------------
+KB_FN void fe_reduce512(fe& r, uint32_t* t)
+{
+    // even high words: (t0..t7) += 38 * {t8,t10,t12,t14}, carry into r8
+    uint32_t r8 = 0;
+    kb_cmad4(t, t[8], t[10], t[12], t[14], 38u, r8);
+    // odd high words: 38*t9, 38*t11, 38*t13, 38*t15 land on word pairs (1,2) (3,4) (5,6) (7,8)
+    uint32_t o[8];
+    KB_UNROLL
+    for (int k = 0; k < 4; k++) {
+        uint64_t p = (uint64_t)t[9 + 2 * k] * 38u;
+        o[2 * k] = (uint32_t)p;
+        o[2 * k + 1] = (uint32_t)(p >> 32);
+    }
+    uint32_t hi[8];
+    KB_UNROLL
+    for (int k = 0; k < 7; k++) hi[k] = t[k + 1];
+    hi[7] = r8;
+    kb_acc8(hi, o);  // cannot carry: total < 39 * 2^256
+    // fold word 8 (< 2^7): value = t0 + 2^32*hi[0..7) + 2^256*hi[7]
+    r.v[0] = t[0];
+    KB_UNROLL
+    for (int k = 0; k < 7; k++) r.v[k + 1] = hi[k];
+    uint32_t c = kb_add_small(r.v, hi[7] * 38u);
+    // a second wrap leaves a value < 38*2^7, so adding 38 once more cannot carry
+    r.v[0] += 38u * c;
+}
+
+// h = f * g   (fe.rs:299 fe_mul)
+KB_FN void fe_mul(fe& h, const fe& f, const fe& g)
+{
+    uint32_t ev[17], od[16];
+    KB_UNROLL
+    for (int i = 0; i < 17; i++) ev[i] = 0;
+    KB_UNROLL
+    for (int i = 0; i < 16; i++) od[i] = 0;
+    const uint32_t* a = f.v;
+    const uint32_t* b = g.v;
+    // Operand scanning over b; products a[j]*b[i] with i+j even accumulate in ev (word i+j),
+    // those with i+j odd in od (od[k] is word k+1), so every IMAD.WIDE is pair-aligned.
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        if ((i & 1) == 0) {
+            kb_cmad4(&ev[i], a[0], a[2], a[4], a[6], b[i], ev[i + 8]);
+            kb_cmad4(&od[i], a[1], a[3], a[5], a[7], b[i], od[i + 8]);
+        } else {
+            kb_cmad4(&ev[i + 1], a[1], a[3], a[5], a[7], b[i], ev[i + 9]);
+            kb_cmad4(&od[i - 1], a[0], a[2], a[4], a[6], b[i], od[i + 7]);
+        }
+    }
+    kb_acc15(&ev[1], &od[0]);
+    fe_reduce512(h, ev);
+}
+
+// h = f^2   (fe.rs:544 fe_square): 28 cross products, doubled, plus 8 squares
+KB_FN void fe_sq(fe& h, const fe& f)
+{
+    uint32_t ev[17], od[16];
+    KB_UNROLL
+    for (int i = 0; i < 17; i++) ev[i] = 0;
+    KB_UNROLL
+    for (int i = 0; i < 16; i++) od[i] = 0;
+    const uint32_t* a = f.v;
+    // row i: a[j]*a[i] for j > i, word i+j
+    kb_cmad4(&od[0], a[1], a[3], a[5], a[7], a[0], od[8]);   // words 1,3,5,7
+    kb_cmad3(&ev[2], a[2], a[4], a[6], a[0], ev[8]);         // words 2,4,6
+    kb_cmad3(&od[2], a[2], a[4], a[6], a[1], od[8]);         // words 3,5,7
+    kb_cmad3(&ev[4], a[3], a[5], a[7], a[1], ev[10]);        // words 4,6,8
+    kb_cmad3(&od[4], a[3], a[5], a[7], a[2], od[10]);        // words 5,7,9
+    kb_cmad2(&ev[6], a[4], a[6], a[2], ev[10]);              // words 6,8
+    kb_cmad2(&od[6], a[4], a[6], a[3], od[10]);              // words 7,9
+    kb_cmad2(&ev[8], a[5], a[7], a[3], ev[12]);              // words 8,10
+    kb_cmad2(&od[8], a[5], a[7], a[4], od[12]);              // words 9,11
+    kb_cmad1(&ev[10], a[6], a[4], ev[12]);                   // word 10
+    kb_cmad1(&od[10], a[6], a[5], od[12]);                   // word 11
+    kb_cmad1(&ev[12], a[7], a[5], ev[14]);                   // word 12
+    kb_cmad1(&od[12], a[7], a[6], od[14]);                   // word 13
+    kb_acc15(&ev[1], &od[0]);
+    kb_dbl16(ev);        // double the cross terms (top bit is clear: sum < 2^511)
+    kb_sqr_acc8(ev, a);  // add the squares a[i]^2 on word pairs (2i, 2i+1)
+    fe_reduce512(h, ev);
+}
+
+// ---------------------------------------------------------------------------------------
+// linear operations (fe.rs: fe_add, fe_sub, fe_neg, fe_c_move)
+// ---------------------------------------------------------------------------------------
+KB_FN void fe_add(fe& h, const fe& f, const fe& g)
+{
+    uint32_t c = kb_add8(h.v, f.v, g.v);
+    c = kb_add_small(h.v, 38u * c);  // 2^256 = 38
+    h.v[0] += 38u * c;               // after a second wrap the value is < 38: cannot carry
+}
+KB_FN void fe_sub(fe& h, const fe& f, const fe& g)
+{
+    uint32_t b = kb_sub8(h.v, f.v, g.v);
+    b = kb_sub_small(h.v, 38u * b);  // -2^256 = -38
+    h.v[0] -= 38u * b;               // after a second wrap the value is >= 2^256-38: cannot borrow
+}
+KB_FN void fe_set(fe& h, uint32_t x)
+{
+    h.v[0] = x;
+    KB_UNROLL
+    for (int i = 1; i < 8; i++) h.v[i] = 0;
+}
+KB_FN void fe_neg(fe& h, const fe& f)
+{
+    fe z;
+    fe_set(z, 0);
+    fe_sub(h, z, f);
+}
+// f = b ? g : f   (b in {0,1}); no branch on b
+KB_FN void fe_cmov(fe& f, const fe& g, uint32_t b)
+{
+    uint32_t m = 0u - b;
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) f.v[i] ^= m & (f.v[i] ^ g.v[i]);
+}
+KB_FN void fe_dbl(fe& h, const fe& f) { fe_add(h, f, f); }
+
+// ---------------------------------------------------------------------------------------
+// canonical form and byte I/O (fe.rs:67 fe_from_bytes, :147 fe_to_bytes, :240, :246)
+// ---------------------------------------------------------------------------------------
+// words = little-endian 32-bit words of the 32-byte encoding; bit 255 is dropped and values
+// >= p are NOT rejected (fe.rs:67-77).
+KB_FN void fe_from_words(fe& h, const uint32_t* w)
+{
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) h.v[i] = w[i];
+    h.v[7] &= 0x7fffffffu;
+}
+// fully reduced representative in [0, p)
+KB_FN void fe_canon(fe& h, const fe& f)
+{
+    fe t = f;
+    // fold bit 255: t < 2^255 + 19
+    uint32_t top = t.v[7] >> 31;
+    t.v[7] &= 0x7fffffffu;
+    kb_add_small(t.v, 19u * top);
+    // t >= p  <=>  t + 19 >= 2^255
+    fe u = t;
+    kb_add_small(u.v, 19u);
+    uint32_t ge = u.v[7] >> 31;
+    u.v[7] &= 0x7fffffffu;
+    fe_cmov(t, u, ge);
+    h = t;
+}
+KB_FN void fe_to_words(uint32_t* w, const fe& f)
+{
+    fe t;
+    fe_canon(t, f);
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) w[i] = t.v[i];
+}
+KB_FN uint32_t fe_is_negative(const fe& f)
+{
+    fe t;
+    fe_canon(t, f);
+    return t.v[0] & 1u;
+}
+KB_FN uint32_t fe_is_zero(const fe& f)
+{
+    fe t;
+    fe_canon(t, f);
+    uint32_t x = 0;
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) x |= t.v[i];
+    return x == 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// exponentiations (fe.rs:857 fe_invert, :946 fe_pow22523)
+// ---------------------------------------------------------------------------------------
+KB_FN void fe_sqn(fe& h, const fe& f, int n)
+{
+    fe_sq(h, f);
+    KB_NOUNROLL
+    for (int i = 1; i < n; i++) fe_sq(h, h);
+}
+// t = z^(2^250-1), z11 = z^11
+KB_FN void fe_pow_2_250_1(fe& t, fe& z11, const fe& z)
+{
+    fe t0, t1, t2, t3;
+    fe_sq(t0, z);
+    fe_sqn(t1, t0, 2);
+    fe_mul(t1, z, t1);   // z^9
+    fe_mul(t0, t0, t1);  // z^11
+    z11 = t0;
+    fe_sq(t2, t0);       // z^22
+    fe_mul(t1, t1, t2);  // 2^5 - 1
+    fe_sqn(t2, t1, 5);
+    fe_mul(t1, t2, t1);  // 2^10 - 1
+    fe_sqn(t2, t1, 10);
+    fe_mul(t2, t2, t1);  // 2^20 - 1
+    fe_sqn(t3, t2, 20);
+    fe_mul(t2, t3, t2);  // 2^40 - 1
+    fe_sqn(t2, t2, 10);
+    fe_mul(t1, t2, t1);  // 2^50 - 1
+    fe_sqn(t2, t1, 50);
+    fe_mul(t2, t2, t1);  // 2^100 - 1
+    fe_sqn(t3, t2, 100);
+    fe_mul(t2, t3, t2);  // 2^200 - 1
+    fe_sqn(t2, t2, 50);
+    fe_mul(t, t2, t1);   // 2^250 - 1
+}
+KB_FN void fe_invert(fe& out, const fe& z)
+{
+    fe t, z11;
+    fe_pow_2_250_1(t, z11, z);
+    fe_sqn(t, t, 5);
+    fe_mul(out, t, z11);  // z^(2^255-21)
+}
+KB_FN void fe_pow22523(fe& out, const fe& z)
+{
+    fe t, z11;
+    fe_pow_2_250_1(t, z11, z);
+    fe_sqn(t, t, 2);
+    fe_mul(out, t, z);  // z^(2^252-3)
+}
+
+// curve constants (constants.rs:56,60,65) as 32-bit little-endian words
+#define KB_FE_D      {{0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu}}
+#define KB_FE_D2     {{0x26b2f159u, 0xebd69b94u, 0x8283b156u, 0x00e0149au, 0xeef3d130u, 0x198e80f2u, 0x56dffce7u, 0x2406d9dcu}}
+#define KB_FE_SQRTM1 {{0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u}}
+#define KB_FE_BX     {{0x8f25d51au, 0xc9562d60u, 0x9525a7b2u, 0x692cc760u, 0xfdd6dc5cu, 0xc0a4e231u, 0xcd6e53feu, 0x216936d3u}}
+#define KB_FE_BY     {{0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u}}
+#define KB_FE_BT     {{0xa5b7dda3u, 0x6dde8ab3u, 0x775152f5u, 0x20f09f80u, 0x64abe37du, 0x66ea4e8eu, 0xd78b7665u, 0x67875f0fu}}

@@ -1,0 +1,359 @@
+// kernels.cuh — __global__ entry points.  One thread owns one item; the math lives in
+// ops.cuh / poly.cuh.  Data crosses HBM in the reference's wire encodings (32-byte points
+// and scalars), loaded and stored as 128-bit vectors.
+#pragma once
+#include <cuda_runtime.h>
+#include "ops.cuh"
+#include "poly.cuh"
+
+#define KB_THREADS 128
+
+// 32-byte record i of a 16-byte-aligned array -> 8 LE words (two 128-bit loads)
+__device__ __forceinline__ void kb_load32(uint32_t* w, const uint8_t* base, size_t i)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(base + 32 * i);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void kb_store32(uint8_t* base, size_t i, const uint32_t* w)
+{
+    uint4* p = reinterpret_cast<uint4*>(base + 32 * i);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void kb_load_fe(fe& f, const uint32_t* p)
+{
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    f.v[0] = a.x; f.v[1] = a.y; f.v[2] = a.z; f.v[3] = a.w;
+    f.v[4] = b.x; f.v[5] = b.y; f.v[6] = b.z; f.v[7] = b.w;
+}
+__device__ __forceinline__ void kb_store_fe(uint32_t* p, const fe& f)
+{
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(f.v[0], f.v[1], f.v[2], f.v[3]);
+    q[1] = make_uint4(f.v[4], f.v[5], f.v[6], f.v[7]);
+}
+// cooperative copy of `words` 32-bit words from global to shared
+__device__ __forceinline__ void kb_stage(uint32_t* dst, const uint32_t* src, int words)
+{
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d[i] = __ldg(s + i);
+    __syncthreads();
+}
+
+// ---- base-point table: table[w*8 + j] = (j+1) * 16^w * B, w = 0..63 (replaces constants.rs:89 BASE)
+__global__ void k_base_init(ge_precomp* table)
+{
+    const int w = threadIdx.x;
+    if (w >= 64) return;
+    ge_p3 pos;
+    const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
+    pos.X = bx; pos.Y = by; pos.T = bt;
+    fe_set(pos.Z, 1);
+    for (int k = 0; k < 4 * w; k++) ge_dbl<true>(pos, pos);
+    kb_base_window(table + 8 * w, pos);
+}
+
+// ---- Point::mul(s, None): out[i] = compress(s_i * B)   (point.rs:207, ge.rs:442)
+template <bool CT>
+__global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint8_t* out, const ge_precomp* table)
+{
+    extern __shared__ uint4 smem4[];
+    ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
+    kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8], o[8];
+    int8_t e[64];
+    kb_load32(s, scalars, i);
+    sc_recode16(e, s);
+    ge_p3 h;
+    ge_scalarmult_base<CT>(h, e, base);
+    ge_compress(o, h);
+    kb_store32(out, i, o);
+}
+
+// ---- Point::mul(s, Some(p)): out[i] = compress(s_i * P_i)   (point.rs:207, ge.rs:508)
+template <bool CT>
+__global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint8_t* out, uint8_t* status)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8], w[8], o[8];
+    int8_t e[64];
+    ge_cached tbl[8];
+    kb_load32(s, scalars, i);
+    kb_load32(w, points, shared_point ? 0 : i);
+    ge_p3 p, h;
+    const uint32_t ok = ge_decompress(p, w);
+    sc_recode16(e, s);
+    ge_build_table8(tbl, p);
+    ge_scalarmult<CT>(h, e, tbl);
+    ge_compress(o, h);
+    if (!ok) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = 0;
+    }
+    kb_store32(out, i, o);
+    if (status) status[i] = (uint8_t)(ok ^ 1u);
+}
+
+// ---- Point::unmarshal_binary + marshal_binary   (ge.rs:124, :112)
+__global__ void __launch_bounds__(KB_THREADS) k_recode(size_t n, const uint8_t* in, uint8_t* out, uint8_t* status)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8], o[8];
+    kb_load32(w, in, i);
+    ge_p3 p;
+    const uint32_t ok = ge_decompress(p, w);
+    ge_compress(o, p);
+    if (!ok) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = 0;
+    }
+    kb_store32(out, i, o);
+    if (status) status[i] = (uint8_t)(ok ^ 1u);
+}
+
+// ---- Point::add / Point::sub   (point.rs:179, :190)
+__global__ void __launch_bounds__(KB_THREADS) k_point_add(size_t n, const uint8_t* pa, const uint8_t* pb, uint8_t* out, uint8_t* status, int subtract)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8], o[8];
+    ge_p3 p, q, r;
+    kb_load32(w, pa, i);
+    uint32_t ok = ge_decompress(p, w);
+    kb_load32(w, pb, i);
+    ok &= ge_decompress(q, w);
+    ge_cached c;
+    ge_to_cached(c, q);
+    ge_cached_cneg(c, (uint32_t)(subtract != 0));
+    ge_add<false>(r, p, c);
+    ge_compress(o, r);
+    if (!ok) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) o[k] = 0;
+    }
+    kb_store32(out, i, o);
+    if (status) status[i] = (uint8_t)(ok ^ 1u);
+}
+
+// ---- Point::is_canonical / has_small_order / decodes   (point.rs:322, :286; ge.rs:124)
+__global__ void __launch_bounds__(KB_THREADS) k_point_check(size_t n, const uint8_t* in, uint8_t* flags)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8], o[8];
+    kb_load32(w, in, i);
+    ge_p3 p;
+    const uint32_t ok = ge_decompress(p, w);
+    uint32_t small = 0;
+    if (ok) {
+        ge_compress(o, p);  // has_small_order works on the re-encoding
+        small = pt_is_small_order_bytes(o);
+    }
+    flags[i] = (uint8_t)(pt_is_canonical(w) | (small << 1) | (ok << 2));
+}
+
+// ---- scalars   (scalar.rs:175, :279)
+__global__ void __launch_bounds__(KB_THREADS) k_sc_reduce64(size_t n, const uint8_t* in, uint8_t* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[16], r[8];
+    kb_load32(x, in, 2 * i);
+    kb_load32(x + 8, in, 2 * i + 1);
+    sc_reduce512(r, x);
+    kb_store32(out, i, r);
+}
+__global__ void __launch_bounds__(KB_THREADS) k_sc_muladd(size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t A[8], B[8], C[8], r[8];
+    kb_load32(A, a, i);
+    kb_load32(B, b, i);
+    kb_load32(C, c, i);
+    sc_muladd(r, A, B, C);
+    kb_store32(out, i, r);
+}
+// h_i = SHA-512(R_i || A_i || M_i) mod L   (eddsa_sig.rs:195-200)
+__global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t rw[8], aw[8], d[16], h[8];
+    kb_load32(rw, r32, i);
+    kb_load32(aw, a32, i);
+    const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+    sha512_ram(d, rw, aw, msg + lo, hi - lo);
+    sc_reduce512(h, d);
+    kb_store32(out, i, h);
+}
+
+// ---- eddsa::verify_with_checks / schnorr::verify_with_checks
+template <bool SCHNORR>
+__global__ void __launch_bounds__(KB_THREADS) k_verify(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, const ge_precomp* table)
+{
+    __shared__ uint4 base8_raw[8 * 24 / 4];
+    ge_precomp* base8 = reinterpret_cast<ge_precomp*>(base8_raw);
+    kb_stage(reinterpret_cast<uint32_t*>(base8), reinterpret_cast<const uint32_t*>(table), 8 * 24);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pw[8], sw[16];
+    ge_cached tbl[8];
+    kb_load32(pw, pk, i);
+    kb_load32(sw, sig, 2 * i);
+    kb_load32(sw + 8, sig, 2 * i + 1);
+    const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+    status[i] = (uint8_t)sig_verify<SCHNORR>(pw, sw, msg + lo, hi - lo, base8, tbl);
+}
+
+// ---- committed polynomials
+// commitments -> cached operand form, 32 words per commitment; bad[c] = 1 if undecodable
+__global__ void __launch_bounds__(KB_THREADS) k_commit_prepare(size_t ncommit, const uint8_t* commits, uint32_t* cached, uint8_t* bad)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncommit) return;
+    uint32_t w[8];
+    kb_load32(w, commits, i);
+    ge_p3 p;
+    const uint32_t ok = ge_decompress(p, w);
+    ge_cached c;
+    ge_to_cached(c, p);
+    uint32_t* o = cached + 32 * i;
+    kb_store_fe(o, c.YpX);
+    kb_store_fe(o + 8, c.YmX);
+    kb_store_fe(o + 16, c.T2d);
+    kb_store_fe(o + 24, c.Z);
+    bad[i] = (uint8_t)(ok ^ 1u);
+}
+// PubPoly::eval (poly.rs:457-469) and, with shares != nullptr, the verify_deal comparison
+// (vss/pedersen/vss.rs:899-912).  Item k is (poly_id[k], idx[k]); with poly_id == nullptr the
+// items enumerate a DKG round: k = i * npoly + d (verifier-major), so the 32 lanes of a warp
+// hold 32 different dealers and the SAME evaluation point x = i + 1 — the double-and-add over
+// the bits of x is then branch-uniform across the warp.
+__global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, const uint32_t* poly_id,
+                                                          const uint32_t* idx, size_t n_verifiers, const uint8_t* shares, uint8_t* out, uint8_t* status, const ge_precomp* table)
+{
+    extern __shared__ uint4 smem4[];
+    ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
+    if (shares) kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    size_t d, i, slot;
+    if (poly_id) {
+        d = poly_id[k];
+        i = idx[k];
+        slot = k;
+    } else {
+        d = k % npoly;
+        i = k / npoly;
+        slot = d * n_verifiers + i;
+    }
+    const uint32_t* cp = cached + 32 * (d * t);
+    const uint8_t* bp = bad + d * t;
+    ge_p3 v;
+    ge_identity(v);
+    uint32_t anybad = 0;
+    for (size_t j = t; j-- > 0;) {
+        ge_cached c;
+        kb_load_fe(c.YpX, cp + 32 * j);
+        kb_load_fe(c.YmX, cp + 32 * j + 8);
+        kb_load_fe(c.T2d, cp + 32 * j + 16);
+        kb_load_fe(c.Z, cp + 32 * j + 24);
+        anybad |= bp[j];
+        kb_horner_step(v, (uint64_t)i + 1, c);
+    }
+    uint32_t o[8];
+    ge_compress(o, v);
+    if (!shares) {
+        if (anybad) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[q] = 0;
+        }
+        kb_store32(out, slot, o);
+        if (status) status[slot] = (uint8_t)anybad;
+        return;
+    }
+    uint32_t s[8], g[8];
+    int8_t e[64];
+    kb_load32(s, shares, slot);
+    sc_recode16(e, s);
+    ge_p3 h;
+    ge_scalarmult_base<true>(h, e, base);
+    ge_compress(g, h);
+    uint32_t diff = anybad;
+#pragma unroll
+    for (int q = 0; q < 8; q++) diff |= g[q] ^ o[q];
+    out[slot] = (uint8_t)(diff == 0);
+}
+
+// ---- integer-multiply roofline probe
+template <int KIND>
+__global__ void __launch_bounds__(256) k_probe(int iters, uint32_t seed, uint32_t* sink)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (KIND == 0) {
+        // 8 independent 64-bit accumulators: acc += a * b  (IMAD.WIDE.U32)
+        uint64_t acc[8];
+        uint32_t a = seed ^ tid, b = seed * 2654435761u + tid;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = tid + k;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = (uint64_t)((uint32_t)acc[k] ^ a) * b + acc[k];
+        }
+        uint64_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x ^= acc[k];
+        if (x == 0x1234567u) sink[0] = (uint32_t)x;
+    } else if (KIND == 1) {
+        // 8 independent 32-bit accumulators: acc = acc * b + a  (IMAD)
+        uint32_t acc[8];
+        uint32_t a = seed ^ tid, b = (seed * 2654435761u + tid) | 1u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = tid + k;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = acc[k] * b + a;
+        }
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x ^= acc[k];
+        if (x == 0x1234567u) sink[0] = x;
+    } else if (KIND == 2) {
+        // two independent 4-product carry chains per iteration (the fe_mul inner pattern)
+        uint32_t e[9], o[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) { e[k] = tid + k; o[k] = seed + k; }
+        uint32_t a0 = seed ^ tid, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, b = seed + 0x9e3779b9u;
+        for (int it = 0; it < iters; it++) {
+            kb_cmad4(e, a0, a1, a2, a3, b, e[8]);
+            kb_cmad4(o, a1, a2, a3, a0, b, o[8]);
+            b += e[0];
+        }
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) x ^= e[k] ^ o[k];
+        if (x == 0x1234567u) sink[0] = x;
+    } else {
+        // the library's own field multiplication, two independent chains
+        fe x, y, z;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { x.v[k] = tid * 977u + k; y.v[k] = seed + 31u * k; z.v[k] = tid + seed * k; }
+        for (int it = 0; it < iters; it++) {
+            fe_mul(x, x, y);
+            fe_mul(z, z, y);
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc ^= x.v[k] ^ z.v[k];
+        if (acc == 0x1234567u) sink[0] = acc;
+    }
+}

@@ -1,0 +1,457 @@
+// msm.cuh — Pippenger multi-scalar multiplication: out = sum_i s_i * P_i, the fold of
+// Point::mul + Point::add (group/edwards25519/point.rs:179,207) that sits behind
+// PubPoly::commit / recover_commit and the share verifiers.
+//
+// Pipeline (all on device, per chunk of <= 2^22 points):
+//   prepare : decompress P_i (ge.rs:124) to affine (y+x, y-x, 2dxy); effective scalar
+//             (the reference's out-of-domain top-digit rule) -> sign + magnitude
+//   hist    : signed c-bit digits; per-bucket counts (atomicAdd)
+//   scan    : exclusive prefix sum -> bucket offsets
+//   scatter : counting sort of (point index, sign) into bucket order
+//   accum   : LOAD-BALANCED bucket accumulation — every thread owns K consecutive sorted
+//             entries (not one bucket), so skewed scalar distributions cannot starve the
+//             grid; runs cut by a chunk boundary go to head/tail partials
+//   merge   : stitch head/tail partials into their bucket
+//   reduce  : per window, sum_k k * bucket_k by running sums over bucket groups
+//   finish  : warp-shuffle tree over the group partials, then Horner over the windows
+//
+// Every stage body is a KB_FN taking an explicit thread id so tests/emu can run it on the
+// host; only the warp-shuffle tree in finish is GPU-only.
+#pragma once
+#include "ge.cuh"
+#include "poly.cuh"
+#include "sc.cuh"
+
+#define KB_MSM_CHUNK (1u << 22)
+#define KB_MSM_K 16        // sorted entries per accumulation thread
+#define KB_MSM_GROUPS 128  // bucket groups per window in the reduction
+
+#if defined(KB_HOST_EMU)
+KB_FN uint32_t kb_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#else
+KB_FN uint32_t kb_atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#endif
+
+struct kb_msm_plan {
+    uint32_t n;        // points in this chunk
+    uint32_t c;        // window bits
+    uint32_t windows;  // ceil(257 / c)
+    uint32_t half;     // 2^(c-1) buckets per window
+    uint32_t nb;       // windows * half
+};
+
+static inline uint32_t kb_msm_window_bits_host(size_t n)
+{
+    uint32_t lg = 0;
+    while ((n >> (lg + 1)) != 0) lg++;
+    int c = (int)lg - 3;
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    return (uint32_t)c;
+}
+
+// The integer Point::mul multiplies by: a itself when a[31] <= 127; otherwise the
+// reference's top radix-16 digit (nibble 63 + carry) may exceed 8, then matches no table
+// entry and is dropped, leaving low252 - carry * 2^252 (possibly negative).
+KB_FN void sc_effective(uint32_t* mag, uint32_t& neg, const uint32_t* s)
+{
+    const uint32_t c8[8] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x08888888u};
+    uint32_t low[8], t[8];
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) low[i] = s[i];
+    low[7] &= 0x0fffffffu;
+    kb_add8(t, low, c8);
+    const uint32_t carry = t[7] >> 28;  // carry out of the 63 low digits
+    const uint32_t top = (s[7] >> 28) + carry;
+    neg = 0;
+    if (top <= 8) {
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) mag[i] = s[i];
+    } else if (carry == 0) {
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) mag[i] = low[i];
+    } else {
+        const uint32_t p252[8] = {0, 0, 0, 0, 0, 0, 0, 0x10000000u};
+        kb_sub8(mag, p252, low);
+        neg = 1;
+    }
+}
+// bits [pos, pos + c) of the 256-bit magnitude (zero beyond bit 255), c <= 16
+KB_FN uint32_t sc_bits(const uint32_t* mag, uint32_t pos, uint32_t c)
+{
+    if (pos >= 256) return 0;
+    const uint32_t wi = pos >> 5, sh = pos & 31;
+    uint64_t v = mag[wi];
+    if (wi + 1 < 8) v |= (uint64_t)mag[wi + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+// ---- prepare: point -> affine precomp (24 words); scalar -> magnitude (8 words) + sign
+KB_FN void kb_msm_prepare_body(size_t i, const uint32_t* pw, const uint32_t* sw, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad)
+{
+    ge_p3 p;
+    const uint32_t ok = ge_decompress(p, pw);
+    ge_precomp q;
+    const fe d2 = KB_FE_D2;
+    fe_add(q.ypx, p.Y, p.X);
+    fe_sub(q.ymx, p.Y, p.X);
+    fe_mul(q.xy2d, p.T, d2);
+    if (!ok) {
+        ge_precomp_identity(q);
+        kb_atomic_add(bad, 1u);
+    }
+    uint32_t* o = pts + 24 * i;
+    KB_UNROLL
+    for (int k = 0; k < 8; k++) {
+        o[k] = q.ypx.v[k];
+        o[8 + k] = q.ymx.v[k];
+        o[16 + k] = q.xy2d.v[k];
+    }
+    uint32_t mag[8], neg;
+    sc_effective(mag, neg, sw);
+    KB_UNROLL
+    for (int k = 0; k < 8; k++) mags[8 * i + k] = mag[k];
+    negs[i] = (uint8_t)neg;
+}
+
+// signed digits of one magnitude; calls f(w, bucket, sign) for every non-zero digit
+template <typename F>
+KB_FN void kb_msm_digits(const kb_msm_plan& pl, const uint32_t* mag, F f)
+{
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < pl.windows; w++) {
+        uint32_t d = sc_bits(mag, w * pl.c, pl.c) + carry;
+        carry = 0;
+        uint32_t sign = 0;
+        if (d > pl.half) {
+            d = (1u << pl.c) - d;
+            sign = 1;
+            carry = 1;
+        }
+        if (d != 0) f(w, w * pl.half + (d - 1), sign);
+    }
+}
+KB_FN void kb_msm_hist_body(const kb_msm_plan& pl, size_t i, const uint32_t* mags, uint32_t* counts)
+{
+    kb_msm_digits(pl, mags + 8 * i, [&](uint32_t, uint32_t bucket, uint32_t) { kb_atomic_add(counts + bucket, 1u); });
+}
+KB_FN void kb_msm_scatter_body(const kb_msm_plan& pl, size_t i, const uint32_t* mags, const uint8_t* negs, const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted)
+{
+    const uint32_t sneg = negs[i];
+    kb_msm_digits(pl, mags + 8 * i, [&](uint32_t, uint32_t bucket, uint32_t sign) {
+        const uint32_t slot = offsets[bucket] + kb_atomic_add(cursor + bucket, 1u);
+        sorted[slot] = ((uint32_t)i << 1) | (sign ^ sneg);
+    });
+}
+
+KB_FN void kb_store_p3(uint32_t* o, const ge_p3& p)
+{
+    KB_UNROLL
+    for (int k = 0; k < 8; k++) {
+        o[k] = p.X.v[k];
+        o[8 + k] = p.Y.v[k];
+        o[16 + k] = p.Z.v[k];
+        o[24 + k] = p.T.v[k];
+    }
+}
+KB_FN void kb_load_p3(ge_p3& p, const uint32_t* o)
+{
+    KB_UNROLL
+    for (int k = 0; k < 8; k++) {
+        p.X.v[k] = o[k];
+        p.Y.v[k] = o[8 + k];
+        p.Z.v[k] = o[16 + k];
+        p.T.v[k] = o[24 + k];
+    }
+}
+
+// ---- accum: thread t owns sorted entries [t*K, (t+1)*K)
+// flags[t]: bit0 = head partial valid, bit1 = tail partial valid
+KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* offsets, const uint32_t* sorted, const uint32_t* pts, uint32_t* bucket_sum, uint32_t* heads,
+                             uint32_t* tails, uint8_t* flags)
+{
+    const uint32_t total = offsets[pl.nb];
+    const uint64_t s64 = (uint64_t)t * KB_MSM_K;
+    flags[t] = 0;
+    if (s64 >= total) return;
+    const uint32_t s = (uint32_t)s64;
+    const uint32_t e = (total - s < KB_MSM_K) ? total : s + KB_MSM_K;
+    // bucket containing entry s: largest b with offsets[b] <= s (skipping empty buckets)
+    uint32_t lo = 0, hi = pl.nb;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= s) lo = mid;
+        else hi = mid;
+    }
+    uint32_t b = lo;
+    while (offsets[b + 1] <= s) b++;
+    ge_p3 acc;
+    ge_identity(acc);
+    uint32_t fl = 0;
+    for (uint32_t k = s; k < e; k++) {
+        const uint32_t v = sorted[k];
+        const uint32_t* pp = pts + 24 * (size_t)(v >> 1);
+        ge_precomp q;
+        KB_UNROLL
+        for (int j = 0; j < 8; j++) {
+            q.ypx.v[j] = pp[j];
+            q.ymx.v[j] = pp[8 + j];
+            q.xy2d.v[j] = pp[16 + j];
+        }
+        ge_precomp_cneg(q, v & 1u);
+        ge_madd<true>(acc, acc, q);
+        const uint32_t bend = offsets[b + 1];
+        if (k + 1 == bend || k + 1 == e) {
+            // run of bucket b inside this chunk ends here
+            const bool starts_before = offsets[b] < s;
+            const bool ends_after = bend > e;
+            if (starts_before) {
+                kb_store_p3(heads + 32 * t, acc);
+                fl |= 1u;
+            } else if (ends_after) {
+                kb_store_p3(tails + 32 * t, acc);
+                fl |= 2u;
+            } else {
+                kb_store_p3(bucket_sum + 32 * (size_t)b, acc);
+            }
+            ge_identity(acc);
+            if (k + 1 < e) {
+                b++;
+                while (offsets[b + 1] <= k + 1) b++;
+            }
+        }
+    }
+    flags[t] = (uint8_t)fl;
+}
+
+// ---- merge: thread t whose tail partial is valid owns that bucket: tail[t] + head[t+1] + ...
+KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, const uint32_t* offsets, const uint32_t* sorted_unused, uint32_t* bucket_sum, const uint32_t* heads,
+                             const uint32_t* tails, const uint8_t* flags)
+{
+    (void)sorted_unused;
+    if (!(flags[t] & 2u)) return;
+    const uint32_t total = offsets[pl.nb];
+    // the bucket of the last entry of chunk t
+    const uint32_t last = (uint32_t)((t + 1) * KB_MSM_K) - 1;
+    uint32_t lo = 0, hi = pl.nb;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= last) lo = mid;
+        else hi = mid;
+    }
+    uint32_t b = lo;
+    while (offsets[b + 1] <= last) b++;
+    const uint32_t bend = offsets[b + 1];
+    (void)total;
+    ge_p3 acc, h;
+    kb_load_p3(acc, tails + 32 * t);
+    for (size_t u = t + 1; u < nthreads && (uint64_t)u * KB_MSM_K < bend; u++) {
+        if (flags[u] & 1u) {
+            kb_load_p3(h, heads + 32 * u);
+            ge_cached hc;
+            ge_to_cached(hc, h);
+            ge_add<true>(acc, acc, hc);
+        }
+    }
+    kb_store_p3(bucket_sum + 32 * (size_t)b, acc);
+}
+
+// ---- reduce: group g of window w covers buckets [g*gs, (g+1)*gs) (0-based, weight = index+1)
+// partial[w*G + g] = sum_k (k+1) * bucket[w][k] over the group
+KB_FN void kb_msm_reduce_body(const kb_msm_plan& pl, size_t tid, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* partial)
+{
+    const uint32_t w = (uint32_t)(tid / groups), g = (uint32_t)(tid % groups);
+    if (w >= pl.windows) return;
+    const uint32_t gs = (pl.half + groups - 1) / groups;
+    const uint32_t k0 = g * gs;
+    uint32_t k1 = k0 + gs;
+    if (k1 > pl.half) k1 = pl.half;
+    ge_p3 run, tot;
+    ge_identity(run);
+    ge_identity(tot);
+    if (k0 < k1) {
+        for (uint32_t k = k1; k-- > k0;) {
+            const uint32_t b = w * pl.half + k;
+            if (offsets[b + 1] > offsets[b]) {
+                ge_p3 p;
+                kb_load_p3(p, bucket_sum + 32 * (size_t)b);
+                ge_cached pc;
+                ge_to_cached(pc, p);
+                ge_add<true>(run, run, pc);
+            }
+            ge_cached rc;
+            ge_to_cached(rc, run);
+            ge_add<true>(tot, tot, rc);
+        }
+        // tot = sum (k - k0 + 1) b_k ; add k0 * run
+        if (k0 > 0) {
+            ge_cached tc;
+            ge_to_cached(tc, tot);
+            kb_horner_step(run, (uint64_t)k0, tc);  // run = k0 * run + tot
+            tot = run;
+        }
+    }
+    kb_store_p3(partial + 32 * tid, tot);
+}
+
+#if !defined(KB_HOST_EMU)
+// ======================================================================================
+// kernels
+// ======================================================================================
+__global__ void __launch_bounds__(KB_THREADS) k_msm_prepare(size_t n, const uint8_t* points, const uint8_t* scalars, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pw[8], sw[8];
+    kb_load32(pw, points, i);   // coalesced 128-bit loads of the 32-byte encodings
+    kb_load32(sw, scalars, i);
+    kb_msm_prepare_body(i, pw, sw, pts, mags, negs, bad);
+}
+__global__ void __launch_bounds__(256) k_msm_hist(kb_msm_plan pl, const uint32_t* mags, uint32_t* counts)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.n) return;
+    kb_msm_hist_body(pl, i, mags, counts);
+}
+// single-block exclusive scan of counts[0..nb) into offsets[0..nb]; also clears cursor
+__global__ void __launch_bounds__(1024) k_msm_scan(uint32_t nb, const uint32_t* counts, uint32_t* offsets, uint32_t* cursor)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (nb + 1023) / 1024;
+    const uint32_t lo = tid * per;
+    uint32_t hi = lo + per;
+    if (hi > nb) hi = nb;
+    uint32_t sum = 0;
+    for (uint32_t k = lo; k < hi; k++) sum += counts[k];
+    part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = (tid >= off) ? part[tid - off] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = (tid == 0) ? 0 : part[tid - 1];
+    for (uint32_t k = lo; k < hi; k++) {
+        offsets[k] = run;
+        run += counts[k];
+        cursor[k] = 0;
+    }
+    if (tid == 1023) offsets[nb] = part[1023];
+}
+__global__ void __launch_bounds__(256) k_msm_scatter(kb_msm_plan pl, const uint32_t* mags, const uint8_t* negs, const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.n) return;
+    kb_msm_scatter_body(pl, i, mags, negs, offsets, cursor, sorted);
+}
+__global__ void __launch_bounds__(KB_THREADS) k_msm_accum(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, const uint32_t* sorted, const uint32_t* pts, uint32_t* bucket_sum, uint32_t* heads,
+                                                          uint32_t* tails, uint8_t* flags)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    kb_msm_accum_body(pl, t, offsets, sorted, pts, bucket_sum, heads, tails, flags);
+}
+__global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, uint32_t* bucket_sum, const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    kb_msm_merge_body(pl, t, nthreads, offsets, nullptr, bucket_sum, heads, tails, flags);
+}
+__global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* partial)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)pl.windows * groups) return;
+    kb_msm_reduce_body(pl, tid, groups, offsets, bucket_sum, partial);
+}
+
+// butterfly sum of one point per lane: after the call every lane holds the warp total
+__device__ __forceinline__ void kb_warp_sum_point(ge_p3& p)
+{
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+        ge_p3 q;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            q.X.v[k] = __shfl_xor_sync(0xffffffffu, p.X.v[k], off);
+            q.Y.v[k] = __shfl_xor_sync(0xffffffffu, p.Y.v[k], off);
+            q.Z.v[k] = __shfl_xor_sync(0xffffffffu, p.Z.v[k], off);
+            q.T.v[k] = __shfl_xor_sync(0xffffffffu, p.T.v[k], off);
+        }
+        ge_cached qc;
+        ge_to_cached(qc, q);
+        ge_add<true>(p, p, qc);
+    }
+}
+// finish: warp q sums the group partials of windows q, q+nwarps, ... with a shuffle tree;
+// thread 0 then folds the windows (Horner, c doublings per window), adds the result to the
+// running total `acc128` (X,Y,Z,T words) and, if out32 != nullptr, writes its encoding.
+__global__ void __launch_bounds__(1024) k_msm_finish(kb_msm_plan pl, uint32_t groups, const uint32_t* partial, uint32_t* acc128, int first_chunk, uint8_t* out32)
+{
+    extern __shared__ uint32_t win_sum[];  // windows * 32 words
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t w = warp; w < pl.windows; w += nwarps) {
+        ge_p3 s;
+        ge_identity(s);
+        for (uint32_t g = lane; g < groups; g += 32) {
+            ge_p3 p;
+            kb_load_p3(p, partial + 32 * ((size_t)w * groups + g));
+            ge_cached pc;
+            ge_to_cached(pc, p);
+            ge_add<true>(s, s, pc);
+        }
+        kb_warp_sum_point(s);
+        if (lane == 0) kb_store_p3(win_sum + 32 * w, s);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    ge_p3 tot;
+    ge_identity(tot);
+    for (uint32_t w = pl.windows; w-- > 0;) {
+        for (uint32_t k = 0; k < pl.c; k++) ge_dbl<true>(tot, tot);
+        ge_p3 s;
+        kb_load_p3(s, win_sum + 32 * w);
+        ge_cached sc;
+        ge_to_cached(sc, s);
+        ge_add<true>(tot, tot, sc);
+    }
+    if (!first_chunk) {
+        ge_p3 prev;
+        kb_load_p3(prev, acc128);
+        ge_cached pc;
+        ge_to_cached(pc, prev);
+        ge_add<true>(tot, tot, pc);
+    }
+    kb_store_p3(acc128, tot);
+    if (out32) {
+        uint32_t o[8];
+        ge_compress(o, tot);
+        kb_store32(out32, 0, o);
+    }
+}
+// out = compress(sum of k uncompressed partials): the fold after the cross-GPU gather
+__global__ void k_point_sum(size_t k, const uint32_t* partials, uint8_t* out32)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    ge_p3 s;
+    ge_identity(s);
+    for (size_t g = lane; g < k; g += 32) {
+        ge_p3 p;
+        kb_load_p3(p, partials + 32 * g);
+        ge_cached pc;
+        ge_to_cached(pc, p);
+        ge_add<true>(s, s, pc);
+    }
+    kb_warp_sum_point(s);
+    if (lane == 0) {
+        uint32_t o[8];
+        ge_compress(o, s);
+        kb_store32(out32, 0, o);
+    }
+}
+
+struct kb_ctx;
+static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st);
+#endif  // !KB_HOST_EMU

@@ -1,0 +1,280 @@
+// ops.cuh — per-thread algorithms: table selection, scalar multiplication, byte-level point
+// checks and the EdDSA / Schnorr verification state machine.  One GPU thread owns one item
+// (scalar, point, signature); the kernels in kernels.cu are thin launch wrappers around these.
+//
+// Citations are to /root/reference/src.
+#pragma once
+#include "fe.cuh"
+#include "ge.cuh"
+#include "sc.cuh"
+#include "sha512.cuh"
+
+// kb_sig_status (include/kyber_b200.h) — sign/error.rs:6-25
+#define KB_SIG_OK 0
+#define KB_SIG_LENGTH 1
+#define KB_SIG_NOT_CANONICAL 2
+#define KB_SIG_R_NOT_CANONICAL 3
+#define KB_SIG_R_SMALL_ORDER 4
+#define KB_SIG_PK_NOT_CANONICAL 5
+#define KB_SIG_PK_SMALL_ORDER 6
+#define KB_SIG_MARSHALLING 7
+#define KB_SIG_INVALID 8
+
+// ---------------------------------------------------------------------------------------
+// byte-level checks on a 32-byte encoding held as 8 little-endian words
+// ---------------------------------------------------------------------------------------
+// Point::is_canonical (group/edwards25519/point.rs:322-337), bug-compatible: the low-byte
+// test is 0xED - (1 - b[0]) in wrapping u16, so with bytes 1..30 = 0xff and b[31]&0x7f = 0x7f
+// the encoding is reported NON-canonical for every b[0] >= 0x14.
+KB_FN uint32_t pt_is_canonical(const uint32_t* w)
+{
+    uint32_t ones = ((w[7] & 0x7fffffffu) == 0x7fffffffu) & ((w[0] >> 8) == 0x00ffffffu);
+    KB_UNROLL
+    for (int i = 1; i < 7; i++) ones &= (w[i] == 0xffffffffu);
+    return !(ones & ((w[0] & 0xffu) >= 0x14u));
+}
+// Point::has_small_order (point.rs:286-310) for an encoding that is canonical and on the
+// curve: the reference re-encodes the decoded point and compares bytes 0..30 and byte 31
+// & 0x7f with WEAK_KEYS (constants.rs:3744); for such encodings the re-encoding equals the
+// input up to bit 255, so the comparison can run on the raw words.
+KB_FN uint32_t pt_is_small_order_bytes(const uint32_t* w)
+{
+    const uint32_t top = w[7] & 0x7fffffffu;
+    uint32_t mid0 = 1, midf = 1;
+    KB_UNROLL
+    for (int i = 1; i < 7; i++) {
+        mid0 &= (w[i] == 0u);
+        midf &= (w[i] == 0xffffffffu);
+    }
+    uint32_t k0 = mid0 & (top == 0u) & (w[0] == 0u);                 // y = 0      (order 4)
+    uint32_t k1 = mid0 & (top == 0u) & (w[0] == 1u);                 // y = 1      (order 1)
+    uint32_t k4 = midf & (top == 0x7fffffffu) & (w[0] == 0xffffffecu);  // y = p - 1  (order 2)
+    const uint32_t o8a[8] = {0x8f95e826u, 0xb027b2c2u, 0x89f4c345u, 0xf098eff2u, 0x05acdfd5u, 0x3933c6d3u, 0x880238b1u, 0x05fc536du};
+    const uint32_t o8b[8] = {0x706a17c7u, 0x4fd84d3du, 0x760b3cbau, 0x0f67100du, 0xfa53202au, 0xc6cc392cu, 0x77fdc74eu, 0x7a03ac92u};
+    uint32_t k2 = (top == o8a[7]), k3 = (top == o8b[7]);
+    KB_UNROLL
+    for (int i = 0; i < 7; i++) {
+        k2 &= (w[i] == o8a[i]);
+        k3 &= (w[i] == o8b[i]);
+    }
+    return k0 | k1 | k2 | k3 | k4;
+}
+
+// ---------------------------------------------------------------------------------------
+// table selection
+// ---------------------------------------------------------------------------------------
+// select_cached (ge.rs:488-500): c = d * P from tbl[j] = (j+1) P, d in [-8, 8]; d = 0 gives
+// the identity.  CT=true scans all 8 entries with conditional moves (no secret-dependent
+// address or branch); CT=false indexes directly (public scalars only).
+template <bool CT>
+KB_FN void ge_select_cached(ge_cached& c, const ge_cached* tbl, int d)
+{
+    const uint32_t neg = (uint32_t)d >> 31;
+    const int babs = (d ^ -(int)neg) + (int)neg;
+    ge_cached_identity(c);
+    if (CT) {
+        KB_NOUNROLL
+        for (int j = 0; j < 8; j++) {
+            const uint32_t hit = (uint32_t)(babs == j + 1);
+            fe_cmov(c.YpX, tbl[j].YpX, hit);
+            fe_cmov(c.YmX, tbl[j].YmX, hit);
+            fe_cmov(c.T2d, tbl[j].T2d, hit);
+            fe_cmov(c.Z, tbl[j].Z, hit);
+        }
+    } else {
+        if (babs != 0) c = tbl[babs - 1];
+    }
+    ge_cached_cneg(c, neg);
+}
+// select_pre_computed (ge.rs:423-434) on one window of the base-point table
+template <bool CT>
+KB_FN void ge_select_precomp(ge_precomp& c, const ge_precomp* win, int d)
+{
+    const uint32_t neg = (uint32_t)d >> 31;
+    const int babs = (d ^ -(int)neg) + (int)neg;
+    ge_precomp_identity(c);
+    if (CT) {
+        KB_NOUNROLL
+        for (int j = 0; j < 8; j++) {
+            const uint32_t hit = (uint32_t)(babs == j + 1);
+            fe_cmov(c.ypx, win[j].ypx, hit);
+            fe_cmov(c.ymx, win[j].ymx, hit);
+            fe_cmov(c.xy2d, win[j].xy2d, hit);
+        }
+    } else {
+        if (babs != 0) c = win[babs - 1];
+    }
+    ge_precomp_cneg(c, neg);
+}
+
+// tbl[j] = (j+1) P, j = 0..7   (ge.rs:537-543)
+KB_FN void ge_build_table8(ge_cached* tbl, const ge_p3& p)
+{
+    ge_p3 m = p;
+    ge_to_cached(tbl[0], p);
+    KB_NOUNROLL
+    for (int j = 1; j < 8; j++) {
+        ge_add<true>(m, m, tbl[0]);
+        ge_to_cached(tbl[j], m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// scalar multiplication
+// ---------------------------------------------------------------------------------------
+// h = a * P, ge_scalar_mult (ge.rs:508-568): signed radix-16 fixed window over the
+// per-thread table tbl[8]; e = sc_recode16(a).
+template <bool CT>
+KB_FN void ge_scalarmult(ge_p3& h, const int8_t* e, const ge_cached* tbl)
+{
+    ge_cached c;
+    ge_identity(h);
+    ge_select_cached<CT>(c, tbl, e[63]);
+    ge_add<false>(h, h, c);
+    KB_NOUNROLL
+    for (int i = 62; i >= 0; i--) {
+        ge_dbl<false>(h, h);
+        ge_dbl<false>(h, h);
+        ge_dbl<false>(h, h);
+        ge_dbl<true>(h, h);
+        ge_select_cached<CT>(c, tbl, e[i]);
+        if (i == 0) ge_add<true>(h, h, c);
+        else ge_add<false>(h, h, c);
+    }
+}
+// h = a * B, ge_scalar_mult_base (ge.rs:442-486) restated as a 64-window comb:
+// base[w*8 + j] = (j+1) * 16^w * B, so no doublings are needed at all.
+template <bool CT>
+KB_FN void ge_scalarmult_base(ge_p3& h, const int8_t* e, const ge_precomp* base)
+{
+    ge_precomp c;
+    ge_identity(h);
+    KB_NOUNROLL
+    for (int w = 0; w < 64; w++) {
+        ge_select_precomp<CT>(c, base + 8 * w, e[w]);
+        ge_madd<true>(h, h, c);
+    }
+}
+// h = s * B + k * A  (public data; Straus with shared doublings).  es / ek are the signed
+// radix-16 digits of s and k, tbl[j] = (j+1) A, base8[j] = (j+1) B.
+KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int8_t* es, const int8_t* ek, const ge_cached* tbl, const ge_precomp* base8)
+{
+    ge_cached c;
+    ge_precomp b;
+    ge_identity(h);
+    KB_NOUNROLL
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            ge_dbl<false>(h, h);
+            ge_dbl<false>(h, h);
+            ge_dbl<false>(h, h);
+            ge_dbl<true>(h, h);
+        }
+        ge_select_cached<false>(c, tbl, ek[i]);
+        ge_add<true>(h, h, c);
+        ge_select_precomp<false>(b, base8, es[i]);
+        if (i == 0) ge_madd<true>(h, h, b);
+        else ge_madd<false>(h, h, b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// EdDSA / Schnorr verification
+// ---------------------------------------------------------------------------------------
+// Both verifiers check compress(s*B - h*A) == R-bytes, which is the reference's
+// "R + h*A == s*B on canonical encodings" (eddsa_sig.rs:201-210, schnorr_sig.rs:96-106)
+// once R is canonical, on the curve and not of small order.  When that fast path does not
+// accept, the reference's own check ORDER decides which error is reported; deciding it
+// needs to know whether R decodes, which is only computed then.
+//
+// SCHNORR=false: eddsa::verify_with_checks (sign/eddsa/eddsa_sig.rs:159-212)
+// SCHNORR=true : schnorr::verify_with_checks (sign/schnorr/schnorr_sig.rs:53-110); its
+//   challenge hashes the re-encoded R and A (:128-141), which equal the raw bytes whenever
+//   the fast path is entered.
+template <bool SCHNORR>
+KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base8, ge_cached* tbl)
+{
+    const uint32_t* r_w = sig_w;
+    const uint32_t* s_w = sig_w + 8;
+    const uint32_t s_canon = sc_is_canonical(s_w);
+    const uint32_t r_canon = pt_is_canonical(r_w);
+    const uint32_t r_small = pt_is_small_order_bytes(r_w);
+    const uint32_t a_canon = pt_is_canonical(pk_w);
+    const uint32_t a_small = pt_is_small_order_bytes(pk_w);
+
+    if (!SCHNORR) {
+        // everything before "R decodes" in the EdDSA order needs no curve arithmetic
+        if (!s_canon) return KB_SIG_NOT_CANONICAL;
+        if (!r_canon) return KB_SIG_R_NOT_CANONICAL;
+        if (r_small) return KB_SIG_R_SMALL_ORDER;  // weak encodings are on the curve
+    }
+
+    ge_p3 A;
+    uint32_t a_ok = 0;
+    if (SCHNORR || a_canon) a_ok = ge_decompress(A, pk_w);
+
+    const uint32_t fast = s_canon & r_canon & (r_small ^ 1u) & a_canon & a_ok & (a_small ^ 1u);
+    if (fast) {
+        uint32_t digest[16], hk[8];
+        sha512_ram(digest, r_w, pk_w, msg, mlen);
+        sc_reduce512(hk, digest);
+        int8_t es[64], ek[64];
+        sc_recode16(es, s_w);
+        sc_recode16(ek, hk);
+        ge_p3 nA, Q;
+        ge_neg(nA, A);
+        ge_build_table8(tbl, nA);
+        ge_double_scalarmult_vartime(Q, es, ek, tbl, base8);
+        uint32_t enc[8];
+        ge_compress(enc, Q);
+        uint32_t diff = 0;
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) diff |= enc[i] ^ r_w[i];
+        if (diff == 0) return KB_SIG_OK;
+    }
+    // slow path: report the FIRST failing check in the reference's order
+    uint32_t r_ok = 1;
+    if (!r_small) {
+        ge_p3 R;
+        r_ok = ge_decompress(R, r_w);
+    }
+    if (SCHNORR) {
+        if (!r_ok) return KB_SIG_MARSHALLING;
+        if (!r_canon) return KB_SIG_R_NOT_CANONICAL;
+        if (r_small) return KB_SIG_R_SMALL_ORDER;
+        if (!s_canon) return KB_SIG_NOT_CANONICAL;
+        if (!a_ok) return KB_SIG_MARSHALLING;
+        if (!a_canon) return KB_SIG_PK_NOT_CANONICAL;
+        if (a_small) return KB_SIG_PK_SMALL_ORDER;
+    } else {
+        if (!r_ok) return KB_SIG_MARSHALLING;
+        if (!a_canon) return KB_SIG_PK_NOT_CANONICAL;
+        if (!a_ok) return KB_SIG_MARSHALLING;
+        if (a_small) return KB_SIG_PK_SMALL_ORDER;
+    }
+    return KB_SIG_INVALID;
+}
+
+// ---------------------------------------------------------------------------------------
+// base-point table construction (replaces the transcribed BASE table, constants.rs:89)
+// ---------------------------------------------------------------------------------------
+// win[j] = (j+1) * pos in affine (y+x, y-x, 2dxy) form, j = 0..7
+KB_FN void kb_base_window(ge_precomp* win, const ge_p3& pos)
+{
+    const fe d2 = KB_FE_D2;
+    ge_cached pc;
+    ge_to_cached(pc, pos);
+    ge_p3 m = pos;
+    KB_NOUNROLL
+    for (int j = 0; j < 8; j++) {
+        fe zinv, x, y, xy;
+        fe_invert(zinv, m.Z);
+        fe_mul(x, m.X, zinv);
+        fe_mul(y, m.Y, zinv);
+        fe_add(win[j].ypx, y, x);
+        fe_sub(win[j].ymx, y, x);
+        fe_mul(xy, x, y);
+        fe_mul(win[j].xy2d, xy, d2);
+        ge_add<true>(m, m, pc);
+    }
+}

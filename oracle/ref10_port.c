@@ -127,44 +127,10 @@ static int fe_isnonzero(const fe f)                                             
     return x != 0;
 }
 
-/* fe.rs:299 fe_mul — 100 i32xi32->i64 products with the 19x / 2x pre-multiplications */
-static void fe_mul(fe out, const fe f, const fe g)
-{
-    int32_t g19[10], f2[10];
-    for (int i = 0; i < 10; i++) { g19[i] = 19 * g[i]; f2[i] = (i & 1) ? 2 * f[i] : f[i]; }
-    int64_t h[10];
-    for (int k = 0; k < 10; k++) {
-        int64_t acc = 0;
-        for (int i = 0; i < 10; i++) {
-            int j = k - i;
-            if (j >= 0) {
-                int32_t fi = ((i & 1) && (j & 1)) ? f2[i] : f[i];
-                acc += (int64_t)fi * g[j];
-            } else {
-                j += 10;
-                int32_t fi = ((i & 1) && (j & 1)) ? f2[i] : f[i];
-                acc += (int64_t)fi * g19[j];
-            }
-        }
-        h[k] = acc;
-    }
-    fe_carry_store(out, h);
-}
-
-/* fe.rs:544 fe_square — 55 products */
-static inline void fe_sq_raw(int64_t h[10], const fe f)
-{
-    for (int k = 0; k < 10; k++) h[k] = 0;
-    for (int i = 0; i < 10; i++) {
-        for (int j = i; j < 10; j++) {
-            int64_t m = (i == j) ? 1 : 2;
-            if ((i & 1) && (j & 1)) m *= 2;
-            int k = i + j;
-            if (k >= 10) { k -= 10; m *= 19; }
-            h[k] += (int64_t)f[i] * f[j] * m;
-        }
-    }
-}
+/* fe.rs:299 fe_mul (100 products) and fe.rs:544 fe_square (55 products): straight-line product
+ * sums emitted by oracle/gen_fe.py, closed by the 12-step carry chain above. */
+#include "fe_gen.inc"
+static void fe_mul(fe out, const fe f, const fe g) { int64_t h[10]; fe_mul_raw(h, f, g); fe_carry_store(out, h); }
 static void fe_sq(fe out, const fe f) { int64_t h[10]; fe_sq_raw(h, f); fe_carry_store(out, h); }
 /* fe.rs:700 fe_square2 */
 static void fe_sq2(fe out, const fe f)

@@ -1,0 +1,194 @@
+// tests/emu/emu.cpp — HOST EMULATION of the per-thread device math.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles kyber-rs_b200/csrc/{fe,ge,sc,sha512,ops}.cuh with KB_HOST_EMU so that the exact
+// source the GPU kernels inline (everything except the PTX carry-chain primitives, which have
+// a plain-C twin next to each asm block) can be checked against the oracle on a machine with
+// no GPU.  It is never linked into libkyber_b200.so and is not a CPU fallback: the product
+// library has no host compute path.
+#define KB_HOST_EMU 1
+#include <string.h>
+#include "../../kyber-rs_b200/csrc/ops.cuh"
+#include "../../kyber-rs_b200/csrc/poly.cuh"
+#include "../../kyber-rs_b200/csrc/msm.cuh"
+#include <vector>
+
+static void ld(uint32_t* w, const uint8_t* b, int nwords) { memcpy(w, b, 4 * nwords); }
+static void st(uint8_t* b, const uint32_t* w, int nwords) { memcpy(b, w, 4 * nwords); }
+
+static ge_precomp g_base[64 * 8];
+static int g_base_ready = 0;
+static void base_init()
+{
+    if (g_base_ready) return;
+    ge_p3 pos;
+    const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
+    pos.X = bx; pos.Y = by; pos.T = bt; fe_set(pos.Z, 1);
+    for (int w = 0; w < 64; w++) {
+        kb_base_window(g_base + 8 * w, pos);
+        for (int k = 0; k < 4; k++) ge_dbl<true>(pos, pos);
+    }
+    g_base_ready = 1;
+}
+
+extern "C" {
+// op: 0 mul, 1 sq, 2 add, 3 sub, 4 invert, 5 pow22523, 6 canon(a)
+void emu_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b)
+{
+    fe x, y, r;
+    ld(x.v, a, 8); ld(y.v, b, 8);
+    switch (op) {
+    case 0: fe_mul(r, x, y); break;
+    case 1: fe_sq(r, x); break;
+    case 2: fe_add(r, x, y); break;
+    case 3: fe_sub(r, x, y); break;
+    case 4: fe_invert(r, x); break;
+    case 5: fe_pow22523(r, x); break;
+    default: r = x; break;
+    }
+    uint32_t w[8];
+    fe_to_words(w, r);
+    st(out, w, 8);
+}
+int emu_point_recode(uint8_t* out, const uint8_t* in)
+{
+    uint32_t w[8], o[8];
+    ge_p3 p;
+    ld(w, in, 8);
+    uint32_t ok = ge_decompress(p, w);
+    ge_compress(o, p);
+    st(out, o, 8);
+    return (int)ok;
+}
+int emu_point_checks(const uint8_t* in)  // bit0 canonical, bit1 small-order(bytes)
+{
+    uint32_t w[8];
+    ld(w, in, 8);
+    return (int)(pt_is_canonical(w) | (pt_is_small_order_bytes(w) << 1));
+}
+int emu_mul(uint8_t* out, const uint8_t* scalar, const uint8_t* point, int ct)
+{
+    uint32_t s[8], w[8], o[8];
+    ge_p3 p, h;
+    ge_cached tbl[8];
+    int8_t e[64];
+    ld(s, scalar, 8); ld(w, point, 8);
+    uint32_t ok = ge_decompress(p, w);
+    sc_recode16(e, s);
+    ge_build_table8(tbl, p);
+    if (ct) ge_scalarmult<true>(h, e, tbl); else ge_scalarmult<false>(h, e, tbl);
+    ge_compress(o, h);
+    st(out, o, 8);
+    return (int)ok;
+}
+void emu_mul_base(uint8_t* out, const uint8_t* scalar, int ct)
+{
+    uint32_t s[8], o[8];
+    ge_p3 h;
+    int8_t e[64];
+    base_init();
+    ld(s, scalar, 8);
+    sc_recode16(e, s);
+    if (ct) ge_scalarmult_base<true>(h, e, g_base); else ge_scalarmult_base<false>(h, e, g_base);
+    ge_compress(o, h);
+    st(out, o, 8);
+}
+void emu_sc_reduce512(uint8_t* out, const uint8_t* in)
+{
+    uint32_t x[16], r[8];
+    ld(x, in, 16);
+    sc_reduce512(r, x);
+    st(out, r, 8);
+}
+void emu_sc_muladd(uint8_t* out, const uint8_t* a, const uint8_t* b, const uint8_t* c)
+{
+    uint32_t A[8], B[8], C[8], r[8];
+    ld(A, a, 8); ld(B, b, 8); ld(C, c, 8);
+    sc_muladd(r, A, B, C);
+    st(out, r, 8);
+}
+int emu_sc_is_canonical(const uint8_t* s)
+{
+    uint32_t w[8];
+    ld(w, s, 8);
+    return (int)sc_is_canonical(w);
+}
+void emu_sha512_ram(uint8_t* out, const uint8_t* r, const uint8_t* a, const uint8_t* msg, uint64_t mlen)
+{
+    uint32_t rw[8], aw[8], d[16];
+    ld(rw, r, 8); ld(aw, a, 8);
+    sha512_ram(d, rw, aw, msg, mlen);
+    st(out, d, 16);
+}
+int emu_sig_verify(int schnorr, const uint8_t* pk, const uint8_t* msg, uint64_t mlen, const uint8_t* sig)
+{
+    uint32_t pw[8], sw[16];
+    ge_cached tbl[8];
+    base_init();
+    ld(pw, pk, 8); ld(sw, sig, 16);
+    return schnorr ? (int)sig_verify<true>(pw, sw, msg, mlen, g_base, tbl) : (int)sig_verify<false>(pw, sw, msg, mlen, g_base, tbl);
+}
+// PubPoly::eval via the short-scalar Horner used by the eval kernel
+int emu_pubpoly_eval(uint8_t* out, const uint8_t* commits, int t, uint32_t idx)
+{
+    ge_p3 v, c;
+    uint32_t w[8], o[8];
+    ge_identity(v);
+    for (int j = t - 1; j >= 0; j--) {
+        ld(w, commits + 32 * j, 8);
+        if (!ge_decompress(c, w)) return 0;
+        ge_cached cc;
+        ge_to_cached(cc, c);
+        kb_horner_step(v, (uint64_t)idx + 1, cc);
+    }
+    ge_compress(o, v);
+    st(out, o, 8);
+    return 1;
+}
+
+// Pippenger stage bodies of msm.cuh, run "thread by thread" on the host; the final
+// warp-shuffle tree (GPU only) is replaced by a plain sum of the same group partials.
+int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* points, int c_override)
+{
+    kb_msm_plan pl;
+    pl.n = (uint32_t)n;
+    pl.c = c_override ? (uint32_t)c_override : kb_msm_window_bits_host(n);
+    pl.windows = (257 + pl.c - 1) / pl.c;
+    pl.half = 1u << (pl.c - 1);
+    pl.nb = pl.windows * pl.half;
+    const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
+    const size_t nthreads = (n * pl.windows + KB_MSM_K - 1) / KB_MSM_K;
+    std::vector<uint32_t> pts(24 * n + 24), mags(8 * n + 8), counts(pl.nb, 0), offsets(pl.nb + 1), cursor(pl.nb, 0), sorted(n * pl.windows + 1);
+    std::vector<uint32_t> bucket_sum(32 * (size_t)pl.nb), heads(32 * nthreads + 32), tails(32 * nthreads + 32), partial(32 * (size_t)pl.windows * groups);
+    std::vector<uint8_t> negs(n + 1), flags(nthreads + 1);
+    uint32_t bad = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t pw[8], sw[8];
+        ld(pw, points + 32 * i, 8); ld(sw, scalars + 32 * i, 8);
+        kb_msm_prepare_body(i, pw, sw, pts.data(), mags.data(), negs.data(), &bad);
+    }
+    for (size_t i = 0; i < n; i++) kb_msm_hist_body(pl, i, mags.data(), counts.data());
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < pl.nb; b++) { offsets[b] = run; run += counts[b]; }
+    offsets[pl.nb] = run;
+    for (size_t i = 0; i < n; i++) kb_msm_scatter_body(pl, i, mags.data(), negs.data(), offsets.data(), cursor.data(), sorted.data());
+    for (size_t t = 0; t < nthreads; t++) kb_msm_accum_body(pl, t, offsets.data(), sorted.data(), pts.data(), bucket_sum.data(), heads.data(), tails.data(), flags.data());
+    for (size_t t = 0; t < nthreads; t++) kb_msm_merge_body(pl, t, nthreads, offsets.data(), nullptr, bucket_sum.data(), heads.data(), tails.data(), flags.data());
+    for (size_t t = 0; t < (size_t)pl.windows * groups; t++) kb_msm_reduce_body(pl, t, groups, offsets.data(), bucket_sum.data(), partial.data());
+    ge_p3 tot;
+    ge_identity(tot);
+    for (uint32_t w = pl.windows; w-- > 0;) {
+        for (uint32_t k = 0; k < pl.c; k++) ge_dbl<true>(tot, tot);
+        for (uint32_t g = 0; g < groups; g++) {
+            ge_p3 p;
+            kb_load_p3(p, partial.data() + 32 * ((size_t)w * groups + g));
+            ge_cached pc;
+            ge_to_cached(pc, p);
+            ge_add<true>(tot, tot, pc);
+        }
+    }
+    uint32_t o[8];
+    ge_compress(o, tot);
+    st(out, o, 8);
+    return (int)bad;
+}
+}

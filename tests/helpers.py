@@ -199,3 +199,94 @@ def random_scalars(seed: str, n: int) -> np.ndarray:
         v = int.from_bytes(raw[i].tobytes(), "little") % L_ORDER
         out[i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# adversarial signature batches (valid items + every reject class the reference tests)
+# ---------------------------------------------------------------------------------------------
+WEAK_KEYS = [
+    bytes(32),
+    bytes([1]) + bytes(31),
+    bytes.fromhex("26e8958fc2b227b045c3f489f2ef98f0d5dfac05d3c63339b13802886d53fc05"),
+    bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a"),
+    bytes([0xEC]) + b"\xff" * 30 + b"\x7f",
+]
+NONCANONICAL = bytes([0xEF]) + b"\xff" * 31
+
+
+def _off_curve(seed: int) -> bytes:
+    """A canonical-looking 32-byte string that is not a curve point (found by search with the C oracle)."""
+    C = load_c_oracle()
+    k = 0
+    while True:
+        cand = hashlib.sha256(b"offcurve%d/%d" % (seed, k)).digest()
+        cand = cand[:31] + bytes([cand[31] & 0x7F])
+        if not C.point_decode_ok(cand):
+            return cand
+        k += 1
+
+
+def mutate_signature(kind: int, rec, other):
+    """Returns (pk, msg, sig) for mutation class `kind` of golden record `rec`."""
+    seed, pk, sig, msg = rec
+    L = L_ORDER
+    s_plus_l = ((int.from_bytes(sig[32:], "little") + L) % (1 << 256)).to_bytes(32, "little")
+    kind %= 24
+    if kind == 0:
+        return pk, msg, sig
+    if kind == 1:
+        m = bytearray(msg or b"\0"); m[0] ^= 1
+        return pk, bytes(m), sig
+    if kind == 2:
+        return pk, msg, sig[:32] + s_plus_l
+    if kind == 3:
+        return pk, msg, NONCANONICAL + sig[32:]
+    if kind == 4:
+        return NONCANONICAL, msg, sig
+    if kind in (5, 6, 7, 8, 9):
+        return pk, msg, WEAK_KEYS[kind - 5] + sig[32:]
+    if kind in (10, 11, 12, 13, 14):
+        return WEAK_KEYS[kind - 10], msg, sig
+    if kind == 15:
+        return pk, msg, _off_curve(1) + sig[32:]
+    if kind == 16:
+        return _off_curve(2), msg, sig
+    if kind == 17:   # quirk range (SURVEY §A1): canonical y reported non-canonical
+        return pk, msg, bytes([0x14 + (len(msg) % 0xD9)]) + b"\xff" * 30 + b"\x7f" + sig[32:]
+    if kind == 18:
+        return bytes([0x14 + (len(msg) % 0xD9)]) + b"\xff" * 30 + b"\xff", msg, sig
+    if kind == 19:   # several things wrong at once: the verifiers' check ORDER decides
+        return NONCANONICAL, msg, NONCANONICAL + s_plus_l
+    if kind == 20:
+        return NONCANONICAL, msg, _off_curve(3) + sig[32:]
+    if kind == 21:
+        return _off_curve(4), msg, WEAK_KEYS[3] + s_plus_l
+    if kind == 22:   # a different (valid) R
+        return pk, msg, other[2][:32] + sig[32:]
+    w = bytearray(WEAK_KEYS[1]); w[31] |= 0x80   # identity with the sign bit set (x = 0, SURVEY §A2)
+    return pk, msg, bytes(w) + sig[32:]
+
+
+def make_sig_batch(records, n: int, bad_every: int = 4):
+    """n (pk, msg, sig) triples cycling through the golden records; every `bad_every`-th item is a
+    mutation, cycling through all classes.  Returns (pks, msgs, sigs) lists."""
+    pks, msgs, sigs = [], [], []
+    kind = 1
+    for i in range(n):
+        rec = records[i % len(records)]
+        if bad_every and i % bad_every == bad_every - 1:
+            pk, msg, sig = mutate_signature(kind, rec, records[(i + 7) % len(records)])
+            kind += 1
+        else:
+            _, pk, sig, msg = rec
+        pks.append(pk); msgs.append(msg); sigs.append(sig)
+    return pks, msgs, sigs
+
+
+def pack_batch(pks, msgs, sigs):
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    flat = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy()
+    pk = np.frombuffer(b"".join(pks), dtype=np.uint8).reshape(-1, 32).copy()
+    sg = np.frombuffer(b"".join(sigs), dtype=np.uint8).reshape(-1, 64).copy()
+    return pk, flat, off, sg

@@ -1,0 +1,173 @@
+"""Host emulation of the per-thread device math (tests/emu/emu.cpp compiles the SAME headers the
+GPU kernels inline, with KB_HOST_EMU) against the oracles.  CPU only.  This is how the field /
+curve / scalar / hash / verify / Pippenger logic is checked on a machine with no GPU; the PTX
+carry-chain primitives themselves are covered by the -m gpu tests."""
+import ctypes
+import hashlib
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, load_c_oracle, load_sign_input, make_sig_batch
+from oracle import ed25519_bigint as O
+
+P = O.P
+
+
+@pytest.fixture(scope="module")
+def emu():
+    d = os.path.join(ROOT, "tests", "emu")
+    so = os.path.join(d, "_emu.so")
+    srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "kyber-rs_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "kyber-rs_b200", "csrc")) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused-function", "-o", so, os.path.join(d, "emu.cpp")])
+    E = ctypes.CDLL(so)
+    E.emu_sha512_ram.argtypes = [ctypes.c_char_p] * 4 + [ctypes.c_uint64]
+    E.emu_sig_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
+    return E
+
+
+def b32(x):
+    return x.to_bytes(32, "little")
+
+
+def test_field_ops(emu):
+    def feop(op, a, b=bytes(32)):
+        out = ctypes.create_string_buffer(32)
+        emu.emu_fe_op(op, out, a, b)
+        return out.raw
+
+    rnd = random.Random(7)
+    edge = [0, 1, 2, 19, 38, P - 1, P, P + 1, 2**255 - 1, 2**255, 2**255 + 18, 2**255 + 19, 2**256 - 1, 2**256 - 38, 2**256 - 39, 2**256 - 19, 2**256 - 2**32, 2**224 - 1]
+    vals = edge + [rnd.getrandbits(256) for _ in range(150)]
+    for x in vals:
+        for y in rnd.sample(vals, 8) + edge[:8]:
+            assert feop(0, b32(x), b32(y)) == b32(x * y % P)
+            assert feop(2, b32(x), b32(y)) == b32((x + y) % P)
+            assert feop(3, b32(x), b32(y)) == b32((x - y) % P)
+        assert feop(1, b32(x)) == b32(x * x % P)
+        assert feop(6, b32(x)) == b32(x % P)
+    for x in vals[:40]:
+        assert feop(4, b32(x)) == b32(pow(x, P - 2, P))
+        assert feop(5, b32(x)) == b32(pow(x, (P - 5) // 8, P))
+
+
+def test_points_and_checks(emu, coracle, golden_records):
+    def recode(s):
+        out = ctypes.create_string_buffer(32)
+        return out.raw if emu.emu_point_recode(out, s) else None
+
+    for _, pk, sig, _ in golden_records[:64]:
+        assert recode(pk) == pk and recode(sig[:32]) == sig[:32]
+    rnd = random.Random(3)
+    for _ in range(200):
+        s = rnd.randbytes(32)
+        assert recode(s) == coracle.point_recode(s)
+    for k in O.WEAK_KEYS:
+        assert recode(k) == coracle.point_recode(k)
+        assert emu.emu_point_checks(k) & 2
+    for b0 in range(256):
+        for top in (0x7F, 0xFF, 0x7E):
+            e = bytes([b0]) + b"\xff" * 30 + bytes([top])
+            assert (emu.emu_point_checks(e) & 1) == O.point_is_canonical(e)
+
+
+def test_scalars_and_hash(emu):
+    rnd = random.Random(5)
+    out = ctypes.create_string_buffer(32)
+    for _ in range(200):
+        d = rnd.randbytes(64)
+        emu.emu_sc_reduce512(out, d)
+        assert out.raw == O.scalar_set_bytes(d)
+        a, b, c = rnd.randbytes(32), rnd.randbytes(32), rnd.randbytes(32)
+        emu.emu_sc_muladd(out, a, b, c)
+        assert out.raw == O.sc_mul_add(a, b, c)
+    for d in (b"\xff" * 64, bytes(64)):
+        emu.emu_sc_reduce512(out, d)
+        assert out.raw == O.scalar_set_bytes(d)
+    for k in range(-3, 3):
+        assert bool(emu.emu_sc_is_canonical(b32(O.L + k))) == (k < 0)
+    dg = ctypes.create_string_buffer(64)
+    for n in (0, 1, 3, 47, 48, 55, 56, 63, 64, 65, 100, 128, 191, 192, 193, 500):
+        r, a, m = rnd.randbytes(32), rnd.randbytes(32), rnd.randbytes(n)
+        emu.emu_sha512_ram(dg, r, a, m, n)
+        assert dg.raw == hashlib.sha512(r + a + m).digest()
+
+
+def test_scalar_mults(emu, coracle, golden_records):
+    rnd = random.Random(11)
+    out = ctypes.create_string_buffer(32)
+    for _, pk, _, _ in golden_records[:24]:
+        for ct in (0, 1):
+            for s in (rnd.randbytes(32), rnd.randbytes(31) + b"\x0f", b"\xff" * 32, bytes(32)):
+                emu.emu_mul(out, s, pk, ct)
+                assert out.raw == coracle.mul(s, pk)
+                emu.emu_mul_base(out, s, ct)
+                assert out.raw == coracle.mul_base(s)
+
+
+def test_verify_state_machine(emu, coracle, golden_records):
+    """Every mutation class, both verifiers, against the C oracle (itself pinned to the big-int
+    oracle and the reference's vectors in test_oracle_golden.py)."""
+    pks, msgs, sigs = make_sig_batch(golden_records[:256:3], 24 * 6, bad_every=1)
+    seen = set()
+    for pk, msg, sig in zip(pks, msgs, sigs):
+        for sch in (0, 1):
+            want = coracle.schnorr_verify(pk, msg, sig) if sch else coracle.eddsa_verify(pk, msg, sig)
+            assert emu.emu_sig_verify(sch, pk, msg, len(msg), sig) == want
+            seen.add(want)
+    assert seen == {0, 2, 3, 4, 5, 6, 7, 8}
+    for _, pk, sig, msg in golden_records[::32]:
+        assert emu.emu_sig_verify(0, pk, msg, len(msg), sig) == 0
+        assert emu.emu_sig_verify(1, pk, msg, len(msg), sig) == 0
+
+
+def test_verify_oracles_agree_on_mutations(coracle, golden_records):
+    pks, msgs, sigs = make_sig_batch(golden_records[:48], 48, bad_every=1)
+    for pk, msg, sig in zip(pks, msgs, sigs):
+        assert coracle.eddsa_verify(pk, msg, sig) == O.eddsa_verify(pk, msg, sig)
+        assert coracle.schnorr_verify(pk, msg, sig) == O.schnorr_verify(pk, msg, sig)
+
+
+def test_pubpoly_short_horner(emu, coracle, golden_records):
+    commits = [r[1] for r in golden_records[:7]]
+    t8 = O.point_encode(O.point_add(O.point_decode(commits[1]), O.point_decode(O.WEAK_KEYS[2])))
+    out = ctypes.create_string_buffer(32)
+    for cs in (commits, [commits[0], t8] + commits[2:]):   # second: torsion-contaminated
+        flat = b"".join(cs)
+        for idx in (0, 1, 2, 6, 255, 1023, 65535, 2**32 - 1):
+            assert emu.emu_pubpoly_eval(out, flat, len(cs), idx) == 1
+            assert out.raw == coracle.pubpoly_eval(cs, idx)
+
+
+def test_pippenger_stages(emu, coracle, golden_records):
+    pks = np.frombuffer(b"".join(r[1] for r in golden_records), dtype=np.uint8).reshape(-1, 32)
+    rng = np.random.default_rng(1)
+
+    def run(s, p, c=0):
+        out = ctypes.create_string_buffer(32)
+        bad = emu.emu_msm(out, s.shape[0], s.ctypes.data, p.ctypes.data, c)
+        return out.raw, bad
+
+    for n, c in [(1, 0), (2, 4), (17, 4), (50, 5), (300, 6), (700, 0), (500, 8)]:
+        s = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)   # includes out-of-domain scalars (a[31] > 127)
+        p = pks[:n].copy()
+        got, bad = run(s, p, c)
+        assert bad == 0 and got == coracle.msm(s, p)
+    n = 200
+    p = pks[:n].copy()
+    same = np.tile(rng.integers(0, 256, size=(1, 32), dtype=np.uint8), (n, 1))   # one giant bucket per window
+    assert run(same, p, 4)[0] == coracle.msm(same, p)
+    z = np.zeros((n, 32), dtype=np.uint8)
+    assert run(z, p)[0] == coracle.msm(z, p)
+    z[:, 0] = 1
+    assert run(z, p, 5)[0] == coracle.msm(z, p)
+    bad_pt = p.copy()
+    bad_pt[3] = np.frombuffer(hashlib.sha256(b"x").digest(), dtype=np.uint8)
+    if not coracle.point_decode_ok(bad_pt[3].tobytes()):
+        assert run(z, bad_pt)[1] == 1

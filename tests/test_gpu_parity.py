@@ -1,0 +1,310 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle on
+the same inputs.  Bit-exact: compressed encodings and accept/reject statuses.  Needs a B200."""
+import hashlib
+import importlib
+
+import numpy as np
+import pytest
+
+from helpers import load_sign_input, make_sig_batch, pack_batch, random_scalars, xof_bytes
+from oracle import ed25519_bigint as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kb():
+    return importlib.import_module("kyber-rs_b200")
+
+
+@pytest.fixture(scope="module")
+def ctx(kb):
+    c = kb.Context(0)
+    kb.host.set_default_context(c)
+    yield c
+
+
+def _golden_pks(records, n):
+    return np.frombuffer(b"".join(r[1] for r in records[:n]), dtype=np.uint8).reshape(-1, 32).copy()
+
+
+# ---- Point::mul ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, 1])
+def test_mul_base_matches_oracle(ctx, coracle, flags):
+    """config 1, base-point half: Point::mul(s, None) (point.rs:207 -> ge.rs:442)."""
+    n = 4096
+    s = random_scalars("kyber-b200/cfg1/scalars", n)
+    s[:64] = np.frombuffer(xof_bytes("raw", 64 * 32), dtype=np.uint8).reshape(64, 32)   # unreduced / out-of-domain
+    s[64] = 0
+    s[65] = 255
+    got = ctx.point_mul_base_batch(s, flags)
+    want = coracle.mul_base_batch(s, nthreads=8)
+    assert (got == want).all()
+
+
+def test_mul_base_golden_public_keys(ctx, golden_records):
+    """pk = clamp(SHA512(seed)) * B for all 1024 golden lines (tests/sign/eddsa.rs:37-94)."""
+    sc = np.frombuffer(b"".join(O.clamp_key(r[0])[0] for r in golden_records), dtype=np.uint8).reshape(-1, 32)
+    got = ctx.point_mul_base_batch(sc)
+    assert got.tobytes() == b"".join(r[1] for r in golden_records)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_mul_var_base_matches_oracle(ctx, coracle, golden_records, flags):
+    """config 1, variable-base half: Point::mul(s, Some(p)) (ge.rs:508), distinct and shared point."""
+    n = 1024
+    s = random_scalars("kyber-b200/cfg1/scalars2", n)
+    s[:32] = np.frombuffer(xof_bytes("raw2", 32 * 32), dtype=np.uint8).reshape(32, 32)
+    pts = _golden_pks(golden_records, n)
+    pts[7] = np.frombuffer(O.WEAK_KEYS[2], dtype=np.uint8)          # torsion point
+    pts[8] = np.frombuffer(bytes([0xEE]) + b"\xff" * 30 + b"\x7f", dtype=np.uint8)  # y >= p is accepted by decode
+    got, st = ctx.point_mul_batch(s, pts, flags)
+    want = coracle.mul_batch(s, pts, nthreads=8)
+    assert (got == want).all()
+    ok = np.array([coracle.point_decode_ok(p.tobytes()) for p in pts])
+    assert (st == (~ok).astype(np.uint8)).all()
+    got1, _ = ctx.point_mul_batch(s[:256], pts[3:4], flags)
+    want1 = coracle.mul_batch(s[:256], np.repeat(pts[3:4], 256, axis=0), nthreads=8)
+    assert (got1 == want1).all()
+
+
+def test_undecodable_point_is_flagged(ctx, coracle):
+    bad = None
+    k = 0
+    while bad is None:
+        c = hashlib.sha256(b"bad%d" % k).digest()
+        if not coracle.point_decode_ok(c):
+            bad = c
+        k += 1
+    out, st = ctx.point_mul_batch(np.ones((1, 32), dtype=np.uint8), np.frombuffer(bad, dtype=np.uint8))
+    assert st[0] == 1 and not out.any()
+
+
+# ---- encodings, add, checks -----------------------------------------------------------------------
+def test_recode_add_check(ctx, coracle, golden_records):
+    rnd = np.frombuffer(xof_bytes("recode", 2048 * 32), dtype=np.uint8).reshape(-1, 32).copy()
+    rnd[:5] = np.frombuffer(b"".join(O.WEAK_KEYS), dtype=np.uint8).reshape(5, 32)
+    for b0 in range(256):
+        rnd[16 + b0] = np.frombuffer(bytes([b0]) + b"\xff" * 30 + b"\x7f", dtype=np.uint8)
+    out, st = ctx.point_recode_batch(rnd)
+    flags = ctx.point_check_batch(rnd)
+    for i, r in enumerate(rnd):
+        want = coracle.point_recode(r.tobytes())
+        assert (st[i] == 0) == (want is not None)
+        if want is not None:
+            assert out[i].tobytes() == want
+        assert bool(flags[i] & 1) == O.point_is_canonical(r.tobytes())
+        assert bool(flags[i] & 4) == (want is not None)
+        if want is not None:
+            assert bool(flags[i] & 2) == bool(coracle.point_has_small_order(r.tobytes()))
+    p = _golden_pks(golden_records, 512)
+    q = np.roll(p, 1, axis=0)
+    for sub in (False, True):
+        got, st = ctx.point_add_batch(p, q, subtract=sub)
+        assert not st.any()
+        for i in range(0, 512, 7):
+            assert got[i].tobytes() == coracle.point_add(p[i].tobytes(), q[i].tobytes(), sub)
+    same, _ = ctx.point_add_batch(p[:8], p[:8])                       # doubling through the unified law
+    assert same[0].tobytes() == coracle.point_add(p[0].tobytes(), p[0].tobytes())
+    zero, _ = ctx.point_add_batch(p[:8], p[:8], subtract=True)
+    assert zero[0].tobytes() == (1).to_bytes(32, "little")
+
+
+# ---- scalars and the challenge hash ---------------------------------------------------------------
+def test_scalar_ops_and_challenge(ctx, coracle, golden_records):
+    d = np.frombuffer(xof_bytes("digests", 1000 * 64), dtype=np.uint8).reshape(-1, 64).copy()
+    d[0] = 255
+    d[1] = 0
+    got = ctx.sc_reduce64_batch(d)
+    for i in range(len(d)):
+        assert got[i].tobytes() == O.scalar_set_bytes(d[i].tobytes())
+    abc = np.frombuffer(xof_bytes("abc", 3 * 500 * 32), dtype=np.uint8).reshape(3, -1, 32)
+    got = ctx.sc_muladd_batch(abc[0], abc[1], abc[2])
+    for i in range(500):
+        assert got[i].tobytes() == O.sc_mul_add(abc[0][i].tobytes(), abc[1][i].tobytes(), abc[2][i].tobytes())
+    recs = golden_records[::4]            # message lengths 0..1020: every SHA-512 padding case
+    pk, flat, off, sg = pack_batch([r[1] for r in recs], [r[3] for r in recs], [r[2] for r in recs])
+    h = ctx.challenge_batch(sg[:, :32], pk, flat, off)
+    for i, r in enumerate(recs):
+        assert h[i].tobytes() == O.challenge(r[2][:32], r[1], r[3])
+
+
+# ---- signatures -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_verify_golden_file(ctx, golden_records, schnorr):
+    """All 1024 golden signatures verify (tests/sign/eddsa.rs:37-94; schnorr_test.rs:43-51 says the
+    two verifiers accept each other's signatures)."""
+    pk, flat, off, sg = pack_batch([r[1] for r in golden_records], [r[3] for r in golden_records], [r[2] for r in golden_records])
+    st = ctx.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+    assert not st.any()
+
+
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_verify_reject_classes(ctx, coracle, golden_records, schnorr):
+    """Every mutation class (eddsa_test.rs:111-272, schnorr_test.rs:6-110 and SURVEY §A cases):
+    status must equal the oracle's, i.e. the reference's error variant in ITS check order."""
+    pks, msgs, sigs = make_sig_batch(golden_records, 4096, bad_every=2)
+    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+    got = ctx.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+    want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    assert set(np.unique(want)) == {0, 2, 3, 4, 5, 6, 7, 8}
+
+
+def test_verify_host_mirror_errors(kb, ctx, golden_records):
+    """Reads like sign/eddsa/eddsa_test.rs: error strings are the reference's."""
+    H = kb.host
+    _, pk, sig, msg = golden_records[33]
+    public = H.Point.unmarshal_binary(pk)
+    H.eddsa_verify(public, msg, sig)
+    H.schnorr_verify(public, msg, sig)
+    s_plus_l = ((int.from_bytes(sig[32:], "little") + O.L) % 2**256).to_bytes(32, "little")
+    cases = [
+        (pk, msg, sig[:32] + s_plus_l, "signature is not canonical"),
+        (pk, msg, bytes([0xEF]) + b"\xff" * 31 + sig[32:], "R is not canonical"),
+        (bytes([0xEF]) + b"\xff" * 31, msg, sig, "public key is not canonical"),
+        (pk, msg, O.WEAK_KEYS[3] + sig[32:], "R has small order"),
+        (O.WEAK_KEYS[3], msg, sig, "public key has small order"),
+        (pk, msg + b"!", sig, "signature is not valid"),
+        (pk, msg, sig[:63], "wrong signature length"),
+    ]
+    for p, m, s, text in cases:
+        with pytest.raises(H.SignatureError) as e:
+            H.eddsa_verify_with_checks(p, m, s)
+        assert str(e.value) == text
+    with pytest.raises(H.MarshallingError):
+        H.Point.unmarshal_binary(hashlib.sha256(b"bad0").digest() if not ctx.point_check_batch(np.frombuffer(hashlib.sha256(b"bad0").digest(), np.uint8))[0] & 4 else b"\x02" + bytes(31))
+
+
+def test_group_laws_host_mirror(kb, ctx):
+    """util/test/group_test.rs:210-555 in miniature: 2G, -1*G + G = 0, DH commutativity, homomorphisms."""
+    H = kb.host
+    g = H.Point.base()
+    two = H.Scalar.set_int64(2)
+    assert H.Point().add(g, g) == H.Point().mul(two)
+    minus1 = H.Scalar(O.scalar_set_int64(-1))
+    assert H.Point().add(H.Point().mul(minus1), g) == H.Point.null()
+    a = H.Scalar.set_bytes(hashlib.sha512(b"a").digest())
+    b = H.Scalar.set_bytes(hashlib.sha512(b"b").digest())
+    pa, pb = H.Point().mul(a), H.Point().mul(b)
+    assert H.Point().mul(a, pb) == H.Point().mul(b, pa)
+    assert H.Point().add(pa, pb) == H.Point().mul(a + b)
+    assert H.Point().mul(a * b) == H.Point().mul(a, pb)
+    assert H.Point().sub(pa, pa) == H.Point.null()
+    assert H.Scalar.set_int64(0x100) + H.Scalar.one() == H.Scalar(bytes([1, 1]) + bytes(30))   # scalar_test.rs:27-35
+    assert H.Scalar.set_bytes(bytes([0, 1, 2, 3])).v.hex() == "00010203" + "00" * 28            # scalar_test.rs:68-75
+
+
+# ---- committed polynomials / VSS / DKG -------------------------------------------------------------
+def _poly(seed, t):
+    coeffs = [O.scalar_set_bytes(hashlib.sha512(b"%s/%d" % (seed, j)).digest()) for j in range(t)]
+    return coeffs
+
+
+def test_pubpoly_eval_and_check(kb, ctx, coracle):
+    """config 3 shape at reduced size (oracle is O(t) full scalar mults per eval): t=23 commits,
+    evaluation points incl. large indices; plus a torsion-contaminated polynomial."""
+    t, npoly = 23, 3
+    polys = [_poly(b"p%d" % k, t) for k in range(npoly)]
+    commits = ctx.point_mul_base_batch(np.frombuffer(b"".join(b"".join(p) for p in polys), dtype=np.uint8).reshape(-1, 32))
+    tors = ctx.point_add_batch(commits[t + 1], np.frombuffer(O.WEAK_KEYS[2], dtype=np.uint8))[0]
+    commits[t + 1] = tors[0]
+    idx = np.array([0, 1, 2, 5, 255, 256, 1023, 40000, 2**32 - 1] * npoly, dtype=np.uint32)
+    pid = np.repeat(np.arange(npoly, dtype=np.uint32), 9)
+    got, st = ctx.pubpoly_eval_batch(commits, t, pid, idx)
+    assert not st.any()
+    for k in range(len(idx)):
+        cs = [c.tobytes() for c in commits[pid[k] * t:(pid[k] + 1) * t]]
+        assert got[k].tobytes() == coracle.pubpoly_eval(cs, int(idx[k]))
+    # shares: honest, corrupted
+    shares = np.frombuffer(b"".join(O.pripoly_eval(polys[pid[k]], int(idx[k])) for k in range(len(idx))), dtype=np.uint8).reshape(-1, 32).copy()
+    shares[4, 0] ^= 1
+    verdict = ctx.vss_verify_deals_batch(commits, t, pid, idx, shares)
+    want = np.array([coracle.vss_verify_deal([c.tobytes() for c in commits[pid[k] * t:(pid[k] + 1) * t]], int(idx[k]), shares[k].tobytes()) == 1 for k in range(len(idx))])
+    assert (verdict.astype(bool) == want).all()
+    assert verdict[0] == 1 and verdict[4] == 0
+    # host mirror, poly_test.rs:121-137 style
+    pp = kb.host.PubPoly([c.tobytes() for c in commits[:t]])
+    assert pp.check(3, kb.host.Scalar(O.pripoly_eval(polys[0], 3)))
+    assert not pp.check(3, kb.host.Scalar(O.pripoly_eval(polys[0], 4)))
+    assert pp.add(pp).eval(2) == kb.host.Point().add(pp.eval(2), pp.eval(2))
+
+
+def test_dkg_round_small(ctx, coracle):
+    """config 4 shape at n=24, t=16: all n^2 (dealer, verifier) share checks, some corrupted."""
+    n, t = 24, 16
+    polys = [_poly(b"d%d" % d, t) for d in range(n)]
+    commits = ctx.point_mul_base_batch(np.frombuffer(b"".join(b"".join(p) for p in polys), dtype=np.uint8).reshape(-1, 32))
+    shares = np.frombuffer(b"".join(O.pripoly_eval(polys[d], i) for d in range(n) for i in range(n)), dtype=np.uint8).reshape(-1, 32).copy()
+    bad = [(0, 0), (3, 17), (23, 23), (11, 5)]
+    for d, i in bad:
+        shares[d * n + i, 5] ^= 0x40
+    verdict = ctx.dkg_verify_round(n, t, commits, shares)
+    want = np.ones((n, n), dtype=np.uint8)
+    for d, i in bad:
+        want[d, i] = 0
+    assert (verdict.reshape(n, n) == want).all()
+    for d in (0, 11):   # oracle cross-check of two dealers' rows
+        row = coracle.vss_verify_batch(commits[d * t:(d + 1) * t], np.arange(n, dtype=np.uint32), shares[d * n:(d + 1) * n], nthreads=8)
+        assert (row == want[d]).all()
+    part = ctx.dkg_verify_round(n, t, commits, shares, dealer_lo=8, dealer_hi=16)
+    assert (part.reshape(n, n)[8:16] == want[8:16]).all()
+
+
+# ---- MSM -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 1000, 5000])
+def test_msm_matches_oracle(ctx, coracle, golden_records, n):
+    pts = np.tile(_golden_pks(golden_records, 1024), (5, 1))[:n]
+    s = np.frombuffer(xof_bytes("msm%d" % n, 32 * max(n, 1)), dtype=np.uint8).reshape(-1, 32)[:n].copy()
+    if n >= 1000:
+        s[:, 31] &= 0x7F
+    enc, bad = ctx.msm(s, pts)
+    assert bad == 0
+    want = coracle.msm(s, pts) if n else (1).to_bytes(32, "little")
+    assert enc == want
+
+
+def test_msm_skew_and_linearity(ctx, coracle, golden_records):
+    """Size-independent properties at a size the oracle cannot reach quickly (2^16): linearity in the
+    scalars, equal scalars (one giant bucket per window), partial + point_sum == whole."""
+    n = 1 << 16
+    pts = np.tile(_golden_pks(golden_records, 1024), (n // 1024, 1))
+    a = random_scalars("msm/a", 1024)
+    a = np.tile(a, (n // 1024, 1))
+    ones = np.zeros((n, 32), dtype=np.uint8)
+    ones[:, 0] = 1
+    ea, _ = ctx.msm(a, pts)
+    e1, _ = ctx.msm(ones, pts)
+    a1 = ctx.sc_muladd_batch(a, ones, ones)           # a*1 + 1
+    ea1, _ = ctx.msm(a1, pts)
+    assert ctx.point_add_batch(np.frombuffer(ea, np.uint8), np.frombuffer(e1, np.uint8))[0][0].tobytes() == ea1
+    # sum of the 1024 distinct points times 64, via the oracle on the small set
+    small = coracle.msm(ones[:1024], pts[:1024])
+    sixty4 = np.zeros((1, 32), dtype=np.uint8)
+    sixty4[0, 0] = 64
+    assert e1 == coracle.mul(sixty4[0].tobytes(), small)
+    same = np.tile(a[:1], (n, 1))
+    es, _ = ctx.msm(same, pts)
+    assert es == coracle.mul(a[0].tobytes(), e1)
+    # sharded: two halves -> partials -> fold
+    _, p0, _ = ctx.msm(a[: n // 2], pts[: n // 2], want_partial=True)
+    _, p1, _ = ctx.msm(a[n // 2:], pts[n // 2:], want_partial=True)
+    assert ctx.point_sum(np.stack([p0, p1])) == ea
+
+
+def test_full_size_signature_batch_properties(ctx, coracle, golden_records):
+    """BASELINE config 2 size (2^20): statuses of a tiled batch must be periodic with the tile, and the
+    first tile must equal the oracle's."""
+    tile = 4096
+    pks, msgs, sigs = make_sig_batch(golden_records[:256], tile, bad_every=8)
+    msgs = [m[:64].ljust(64, b"\0") if False else m for m in msgs]
+    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+    reps = (1 << 20) // tile
+    pk_f = np.tile(pk, (reps, 1))
+    sg_f = np.tile(sg, (reps, 1))
+    flat_f = np.tile(flat, reps)
+    off_f = (np.arange(reps, dtype=np.uint64)[:, None] * np.uint64(off[-1]) + off[None, :-1]).reshape(-1)
+    off_f = np.concatenate([off_f, [np.uint64(reps) * off[-1]]]).astype(np.uint64)
+    st = ctx.verify_batch(pk_f, flat_f, off_f, sg_f)
+    want = coracle.verify_batch(pk, flat, off, sg, nthreads=8)
+    assert (st.reshape(reps, tile) == want[None, :]).all()
