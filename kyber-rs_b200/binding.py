@@ -204,13 +204,13 @@ class Context:
         self._check(self.L.kb_challenge_batch(self.h, r.shape[0], _ptr(r), _ptr(a), _ptr(msg), _ptr(msg_off), _ptr(out)), "kb_challenge_batch")
         return out
 
-    def verify_batch(self, pk, msg, msg_off, sig, schnorr=False):
+    def verify_batch(self, pk, msg, msg_off, sig, schnorr=False, out=None):
         pk, sig = _u8(pk, (-1, 32)), _u8(sig, (-1, 64))
         msg = _u8(msg)
         msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
         n = pk.shape[0]
         assert sig.shape[0] == n and msg_off.shape[0] == n + 1
-        st = np.empty(n, dtype=np.uint8)
+        st = out if out is not None else np.empty(n, dtype=np.uint8)
         fn = self.L.kb_schnorr_verify_batch if schnorr else self.L.kb_eddsa_verify_batch
         self._check(fn(self.h, n, _ptr(pk), _ptr(msg), _ptr(msg_off), _ptr(sig), _ptr(st)), "kb_verify_batch")
         return st

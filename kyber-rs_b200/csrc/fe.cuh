@@ -237,7 +237,7 @@ KB_FN uint32_t kb_add8(uint32_t* r, const uint32_t* a, const uint32_t* b)
         "addc.cc.u32 %6, %15, %23;\n\t"
         "addc.cc.u32 %7, %16, %24;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(c)
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     KB_UNROLL
     for (int i = 0; i < 8; i++) r[i] = t[i];
@@ -266,7 +266,7 @@ KB_FN uint32_t kb_sub8(uint32_t* r, const uint32_t* a, const uint32_t* b)
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(c)
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     KB_UNROLL
     for (int i = 0; i < 8; i++) r[i] = t[i];
@@ -295,7 +295,7 @@ KB_FN uint32_t kb_add_small(uint32_t* r, uint32_t k)
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=&r"(c)
         : "r"(k));
     return c;
 #endif
@@ -322,7 +322,7 @@ KB_FN uint32_t kb_sub_small(uint32_t* r, uint32_t k)
         "subc.cc.u32 %6, %6, 0;\n\t"
         "subc.cc.u32 %7, %7, 0;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=&r"(c)
         : "r"(k));
     return c & 1;
 #endif
