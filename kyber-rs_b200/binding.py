@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkyber_b200.so")
+LIB_PATH = os.environ.get("KYBER_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkyber_b200.so")
 
 FLAG_VARTIME = 1
 FLAG_SHARED_POINT = 2

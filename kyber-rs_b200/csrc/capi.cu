@@ -80,7 +80,7 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
     KB_CUDA(cudaMemsetAsync(bad, 0, 8, st));
     if (n == 0) {
         kb_msm_plan pl = {0, 4, 0, 8, 0};
-        k_msm_finish<<<1, 32, 0, st>>>(pl, 1, nullptr, acc128, 1, d_out32);
+        k_msm_finish<<<1, 32, 0, st>>>(pl, nullptr, acc128, 1, d_out32);
         KB_LAUNCHED();
         return KB_OK;
     }
@@ -94,7 +94,7 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         pl.nb = pl.windows * pl.half;
         const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
         const size_t nthreads = (cn * pl.windows + KB_MSM_K - 1) / KB_MSM_K;
-        uint32_t *pts, *mags, *counts, *offsets, *cursor, *sorted, *bucket_sum, *heads, *tails, *partial;
+        uint32_t *pts, *mags, *counts, *offsets, *cursor, *sorted, *bucket_sum, *heads, *tails, *partial, *tile_sums, *long_list, *win_sum;
         uint8_t *negs, *flags;
         KB_SCRATCH(12, 96 * cn, pts);
         KB_SCRATCH(13, 32 * cn, mags);
@@ -108,23 +108,37 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         KB_SCRATCH(21, 128 * nthreads, tails);
         KB_SCRATCH(22, nthreads, flags);
         KB_SCRATCH(23, 128 * (size_t)pl.windows * groups, partial);
+        KB_SCRATCH(24, 4 * 2048, tile_sums);
+        KB_SCRATCH(25, 16 + 12 * (size_t)pl.nb, long_list);  // at most one long run per bucket
+        KB_SCRATCH(26, 128 * (size_t)pl.windows, win_sum);
+        if (pl.nb > 2048u * KB_SCAN_TILE) return KB_ERR_ARG;
         KB_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)pl.nb, st));
         k_msm_prepare<<<kb_blocks(cn, KB_THREADS), KB_THREADS, 0, st>>>(cn, d_points + 32 * off, d_scalars + 32 * off, pts, mags, negs, bad);
         KB_LAUNCHED();
         k_msm_hist<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, counts);
         KB_LAUNCHED();
-        k_msm_scan<<<1, 1024, 0, st>>>(pl.nb, counts, offsets, cursor);
+        const uint32_t ntiles = (pl.nb + KB_SCAN_TILE - 1) / KB_SCAN_TILE;
+        k_msm_scan_tiles<<<ntiles, 256, 0, st>>>(pl.nb, counts, offsets, tile_sums);
+        KB_LAUNCHED();
+        k_msm_scan_sums<<<1, 1024, 0, st>>>(ntiles, pl.nb, tile_sums, offsets);
+        KB_LAUNCHED();
+        k_msm_scan_add<<<kb_blocks(pl.nb, 256), 256, 0, st>>>(pl.nb, tile_sums, offsets, cursor);
         KB_LAUNCHED();
         k_msm_scatter<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, negs, offsets, cursor, sorted);
         KB_LAUNCHED();
         k_msm_accum<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, sorted, pts, bucket_sum, heads, tails, flags);
         KB_LAUNCHED();
-        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, bucket_sum, heads, tails, flags);
+        KB_CUDA(cudaMemsetAsync(long_list, 0, 4, st));  // word 0 of the block is the queue length
+        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, long_list, long_list + 4, bucket_sum, heads, tails, flags);
+        KB_LAUNCHED();
+        k_msm_merge_long<<<ctx->sm_count * 2, KB_THREADS, 0, st>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
         KB_LAUNCHED();
         k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial);
         KB_LAUNCHED();
+        k_msm_window_sums<<<pl.windows, 256, 0, st>>>(groups, partial, win_sum);
+        KB_LAUNCHED();
         const bool last = off + cn >= n;
-        k_msm_finish<<<1, 1024, 128 * pl.windows, st>>>(pl, groups, partial, acc128, off == 0 ? 1 : 0, last ? d_out32 : nullptr);
+        k_msm_finish<<<1, 32, 0, st>>>(pl, win_sum, acc128, off == 0 ? 1 : 0, last ? d_out32 : nullptr);
         KB_LAUNCHED();
     }
     return KB_OK;
@@ -560,7 +574,10 @@ int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double
     cudaEvent_t e0, e1;
     KB_CUDA(cudaEventCreate(&e0));
     KB_CUDA(cudaEventCreate(&e1));
-    for (int rep = 0; rep < 2; rep++) {  // rep 0 warms up
+    // Repeat until two consecutive launches agree within 1% (the SM clock ramps up from idle over
+    // the first tens of milliseconds), at most 40 launches; the last one is reported.
+    float ms = 0, prev = 0;
+    for (int rep = 0; rep < 40; rep++) {
         KB_CUDA(cudaEventRecord(e0, ctx->stream));
         switch (kind) {
         case 0: k_probe<0><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, sink); break;
@@ -571,9 +588,10 @@ int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double
         KB_LAUNCHED();
         KB_CUDA(cudaEventRecord(e1, ctx->stream));
         KB_CUDA(cudaEventSynchronize(e1));
+        KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep >= 3 && prev > 0 && ms > 0.99f * prev && ms < 1.01f * prev) break;
+        prev = ms;
     }
-    float ms = 0;
-    KB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     const double per_thread = (kind == 3) ? 2.0 * 72.0 : 8.0;  // MACs per loop iteration

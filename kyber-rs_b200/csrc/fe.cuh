@@ -28,6 +28,15 @@ struct fe {
     uint32_t v[8];
 };
 
+// Code-size knob.  With every fe_mul / fe_sq inlined the verify kernel is ~29 k instructions
+// (460 KB) and its window loop alone overflows the 32 KB L1.5 instruction cache: ncu shows
+// "no_instruction" as the largest stall.  KB_FE_CALLS makes the two big bodies real functions.
+#if defined(KB_FE_CALLS) && !defined(KB_HOST_EMU)
+#define KB_FE_BIG __device__ __noinline__
+#else
+#define KB_FE_BIG KB_FN
+#endif
+
 // ---------------------------------------------------------------------------------------
 // carry-chain primitives
 // ---------------------------------------------------------------------------------------
@@ -395,7 +404,7 @@ KB_FN void fe_reduce512(fe& r, uint32_t* t)
 }
 
 // h = f * g   (fe.rs:299 fe_mul)
-KB_FN void fe_mul(fe& h, const fe& f, const fe& g)
+KB_FE_BIG void fe_mul(fe& h, const fe& f, const fe& g)
 {
     uint32_t ev[17], od[16];
     KB_UNROLL
@@ -421,7 +430,7 @@ KB_FN void fe_mul(fe& h, const fe& f, const fe& g)
 }
 
 // h = f^2   (fe.rs:544 fe_square): 28 cross products, doubled, plus 8 squares
-KB_FN void fe_sq(fe& h, const fe& f)
+KB_FE_BIG void fe_sq(fe& h, const fe& f)
 {
     uint32_t ev[17], od[16];
     KB_UNROLL

@@ -24,7 +24,7 @@
 
 #define KB_MSM_CHUNK (1u << 22)
 #define KB_MSM_K 16        // sorted entries per accumulation thread
-#define KB_MSM_GROUPS 128  // bucket groups per window in the reduction
+#define KB_MSM_GROUPS 1024  // bucket groups per window in the reduction
 
 #if defined(KB_HOST_EMU)
 KB_FN uint32_t kb_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
@@ -225,12 +225,12 @@ KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* of
 }
 
 // ---- merge: thread t whose tail partial is valid owns that bucket: tail[t] + head[t+1] + ...
-KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, const uint32_t* offsets, const uint32_t* sorted_unused, uint32_t* bucket_sum, const uint32_t* heads,
-                             const uint32_t* tails, const uint8_t* flags)
+// Runs that continue over more than max_serial following chunks (skewed scalars; the top window
+// of any reduced scalar set) are queued in long_list and summed by a whole warp (k_msm_merge_long).
+KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, const uint32_t* offsets, uint32_t max_serial, uint32_t* long_count, uint32_t* long_list,
+                             uint32_t* bucket_sum, const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
 {
-    (void)sorted_unused;
     if (!(flags[t] & 2u)) return;
-    const uint32_t total = offsets[pl.nb];
     // the bucket of the last entry of chunk t
     const uint32_t last = (uint32_t)((t + 1) * KB_MSM_K) - 1;
     uint32_t lo = 0, hi = pl.nb;
@@ -239,13 +239,19 @@ KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, c
         if (offsets[mid] <= last) lo = mid;
         else hi = mid;
     }
-    uint32_t b = lo;
-    while (offsets[b + 1] <= last) b++;
+    const uint32_t b = lo;
     const uint32_t bend = offsets[b + 1];
-    (void)total;
+    const size_t u_end = ((size_t)bend + KB_MSM_K - 1) / KB_MSM_K;  // chunks t+1 .. u_end-1 start inside the bucket
+    if (u_end - (t + 1) > max_serial) {
+        const uint32_t slot = kb_atomic_add(long_count, 1u);
+        long_list[3 * slot] = (uint32_t)t;
+        long_list[3 * slot + 1] = (uint32_t)u_end;
+        long_list[3 * slot + 2] = b;
+        return;
+    }
     ge_p3 acc, h;
     kb_load_p3(acc, tails + 32 * t);
-    for (size_t u = t + 1; u < nthreads && (uint64_t)u * KB_MSM_K < bend; u++) {
+    for (size_t u = t + 1; u < u_end && u < nthreads; u++) {
         if (flags[u] & 1u) {
             kb_load_p3(h, heads + 32 * u);
             ge_cached hc;
@@ -313,33 +319,77 @@ __global__ void __launch_bounds__(256) k_msm_hist(kb_msm_plan pl, const uint32_t
     if (i >= pl.n) return;
     kb_msm_hist_body(pl, i, mags, counts);
 }
-// single-block exclusive scan of counts[0..nb) into offsets[0..nb]; also clears cursor
-__global__ void __launch_bounds__(1024) k_msm_scan(uint32_t nb, const uint32_t* counts, uint32_t* offsets, uint32_t* cursor)
+// exclusive scan of counts[0..nb) into offsets[0..nb], three launches:
+//   tiles : each block scans a 2048-element tile (coalesced through shared memory), emits its total
+//   sums  : one block scans the tile totals (<= 2048 tiles) and writes offsets[nb]
+//   add   : adds each tile's base; clears cursor
+#define KB_SCAN_TILE 2048
+__global__ void __launch_bounds__(256) k_msm_scan_tiles(uint32_t nb, const uint32_t* counts, uint32_t* offsets, uint32_t* tile_sums)
+{
+    __shared__ uint32_t buf[KB_SCAN_TILE];
+    __shared__ uint32_t wsum[8];
+    const uint32_t tid = threadIdx.x, base = blockIdx.x * KB_SCAN_TILE;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t i = base + tid + 256 * k;
+        buf[tid + 256 * k] = (i < nb) ? counts[i] : 0u;
+    }
+    __syncthreads();
+    uint32_t v[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = sum;
+        sum += buf[8 * tid + k];
+    }
+    // exclusive scan of the 256 per-thread sums: warp shuffles, then the 8 warp totals
+    uint32_t inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, off);
+        if ((tid & 31) >= (uint32_t)off) inc += n;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < (tid >> 5); w++) wbase += wsum[w];
+    const uint32_t excl = wbase + inc - sum;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) buf[8 * tid + k] = excl + v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t i = base + tid + 256 * k;
+        if (i < nb) offsets[i] = buf[tid + 256 * k];
+    }
+    if (tid == 255) tile_sums[blockIdx.x] = excl + sum;
+}
+__global__ void __launch_bounds__(1024) k_msm_scan_sums(uint32_t ntiles, uint32_t nb, uint32_t* tile_sums, uint32_t* offsets)
 {
     __shared__ uint32_t part[1024];
     const uint32_t tid = threadIdx.x;
-    const uint32_t per = (nb + 1023) / 1024;
-    const uint32_t lo = tid * per;
-    uint32_t hi = lo + per;
-    if (hi > nb) hi = nb;
-    uint32_t sum = 0;
-    for (uint32_t k = lo; k < hi; k++) sum += counts[k];
-    part[tid] = sum;
+    // each thread owns two consecutive tiles (ntiles <= 2048)
+    const uint32_t a = (2 * tid < ntiles) ? tile_sums[2 * tid] : 0u;
+    const uint32_t b = (2 * tid + 1 < ntiles) ? tile_sums[2 * tid + 1] : 0u;
+    part[tid] = a + b;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
     for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v = (tid >= off) ? part[tid - off] : 0;
+        const uint32_t v = (tid >= off) ? part[tid - off] : 0u;
         __syncthreads();
         part[tid] += v;
         __syncthreads();
     }
-    uint32_t run = (tid == 0) ? 0 : part[tid - 1];
-    for (uint32_t k = lo; k < hi; k++) {
-        offsets[k] = run;
-        run += counts[k];
-        cursor[k] = 0;
-    }
+    const uint32_t excl = part[tid] - (a + b);
+    if (2 * tid < ntiles) tile_sums[2 * tid] = excl;
+    if (2 * tid + 1 < ntiles) tile_sums[2 * tid + 1] = excl + a;
     if (tid == 1023) offsets[nb] = part[1023];
+}
+__global__ void __launch_bounds__(256) k_msm_scan_add(uint32_t nb, const uint32_t* tile_sums, uint32_t* offsets, uint32_t* cursor)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    offsets[i] += tile_sums[i / KB_SCAN_TILE];
+    cursor[i] = 0;
 }
 __global__ void __launch_bounds__(256) k_msm_scatter(kb_msm_plan pl, const uint32_t* mags, const uint8_t* negs, const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted)
 {
@@ -354,11 +404,12 @@ __global__ void __launch_bounds__(KB_THREADS) k_msm_accum(kb_msm_plan pl, size_t
     if (t >= nthreads) return;
     kb_msm_accum_body(pl, t, offsets, sorted, pts, bucket_sum, heads, tails, flags);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, uint32_t* bucket_sum, const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
+__global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, uint32_t* long_count, uint32_t* long_list, uint32_t* bucket_sum,
+                                                          const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    kb_msm_merge_body(pl, t, nthreads, offsets, nullptr, bucket_sum, heads, tails, flags);
+    kb_msm_merge_body(pl, t, nthreads, offsets, 4u, long_count, long_list, bucket_sum, heads, tails, flags);
 }
 __global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* partial)
 {
@@ -385,28 +436,72 @@ __device__ __forceinline__ void kb_warp_sum_point(ge_p3& p)
         ge_add<true>(p, p, qc);
     }
 }
-// finish: warp q sums the group partials of windows q, q+nwarps, ... with a shuffle tree;
-// thread 0 then folds the windows (Horner, c doublings per window), adds the result to the
-// running total `acc128` (X,Y,Z,T words) and, if out32 != nullptr, writes its encoding.
-__global__ void __launch_bounds__(1024) k_msm_finish(kb_msm_plan pl, uint32_t groups, const uint32_t* partial, uint32_t* acc128, int first_chunk, uint8_t* out32)
+// long runs: one warp per queued (t, u_end, bucket): lanes stride over the head partials of chunks
+// t+1 .. u_end-1, butterfly-sum them with shuffles, lane 0 adds tail[t] and owns the bucket.
+__global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nthreads, const uint32_t* long_count, const uint32_t* long_list, uint32_t* bucket_sum, const uint32_t* heads,
+                                                               const uint32_t* tails, const uint8_t* flags)
 {
-    extern __shared__ uint32_t win_sum[];  // windows * 32 words
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (uint32_t w = warp; w < pl.windows; w += nwarps) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t count = *long_count;
+    for (uint32_t e = warp; e < count; e += nwarps) {
+        const size_t t = long_list[3 * e];
+        size_t u_end = long_list[3 * e + 1];
+        if (u_end > nthreads) u_end = nthreads;
+        const uint32_t b = long_list[3 * e + 2];
         ge_p3 s;
         ge_identity(s);
-        for (uint32_t g = lane; g < groups; g += 32) {
-            ge_p3 p;
-            kb_load_p3(p, partial + 32 * ((size_t)w * groups + g));
-            ge_cached pc;
-            ge_to_cached(pc, p);
-            ge_add<true>(s, s, pc);
+        for (size_t u = t + 1 + lane; u < u_end; u += 32) {
+            if (flags[u] & 1u) {
+                ge_p3 h;
+                kb_load_p3(h, heads + 32 * u);
+                ge_cached hc;
+                ge_to_cached(hc, h);
+                ge_add<true>(s, s, hc);
+            }
         }
         kb_warp_sum_point(s);
-        if (lane == 0) kb_store_p3(win_sum + 32 * w, s);
+        if (lane == 0) {
+            ge_p3 tl;
+            kb_load_p3(tl, tails + 32 * t);
+            ge_cached tc;
+            ge_to_cached(tc, tl);
+            ge_add<true>(s, s, tc);
+            kb_store_p3(bucket_sum + 32 * (size_t)b, s);
+        }
     }
+}
+// window sums: block w adds the `groups` partials of window w (threads stride, warp-shuffle butterfly,
+// then the 8 warp totals through shared memory)
+__global__ void __launch_bounds__(256) k_msm_window_sums(uint32_t groups, const uint32_t* partial, uint32_t* win_sum)
+{
+    __shared__ uint32_t wtot[8 * 32];
+    const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ge_p3 s;
+    ge_identity(s);
+    for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
+        ge_p3 p;
+        kb_load_p3(p, partial + 32 * ((size_t)w * groups + g));
+        ge_cached pc;
+        ge_to_cached(pc, p);
+        ge_add<true>(s, s, pc);
+    }
+    kb_warp_sum_point(s);
+    if (lane == 0) kb_store_p3(wtot + 32 * warp, s);
     __syncthreads();
-    if (threadIdx.x != 0) return;
+    if (warp == 0) {
+        ge_p3 p;
+        ge_identity(p);
+        if (lane < 8) kb_load_p3(p, wtot + 32 * lane);
+        kb_warp_sum_point(p);
+        if (lane == 0) kb_store_p3(win_sum + 32 * w, p);
+    }
+}
+// finish: Horner over the windows (c doublings per window), add to the running total `acc128`
+// (X,Y,Z,T words) and, if out32 != nullptr, write its encoding.
+__global__ void k_msm_finish(kb_msm_plan pl, const uint32_t* win_sum, uint32_t* acc128, int first_chunk, uint8_t* out32)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ge_p3 tot;
     ge_identity(tot);
     for (uint32_t w = pl.windows; w-- > 0;) {

@@ -133,9 +133,8 @@ KB_FN void ge_scalarmult(ge_p3& h, const int8_t* e, const ge_cached* tbl)
     ge_add<false>(h, h, c);
     KB_NOUNROLL
     for (int i = 62; i >= 0; i--) {
-        ge_dbl<false>(h, h);
-        ge_dbl<false>(h, h);
-        ge_dbl<false>(h, h);
+        KB_NOUNROLL
+        for (int k = 0; k < 3; k++) ge_dbl<false>(h, h);
         ge_dbl<true>(h, h);
         ge_select_cached<CT>(c, tbl, e[i]);
         if (i == 0) ge_add<true>(h, h, c);
@@ -165,9 +164,8 @@ KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int8_t* es, const int8_t
     KB_NOUNROLL
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
-            ge_dbl<false>(h, h);
-            ge_dbl<false>(h, h);
-            ge_dbl<false>(h, h);
+            KB_NOUNROLL
+            for (int k = 0; k < 3; k++) ge_dbl<false>(h, h);
             ge_dbl<true>(h, h);
         }
         ge_select_cached<false>(c, tbl, ek[i]);

@@ -1,0 +1,57 @@
+//! `extern "C"` declarations for `include/kyber_b200.h` — one per exported symbol.
+//! NOT COMPILED in the environment this repository is built in (no rustc/cargo); kept in
+//! lock-step with the header by `tests/test_abi_cpu.py::test_rust_sys_matches_header`.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_double, c_int, c_void};
+
+#[repr(C)]
+pub struct kb_ctx {
+    _private: [u8; 0],
+}
+
+pub const KB_OK: c_int = 0;
+pub const KB_ERR_ARG: c_int = -1;
+pub const KB_ERR_CUDA: c_int = -2;
+pub const KB_ERR_NOMEM: c_int = -3;
+pub const KB_FLAG_VARTIME: u32 = 1;
+pub const KB_FLAG_SHARED_POINT: u32 = 2;
+
+#[link(name = "kyber_b200")]
+extern "C" {
+    pub fn kb_ctx_create(device: c_int, out: *mut *mut kb_ctx) -> c_int;
+    pub fn kb_ctx_destroy(ctx: *mut kb_ctx);
+    pub fn kb_last_error(ctx: *const kb_ctx) -> *const c_char;
+    pub fn kb_device_sm_count(ctx: *const kb_ctx) -> c_int;
+    pub fn kb_launch_count(ctx: *const kb_ctx) -> u64;
+    pub fn kb_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn kb_host_free(p: *mut c_void);
+
+    pub fn kb_point_mul_base_batch(ctx: *mut kb_ctx, n: usize, scalars: *const u8, out: *mut u8, flags: u32) -> c_int;
+    pub fn kb_point_mul_batch(ctx: *mut kb_ctx, n: usize, scalars: *const u8, points: *const u8, out: *mut u8, status: *mut u8, flags: u32) -> c_int;
+    pub fn kb_point_recode_batch(ctx: *mut kb_ctx, n: usize, input: *const u8, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_point_add_batch(ctx: *mut kb_ctx, n: usize, p: *const u8, q: *const u8, out: *mut u8, status: *mut u8, subtract: c_int) -> c_int;
+    pub fn kb_point_check_batch(ctx: *mut kb_ctx, n: usize, input: *const u8, flags_out: *mut u8) -> c_int;
+
+    pub fn kb_sc_reduce64_batch(ctx: *mut kb_ctx, n: usize, in64: *const u8, out32: *mut u8) -> c_int;
+    pub fn kb_sc_muladd_batch(ctx: *mut kb_ctx, n: usize, a: *const u8, b: *const u8, c: *const u8, out: *mut u8) -> c_int;
+    pub fn kb_challenge_batch(ctx: *mut kb_ctx, n: usize, r32: *const u8, a32: *const u8, msg: *const u8, msg_off: *const u64, out32: *mut u8) -> c_int;
+
+    pub fn kb_eddsa_verify_batch(ctx: *mut kb_ctx, n: usize, pk: *const u8, msg: *const u8, msg_off: *const u64, sig: *const u8, status: *mut u8) -> c_int;
+    pub fn kb_schnorr_verify_batch(ctx: *mut kb_ctx, n: usize, pk: *const u8, msg: *const u8, msg_off: *const u64, sig: *const u8, status: *mut u8) -> c_int;
+
+    pub fn kb_pubpoly_eval_batch(ctx: *mut kb_ctx, npoly: usize, t: usize, commits: *const u8, m: usize, poly_id: *const u32, idx: *const u32, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_vss_verify_deals_batch(ctx: *mut kb_ctx, npoly: usize, t: usize, commits: *const u8, m: usize, poly_id: *const u32, idx: *const u32, shares: *const u8, verdict: *mut u8) -> c_int;
+    pub fn kb_dkg_verify_round(ctx: *mut kb_ctx, n: usize, t: usize, dealer_lo: usize, dealer_hi: usize, commits: *const u8, shares: *const u8, verdict: *mut u8) -> c_int;
+
+    pub fn kb_msm(ctx: *mut kb_ctx, n: usize, scalars: *const u8, points: *const u8, out32: *mut u8, partial128: *mut u8, bad_points: *mut u64) -> c_int;
+    pub fn kb_point_sum(ctx: *mut kb_ctx, k: usize, partials128: *const u8, out32: *mut u8) -> c_int;
+
+    pub fn kb_dev_eddsa_verify(ctx: *mut kb_ctx, n: usize, d_pk: *const c_void, d_msg: *const c_void, d_msg_off: *const c_void, d_sig: *const c_void, d_status: *mut c_void, schnorr: c_int, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_point_mul_base(ctx: *mut kb_ctx, n: usize, d_scalars: *const c_void, d_out: *mut c_void, flags: u32, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_point_mul(ctx: *mut kb_ctx, n: usize, d_scalars: *const c_void, d_points: *const c_void, d_out: *mut c_void, d_status: *mut c_void, flags: u32, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_msm(ctx: *mut kb_ctx, n: usize, d_scalars: *const c_void, d_points: *const c_void, d_out32: *mut c_void, d_partial128: *mut c_void, d_bad_points: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_dkg_verify_round(ctx: *mut kb_ctx, n: usize, t: usize, ndealers: usize, d_commits: *const c_void, d_shares: *const c_void, d_verdict: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_point_sum(ctx: *mut kb_ctx, k: usize, d_partials128: *const c_void, d_out32: *mut c_void, stream: *mut c_void) -> c_int;
+
+    pub fn kb_probe_imad(ctx: *mut kb_ctx, kind: c_int, iters: c_int, macs_per_sec: *mut c_double, elapsed_ms: *mut c_double) -> c_int;
+}

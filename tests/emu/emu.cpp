@@ -172,7 +172,7 @@ int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* point
     offsets[pl.nb] = run;
     for (size_t i = 0; i < n; i++) kb_msm_scatter_body(pl, i, mags.data(), negs.data(), offsets.data(), cursor.data(), sorted.data());
     for (size_t t = 0; t < nthreads; t++) kb_msm_accum_body(pl, t, offsets.data(), sorted.data(), pts.data(), bucket_sum.data(), heads.data(), tails.data(), flags.data());
-    for (size_t t = 0; t < nthreads; t++) kb_msm_merge_body(pl, t, nthreads, offsets.data(), nullptr, bucket_sum.data(), heads.data(), tails.data(), flags.data());
+    for (size_t t = 0; t < nthreads; t++) kb_msm_merge_body(pl, t, nthreads, offsets.data(), 0xffffffffu, nullptr, nullptr, bucket_sum.data(), heads.data(), tails.data(), flags.data());
     for (size_t t = 0; t < (size_t)pl.windows * groups; t++) kb_msm_reduce_body(pl, t, groups, offsets.data(), bucket_sum.data(), partial.data());
     ge_p3 tot;
     ge_identity(tot);

@@ -60,3 +60,11 @@ def test_shard_ranges():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_rust_sys_matches_header():
+    """The (uncompiled) Rust -sys crate declares exactly the symbols of include/kyber_b200.h."""
+    kb = _pkg()
+    rs = open(os.path.join(ROOT, "kyber-rs_b200", "rust", "kyber-b200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (kb_[a-z0-9_]+)\(", rs))
+    assert declared == set(kb.binding.EXPORTS), declared ^ set(kb.binding.EXPORTS)
