@@ -9,13 +9,16 @@
 #include "kernels.cuh"
 #include "msm.cuh"
 
-#define KB_NSLOTS 28
+#define KB_NSLOTS 32
+#define KB_SLOT_XYZ 28
+#define KB_SLOT_FLAGS 29
 
 struct kb_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;
-    ge_precomp* base_table;  // 64 x 8 entries
+    ge_precomp* base_table;  // 64 x 8 entries: (j+1) * 16^w * B
+    ge_precomp* base128;     // 128 entries: (j+1) * B
     void* slot[KB_NSLOTS];
     size_t slot_bytes[KB_NSLOTS];
     uint64_t launches;
@@ -162,13 +165,16 @@ int kb_ctx_create(int device, kb_ctx** out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
     if (cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
+    if (cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) != cudaSuccess) { cudaFree(ctx->base_table); free(ctx); return KB_ERR_CUDA; }
     k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
-    ctx->launches++;
+    k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
+    ctx->launches += 2;
     cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
     cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
     cudaFuncSetAttribute(k_poly_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         cudaFree(ctx->base_table);
+        cudaFree(ctx->base128);
         free(ctx);
         return KB_ERR_CUDA;
     }
@@ -184,6 +190,7 @@ void kb_ctx_destroy(kb_ctx* ctx)
     for (int s = 0; s < KB_NSLOTS; s++)
         if (ctx->slot[s]) cudaFree(ctx->slot[s]);
     cudaFree(ctx->base_table);
+    cudaFree(ctx->base128);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
 }
@@ -209,11 +216,15 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
     if (!ctx || (n && (!d_scalars || !d_out))) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* xyz;
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
     const size_t smem = 64 * 8 * 96;
     if (flags & KB_FLAG_VARTIME)
-        k_mul_base<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, (uint8_t*)d_out, ctx->base_table);
+        k_mul_base<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table);
     else
-        k_mul_base<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, (uint8_t*)d_out, ctx->base_table);
+        k_mul_base<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, nullptr, (uint8_t*)d_out);
     KB_LAUNCHED();
     return KB_OK;
 }
@@ -222,11 +233,17 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
     if (!ctx || (n && (!d_scalars || !d_points || !d_out))) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* xyz;
+    uint8_t* bad = (uint8_t*)d_status;
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
+    if (!bad) KB_SCRATCH(KB_SLOT_FLAGS, n, bad);
     const int shared_pt = (flags & KB_FLAG_SHARED_POINT) ? 1 : 0;
     if (flags & KB_FLAG_VARTIME)
-        k_mul<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, (uint8_t*)d_out, (uint8_t*)d_status);
+        k_mul<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, xyz, bad);
     else
-        k_mul<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, (uint8_t*)d_out, (uint8_t*)d_status);
+        k_mul<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, xyz, bad);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, bad, (uint8_t*)d_out);
     KB_LAUNCHED();
     return KB_OK;
 }
@@ -235,10 +252,20 @@ int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_m
     if (!ctx || (n && (!d_pk || !d_msg_off || !d_sig || !d_status))) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (schnorr)
-        k_verify<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, (uint8_t*)d_status, ctx->base_table);
-    else
-        k_verify<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, (uint8_t*)d_status, ctx->base_table);
+    uint32_t* xyz;
+    uint8_t* fl;
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
+    KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
+    const unsigned g1 = kb_blocks(n, KB_THREADS), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    if (schnorr) {
+        k_verify_stage1<true><<<g1, KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, xyz, fl, ctx->base128);
+        KB_LAUNCHED();
+        k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, (const uint8_t*)d_sig, (uint8_t*)d_status);
+    } else {
+        k_verify_stage1<false><<<g1, KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, xyz, fl, ctx->base128);
+        KB_LAUNCHED();
+        k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, (const uint8_t*)d_sig, (uint8_t*)d_status);
+    }
     KB_LAUNCHED();
     return KB_OK;
 }
@@ -253,9 +280,17 @@ static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_com
     KB_SCRATCH(9, nc, bad);
     k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, st>>>(nc, d_commits, cached, bad);
     KB_LAUNCHED();
-    const size_t smem = d_shares ? 64 * 8 * 96 : 0;
-    k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, smem, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, d_shares, d_out, d_status, ctx->base_table);
-    KB_LAUNCHED();
+    if (d_shares) {
+        k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, d_shares, nullptr, nullptr, d_out, ctx->base_table);
+        KB_LAUNCHED();
+    } else {
+        uint32_t* xyz;
+        KB_SCRATCH(KB_SLOT_XYZ, 96 * m, xyz);
+        k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 0, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, nullptr, xyz, d_status, nullptr, ctx->base_table);
+        KB_LAUNCHED();
+        k_compress_batch<<<kb_blocks((m + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(m, xyz, d_status, d_out);
+        KB_LAUNCHED();
+    }
     return KB_OK;
 }
 int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream)

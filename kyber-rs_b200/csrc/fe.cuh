@@ -28,14 +28,7 @@ struct fe {
     uint32_t v[8];
 };
 
-// Code-size knob.  With every fe_mul / fe_sq inlined the verify kernel is ~29 k instructions
-// (460 KB) and its window loop alone overflows the 32 KB L1.5 instruction cache: ncu shows
-// "no_instruction" as the largest stall.  KB_FE_CALLS makes the two big bodies real functions.
-#if defined(KB_FE_CALLS) && !defined(KB_HOST_EMU)
-#define KB_FE_BIG __device__ __noinline__
-#else
 #define KB_FE_BIG KB_FN
-#endif
 
 // ---------------------------------------------------------------------------------------
 // carry-chain primitives

@@ -57,32 +57,104 @@ __global__ void k_base_init(ge_precomp* table)
     kb_base_window(table + 8 * w, pos);
 }
 
+// base128[j] = (j+1) * B, j = 0..127: the radix-256 fixed-base table of the verifiers
+__global__ void k_base128_init(ge_precomp* table)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ge_p3 pos;
+    const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
+    pos.X = bx; pos.Y = by; pos.T = bt;
+    fe_set(pos.Z, 1);
+    kb_base_window(table, pos, 128);
+}
+
+// ---- shared tail of every point-producing kernel: Montgomery's trick over KB_INV_K results -----
+// Stage-1 kernels leave (X, Y, Z) in `xyz` (24 words per item).  One thread then owns KB_INV_K
+// consecutive items, multiplies their Z's together, inverts ONCE (fe_invert, 254S + 11M) and
+// unwinds: 3 multiplications per item instead of an inversion each (write_bytes, ge.rs:112-122,
+// pays one per point).  Items whose stage 1 failed carry Z = 1.
+#define KB_INV_K 8
+__device__ __forceinline__ void kb_store_xyz(uint32_t* xyz, size_t i, const ge_p3& p)
+{
+    uint32_t* o = xyz + 24 * i;
+    kb_store_fe(o, p.X);
+    kb_store_fe(o + 8, p.Y);
+    kb_store_fe(o + 16, p.Z);
+}
+// calls emit(i, enc[8]) for every item of this thread's group, enc = canonical encoding
+template <typename F>
+__device__ __forceinline__ void kb_batch_compress(size_t n, const uint32_t* xyz, F emit)
+{
+    const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * KB_INV_K;
+    if (base >= n) return;
+    const int cnt = (n - base < KB_INV_K) ? (int)(n - base) : KB_INV_K;
+    fe pref[KB_INV_K];
+    fe acc, z;
+    kb_load_fe(acc, xyz + 24 * base + 16);
+    pref[0] = acc;
+#pragma unroll 1
+    for (int k = 1; k < cnt; k++) {
+        kb_load_fe(z, xyz + 24 * (base + k) + 16);
+        fe_mul(acc, acc, z);
+        pref[k] = acc;
+    }
+    fe inv;
+    fe_invert(inv, acc);
+#pragma unroll 1
+    for (int k = cnt - 1; k >= 0; k--) {
+        fe zinv;
+        if (k > 0) {
+            fe_mul(zinv, inv, pref[k - 1]);
+            kb_load_fe(z, xyz + 24 * (base + k) + 16);
+            fe_mul(inv, inv, z);
+        } else {
+            zinv = inv;
+        }
+        ge_p3 p;
+        kb_load_fe(p.X, xyz + 24 * (base + k));
+        kb_load_fe(p.Y, xyz + 24 * (base + k) + 8);
+        uint32_t enc[8];
+        ge_compress_with_zinv(enc, p, zinv);
+        emit(base + k, enc);
+    }
+}
+// out[i] = encoding of item i; zeroed where bad[i] != 0
+__global__ void __launch_bounds__(KB_THREADS) k_compress_batch(size_t n, const uint32_t* xyz, const uint8_t* bad, uint8_t* out)
+{
+    kb_batch_compress(n, xyz, [&](size_t i, uint32_t* enc) {
+        if (bad && bad[i]) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) enc[q] = 0;
+        }
+        kb_store32(out, i, enc);
+    });
+}
+
 // ---- Point::mul(s, None): out[i] = compress(s_i * B)   (point.rs:207, ge.rs:442)
 template <bool CT>
-__global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint8_t* out, const ge_precomp* table)
+__global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* table)
 {
     extern __shared__ uint4 smem4[];
     ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
     kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t s[8], o[8];
+    uint32_t s[8];
     int8_t e[64];
     kb_load32(s, scalars, i);
     sc_recode16(e, s);
     ge_p3 h;
     ge_scalarmult_base<CT>(h, e, base);
-    ge_compress(o, h);
-    kb_store32(out, i, o);
+    kb_store_xyz(xyz, i, h);
 }
 
 // ---- Point::mul(s, Some(p)): out[i] = compress(s_i * P_i)   (point.rs:207, ge.rs:508)
 template <bool CT>
-__global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint8_t* out, uint8_t* status)
+__global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint32_t* xyz, uint8_t* status)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t s[8], w[8], o[8];
+    uint32_t s[8], w[8];
     int8_t e[64];
     ge_cached tbl[8];
     kb_load32(s, scalars, i);
@@ -92,12 +164,8 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* sca
     sc_recode16(e, s);
     ge_build_table8(tbl, p);
     ge_scalarmult<CT>(h, e, tbl);
-    ge_compress(o, h);
-    if (!ok) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) o[k] = 0;
-    }
-    kb_store32(out, i, o);
+    if (!ok) ge_identity(h);
+    kb_store_xyz(xyz, i, h);
     if (status) status[i] = (uint8_t)(ok ^ 1u);
 }
 
@@ -196,13 +264,14 @@ __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_
     kb_store32(out, i, h);
 }
 
-// ---- eddsa::verify_with_checks / schnorr::verify_with_checks
+// ---- eddsa::verify_with_checks / schnorr::verify_with_checks, two launches (ops.cuh: sig_stage1 / sig_finish)
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS) k_verify(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, const ge_precomp* table)
+__global__ void __launch_bounds__(KB_THREADS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
+                                                              const ge_precomp* table128)
 {
-    __shared__ uint4 base8_raw[8 * 24 / 4];
-    ge_precomp* base8 = reinterpret_cast<ge_precomp*>(base8_raw);
-    kb_stage(reinterpret_cast<uint32_t*>(base8), reinterpret_cast<const uint32_t*>(table), 8 * 24);
+    __shared__ uint4 base_raw[128 * 24 / 4];
+    ge_precomp* base128 = reinterpret_cast<ge_precomp*>(base_raw);
+    kb_stage(reinterpret_cast<uint32_t*>(base128), reinterpret_cast<const uint32_t*>(table128), 128 * 24);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t pw[8], sw[16];
@@ -211,7 +280,19 @@ __global__ void __launch_bounds__(KB_THREADS) k_verify(size_t n, const uint8_t* 
     kb_load32(sw, sig, 2 * i);
     kb_load32(sw + 8, sig, 2 * i + 1);
     const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
-    status[i] = (uint8_t)sig_verify<SCHNORR>(pw, sw, msg + lo, hi - lo, base8, tbl);
+    ge_p3 Q;
+    const uint32_t f = sig_stage1<SCHNORR>(Q, pw, sw, msg + lo, hi - lo, base128, tbl);
+    kb_store_xyz(xyz, i, Q);
+    flags[i] = (uint8_t)f;
+}
+template <bool SCHNORR>
+__global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const uint32_t* xyz, const uint8_t* flags, const uint8_t* sig, uint8_t* status)
+{
+    kb_batch_compress(n, xyz, [&](size_t i, uint32_t* enc) {
+        uint32_t rw[8];
+        kb_load32(rw, sig, 2 * i);
+        status[i] = (uint8_t)sig_finish<SCHNORR>(flags[i], enc, rw);
+    });
 }
 
 // ---- committed polynomials
@@ -239,7 +320,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_commit_prepare(size_t ncommit, c
 // hold 32 different dealers and the SAME evaluation point x = i + 1 — the double-and-add over
 // the bits of x is then branch-uniform across the warp.
 __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, const uint32_t* poly_id,
-                                                          const uint32_t* idx, size_t n_verifiers, const uint8_t* shares, uint8_t* out, uint8_t* status, const ge_precomp* table)
+                                                          const uint32_t* idx, size_t n_verifiers, const uint8_t* shares, uint32_t* xyz, uint8_t* status, uint8_t* verdict, const ge_precomp* table)
 {
     extern __shared__ uint4 smem4[];
     ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
@@ -270,28 +351,30 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
         anybad |= bp[j];
         kb_horner_step(v, (uint64_t)i + 1, c);
     }
-    uint32_t o[8];
-    ge_compress(o, v);
     if (!shares) {
-        if (anybad) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) o[q] = 0;
-        }
-        kb_store32(out, slot, o);
-        if (status) status[slot] = (uint8_t)anybad;
+        if (anybad) ge_identity(v);
+        kb_store_xyz(xyz, slot, v);
+        status[slot] = (uint8_t)anybad;
         return;
     }
-    uint32_t s[8], g[8];
+    uint32_t s[8];
     int8_t e[64];
     kb_load32(s, shares, slot);
     sc_recode16(e, s);
     ge_p3 h;
     ge_scalarmult_base<true>(h, e, base);
-    ge_compress(g, h);
-    uint32_t diff = anybad;
-#pragma unroll
-    for (int q = 0; q < 8; q++) diff |= g[q] ^ o[q];
-    out[slot] = (uint8_t)(diff == 0);
+    // Point::eq compares canonical encodings (point.rs:227): equal affine points <=> X1 Z2 = X2 Z1 and
+    // Y1 Z2 = Y2 Z1 (Z never vanishes on the curve), so no inversion is needed for a verdict.
+    fe l, r, df;
+    fe_mul(l, v.X, h.Z);
+    fe_mul(r, h.X, v.Z);
+    fe_sub(df, l, r);
+    uint32_t same = fe_is_zero(df);
+    fe_mul(l, v.Y, h.Z);
+    fe_mul(r, h.Y, v.Z);
+    fe_sub(df, l, r);
+    same &= fe_is_zero(df);
+    verdict[slot] = (uint8_t)(same & (anybad ^ 1u));
 }
 
 // ---- integer-multiply roofline probe

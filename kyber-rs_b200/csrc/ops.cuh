@@ -154,12 +154,24 @@ KB_FN void ge_scalarmult_base(ge_p3& h, const int8_t* e, const ge_precomp* base)
         ge_madd<true>(h, h, c);
     }
 }
-// h = s * B + k * A  (public data; Straus with shared doublings).  es / ek are the signed
-// radix-16 digits of s and k, tbl[j] = (j+1) A, base8[j] = (j+1) B.
-KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int8_t* es, const int8_t* ek, const ge_cached* tbl, const ge_precomp* base8)
+// signed radix-256 digits of a scalar < 2^253: d[0..31] in (-128, 128]
+KB_FN void sc_recode256(int16_t* d, const uint32_t* s)
+{
+    int carry = 0;
+    KB_UNROLL
+    for (int i = 0; i < 32; i++) {
+        int v = (int)((s[i >> 2] >> (8 * (i & 3))) & 255u) + carry;
+        carry = v > 128;
+        d[i] = (int16_t)(v - (carry << 8));
+    }
+}
+// h = s * B + k * A (public data), Straus with shared doublings; the fixed base uses signed
+// radix-256 digits against base128[j] = (j+1) B, j = 0..127 (one mixed addition every EIGHT
+// doublings instead of every four), the variable base signed radix-16 digits against the
+// per-thread table tbl[j] = (j+1) A.
+KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int16_t* ds, const int8_t* ek, const ge_cached* tbl, const ge_precomp* base128)
 {
     ge_cached c;
-    ge_precomp b;
     ge_identity(h);
     KB_NOUNROLL
     for (int i = 63; i >= 0; i--) {
@@ -169,10 +181,20 @@ KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int8_t* es, const int8_t
             ge_dbl<true>(h, h);
         }
         ge_select_cached<false>(c, tbl, ek[i]);
-        ge_add<true>(h, h, c);
-        ge_select_precomp<false>(b, base8, es[i]);
-        if (i == 0) ge_madd<true>(h, h, b);
-        else ge_madd<false>(h, h, b);
+        if (i & 1) {
+            ge_add<false>(h, h, c);
+        } else {
+            ge_add<true>(h, h, c);
+            const int d = ds[i >> 1];
+            const uint32_t neg = (uint32_t)d >> 31;
+            const int babs = (d ^ -(int)neg) + (int)neg;
+            ge_precomp b;
+            ge_precomp_identity(b);
+            if (babs != 0) b = base128[babs - 1];
+            ge_precomp_cneg(b, neg);
+            if (i == 0) ge_madd<true>(h, h, b);
+            else ge_madd<false>(h, h, b);
+        }
     }
 }
 
@@ -189,82 +211,108 @@ KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int8_t* es, const int8_t
 // SCHNORR=true : schnorr::verify_with_checks (sign/schnorr/schnorr_sig.rs:53-110); its
 //   challenge hashes the re-encoded R and A (:128-141), which equal the raw bytes whenever
 //   the fast path is entered.
+//
+// The work is split so that the final compression can share one field inversion between
+// several signatures (Montgomery's trick, kernels.cuh):
+//   sig_stage1   byte-level checks, decompress A, challenge hash, Q = s*B - h*A  -> flags, Q
+//   sig_finish   compare compress(Q) with the R bytes / classify the failure      -> status
+#define KB_F_SC 1u     // s canonical           (scalar.rs:54)
+#define KB_F_RC 2u     // R canonical           (point.rs:322)
+#define KB_F_RS 4u     // R small order         (point.rs:286)
+#define KB_F_AC 8u     // A canonical
+#define KB_F_AS 16u    // A small order
+#define KB_F_AOK 32u   // A decodes             (ge.rs:124)
+#define KB_F_FAST 64u  // Q was computed
+
 template <bool SCHNORR>
-KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base8, ge_cached* tbl)
+KB_FN uint32_t sig_stage1(ge_p3& Q, const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base128, ge_cached* tbl)
 {
     const uint32_t* r_w = sig_w;
     const uint32_t* s_w = sig_w + 8;
-    const uint32_t s_canon = sc_is_canonical(s_w);
-    const uint32_t r_canon = pt_is_canonical(r_w);
-    const uint32_t r_small = pt_is_small_order_bytes(r_w);
-    const uint32_t a_canon = pt_is_canonical(pk_w);
-    const uint32_t a_small = pt_is_small_order_bytes(pk_w);
-
-    if (!SCHNORR) {
-        // everything before "R decodes" in the EdDSA order needs no curve arithmetic
-        if (!s_canon) return KB_SIG_NOT_CANONICAL;
-        if (!r_canon) return KB_SIG_R_NOT_CANONICAL;
-        if (r_small) return KB_SIG_R_SMALL_ORDER;  // weak encodings are on the curve
-    }
-
+    uint32_t f = 0;
+    f |= sc_is_canonical(s_w) ? KB_F_SC : 0u;
+    f |= pt_is_canonical(r_w) ? KB_F_RC : 0u;
+    f |= pt_is_small_order_bytes(r_w) ? KB_F_RS : 0u;
+    f |= pt_is_canonical(pk_w) ? KB_F_AC : 0u;
+    f |= pt_is_small_order_bytes(pk_w) ? KB_F_AS : 0u;
+    ge_identity(Q);
+    // EdDSA never looks at A when an earlier check fails; Schnorr decodes A before is_canonical(A)
+    const uint32_t pre_ok = (f & (KB_F_SC | KB_F_RC | KB_F_RS)) == (KB_F_SC | KB_F_RC);
+    if (!SCHNORR && !(pre_ok && (f & KB_F_AC))) return f;
     ge_p3 A;
-    uint32_t a_ok = 0;
-    if (SCHNORR || a_canon) a_ok = ge_decompress(A, pk_w);
-
-    const uint32_t fast = s_canon & r_canon & (r_small ^ 1u) & a_canon & a_ok & (a_small ^ 1u);
-    if (fast) {
-        uint32_t digest[16], hk[8];
-        sha512_ram(digest, r_w, pk_w, msg, mlen);
-        sc_reduce512(hk, digest);
-        int8_t es[64], ek[64];
-        sc_recode16(es, s_w);
-        sc_recode16(ek, hk);
-        ge_p3 nA, Q;
-        ge_neg(nA, A);
-        ge_build_table8(tbl, nA);
-        ge_double_scalarmult_vartime(Q, es, ek, tbl, base8);
-        uint32_t enc[8];
-        ge_compress(enc, Q);
+    if (ge_decompress(A, pk_w)) f |= KB_F_AOK;
+    if (!pre_ok || (f & (KB_F_AC | KB_F_AS | KB_F_AOK)) != (KB_F_AC | KB_F_AOK)) return f;
+    uint32_t digest[16], hk[8];
+    sha512_ram(digest, r_w, pk_w, msg, mlen);
+    sc_reduce512(hk, digest);
+    int16_t ds[32];
+    int8_t ek[64];
+    sc_recode256(ds, s_w);
+    sc_recode16(ek, hk);
+    ge_p3 nA;
+    ge_neg(nA, A);
+    ge_build_table8(tbl, nA);
+    ge_double_scalarmult_vartime(Q, ds, ek, tbl, base128);
+    return f | KB_F_FAST;
+}
+// enc = compress(Q) (only meaningful with KB_F_FAST)
+template <bool SCHNORR>
+KB_FN uint32_t sig_finish(uint32_t f, const uint32_t* enc, const uint32_t* r_w)
+{
+    if (f & KB_F_FAST) {
         uint32_t diff = 0;
         KB_UNROLL
         for (int i = 0; i < 8; i++) diff |= enc[i] ^ r_w[i];
         if (diff == 0) return KB_SIG_OK;
     }
-    // slow path: report the FIRST failing check in the reference's order
+    // report the FIRST failing check in the reference's order
+    if (!SCHNORR) {
+        if (!(f & KB_F_SC)) return KB_SIG_NOT_CANONICAL;
+        if (!(f & KB_F_RC)) return KB_SIG_R_NOT_CANONICAL;
+        if (f & KB_F_RS) return KB_SIG_R_SMALL_ORDER;  // weak encodings are on the curve
+    }
     uint32_t r_ok = 1;
-    if (!r_small) {
+    if (!(f & KB_F_RS)) {
         ge_p3 R;
         r_ok = ge_decompress(R, r_w);
     }
+    if (!r_ok) return KB_SIG_MARSHALLING;
     if (SCHNORR) {
-        if (!r_ok) return KB_SIG_MARSHALLING;
-        if (!r_canon) return KB_SIG_R_NOT_CANONICAL;
-        if (r_small) return KB_SIG_R_SMALL_ORDER;
-        if (!s_canon) return KB_SIG_NOT_CANONICAL;
-        if (!a_ok) return KB_SIG_MARSHALLING;
-        if (!a_canon) return KB_SIG_PK_NOT_CANONICAL;
-        if (a_small) return KB_SIG_PK_SMALL_ORDER;
+        if (!(f & KB_F_RC)) return KB_SIG_R_NOT_CANONICAL;
+        if (f & KB_F_RS) return KB_SIG_R_SMALL_ORDER;
+        if (!(f & KB_F_SC)) return KB_SIG_NOT_CANONICAL;
+        if (!(f & KB_F_AOK)) return KB_SIG_MARSHALLING;
+        if (!(f & KB_F_AC)) return KB_SIG_PK_NOT_CANONICAL;
     } else {
-        if (!r_ok) return KB_SIG_MARSHALLING;
-        if (!a_canon) return KB_SIG_PK_NOT_CANONICAL;
-        if (!a_ok) return KB_SIG_MARSHALLING;
-        if (a_small) return KB_SIG_PK_SMALL_ORDER;
+        if (!(f & KB_F_AC)) return KB_SIG_PK_NOT_CANONICAL;
+        if (!(f & KB_F_AOK)) return KB_SIG_MARSHALLING;
     }
+    if (f & KB_F_AS) return KB_SIG_PK_SMALL_ORDER;
     return KB_SIG_INVALID;
+}
+// one signature start to finish (own inversion) — the composition the two-stage kernels implement
+template <bool SCHNORR>
+KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base128, ge_cached* tbl)
+{
+    ge_p3 Q;
+    const uint32_t f = sig_stage1<SCHNORR>(Q, pk_w, sig_w, msg, mlen, base128, tbl);
+    uint32_t enc[8];
+    ge_compress(enc, Q);
+    return sig_finish<SCHNORR>(f, enc, sig_w);
 }
 
 // ---------------------------------------------------------------------------------------
 // base-point table construction (replaces the transcribed BASE table, constants.rs:89)
 // ---------------------------------------------------------------------------------------
-// win[j] = (j+1) * pos in affine (y+x, y-x, 2dxy) form, j = 0..7
-KB_FN void kb_base_window(ge_precomp* win, const ge_p3& pos)
+// win[j] = (j+1) * pos in affine (y+x, y-x, 2dxy) form, j = 0..count-1
+KB_FN void kb_base_window(ge_precomp* win, const ge_p3& pos, int count = 8)
 {
     const fe d2 = KB_FE_D2;
     ge_cached pc;
     ge_to_cached(pc, pos);
     ge_p3 m = pos;
     KB_NOUNROLL
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < count; j++) {
         fe zinv, x, y, xy;
         fe_invert(zinv, m.Z);
         fe_mul(x, m.X, zinv);

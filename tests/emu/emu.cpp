@@ -16,6 +16,7 @@ static void ld(uint32_t* w, const uint8_t* b, int nwords) { memcpy(w, b, 4 * nwo
 static void st(uint8_t* b, const uint32_t* w, int nwords) { memcpy(b, w, 4 * nwords); }
 
 static ge_precomp g_base[64 * 8];
+static ge_precomp g_base128[128];
 static int g_base_ready = 0;
 static void base_init()
 {
@@ -23,6 +24,7 @@ static void base_init()
     ge_p3 pos;
     const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
     pos.X = bx; pos.Y = by; pos.T = bt; fe_set(pos.Z, 1);
+    kb_base_window(g_base128, pos, 128);
     for (int w = 0; w < 64; w++) {
         kb_base_window(g_base + 8 * w, pos);
         for (int k = 0; k < 4; k++) ge_dbl<true>(pos, pos);
@@ -125,7 +127,7 @@ int emu_sig_verify(int schnorr, const uint8_t* pk, const uint8_t* msg, uint64_t 
     ge_cached tbl[8];
     base_init();
     ld(pw, pk, 8); ld(sw, sig, 16);
-    return schnorr ? (int)sig_verify<true>(pw, sw, msg, mlen, g_base, tbl) : (int)sig_verify<false>(pw, sw, msg, mlen, g_base, tbl);
+    return schnorr ? (int)sig_verify<true>(pw, sw, msg, mlen, g_base128, tbl) : (int)sig_verify<false>(pw, sw, msg, mlen, g_base128, tbl);
 }
 // PubPoly::eval via the short-scalar Horner used by the eval kernel
 int emu_pubpoly_eval(uint8_t* out, const uint8_t* commits, int t, uint32_t idx)
