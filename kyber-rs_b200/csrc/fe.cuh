@@ -28,8 +28,6 @@ struct fe {
     uint32_t v[8];
 };
 
-#define KB_FE_BIG KB_FN
-
 // ---------------------------------------------------------------------------------------
 // carry-chain primitives
 // ---------------------------------------------------------------------------------------
@@ -397,7 +395,7 @@ KB_FN void fe_reduce512(fe& r, uint32_t* t)
 }
 
 // h = f * g   (fe.rs:299 fe_mul)
-KB_FE_BIG void fe_mul(fe& h, const fe& f, const fe& g)
+KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g)
 {
     uint32_t ev[17], od[16];
     KB_UNROLL
@@ -423,7 +421,7 @@ KB_FE_BIG void fe_mul(fe& h, const fe& f, const fe& g)
 }
 
 // h = f^2   (fe.rs:544 fe_square): 28 cross products, doubled, plus 8 squares
-KB_FE_BIG void fe_sq(fe& h, const fe& f)
+KB_FN void fe_sq_inl(fe& h, const fe& f)
 {
     uint32_t ev[17], od[16];
     KB_UNROLL
@@ -450,6 +448,32 @@ KB_FE_BIG void fe_sq(fe& h, const fe& f)
     kb_sqr_acc8(ev, a);  // add the squares a[i]^2 on word pairs (2i, 2i+1)
     fe_reduce512(h, ev);
 }
+
+// Code-size knob.  With every multiplication inlined, the verify kernel is ~29 k instructions and
+// its window loop alone (75 KB) overflows the 32 KB L1.5 instruction cache: ncu reports
+// "no_instruction" as the largest stall reason.  With KB_FE_CALLS the two big bodies exist ONCE per
+// kernel and are reached by CALL with operands and result passed BY VALUE — the ABI keeps a
+// 32-byte struct in registers (checked in SASS: MOVs + CALL.REL, 0 bytes of stack), so a call
+// costs ~26 register moves and no memory traffic.
+#if defined(KB_FE_CALLS) && !defined(KB_HOST_EMU)
+__device__ __noinline__ fe fe_mul_call(fe f, fe g)
+{
+    fe h;
+    fe_mul_inl(h, f, g);
+    return h;
+}
+__device__ __noinline__ fe fe_sq_call(fe f)
+{
+    fe h;
+    fe_sq_inl(h, f);
+    return h;
+}
+KB_FN void fe_mul(fe& h, const fe& f, const fe& g) { h = fe_mul_call(f, g); }
+KB_FN void fe_sq(fe& h, const fe& f) { h = fe_sq_call(f); }
+#else
+KB_FN void fe_mul(fe& h, const fe& f, const fe& g) { fe_mul_inl(h, f, g); }
+KB_FN void fe_sq(fe& h, const fe& f) { fe_sq_inl(h, f); }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // linear operations (fe.rs: fe_add, fe_sub, fe_neg, fe_c_move)

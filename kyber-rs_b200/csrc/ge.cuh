@@ -79,8 +79,7 @@ KB_FN void ge_precomp_cneg(ge_precomp& c, uint32_t neg)
 
 // r = p + q   (ge.rs:217 add + :292 to_extended; 8M).  WITH_T=false skips T3 (7M) when the
 // next operation is a doubling.
-template <bool WITH_T = true>
-KB_FN void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q)
+KB_FN void ge_add_rt(ge_p3& r, const ge_p3& p, const ge_cached& q, bool WITH_T)
 {
     fe a, b, c, d, e, f, g, h;
     fe_sub(a, p.Y, p.X);
@@ -100,8 +99,7 @@ KB_FN void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q)
     if (WITH_T) fe_mul(r.T, e, h);
 }
 // r = p + q with q affine-precomputed (ge.rs:274 mixed_add; 7M / 6M)
-template <bool WITH_T = true>
-KB_FN void ge_madd(ge_p3& r, const ge_p3& p, const ge_precomp& q)
+KB_FN void ge_madd_rt(ge_p3& r, const ge_p3& p, const ge_precomp& q, bool WITH_T)
 {
     fe a, b, c, d, e, f, g, h;
     fe_sub(a, p.Y, p.X);
@@ -120,8 +118,7 @@ KB_FN void ge_madd(ge_p3& r, const ge_p3& p, const ge_precomp& q)
     if (WITH_T) fe_mul(r.T, e, h);
 }
 // r = 2p   (ge.rs:35 ProjectiveGroupElement::double; 4S + 4M, or 4S + 3M without T)
-template <bool WITH_T = true>
-KB_FN void ge_dbl(ge_p3& r, const ge_p3& p)
+KB_FN void ge_dbl_rt(ge_p3& r, const ge_p3& p, bool WITH_T)
 {
     fe a, b, c, e, f, g, h;
     fe_sq(a, p.X);
@@ -139,6 +136,14 @@ KB_FN void ge_dbl(ge_p3& r, const ge_p3& p)
     fe_mul(r.Z, f, g);
     if (WITH_T) fe_mul(r.T, e, h);
 }
+
+// compile-time flavours (the flag folds away when the call is inlined with a constant)
+template <bool WITH_T = true>
+KB_FN void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { ge_add_rt(r, p, q, WITH_T); }
+template <bool WITH_T = true>
+KB_FN void ge_madd(ge_p3& r, const ge_p3& p, const ge_precomp& q) { ge_madd_rt(r, p, q, WITH_T); }
+template <bool WITH_T = true>
+KB_FN void ge_dbl(ge_p3& r, const ge_p3& p) { ge_dbl_rt(r, p, WITH_T); }
 
 // ExtendedGroupElement::set_bytes (ge.rs:124-179).  w = the 32-byte encoding as 8 LE words.
 // Returns 1 on success.  y >= p is accepted (taken mod p); x = 0 with the sign bit set is

@@ -129,16 +129,16 @@ KB_FN void ge_scalarmult(ge_p3& h, const int8_t* e, const ge_cached* tbl)
 {
     ge_cached c;
     ge_identity(h);
-    ge_select_cached<CT>(c, tbl, e[63]);
-    ge_add<false>(h, h, c);
+    // one doubling body and one addition body in the loop (runtime T flags): keeps the loop small
+    // enough for the instruction cache
     KB_NOUNROLL
-    for (int i = 62; i >= 0; i--) {
-        KB_NOUNROLL
-        for (int k = 0; k < 3; k++) ge_dbl<false>(h, h);
-        ge_dbl<true>(h, h);
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            KB_NOUNROLL
+            for (int k = 0; k < 4; k++) ge_dbl_rt(h, h, k == 3);
+        }
         ge_select_cached<CT>(c, tbl, e[i]);
-        if (i == 0) ge_add<true>(h, h, c);
-        else ge_add<false>(h, h, c);
+        ge_add_rt(h, h, c, i == 0);
     }
 }
 // h = a * B, ge_scalar_mult_base (ge.rs:442-486) restated as a 64-window comb:
@@ -177,14 +177,11 @@ KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int16_t* ds, const int8_
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
             KB_NOUNROLL
-            for (int k = 0; k < 3; k++) ge_dbl<false>(h, h);
-            ge_dbl<true>(h, h);
+            for (int k = 0; k < 4; k++) ge_dbl_rt(h, h, k == 3);
         }
         ge_select_cached<false>(c, tbl, ek[i]);
-        if (i & 1) {
-            ge_add<false>(h, h, c);
-        } else {
-            ge_add<true>(h, h, c);
+        ge_add_rt(h, h, c, (i & 1) == 0);
+        if ((i & 1) == 0) {
             const int d = ds[i >> 1];
             const uint32_t neg = (uint32_t)d >> 31;
             const int babs = (d ^ -(int)neg) + (int)neg;
@@ -192,8 +189,7 @@ KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int16_t* ds, const int8_
             ge_precomp_identity(b);
             if (babs != 0) b = base128[babs - 1];
             ge_precomp_cneg(b, neg);
-            if (i == 0) ge_madd<true>(h, h, b);
-            else ge_madd<false>(h, h, b);
+            ge_madd_rt(h, h, b, i == 0);
         }
     }
 }
