@@ -223,6 +223,11 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Everything except the final JSON line goes to stderr: libraries (NCCL prints its version banner
+    # on stdout when NCCL_DEBUG is set) must not pollute the one-line contract.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -248,9 +253,9 @@ def main():
     # we divide by is the best IMAD.WIDE stream we can MEASURE on this GPU now: back-to-back field
     # multiplications (73 IMAD.WIDE each), which reach ~93 % of that architectural rate.
     probe_wide_plain, _ = ctx.probe_imad(0, 1 << 14)
-    probe_wide_chain, _ = ctx.probe_imad(2, 1 << 14)
+    probe_wide_chain, _ = ctx.probe_imad(2, 1 << 13)
     imad_peak_lo, _ = ctx.probe_imad(1, 1 << 14)
-    fe_mul_rate, _ = ctx.probe_imad(3, 1 << 12)
+    fe_mul_rate, _ = ctx.probe_imad(3, 1 << 10)
     imad_peak = max(probe_wide_plain, probe_wide_chain, fe_mul_rate * 73.0 / 72.0)
 
     # ---- inputs
@@ -407,7 +412,7 @@ def main():
         "cpu_baseline": cpu,
         "extras": extras,
     }
-    print(json.dumps(out))
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -299,3 +299,54 @@ def msm(scalars, points, ctx: Context | None = None) -> Point:
     if bad:
         raise MarshallingError("invalid Ed25519 curve point")
     return Point(enc)
+
+
+def vss_rabin_verify_deals_batch(commits, idx, f_shares, g_shares, h_point: Point, ctx: Context | None = None):
+    """vss::rabin verify_deal group math (share/vss/rabin/vss.rs:889-900): fi*G + gi*H == eval(fi.i) on
+    canonical encodings, for m (index, f share, g share) triples against one polynomial.
+    Composed from the batch primitives (eval, fixed-base mul, shared-point mul, add)."""
+    ctx = ctx or default_context()
+    poly = PubPoly(commits)
+    idx = np.asarray(idx, dtype=np.uint32)
+    ev, st = ctx.pubpoly_eval_batch(poly._flat(), poly.threshold(), np.zeros_like(idx), idx)
+    f = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in f_shares), np.uint8).reshape(-1, 32)
+    g = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in g_shares), np.uint8).reshape(-1, 32)
+    fg = ctx.point_mul_base_batch(f)
+    gh, st2 = ctx.point_mul_batch(g, np.frombuffer(h_point.b, np.uint8).reshape(1, 32))
+    ci, st3 = ctx.point_add_batch(fg, gh)
+    return ((ci == ev).all(axis=1) & (st == 0) & (st2 == 0) & (st3 == 0)).astype(np.uint8)
+
+
+def dss_verify_partials_batch(random_commits, long_commits, idx, partials, hash_scalar: Scalar, ctx: Context | None = None):
+    """Group math of DSS::process_partial_sig (sign/dss/dss_sig.rs:263-273) for m partial signatures:
+    partial_i * B == random_poly.eval(i) + hash * long_poly.eval(i)."""
+    ctx = ctx or default_context()
+    idx = np.asarray(idx, dtype=np.uint32)
+    rp, lp = PubPoly(random_commits), PubPoly(long_commits)
+    both = np.concatenate([rp._flat().reshape(-1, 32), lp._flat().reshape(-1, 32)])
+    assert rp.threshold() == lp.threshold()
+    pid = np.concatenate([np.zeros_like(idx), np.ones_like(idx)])
+    ev, st = ctx.pubpoly_eval_batch(both, rp.threshold(), pid, np.concatenate([idx, idx]))
+    m = idx.shape[0]
+    rand_share, long_share = ev[:m], ev[m:]
+    hs = np.tile(np.frombuffer(hash_scalar.v, np.uint8), (m, 1))
+    hl, st2 = ctx.point_mul_batch(hs, long_share, 1)   # public data: vartime
+    right, st3 = ctx.point_add_batch(rand_share, hl)
+    p = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in partials), np.uint8).reshape(-1, 32)
+    left = ctx.point_mul_base_batch(p)
+    return ((left == right).all(axis=1) & (st[:m] == 0) & (st[m:] == 0) & (st2 == 0) & (st3 == 0)).astype(np.uint8)
+
+
+def schnorr_sign_batch(privates, msgs, nonces, ctx: Context | None = None):
+    """schnorr::sign (sign/schnorr/schnorr_sig.rs:25-47) for n (private scalar, message) pairs with the
+    nonces k supplied by the caller (the reference draws them from its RNG): R = k*B, h = H(R || A || M),
+    s = k + x*h.  Returns (signatures[n,64], public keys[n,32]).  The fixed-base mults run constant-time."""
+    ctx = ctx or default_context()
+    x = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in privates), np.uint8).reshape(-1, 32)
+    k = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in nonces), np.uint8).reshape(-1, 32)
+    flat, off = pack_messages(list(msgs))
+    pub = ctx.point_mul_base_batch(x)
+    r = ctx.point_mul_base_batch(k)
+    h = ctx.challenge_batch(r, pub, flat, off)
+    s = ctx.sc_muladd_batch(x, h, k)
+    return np.concatenate([r, s], axis=1), pub

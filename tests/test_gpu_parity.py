@@ -308,3 +308,39 @@ def test_full_size_signature_batch_properties(ctx, coracle, golden_records):
     st = ctx.verify_batch(pk_f, flat_f, off_f, sg_f)
     want = coracle.verify_batch(pk, flat, off, sg, nthreads=8)
     assert (st.reshape(reps, tile) == want[None, :]).all()
+
+
+def test_rabin_dss_and_signing_compositions(kb, ctx, coracle):
+    """Rows a18 (rabin verify_deal), a20 (DSS partial signatures) and next-row f1 (batched signing), built
+    from the batch primitives in host.py, against the big-int oracle."""
+    H = kb.host
+    t, n = 6, 10
+    f = _poly(b"rabin-f", t)
+    g = _poly(b"rabin-g", t)
+    h_pt = O.point_mul(O.scalar_set_bytes(hashlib.sha512(b"H").digest()))
+    commits = [O.point_add(O.point_mul(a), O.point_mul(b, h_pt)) for a, b in zip(f, g)]   # rabin/vss.rs:317-367
+    enc = [O.point_encode(c) for c in commits]
+    fs = [O.pripoly_eval(f, i) for i in range(n)]
+    gs = [O.pripoly_eval(g, i) for i in range(n)]
+    gs[4] = O.sc_add(gs[4], O.scalar_set_int64(1))
+    got = H.vss_rabin_verify_deals_batch(enc, range(n), fs, gs, H.Point(O.point_encode(h_pt)))
+    want = [O.vss_rabin_verify_deal(commits, i, fs[i], gs[i], h_pt) for i in range(n)]
+    assert got.astype(bool).tolist() == want and want.count(False) == 1
+    # DSS: partial_i = r_i + hash * l_i verifies; a corrupted one does not (dss_test.rs)
+    rp, lp = _poly(b"dss-r", t), _poly(b"dss-l", t)
+    rc, lc = O.pripoly_commit(rp), O.pripoly_commit(lp)
+    hs = O.scalar_set_bytes(hashlib.sha512(b"msg").digest())
+    parts = [O.sc_add(O.pripoly_eval(rp, i), O.sc_mul(hs, O.pripoly_eval(lp, i))) for i in range(n)]
+    parts[7] = O.sc_add(parts[7], O.scalar_set_int64(2))
+    got = H.dss_verify_partials_batch([O.point_encode(c) for c in rc], [O.point_encode(c) for c in lc], range(n), parts, H.Scalar(hs))
+    want = [O.dss_verify_partial(rc, lc, i, parts[i], hs) for i in range(n)]
+    assert got.astype(bool).tolist() == want and want.count(False) == 1
+    # batched Schnorr signing: equals the oracle's signatures and verifies under BOTH verifiers
+    priv = [O.scalar_set_bytes(hashlib.sha512(b"x%d" % i).digest()) for i in range(16)]
+    nonce = [O.scalar_set_bytes(hashlib.sha512(b"k%d" % i).digest()) for i in range(16)]
+    msgs = [b"m" * i for i in range(16)]
+    sigs, pubs = H.schnorr_sign_batch(priv, msgs, nonce)
+    for i in range(16):
+        assert sigs[i].tobytes() == O.schnorr_sign(priv[i], msgs[i], nonce[i])
+    assert not H.eddsa_verify_batch([p.tobytes() for p in pubs], msgs, [s.tobytes() for s in sigs]).any()
+    assert not H.schnorr_verify_batch([p.tobytes() for p in pubs], msgs, [s.tobytes() for s in sigs]).any()
