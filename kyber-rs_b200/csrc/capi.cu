@@ -9,7 +9,7 @@
 #include "kernels.cuh"
 #include "msm.cuh"
 
-#define KB_NSLOTS 32
+#define KB_NSLOTS 48
 #define KB_SLOT_XYZ 28
 #define KB_SLOT_FLAGS 29
 
@@ -17,6 +17,7 @@ struct kb_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;
+    cudaStream_t stream2;    // second copy/compute lane of the pipelined host entry points
     ge_precomp* base_table;  // 64 x 8 entries: (j+1) * 16^w * B
     ge_precomp* base128;     // 128 entries: (j+1) * B
     void* slot[KB_NSLOTS];
@@ -82,7 +83,7 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
     else KB_SCRATCH(11, 8, bad);
     KB_CUDA(cudaMemsetAsync(bad, 0, 8, st));
     if (n == 0) {
-        kb_msm_plan pl = {0, 4, 0, 8, 0};
+        kb_msm_plan pl = {0, 4, 0, 8, 0, 16};
         k_msm_finish<<<1, 32, 0, st>>>(pl, nullptr, acc128, 1, d_out32);
         KB_LAUNCHED();
         return KB_OK;
@@ -95,8 +96,9 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         pl.windows = (257 + pl.c - 1) / pl.c;
         pl.half = 1u << (pl.c - 1);
         pl.nb = pl.windows * pl.half;
+        pl.k = kb_msm_chunk_entries(cn, pl.half);
         const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
-        const size_t nthreads = (cn * pl.windows + KB_MSM_K - 1) / KB_MSM_K;
+        const size_t nthreads = (cn * pl.windows + pl.k - 1) / pl.k;
         uint32_t *pts, *mags, *counts, *offsets, *cursor, *sorted, *bucket_sum, *heads, *tails, *partial, *tile_sums, *long_list, *win_sum;
         uint8_t *negs, *flags;
         KB_SCRATCH(12, 96 * cn, pts);
@@ -164,6 +166,7 @@ int kb_ctx_create(int device, kb_ctx** out)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
     if (cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
     if (cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) != cudaSuccess) { cudaFree(ctx->base_table); free(ctx); return KB_ERR_CUDA; }
     k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
@@ -192,6 +195,7 @@ void kb_ctx_destroy(kb_ctx* ctx)
     cudaFree(ctx->base_table);
     cudaFree(ctx->base128);
     cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream2);
     free(ctx);
 }
 const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err : "no context"; }
@@ -247,27 +251,31 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
     KB_LAUNCHED();
     return KB_OK;
 }
+static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, const uint8_t* d_sig, uint8_t* d_status, int schnorr, uint32_t* xyz,
+                            uint8_t* fl, cudaStream_t st)
+{
+    const unsigned g1 = kb_blocks(n, KB_THREADS), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    if (schnorr) {
+        k_verify_stage1<true><<<g1, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        KB_LAUNCHED();
+        k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
+    } else {
+        k_verify_stage1<false><<<g1, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        KB_LAUNCHED();
+        k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
+    }
+    KB_LAUNCHED();
+    return KB_OK;
+}
 int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream)
 {
     if (!ctx || (n && (!d_pk || !d_msg_off || !d_sig || !d_status))) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
-    cudaStream_t st = (cudaStream_t)stream;
     uint32_t* xyz;
     uint8_t* fl;
     KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
     KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
-    const unsigned g1 = kb_blocks(n, KB_THREADS), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
-    if (schnorr) {
-        k_verify_stage1<true><<<g1, KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, xyz, fl, ctx->base128);
-        KB_LAUNCHED();
-        k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, (const uint8_t*)d_sig, (uint8_t*)d_status);
-    } else {
-        k_verify_stage1<false><<<g1, KB_THREADS, 0, st>>>(n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, xyz, fl, ctx->base128);
-        KB_LAUNCHED();
-        k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, (const uint8_t*)d_sig, (uint8_t*)d_status);
-    }
-    KB_LAUNCHED();
-    return KB_OK;
+    return kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, (cudaStream_t)stream);
 }
 // commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel
 static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_commits, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
@@ -454,28 +462,55 @@ int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t*
     KB_SYNC();
     return KB_OK;
 }
+// Host-buffer verification, pipelined: the batch is cut into chunks of KB_VERIFY_CHUNK signatures that
+// alternate between two streams, so the H2D copy of chunk k+1 and the D2H of chunk k-1 overlap the
+// kernels of chunk k (each stream owns its own staging and scratch buffers).
+#define KB_VERIFY_CHUNK (1u << 17)
 static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr)
 {
     KB_ENTER();
     if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
-    const size_t mbytes = (size_t)msg_off[n];
-    if (mbytes && !msg) return KB_ERR_ARG;
-    uint8_t *d_pk, *d_sig, *d_m, *d_st;
-    uint64_t* d_off;
-    KB_SCRATCH(0, 32 * n, d_pk);
-    KB_SCRATCH(2, 64 * n, d_sig);
-    KB_SCRATCH(4, mbytes, d_m);
-    KB_SCRATCH(5, 8 * (n + 1), d_off);
-    KB_SCRATCH(3, n, d_st);
-    KB_H2D(d_pk, pk, 32 * n);
-    KB_H2D(d_sig, sig, 64 * n);
-    if (mbytes) KB_H2D(d_m, msg, mbytes);
-    KB_H2D(d_off, msg_off, 8 * (n + 1));
-    int rc = kb_dev_eddsa_verify(ctx, n, d_pk, d_m, d_off, d_sig, d_st, schnorr, ctx->stream);
-    if (rc != KB_OK) return rc;
-    KB_D2H(status, d_st, n);
-    KB_SYNC();
+    if (msg_off[n] && !msg) return KB_ERR_ARG;
+    const size_t chunk = KB_VERIFY_CHUNK;
+    size_t max_mbytes = 0;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t hi = (lo + chunk < n) ? lo + chunk : n;
+        if (msg_off[hi] < msg_off[lo]) return KB_ERR_ARG;
+        const size_t mb = (size_t)(msg_off[hi] - msg_off[lo]);
+        if (mb > max_mbytes) max_mbytes = mb;
+    }
+    const size_t cn_max = n < chunk ? n : chunk;
+    cudaStream_t lane[2] = {ctx->stream, ctx->stream2};
+    uint8_t *d_pk[2], *d_sig[2], *d_m[2], *d_st[2], *fl[2];
+    uint64_t* d_off[2];
+    uint32_t* xyz[2];
+    for (int l = 0; l < 2; l++) {
+        const int b = 32 + 7 * l;
+        KB_SCRATCH(b + 0, 32 * cn_max, d_pk[l]);
+        KB_SCRATCH(b + 1, 64 * cn_max, d_sig[l]);
+        KB_SCRATCH(b + 2, max_mbytes, d_m[l]);
+        KB_SCRATCH(b + 3, 8 * (cn_max + 1), d_off[l]);
+        KB_SCRATCH(b + 4, cn_max, d_st[l]);
+        KB_SCRATCH(b + 5, 96 * cn_max, xyz[l]);
+        KB_SCRATCH(b + 6, cn_max, fl[l]);
+    }
+    int l = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, l ^= 1) {
+        const size_t hi = (lo + chunk < n) ? lo + chunk : n, cn = hi - lo;
+        const size_t m0 = (size_t)msg_off[lo], mb = (size_t)msg_off[hi] - m0;
+        cudaStream_t st = lane[l];
+        KB_CUDA(cudaMemcpyAsync(d_pk[l], pk + 32 * lo, 32 * cn, cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaMemcpyAsync(d_sig[l], sig + 64 * lo, 64 * cn, cudaMemcpyHostToDevice, st));
+        if (mb) KB_CUDA(cudaMemcpyAsync(d_m[l], msg + m0, mb, cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaMemcpyAsync(d_off[l], msg_off + lo, 8 * (cn + 1), cudaMemcpyHostToDevice, st));
+        // offsets stay absolute: hand the kernel a message base shifted back by this chunk's first offset
+        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l] - m0, d_off[l], d_sig[l], d_st[l], schnorr, xyz[l], fl[l], st);
+        if (rc != KB_OK) return rc;
+        KB_CUDA(cudaMemcpyAsync(status + lo, d_st[l], cn, cudaMemcpyDeviceToHost, st));
+    }
+    KB_CUDA(cudaStreamSynchronize(ctx->stream));
+    KB_CUDA(cudaStreamSynchronize(ctx->stream2));
     return KB_OK;
 }
 int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)

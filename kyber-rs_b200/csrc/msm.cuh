@@ -23,7 +23,6 @@
 #include "sc.cuh"
 
 #define KB_MSM_CHUNK (1u << 22)
-#define KB_MSM_K 16        // sorted entries per accumulation thread
 #define KB_MSM_GROUPS 1024  // bucket groups per window in the reduction
 
 #if defined(KB_HOST_EMU)
@@ -38,7 +37,18 @@ struct kb_msm_plan {
     uint32_t windows;  // ceil(257 / c)
     uint32_t half;     // 2^(c-1) buckets per window
     uint32_t nb;       // windows * half
+    uint32_t k;        // sorted entries per accumulation thread (16..128, ~ the mean bucket size)
 };
+
+// entries per accumulation thread: about one mean bucket, so that most buckets are cut by at most one
+// chunk boundary and the head/tail stitching stays cheap
+static inline uint32_t kb_msm_chunk_entries(size_t n, uint32_t half)
+{
+    const size_t avg = n / half;
+    uint32_t k = 16;
+    while (k < 128 && k < avg) k <<= 1;
+    return k;
+}
 
 static inline uint32_t kb_msm_window_bits_host(size_t n)
 {
@@ -171,11 +181,11 @@ KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* of
                              uint32_t* tails, uint8_t* flags)
 {
     const uint32_t total = offsets[pl.nb];
-    const uint64_t s64 = (uint64_t)t * KB_MSM_K;
+    const uint64_t s64 = (uint64_t)t * pl.k;
     flags[t] = 0;
     if (s64 >= total) return;
     const uint32_t s = (uint32_t)s64;
-    const uint32_t e = (total - s < KB_MSM_K) ? total : s + KB_MSM_K;
+    const uint32_t e = (total - s < pl.k) ? total : s + pl.k;
     // bucket containing entry s: largest b with offsets[b] <= s (skipping empty buckets)
     uint32_t lo = 0, hi = pl.nb;
     while (hi - lo > 1) {
@@ -232,7 +242,7 @@ KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, c
 {
     if (!(flags[t] & 2u)) return;
     // the bucket of the last entry of chunk t
-    const uint32_t last = (uint32_t)((t + 1) * KB_MSM_K) - 1;
+    const uint32_t last = (uint32_t)((t + 1) * pl.k) - 1;
     uint32_t lo = 0, hi = pl.nb;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -241,7 +251,7 @@ KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, c
     }
     const uint32_t b = lo;
     const uint32_t bend = offsets[b + 1];
-    const size_t u_end = ((size_t)bend + KB_MSM_K - 1) / KB_MSM_K;  // chunks t+1 .. u_end-1 start inside the bucket
+    const size_t u_end = ((size_t)bend + pl.k - 1) / pl.k;  // chunks t+1 .. u_end-1 start inside the bucket
     if (u_end - (t + 1) > max_serial) {
         const uint32_t slot = kb_atomic_add(long_count, 1u);
         long_list[3 * slot] = (uint32_t)t;
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    kb_msm_merge_body(pl, t, nthreads, offsets, 4u, long_count, long_list, bucket_sum, heads, tails, flags);
+    kb_msm_merge_body(pl, t, nthreads, offsets, 32u, long_count, long_list, bucket_sum, heads, tails, flags);
 }
 __global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* partial)
 {

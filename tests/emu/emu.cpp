@@ -149,7 +149,7 @@ int emu_pubpoly_eval(uint8_t* out, const uint8_t* commits, int t, uint32_t idx)
 
 // Pippenger stage bodies of msm.cuh, run "thread by thread" on the host; the final
 // warp-shuffle tree (GPU only) is replaced by a plain sum of the same group partials.
-int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* points, int c_override)
+int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* points, int c_override, int k_override)
 {
     kb_msm_plan pl;
     pl.n = (uint32_t)n;
@@ -157,8 +157,9 @@ int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* point
     pl.windows = (257 + pl.c - 1) / pl.c;
     pl.half = 1u << (pl.c - 1);
     pl.nb = pl.windows * pl.half;
+    pl.k = k_override ? (uint32_t)k_override : kb_msm_chunk_entries(n, pl.half);
     const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
-    const size_t nthreads = (n * pl.windows + KB_MSM_K - 1) / KB_MSM_K;
+    const size_t nthreads = (n * pl.windows + pl.k - 1) / pl.k;
     std::vector<uint32_t> pts(24 * n + 24), mags(8 * n + 8), counts(pl.nb, 0), offsets(pl.nb + 1), cursor(pl.nb, 0), sorted(n * pl.windows + 1);
     std::vector<uint32_t> bucket_sum(32 * (size_t)pl.nb), heads(32 * nthreads + 32), tails(32 * nthreads + 32), partial(32 * (size_t)pl.windows * groups);
     std::vector<uint8_t> negs(n + 1), flags(nthreads + 1);

@@ -27,7 +27,7 @@ def emu():
     E = ctypes.CDLL(so)
     E.emu_sha512_ram.argtypes = [ctypes.c_char_p] * 4 + [ctypes.c_uint64]
     E.emu_sig_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
-    E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
     return E
 
@@ -149,16 +149,18 @@ def test_pippenger_stages(emu, coracle, golden_records):
     pks = np.frombuffer(b"".join(r[1] for r in golden_records), dtype=np.uint8).reshape(-1, 32)
     rng = np.random.default_rng(1)
 
-    def run(s, p, c=0):
+    def run(s, p, c=0, k=0):
         out = ctypes.create_string_buffer(32)
-        bad = emu.emu_msm(out, s.shape[0], s.ctypes.data, p.ctypes.data, c)
+        bad = emu.emu_msm(out, s.shape[0], s.ctypes.data, p.ctypes.data, c, k)
         return out.raw, bad
 
     for n, c in [(1, 0), (2, 4), (17, 4), (50, 5), (300, 6), (700, 0), (500, 8)]:
         s = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)   # includes out-of-domain scalars (a[31] > 127)
         p = pks[:n].copy()
-        got, bad = run(s, p, c)
-        assert bad == 0 and got == coracle.msm(s, p)
+        want = coracle.msm(s, p)
+        for k in (0, 32, 128):   # entries per accumulation thread
+            got, bad = run(s, p, c, k)
+            assert bad == 0 and got == want
     n = 200
     p = pks[:n].copy()
     same = np.tile(rng.integers(0, 256, size=(1, 32), dtype=np.uint8), (n, 1))   # one giant bucket per window
