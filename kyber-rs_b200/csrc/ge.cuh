@@ -98,6 +98,37 @@ KB_FN void ge_add_rt(ge_p3& r, const ge_p3& p, const ge_cached& q, bool WITH_T)
     fe_mul(r.Z, f, g);
     if (WITH_T) fe_mul(r.T, e, h);
 }
+// r = p + q or p - q (ge.rs:217 add / :236 sub): subtraction swaps the roles of Y+X / Y-X and of
+// the two sums with 2dT.  `sub` is meant to be warp-uniform (public digit of a shared scalar).
+KB_FN void ge_addsub_rt(ge_p3& r, const ge_p3& p, const ge_cached& q, bool sub, bool WITH_T)
+{
+    fe a, b, c, d, e, f, g, h;
+    fe_sub(a, p.Y, p.X);
+    fe_add(b, p.Y, p.X);
+    if (sub) {
+        fe_mul(a, a, q.YpX);
+        fe_mul(b, b, q.YmX);
+    } else {
+        fe_mul(a, a, q.YmX);
+        fe_mul(b, b, q.YpX);
+    }
+    fe_mul(c, p.T, q.T2d);
+    fe_mul(d, p.Z, q.Z);
+    fe_dbl(d, d);
+    fe_sub(e, b, a);
+    if (sub) {
+        fe_add(f, d, c);
+        fe_sub(g, d, c);
+    } else {
+        fe_sub(f, d, c);
+        fe_add(g, d, c);
+    }
+    fe_add(h, b, a);
+    fe_mul(r.X, e, f);
+    fe_mul(r.Y, g, h);
+    fe_mul(r.Z, f, g);
+    if (WITH_T) fe_mul(r.T, e, h);
+}
 // r = p + q with q affine-precomputed (ge.rs:274 mixed_add; 7M / 6M)
 KB_FN void ge_madd_rt(ge_p3& r, const ge_p3& p, const ge_precomp& q, bool WITH_T)
 {

@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
     ge_p3 v;
     ge_identity(v);
     uint32_t anybad = 0;
+    kb_naf xn;
+    kb_naf_from(xn, (uint64_t)i + 1);
     for (size_t j = t; j-- > 0;) {
         ge_cached c;
         kb_load_fe(c.YpX, cp + 32 * j);
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
         kb_load_fe(c.T2d, cp + 32 * j + 16);
         kb_load_fe(c.Z, cp + 32 * j + 24);
         anybad |= bp[j];
-        kb_horner_step(v, (uint64_t)i + 1, c);
+        kb_horner_step(v, xn, c);
     }
     if (!shares) {
         if (anybad) ge_identity(v);
