@@ -179,17 +179,26 @@ KB_FN void ge_double_scalarmult_vartime(ge_p3& h, const int16_t* ds, const int8_
             KB_NOUNROLL
             for (int k = 0; k < 4; k++) ge_dbl_rt(h, h, k == 3);
         }
-        ge_select_cached<false>(c, tbl, ek[i]);
-        ge_add_rt(h, h, c, (i & 1) == 0);
-        if ((i & 1) == 0) {
-            const int d = ds[i >> 1];
-            const uint32_t neg = (uint32_t)d >> 31;
-            const int babs = (d ^ -(int)neg) + (int)neg;
-            ge_precomp b;
-            ge_precomp_identity(b);
-            if (babs != 0) b = base128[babs - 1];
-            ge_precomp_cneg(b, neg);
-            ge_madd_rt(h, h, b, i == 0);
+        // the fixed-base entry is widened to the cached form (Z = 1) so that both additions of an even
+        // step run through the SAME code (one multiplication by 1 more, ~1000 instructions less)
+        const int nadd = (i & 1) ? 1 : 2;
+        KB_NOUNROLL
+        for (int a = 0; a < nadd; a++) {
+            if (a == 0) {
+                ge_select_cached<false>(c, tbl, ek[i]);
+            } else {
+                const int d = ds[i >> 1];
+                const uint32_t neg = (uint32_t)d >> 31;
+                const int babs = (d ^ -(int)neg) + (int)neg;
+                ge_cached_identity(c);
+                if (babs != 0) {
+                    c.YpX = base128[babs - 1].ypx;
+                    c.YmX = base128[babs - 1].ymx;
+                    c.T2d = base128[babs - 1].xy2d;
+                }
+                ge_cached_cneg(c, neg);
+            }
+            ge_add_rt(h, h, c, (a + 1 < nadd) || i == 0);
         }
     }
 }

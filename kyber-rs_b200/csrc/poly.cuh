@@ -42,7 +42,7 @@ KB_FN void kb_horner_step(ge_p3& v, const kb_naf& x, const ge_cached& c)
         ge_dbl_rt(acc, acc, d != 0 || i == 0);
         if (d != 0) ge_addsub_rt(acc, acc, vc, d < 0, i == 0);
     }
-    ge_add_rt(v, acc, c, true);
+    ge_addsub_rt(v, acc, c, false, true);  // same body as the loop's additions: keeps the kernel loop small
 }
 // convenience form for one-off use
 KB_FN void kb_horner_step(ge_p3& v, uint64_t x, const ge_cached& c)

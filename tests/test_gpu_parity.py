@@ -297,7 +297,6 @@ def test_full_size_signature_batch_properties(ctx, coracle, golden_records):
     first tile must equal the oracle's."""
     tile = 4096
     pks, msgs, sigs = make_sig_batch(golden_records[:256], tile, bad_every=8)
-    msgs = [m[:64].ljust(64, b"\0") if False else m for m in msgs]
     pk, flat, off, sg = pack_batch(pks, msgs, sigs)
     reps = (1 << 20) // tile
     pk_f = np.tile(pk, (reps, 1))
