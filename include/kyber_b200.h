@@ -82,6 +82,11 @@ int kb_point_mul_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint
 /* Point::unmarshal_binary followed by marshal_binary (ge.rs:124-179 then :112-122):
  * out[i] = canonical re-encoding, status[i] = 1 if the input is not a curve point. */
 int kb_point_recode_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out, uint8_t* status);
+/* The reference's serde/bincode wire format of a Point is its raw ExtendedGroupElement: X, Y, Z, T as
+ * 10 signed 25.5-bit i32 limbs each (ge.rs:75-83, fe.rs:8) + a bool, unvalidated on decode (Deal::decode,
+ * share/vss/pedersen/vss.rs:155-159).  limbs = n x 40 int32 (the bool stripped): out[i] = what
+ * marshal_binary (ge.rs:112-122) returns for that element, for ANY limb values (Z = 0 gives 32 zero bytes). */
+int kb_point_from_limbs_batch(kb_ctx* ctx, size_t n, const int32_t* limbs, uint8_t* out);
 /* Point::add / Point::sub (point.rs:179,190) on encodings; status[i] = 1 if either fails to decode */
 int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* out, uint8_t* status, int subtract);
 /* byte-level checks: bit0 = Point::is_canonical (point.rs:322, bug-compatible),
@@ -93,6 +98,8 @@ int kb_point_check_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* flag
 int kb_sc_reduce64_batch(kb_ctx* ctx, size_t n, const uint8_t* in64, uint8_t* out32);
 /* sc_mul_add (scalar.rs:279): out = (a*b + c) mod L; with c = 0 this is Scalar `*`, with b = 1 Scalar `+` */
 int kb_sc_muladd_batch(kb_ctx* ctx, size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out);
+/* Scalar::inv (scalar.rs:192-214): out = a^(L-2) mod L; Scalar::div(a, b) = a * inv(b) via kb_sc_muladd_batch */
+int kb_sc_invert_batch(kb_ctx* ctx, size_t n, const uint8_t* a, uint8_t* out);
 /* h_i = Scalar::set_bytes(SHA-512(R_i || A_i || M_i)) (eddsa_sig.rs:195-200, schnorr_sig.rs:128-141,
  * dss_sig.rs:312-326).  msg_off has n+1 entries; message i is msg[msg_off[i] .. msg_off[i+1]). */
 int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out32);

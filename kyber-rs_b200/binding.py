@@ -35,8 +35,8 @@ _LIB = None
 # every symbol include/kyber_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
-    "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_add_batch", "kb_point_check_batch",
-    "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch",
+    "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch",
+    "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_msm", "kb_point_sum",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
     "kb_probe_imad",
@@ -67,10 +67,12 @@ def load_library(path: str = LIB_PATH):
     L.kb_point_mul_base_batch.argtypes = [vp, sz, vp, vp, u32]
     L.kb_point_mul_batch.argtypes = [vp, sz, vp, vp, vp, vp, u32]
     L.kb_point_recode_batch.argtypes = [vp, sz, vp, vp, vp]
+    L.kb_point_from_limbs_batch.argtypes = [vp, sz, vp, vp]
     L.kb_point_add_batch.argtypes = [vp, sz, vp, vp, vp, vp, i32]
     L.kb_point_check_batch.argtypes = [vp, sz, vp, vp]
     L.kb_sc_reduce64_batch.argtypes = [vp, sz, vp, vp]
     L.kb_sc_muladd_batch.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.kb_sc_invert_batch.argtypes = [vp, sz, vp, vp]
     L.kb_challenge_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_eddsa_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_schnorr_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
@@ -169,6 +171,12 @@ class Context:
         self._check(self.L.kb_point_recode_batch(self.h, p.shape[0], _ptr(p), _ptr(out), _ptr(st)), "kb_point_recode_batch")
         return out, st
 
+    def point_from_limbs_batch(self, limbs):
+        l = np.ascontiguousarray(limbs, dtype=np.int32).reshape(-1, 40)
+        out = np.empty((l.shape[0], 32), dtype=np.uint8)
+        self._check(self.L.kb_point_from_limbs_batch(self.h, l.shape[0], _ptr(l), _ptr(out)), "kb_point_from_limbs_batch")
+        return out
+
     def point_add_batch(self, p, q, subtract=False):
         p = _u8(p, (-1, 32))
         q = _u8(q, (-1, 32))
@@ -194,6 +202,12 @@ class Context:
         a, b, c = _u8(a, (-1, 32)), _u8(b, (-1, 32)), _u8(c, (-1, 32))
         out = np.empty_like(a)
         self._check(self.L.kb_sc_muladd_batch(self.h, a.shape[0], _ptr(a), _ptr(b), _ptr(c), _ptr(out)), "kb_sc_muladd_batch")
+        return out
+
+    def sc_invert_batch(self, a):
+        a = _u8(a, (-1, 32))
+        out = np.empty_like(a)
+        self._check(self.L.kb_sc_invert_batch(self.h, a.shape[0], _ptr(a), _ptr(out)), "kb_sc_invert_batch")
         return out
 
     def challenge_batch(self, r, a, msg, msg_off):

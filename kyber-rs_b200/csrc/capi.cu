@@ -370,6 +370,27 @@ int kb_point_recode_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out
     KB_SYNC();
     return KB_OK;
 }
+int kb_point_from_limbs_batch(kb_ctx* ctx, size_t n, const int32_t* limbs, uint8_t* out)
+{
+    KB_ENTER();
+    if (n && (!limbs || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    int32_t* d_l;
+    uint32_t* xyz;
+    uint8_t *d_z, *d_o;
+    KB_SCRATCH(0, 160 * n, d_l);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
+    KB_SCRATCH(3, n, d_z);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_H2D(d_l, limbs, 160 * n);
+    k_points_from_limbs<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_l, xyz, d_z);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, xyz, d_z, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
 int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* out, uint8_t* status, int subtract)
 {
     KB_ENTER();
@@ -433,6 +454,21 @@ int kb_sc_muladd_batch(kb_ctx* ctx, size_t n, const uint8_t* a, const uint8_t* b
     KB_H2D(d_b, b, 32 * n);
     KB_H2D(d_c, c, 32 * n);
     k_sc_muladd<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_a, d_b, d_c, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_sc_invert_batch(kb_ctx* ctx, size_t n, const uint8_t* a, uint8_t* out)
+{
+    KB_ENTER();
+    if (n && (!a || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_a, *d_o;
+    KB_SCRATCH(0, 32 * n, d_a);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_H2D(d_a, a, 32 * n);
+    k_sc_invert<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_a, d_o);
     KB_LAUNCHED();
     KB_D2H(out, d_o, 32 * n);
     KB_SYNC();

@@ -233,6 +233,58 @@ KB_FN void ge_compress(uint32_t* w, const ge_p3& p)
 }
 
 // ---------------------------------------------------------------------------------------
+// the reference's in-memory / serde field element: 10 signed limbs, radix 2^25.5 (fe.rs:8)
+// ---------------------------------------------------------------------------------------
+// kyber-rs serialises a Point with serde as its raw ExtendedGroupElement (4 x 10 i32 limbs + a bool,
+// 161 bytes: ge.rs:75-83, point.rs:23-27) and does not validate it on decode, so any i32
+// limb values must be accepted: h = sum_i l[i] * 2^ceil(25.5 i) mod p.
+KB_FN void fe_from_ref10(fe& h, const int32_t* l)
+{
+    const int off[10] = {0, 26, 51, 77, 102, 128, 153, 179, 204, 230};
+    uint32_t pos[9], neg[9];
+    KB_UNROLL
+    for (int k = 0; k < 9; k++) pos[k] = neg[k] = 0;
+    KB_UNROLL
+    for (int i = 0; i < 10; i++) {
+        const int64_t v = l[i];
+        const uint64_t mag = (uint64_t)(v < 0 ? -v : v);  // <= 2^31
+        uint32_t* acc = v < 0 ? neg : pos;
+        const int w = off[i] >> 5, sh = off[i] & 31;
+        // mag << sh spans at most 3 words
+        const uint64_t lo = mag << sh;
+        const uint32_t hi3 = sh ? (uint32_t)(mag >> (64 - sh)) : 0u;
+        uint64_t c = (uint64_t)acc[w] + (uint32_t)lo;
+        acc[w] = (uint32_t)c;
+        c = (c >> 32) + acc[w + 1] + (uint32_t)(lo >> 32);
+        acc[w + 1] = (uint32_t)c;
+        c >>= 32;
+        if (w + 2 < 9) {
+            c += (uint64_t)acc[w + 2] + hi3;
+            acc[w + 2] = (uint32_t)c;
+            c >>= 32;
+            KB_UNROLL
+            for (int k = w + 3; k < 9; k++) {
+                c += acc[k];
+                acc[k] = (uint32_t)c;
+                c >>= 32;
+            }
+        }
+    }
+    // fold word 8 (2^256 = 38) of each part, then subtract
+    fe a, b;
+    KB_UNROLL
+    for (int k = 0; k < 8; k++) {
+        a.v[k] = pos[k];
+        b.v[k] = neg[k];
+    }
+    uint32_t c1 = kb_add_small(a.v, pos[8] * 38u);
+    a.v[0] += 38u * c1;
+    uint32_t c2 = kb_add_small(b.v, neg[8] * 38u);
+    b.v[0] += 38u * c2;
+    fe_sub(h, a, b);
+}
+
+// ---------------------------------------------------------------------------------------
 // scalar recoding — the reference's signed radix-16 digits (ge.rs:443-458 / :521-535)
 // ---------------------------------------------------------------------------------------
 // e[0..63]: e[0..62] in [-8, 8), e[63] = top nibble + carry.  A top digit outside 0..8 (only

@@ -130,6 +130,36 @@ __global__ void __launch_bounds__(KB_THREADS) k_compress_batch(size_t n, const u
     });
 }
 
+// ---- serde wire format of the reference: raw ExtendedGroupElement limbs -> (X, Y, Z) for the batch
+// compressor.  Z = 0 (e.g. Point::default(), all-zero limbs) encodes as 32 zero bytes in the reference
+// (fe_invert(0) = 0, ge.rs:112-122): flagged in zero_out and replaced by Z = 1 so that the shared inversion
+// of its group stays valid.
+__global__ void __launch_bounds__(KB_THREADS) k_points_from_limbs(size_t n, const int32_t* limbs, uint32_t* xyz, uint8_t* zero_out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t l[30];
+    const int4* src = reinterpret_cast<const int4*>(limbs + 40 * i);   // 160-byte records: 16-byte aligned
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const int4 q = __ldg(src + k);
+        l[4 * k] = q.x; l[4 * k + 1] = q.y;
+        if (4 * k + 2 < 30) { l[4 * k + 2] = q.z; l[4 * k + 3] = q.w; }
+    }
+    {
+        const int4 q = __ldg(src + 7);
+        l[28] = q.x; l[29] = q.y;
+    }
+    ge_p3 p;
+    fe_from_ref10(p.X, l);
+    fe_from_ref10(p.Y, l + 10);
+    fe_from_ref10(p.Z, l + 20);
+    const uint32_t z0 = fe_is_zero(p.Z);
+    if (z0) ge_identity(p);
+    kb_store_xyz(xyz, i, p);
+    zero_out[i] = (uint8_t)z0;
+}
+
 // ---- Point::mul(s, None): out[i] = compress(s_i * B)   (point.rs:207, ge.rs:442)
 template <bool CT>
 __global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* table)
@@ -248,6 +278,16 @@ __global__ void __launch_bounds__(KB_THREADS) k_sc_muladd(size_t n, const uint8_
     kb_load32(B, b, i);
     kb_load32(C, c, i);
     sc_muladd(r, A, B, C);
+    kb_store32(out, i, r);
+}
+// Scalar::inv (scalar.rs:192)
+__global__ void __launch_bounds__(KB_THREADS) k_sc_invert(size_t n, const uint8_t* a, uint8_t* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t A[8], r[8];
+    kb_load32(A, a, i);
+    sc_invert(r, A);
     kb_store32(out, i, r);
 }
 // h_i = SHA-512(R_i || A_i || M_i) mod L   (eddsa_sig.rs:195-200)

@@ -107,3 +107,24 @@ KB_FN void sc_muladd(uint32_t* s, const uint32_t* a, const uint32_t* b, const ui
     }
     sc_reduce512(s, x);
 }
+
+// r = a^(L-2) mod L — Scalar::inv (scalar.rs:192-214): square-and-multiply over the fixed public exponent
+// L - 2, so the operation sequence does not depend on a (0 maps to 0).
+KB_FN void sc_invert(uint32_t* r, const uint32_t* a)
+{
+    const uint32_t lm2[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+    const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t res[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    KB_NOUNROLL
+    for (int i = 252; i >= 0; i--) {
+        uint32_t t[8];
+        sc_muladd(t, res, res, zero);
+        if ((lm2[i >> 5] >> (i & 31)) & 1u) sc_muladd(res, t, a, zero);
+        else {
+            KB_UNROLL
+            for (int k = 0; k < 8; k++) res[k] = t[k];
+        }
+    }
+    KB_UNROLL
+    for (int k = 0; k < 8; k++) r[k] = res[k];
+}

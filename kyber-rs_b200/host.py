@@ -49,6 +49,7 @@ class SignatureError(Exception):
 
 _ONE = (1).to_bytes(32, "little")
 _ZERO = bytes(32)
+_L_MINUS_1 = bytes.fromhex("ecd3f55c1a631258d69cf7a2def9de1400000000000000000000000000000010")   # scalar_test.rs:38-46
 _BASE = bytes.fromhex("58" + "66" * 31)  # compress(B): y = 4/5, x positive (constants.rs:70 BASEEXT)
 _NULL = _ONE                              # compress((0,1))
 
@@ -103,6 +104,18 @@ class Scalar:
 
     def __add__(self, o: "Scalar") -> "Scalar":   # scalar.rs:138 (sc_add)
         return self._muladd(Scalar(_ONE), o)
+
+    def sub(self, a: "Scalar", b: "Scalar") -> "Scalar":     # scalar.rs:162 (sc_sub): a - b = a + (L-1)*b
+        return b._muladd(Scalar(_L_MINUS_1), a)
+
+    def neg(self, a: "Scalar") -> "Scalar":                  # scalar.rs:216
+        return a._muladd(Scalar(_L_MINUS_1), Scalar(_ZERO))
+
+    def inv(self, a: "Scalar") -> "Scalar":                  # scalar.rs:192-214: a^(L-2)
+        return Scalar(default_context().sc_invert_batch(np.frombuffer(a.v, np.uint8))[0].tobytes())
+
+    def div(self, a: "Scalar", b: "Scalar") -> "Scalar":     # scalar.rs:185
+        return a * Scalar().inv(b)
 
     def __eq__(self, o) -> bool:                  # scalar.rs:78: raw bytes
         return isinstance(o, Scalar) and self.v == o.v

@@ -29,11 +29,13 @@ extern "C" {
     pub fn kb_point_mul_base_batch(ctx: *mut kb_ctx, n: usize, scalars: *const u8, out: *mut u8, flags: u32) -> c_int;
     pub fn kb_point_mul_batch(ctx: *mut kb_ctx, n: usize, scalars: *const u8, points: *const u8, out: *mut u8, status: *mut u8, flags: u32) -> c_int;
     pub fn kb_point_recode_batch(ctx: *mut kb_ctx, n: usize, input: *const u8, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_point_from_limbs_batch(ctx: *mut kb_ctx, n: usize, limbs: *const i32, out: *mut u8) -> c_int;
     pub fn kb_point_add_batch(ctx: *mut kb_ctx, n: usize, p: *const u8, q: *const u8, out: *mut u8, status: *mut u8, subtract: c_int) -> c_int;
     pub fn kb_point_check_batch(ctx: *mut kb_ctx, n: usize, input: *const u8, flags_out: *mut u8) -> c_int;
 
     pub fn kb_sc_reduce64_batch(ctx: *mut kb_ctx, n: usize, in64: *const u8, out32: *mut u8) -> c_int;
     pub fn kb_sc_muladd_batch(ctx: *mut kb_ctx, n: usize, a: *const u8, b: *const u8, c: *const u8, out: *mut u8) -> c_int;
+    pub fn kb_sc_invert_batch(ctx: *mut kb_ctx, n: usize, a: *const u8, out: *mut u8) -> c_int;
     pub fn kb_challenge_batch(ctx: *mut kb_ctx, n: usize, r32: *const u8, a32: *const u8, msg: *const u8, msg_off: *const u64, out32: *mut u8) -> c_int;
 
     pub fn kb_eddsa_verify_batch(ctx: *mut kb_ctx, n: usize, pk: *const u8, msg: *const u8, msg_off: *const u64, sig: *const u8, status: *mut u8) -> c_int;

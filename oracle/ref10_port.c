@@ -671,6 +671,20 @@ int oracle_point_add(uint8_t out[32], const uint8_t p[32], const uint8_t q[32], 
     ge_p3_tobytes(out, &R); return 1;
 }
 
+/* raw ExtendedGroupElement limbs (X,Y,Z,T: 4 x 10 i32 — the reference's serde wire format, ge.rs:75-83) of a*B */
+void oracle_mul_base_limbs(int32_t out[40], const uint8_t a[32])
+{
+    ge_p3 h; oracle_init(); ge_scalarmult_base(&h, a);
+    memcpy(out, h.X, 40); memcpy(out + 10, h.Y, 40); memcpy(out + 20, h.Z, 40); memcpy(out + 30, h.T, 40);
+}
+/* write_bytes (ge.rs:112-122) of an element given by raw limbs */
+void oracle_limbs_tobytes(uint8_t out[32], const int32_t in[40])
+{
+    ge_p3 h; oracle_init();
+    memcpy(h.X, in, 40); memcpy(h.Y, in + 10, 40); memcpy(h.Z, in + 20, 40); memcpy(h.T, in + 30, 40);
+    ge_p3_tobytes(out, &h);
+}
+
 /* ------------------------------------------------------------------ signatures */
 enum { ST_OK = 0, ST_SIG_LENGTH = 1, ST_SIG_NOT_CANONICAL = 2, ST_R_NOT_CANONICAL = 3, ST_R_SMALL_ORDER = 4, ST_PK_NOT_CANONICAL = 5, ST_PK_SMALL_ORDER = 6, ST_MARSHALLING = 7, ST_INVALID_SIGNATURE = 8 };
 

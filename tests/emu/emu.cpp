@@ -61,6 +61,16 @@ int emu_point_recode(uint8_t* out, const uint8_t* in)
     st(out, o, 8);
     return (int)ok;
 }
+void emu_limbs_tobytes(uint8_t* out, const int32_t* limbs)
+{
+    ge_p3 p;
+    uint32_t o[8];
+    fe_from_ref10(p.X, limbs);
+    fe_from_ref10(p.Y, limbs + 10);
+    fe_from_ref10(p.Z, limbs + 20);
+    ge_compress(o, p);
+    st(out, o, 8);
+}
 int emu_point_checks(const uint8_t* in)  // bit0 canonical, bit1 small-order(bytes)
 {
     uint32_t w[8];
@@ -106,6 +116,13 @@ void emu_sc_muladd(uint8_t* out, const uint8_t* a, const uint8_t* b, const uint8
     uint32_t A[8], B[8], C[8], r[8];
     ld(A, a, 8); ld(B, b, 8); ld(C, c, 8);
     sc_muladd(r, A, B, C);
+    st(out, r, 8);
+}
+void emu_sc_invert(uint8_t* out, const uint8_t* a)
+{
+    uint32_t A[8], r[8];
+    ld(A, a, 8);
+    sc_invert(r, A);
     st(out, r, 8);
 }
 int emu_sc_is_canonical(const uint8_t* s)

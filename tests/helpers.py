@@ -55,6 +55,8 @@ class COracle:
         L.oracle_schnorr_verify_batch.argtypes = [ctypes.c_size_t, vp, vp, vp, vp, vp, ctypes.c_int]
         L.oracle_vss_verify_batch.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
         L.oracle_msm.argtypes = [u8p, ctypes.c_size_t, vp, vp]
+        L.oracle_mul_base_limbs.argtypes = [vp, u8p]
+        L.oracle_limbs_tobytes.argtypes = [u8p, vp]
         L.oracle_init()
 
     # ---- single-item wrappers
@@ -101,6 +103,17 @@ class COracle:
     def point_add(self, p, q, subtract=False):
         out = ctypes.create_string_buffer(32)
         return out.raw if self.L.oracle_point_add(out, p, q, int(subtract)) else None
+
+    def mul_base_limbs(self, a):
+        out = np.empty(40, dtype=np.int32)
+        self.L.oracle_mul_base_limbs(self._p(out), a)
+        return out
+
+    def limbs_tobytes(self, limbs):
+        limbs = np.ascontiguousarray(limbs, dtype=np.int32)
+        out = ctypes.create_string_buffer(32)
+        self.L.oracle_limbs_tobytes(out, self._p(limbs))
+        return out.raw
 
     def eddsa_verify(self, pk, msg, sig):
         return self.L.oracle_eddsa_verify(pk, msg, len(msg), sig, len(sig))

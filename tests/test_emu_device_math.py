@@ -87,6 +87,9 @@ def test_scalars_and_hash(emu):
         a, b, c = rnd.randbytes(32), rnd.randbytes(32), rnd.randbytes(32)
         emu.emu_sc_muladd(out, a, b, c)
         assert out.raw == O.sc_mul_add(a, b, c)
+    for a in (rnd.randbytes(32), b32(1), b32(O.L - 1), bytes(32), b"\xff" * 32):
+        emu.emu_sc_invert(out, a)
+        assert out.raw == O.sc_inv(a)
     for d in (b"\xff" * 64, bytes(64)):
         emu.emu_sc_reduce512(out, d)
         assert out.raw == O.scalar_set_bytes(d)
@@ -173,3 +176,27 @@ def test_pippenger_stages(emu, coracle, golden_records):
     bad_pt[3] = np.frombuffer(hashlib.sha256(b"x").digest(), dtype=np.uint8)
     if not coracle.point_decode_ok(bad_pt[3].tobytes()):
         assert run(z, bad_pt)[1] == 1
+
+
+def test_ref10_limb_wire_format(emu, coracle):
+    """serde wire format of the reference (raw 4 x 10 i32 limbs): real elements produced by the
+    oracle's ge_scalarmult_base (un-normalised Z) and arbitrary i32 limb values."""
+    rnd = random.Random(17)
+    out = ctypes.create_string_buffer(32)
+    for _ in range(40):
+        limbs = coracle.mul_base_limbs(rnd.randbytes(32))
+        emu.emu_limbs_tobytes(out, limbs.ctypes.data_as(ctypes.c_void_p))
+        assert out.raw == coracle.limbs_tobytes(limbs)
+    rng = np.random.default_rng(3)
+    for scale in (2**10, 2**26, 2**31 - 1):
+        for _ in range(30):
+            limbs = rng.integers(-scale, scale, size=40, dtype=np.int64).astype(np.int32)
+            emu.emu_limbs_tobytes(out, limbs.ctypes.data_as(ctypes.c_void_p))
+            # the oracle's i32 limb arithmetic is only exact for limbs inside the ref10 bounds: compare with big ints
+            off = [0, 26, 51, 77, 102, 128, 153, 179, 204, 230]
+            val = [sum(int(limbs[10 * c + i]) << off[i] for i in range(10)) % P for c in range(3)]
+            zi = pow(val[2], P - 2, P)
+            x, y = val[0] * zi % P, val[1] * zi % P
+            want = bytearray(b32(y))
+            want[31] ^= (x & 1) << 7
+            assert out.raw == bytes(want)

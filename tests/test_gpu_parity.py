@@ -192,6 +192,9 @@ def test_group_laws_host_mirror(kb, ctx):
     assert H.Point().mul(a * b) == H.Point().mul(a, pb)
     assert H.Point().sub(pa, pa) == H.Point.null()
     assert H.Scalar.set_int64(0x100) + H.Scalar.one() == H.Scalar(bytes([1, 1]) + bytes(30))   # scalar_test.rs:27-35
+    assert H.Scalar().neg(H.Scalar.one()).v == O.scalar_set_int64(-1)                          # scalar_test.rs:38-46
+    assert H.Scalar().sub(a, b).v == O.sc_sub(a.v, b.v)
+    assert H.Scalar().inv(a).v == O.sc_inv(a.v) and (H.Scalar().div(a, b) * b) == a           # group_test.rs inverse/div laws
     assert H.Scalar.set_bytes(bytes([0, 1, 2, 3])).v.hex() == "00010203" + "00" * 28            # scalar_test.rs:68-75
 
 
@@ -343,3 +346,57 @@ def test_rabin_dss_and_signing_compositions(kb, ctx, coracle):
         assert sigs[i].tobytes() == O.schnorr_sign(priv[i], msgs[i], nonce[i])
     assert not H.eddsa_verify_batch([p.tobytes() for p in pubs], msgs, [s.tobytes() for s in sigs]).any()
     assert not H.schnorr_verify_batch([p.tobytes() for p in pubs], msgs, [s.tobytes() for s in sigs]).any()
+
+
+def test_cfg1_full_size(ctx, coracle, golden_records):
+    """BASELINE config 1 at its full size: 2^16 scalars, base point and variable base (2^16 distinct
+    points), constant-time and vartime paths, every output byte against the oracle."""
+    import os as _os
+
+    n = 1 << 16
+    threads = len(_os.sched_getaffinity(0))
+    s = random_scalars("kyber-b200/cfg1/full", n)
+    want_base = coracle.mul_base_batch(s, nthreads=threads)
+    for flags in (0, 1):
+        assert (ctx.point_mul_base_batch(s, flags) == want_base).all()
+    pts = want_base                                  # 2^16 distinct prime-order points
+    s2 = np.roll(s, 1, axis=0)
+    want = coracle.mul_batch(s2, pts, nthreads=threads)
+    for flags in (0, 1):
+        got, st = ctx.point_mul_batch(s2, pts, flags)
+        assert not st.any() and (got == want).all()
+
+
+def test_cfg3_vss_full_size(ctx, coracle):
+    """BASELINE config 3 at its full size: one polynomial with t = 171 commitments, the 256 honest shares
+    plus 8 corrupted ones, every verdict against the oracle (which runs the reference's t full
+    constant-time scalar mults per check)."""
+    import os as _os
+
+    n, t = 256, 171
+    coeffs = _poly(b"cfg3", t)
+    commits = ctx.point_mul_base_batch(np.frombuffer(b"".join(coeffs), dtype=np.uint8).reshape(-1, 32))
+    idx = np.concatenate([np.arange(n), np.arange(0, n, 32)]).astype(np.uint32)
+    shares = np.frombuffer(b"".join(O.pripoly_eval(coeffs, int(i)) for i in idx), dtype=np.uint8).reshape(-1, 32).copy()
+    shares[n:, 7] ^= 0x20
+    verdict = ctx.vss_verify_deals_batch(commits, t, np.zeros_like(idx), idx, shares)
+    want = coracle.vss_verify_batch(commits, idx, shares, nthreads=len(_os.sched_getaffinity(0)))
+    assert (verdict == want).all()
+    assert verdict[:n].all() and not verdict[n:].any()
+    ev, st = ctx.pubpoly_eval_batch(commits, t, np.zeros(4, dtype=np.uint32), np.array([0, 100, 255, 1023], dtype=np.uint32))
+    for k, i in enumerate([0, 100, 255, 1023]):
+        assert ev[k].tobytes() == coracle.pubpoly_eval([c.tobytes() for c in commits], i)
+
+
+def test_ref10_limb_wire_format(ctx, coracle):
+    """kb_point_from_limbs_batch: the reference's serde form of a Point (raw limbs) -> marshal_binary bytes,
+    incl. Point::default() (all-zero limbs -> 32 zero bytes, SURVEY §A4) inside a batch-inversion group."""
+    n = 200
+    sc = random_scalars("limbs", n)
+    limbs = np.stack([coracle.mul_base_limbs(s.tobytes()) for s in sc])
+    limbs[5] = 0          # Point::default()
+    limbs[77, 20:30] = 0  # Z = 0 with X, Y != 0
+    got = ctx.point_from_limbs_batch(limbs)
+    for i in range(n):
+        assert got[i].tobytes() == coracle.limbs_tobytes(limbs[i]), i
+    assert not got[5].any() and not got[77].any()
