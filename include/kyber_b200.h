@@ -125,7 +125,10 @@ int kb_vss_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t
  * to verifier i; verdict[d*n + i] as above.  Dealers [dealer_lo, dealer_hi) only — the unit a
  * rank owns when the round is sharded by dealer. */
 int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const uint8_t* commits, const uint8_t* shares, uint8_t* verdict);
-/* PubPoly::add (poly.rs:486-509): out[j] = a[j] + b[j] — kb_point_add_batch on t points */
+/* PubPoly::add (poly.rs:486-509): out[j] = a[j] + b[j] — kb_point_add_batch on t points.
+ * dkg_key (share/dkg/pedersen/dkg.rs:905-954) folds PubPoly::add over all qualified dealers:
+ * out[j] = sum_d commits[d*t + j], j < t; status[j] = 1 (and out[j] zero) if a commitment of column j is undecodable. */
+int kb_pubpoly_sum(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, uint8_t* out, uint8_t* status);
 
 /* ---- multi-scalar multiplication ------------------------------------------------------ */
 /* out = compress(sum_i scalars[i] * P_i), the fold of Point::mul + Point::add (point.rs:179,207)

@@ -37,7 +37,7 @@ EXPORTS = [
     "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
     "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch",
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch",
-    "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_msm", "kb_point_sum",
+    "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
     "kb_probe_imad",
 ]
@@ -79,6 +79,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_pubpoly_eval_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
     L.kb_vss_verify_deals_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
     L.kb_dkg_verify_round.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
+    L.kb_pubpoly_sum.argtypes = [vp, sz, sz, vp, vp, vp]
     L.kb_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_point_sum.argtypes = [vp, sz, vp, vp]
     L.kb_dev_eddsa_verify.argtypes = [vp, sz, vp, vp, vp, vp, vp, i32, vp]
@@ -263,6 +264,15 @@ class Context:
             verdict = np.zeros(ndealers * n, dtype=np.uint8)
         self._check(self.L.kb_dkg_verify_round(self.h, n, t, dealer_lo, dealer_hi, _ptr(c), _ptr(sh), _ptr(verdict)), "kb_dkg_verify_round")
         return verdict
+
+    def pubpoly_sum(self, commits, t):
+        c = _u8(commits, (-1, 32))
+        npoly = c.shape[0] // t
+        assert npoly * t == c.shape[0]
+        out = np.empty((t, 32), dtype=np.uint8)
+        st = np.empty(t, dtype=np.uint8)
+        self._check(self.L.kb_pubpoly_sum(self.h, npoly, t, _ptr(c), _ptr(out), _ptr(st)), "kb_pubpoly_sum")
+        return out, st
 
     def msm(self, scalars, points, want_partial=False):
         s, p = _u8(scalars, (-1, 32)), _u8(points, (-1, 32))

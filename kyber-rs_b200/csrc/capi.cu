@@ -616,6 +616,32 @@ int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_
     return KB_OK;
 }
 
+int kb_pubpoly_sum(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, uint8_t* out, uint8_t* status)
+{
+    KB_ENTER();
+    if (!npoly || !t || !commits || !out) return KB_ERR_ARG;
+    const size_t nc = npoly * t;
+    uint8_t *d_c, *bad, *d_o, *d_st;
+    uint32_t *cached, *xyz;
+    KB_SCRATCH(0, 32 * nc, d_c);
+    KB_SCRATCH(8, 128 * nc, cached);
+    KB_SCRATCH(9, nc, bad);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * t, xyz);
+    KB_SCRATCH(3, t, d_st);
+    KB_SCRATCH(1, 32 * t, d_o);
+    KB_H2D(d_c, commits, 32 * nc);
+    k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(nc, d_c, cached, bad);
+    KB_LAUNCHED();
+    k_poly_colsum<<<kb_blocks(32 * t, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(npoly, t, cached, bad, xyz, d_st);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((t + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(t, xyz, d_st, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * t);
+    if (status) KB_D2H(status, d_st, t);
+    KB_SYNC();
+    return KB_OK;
+}
+
 // ------------------------------------------------------------------------------------
 // MSM
 // ------------------------------------------------------------------------------------

@@ -557,6 +557,36 @@ __global__ void k_point_sum(size_t k, const uint32_t* partials, uint8_t* out32)
     }
 }
 
+// Column sums of npoly committed polynomials: out[j] = sum_d commits[d][j] — the repeated PubPoly::add of
+// dkg_key (share/dkg/pedersen/dkg.rs:905-954, share/poly.rs:486-509).  One warp per coefficient: lanes
+// stride over the dealers (cached operand form from k_commit_prepare), shuffle butterfly, lane 0 stores.
+__global__ void __launch_bounds__(KB_THREADS) k_poly_colsum(size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, uint32_t* xyz, uint8_t* status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t j = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= t) return;
+    ge_p3 s;
+    ge_identity(s);
+    uint32_t anybad = 0;
+    for (size_t d = lane; d < npoly; d += 32) {
+        const uint32_t* cp = cached + 32 * (d * t + j);
+        ge_cached c;
+        kb_load_fe(c.YpX, cp);
+        kb_load_fe(c.YmX, cp + 8);
+        kb_load_fe(c.T2d, cp + 16);
+        kb_load_fe(c.Z, cp + 24);
+        anybad |= bad[d * t + j];
+        ge_add<true>(s, s, c);
+    }
+    kb_warp_sum_point(s);
+    anybad = __any_sync(0xffffffffu, anybad != 0);
+    if (lane == 0) {
+        if (anybad) ge_identity(s);
+        kb_store_xyz(xyz, j, s);
+        status[j] = (uint8_t)anybad;
+    }
+}
+
 struct kb_ctx;
 static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st);
 #endif  // !KB_HOST_EMU

@@ -400,3 +400,19 @@ def test_ref10_limb_wire_format(ctx, coracle):
     for i in range(n):
         assert got[i].tobytes() == coracle.limbs_tobytes(limbs[i]), i
     assert not got[5].any() and not got[77].any()
+
+
+def test_pubpoly_sum_dkg_key(ctx, coracle, golden_records):
+    """dkg_key (dkg.rs:905-954): the distributed public polynomial is the coefficient-wise sum of the dealers'
+    commitment polynomials (PubPoly::add, poly.rs:486)."""
+    npoly, t = 37, 11
+    pts = _golden_pks(golden_records, npoly * t)
+    got, st = ctx.pubpoly_sum(pts, t)
+    assert not st.any()
+    for j in range(t):
+        acc = (1).to_bytes(32, "little")
+        for d in range(npoly):
+            acc = coracle.point_add(acc, pts[d * t + j].tobytes())
+        assert got[j].tobytes() == acc
+    one, _ = ctx.pubpoly_sum(pts[:t], t)
+    assert (one == pts[:t]).all()
