@@ -254,13 +254,13 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
 static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, const uint8_t* d_sig, uint8_t* d_status, int schnorr, uint32_t* xyz,
                             uint8_t* fl, cudaStream_t st)
 {
-    const unsigned g1 = kb_blocks(n, KB_THREADS), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    const unsigned g1 = kb_blocks(n, KB_VERIFY_THREADS), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
     if (schnorr) {
-        k_verify_stage1<true><<<g1, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        k_verify_stage1<true><<<g1, KB_VERIFY_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
         k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
     } else {
-        k_verify_stage1<false><<<g1, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        k_verify_stage1<false><<<g1, KB_VERIFY_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
         k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
     }

@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t
 template <bool CT>
 __global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint32_t* xyz, uint8_t* status)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;   // ge_scalarmult holds block barriers: tail threads redo the last item
+    if (!live) i = n - 1;
     uint32_t s[8], w[8];
     int8_t e[64];
     ge_cached tbl[8];
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* sca
     ge_build_table8(tbl, p);
     ge_scalarmult<CT>(h, e, tbl);
     if (!ok) ge_identity(h);
+    if (!live) return;
     kb_store_xyz(xyz, i, h);
     if (status) status[i] = (uint8_t)(ok ^ 1u);
 }
@@ -308,15 +310,19 @@ __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_
 #ifndef KB_VERIFY_MINBLOCKS
 #define KB_VERIFY_MINBLOCKS 3
 #endif
+#ifndef KB_VERIFY_THREADS
+#define KB_VERIFY_THREADS KB_THREADS
+#endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
+__global__ void __launch_bounds__(KB_VERIFY_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
                                                               const ge_precomp* table128)
 {
     __shared__ uint4 base_raw[128 * 24 / 4];
     ge_precomp* base128 = reinterpret_cast<ge_precomp*>(base_raw);
     kb_stage(reinterpret_cast<uint32_t*>(base128), reinterpret_cast<const uint32_t*>(table128), 128 * 24);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;   // tail threads redo the last item so that they reach the block barriers
+    if (!live) i = n - 1;
     uint32_t pw[8], sw[16];
     ge_cached tbl[8];
     kb_load32(pw, pk, i);
@@ -325,8 +331,10 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stag
     const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
     ge_p3 Q;
     const uint32_t f = sig_stage1<SCHNORR>(Q, pw, sw, msg + lo, hi - lo, base128, tbl);
-    kb_store_xyz(xyz, i, Q);
-    flags[i] = (uint8_t)f;
+    if (live) {
+        kb_store_xyz(xyz, i, Q);
+        flags[i] = (uint8_t)f;
+    }
 }
 template <bool SCHNORR>
 __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const uint32_t* xyz, const uint8_t* flags, const uint8_t* sig, uint8_t* status)
@@ -368,8 +376,9 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
     extern __shared__ uint4 smem4[];
     ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
     if (shares) kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = k < m;   // the coefficient loop holds a block barrier: tail threads redo the last item
+    if (!live) k = m - 1;
     size_t d, i, slot;
     if (poly_id) {
         d = poly_id[k];
@@ -388,6 +397,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
     kb_naf xn;
     kb_naf_from(xn, (uint64_t)i + 1);
     for (size_t j = t; j-- > 0;) {
+        __syncthreads();   // keeps the block's warps on the same instructions (see KB_LOCKSTEP in ops.cuh)
         ge_cached c;
         kb_load_fe(c.YpX, cp + 32 * j);
         kb_load_fe(c.YmX, cp + 32 * j + 8);
@@ -397,6 +407,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
         kb_horner_step(v, xn, c);
     }
     if (!shares) {
+        if (!live) return;
         if (anybad) ge_identity(v);
         kb_store_xyz(xyz, slot, v);
         status[slot] = (uint8_t)anybad;
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
     fe_mul(r, h.Y, v.Z);
     fe_sub(df, l, r);
     same &= fe_is_zero(df);
-    verdict[slot] = (uint8_t)(same & (anybad ^ 1u));
+    if (live) verdict[slot] = (uint8_t)(same & (anybad ^ 1u));
 }
 
 // ---- integer-multiply roofline probe
