@@ -44,6 +44,9 @@ static int kb_fail(kb_ctx* ctx, cudaError_t e, const char* what)
     } while (0)
 
 static inline unsigned kb_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+// Block size of the long per-item kernels: a batch that fills the GPU less than about twice (config 1 is
+// 2^16 items = 512 blocks of 128 on 148 SMs) is cut into 64-thread blocks so that the SMs end up evenly loaded.
+static inline unsigned kb_item_threads(const kb_ctx* ctx, size_t n) { return n < (size_t)ctx->sm_count * 1024 ? 64u : (unsigned)KB_THREADS; }
 
 // growable device scratch buffer
 static int kb_scratch(kb_ctx* ctx, int s, size_t bytes, void** out)
@@ -242,10 +245,11 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
     KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
     if (!bad) KB_SCRATCH(KB_SLOT_FLAGS, n, bad);
     const int shared_pt = (flags & KB_FLAG_SHARED_POINT) ? 1 : 0;
+    const unsigned th = kb_item_threads(ctx, n);
     if (flags & KB_FLAG_VARTIME)
-        k_mul<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, xyz, bad);
+        k_mul<false><<<kb_blocks(n, th), th, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, xyz, bad);
     else
-        k_mul<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, xyz, bad);
+        k_mul<true><<<kb_blocks(n, th), th, 0, st>>>(n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, shared_pt, xyz, bad);
     KB_LAUNCHED();
     k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, bad, (uint8_t*)d_out);
     KB_LAUNCHED();
@@ -254,13 +258,14 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
 static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, const uint8_t* d_sig, uint8_t* d_status, int schnorr, uint32_t* xyz,
                             uint8_t* fl, cudaStream_t st)
 {
-    const unsigned g1 = kb_blocks(n, KB_VERIFY_THREADS), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    const unsigned th = kb_item_threads(ctx, n);
+    const unsigned g1 = kb_blocks(n, th), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
     if (schnorr) {
-        k_verify_stage1<true><<<g1, KB_VERIFY_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
         k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
     } else {
-        k_verify_stage1<false><<<g1, KB_VERIFY_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
         k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
     }

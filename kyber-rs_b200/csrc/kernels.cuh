@@ -310,11 +310,8 @@ __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_
 #ifndef KB_VERIFY_MINBLOCKS
 #define KB_VERIFY_MINBLOCKS 3
 #endif
-#ifndef KB_VERIFY_THREADS
-#define KB_VERIFY_THREADS KB_THREADS
-#endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_VERIFY_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
+__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
                                                               const ge_precomp* table128)
 {
     __shared__ uint4 base_raw[128 * 24 / 4];

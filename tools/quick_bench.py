@@ -54,6 +54,15 @@ res["mul_base_ct_per_s"] = m / timed(lambda: ctx.dev_point_mul_base(m, d_sc, d_o
 res["mul_base_vt_per_s"] = m / timed(lambda: ctx.dev_point_mul_base(m, d_sc, d_o, 1))
 res["mul_var_ct_per_s"] = m / timed(lambda: ctx.dev_point_mul(m, d_sc, d_pts, d_o, d_st, 0))
 res["mul_var_vt_per_s"] = m / timed(lambda: ctx.dev_point_mul(m, d_sc, d_pts, d_o, d_st, 1))
+if n > m:   # the same kernels on the whole batch: 2^16 items leave a B200 partly idle (512 blocks on 148 SMs)
+    d_scn = d_sig[:, 32:].contiguous()
+    d_on = torch.empty(n, 32, dtype=torch.uint8, device=dev)
+    d_ptn = d_pk.clone()
+    d_ptn[63::64] = d_pk[0]
+    res[f"mul_base_ct_2^{log2n}_per_s"] = n / timed(lambda: ctx.dev_point_mul_base(n, d_scn, d_on, 0), reps=3)
+    res[f"mul_base_vt_2^{log2n}_per_s"] = n / timed(lambda: ctx.dev_point_mul_base(n, d_scn, d_on, 1), reps=3)
+    res[f"mul_var_ct_2^{log2n}_per_s"] = n / timed(lambda: ctx.dev_point_mul(n, d_scn, d_ptn, d_on, d_st, 0), reps=3)
+    res[f"mul_var_vt_2^{log2n}_per_s"] = n / timed(lambda: ctx.dev_point_mul(n, d_scn, d_ptn, d_on, d_st, 1), reps=3)
 d_part = torch.empty(128, dtype=torch.uint8, device=dev)
 d_enc = torch.empty(32, dtype=torch.uint8, device=dev)
 d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
