@@ -167,20 +167,21 @@ def run_reference(args, rank, world):
     # libsodium if present, else reuse the golden file
     from helpers import load_sign_input, make_sig_batch, pack_batch
 
+    NREF = 16384   # signatures available to the reference arm; a step verifies a bounded slice of them
     pks, msgs, sigs = [], [], []
     try:  # random keys / 64-byte messages signed by libsodium (independent of both the GPU path and the oracle)
         import nacl.signing
 
-        seeds = xof("kyber-b200/cfg2/reference-arm/seeds", 32 * 4096).reshape(-1, 32)
-        body = xof("kyber-b200/cfg2/reference-arm/msgs", 64 * 4096).reshape(-1, 64)
-        for i in range(4096):
+        seeds = xof("kyber-b200/cfg2/reference-arm/seeds", 32 * NREF).reshape(-1, 32)
+        body = xof("kyber-b200/cfg2/reference-arm/msgs", 64 * NREF).reshape(-1, 64)
+        for i in range(NREF):
             sk = nacl.signing.SigningKey(seeds[i].tobytes())
             m = body[i].tobytes()
             pks.append(bytes(sk.verify_key)); msgs.append(m); sigs.append(sk.sign(m).signature)
         what = "random keys / 64-byte messages signed by libsodium"
     except ImportError:  # pragma: no cover
         recs = [r for r in load_sign_input() if len(r[3]) >= 64]
-        for i in range(4096):
+        for i in range(NREF):
             _, pk, sig, msg = recs[i % len(recs)]
             pks.append(pk); msgs.append(msg); sigs.append(sig)
         what = "golden-file signatures (messages 64..1023 bytes)"

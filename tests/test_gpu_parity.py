@@ -416,3 +416,58 @@ def test_pubpoly_sum_dkg_key(ctx, coracle, golden_records):
         assert got[j].tobytes() == acc
     one, _ = ctx.pubpoly_sum(pts[:t], t)
     assert (one == pts[:t]).all()
+
+
+def test_cfg4_shape_full_t_two_dealers(ctx, coracle):
+    """BASELINE config 4 shape at full threshold and full verifier count (n = 1024, t = 683) for two dealers
+    (the full round is 1024 dealers — CPU-days for the oracle): honest shares are computed independently with
+    Python integers (PriPoly::eval, poly.rs:133), a few are corrupted, dealer 1 carries a torsion-contaminated
+    commitment (the check then only passes where 8 | x); 12 verdicts are cross-checked with the
+    oracle, which runs the reference's 683 full scalar mults per check."""
+    n, t, nd = 1024, 683, 2
+    L = O.L
+    coeff = [[int.from_bytes(hashlib.sha512(b"cfg4/%d/%d" % (d, j)).digest(), "little") % L for j in range(t)] for d in range(nd)]
+    commits = ctx.point_mul_base_batch(np.frombuffer(b"".join(c.to_bytes(32, "little") for row in coeff for c in row), dtype=np.uint8).reshape(-1, 32))
+    shares = np.zeros((nd * n, 32), dtype=np.uint8)
+    for d in range(nd):
+        for i in range(n):
+            v = 0
+            for cj in reversed(coeff[d]):
+                v = (v * (i + 1) + cj) % L
+            shares[d * n + i] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8)
+    want = np.ones((nd, n), dtype=np.uint8)
+    for d, i in ((0, 0), (0, 511), (0, 1023), (1, 7), (1, 640)):
+        shares[d * n + i, 9] ^= 4
+        want[d, i] = 0
+    t8 = np.frombuffer(O.WEAK_KEYS[2], dtype=np.uint8)
+    commits[t + 1] = ctx.point_add_batch(commits[t + 1], t8)[0][0]
+    torsion_ok = np.zeros(n, dtype=np.uint8)
+    torsion_ok[7::8] = 1            # x = i + 1 divisible by 8
+    want[1] &= torsion_ok
+    got = ctx.dkg_verify_round(n, t, commits, shares).reshape(nd, n)
+    assert (got == want).all(), np.argwhere(got != want)[:10]
+    for d, i in ((0, 0), (0, 1), (0, 1023), (1, 7), (1, 8), (1, 15)):
+        cs = commits[d * t:(d + 1) * t]
+        assert coracle.vss_verify_deal([c.tobytes() for c in cs], i, shares[d * n + i].tobytes()) == int(got[d, i])
+
+
+def test_cfg5_msm_oracle_2p14_and_linearity_2p20(ctx, coracle, golden_records):
+    """BASELINE config 5: direct oracle comparison at 2^14 points (the oracle folds 2^14 full scalar mults),
+    then at 2^20 the size-independent property msm(a, P) + msm(b, P) == msm(a + b, P) and shard-and-fold."""
+    n = 1 << 14
+    sc = random_scalars("cfg5/2p14", n)
+    pts = ctx.point_mul_base_batch(np.roll(sc, 3, axis=0), 1)
+    enc, bad = ctx.msm(sc, pts)
+    assert bad == 0 and enc == coracle.msm(sc, pts)
+    big = 1 << 20
+    a = np.tile(sc, (big // n, 1))
+    a[:, 1] ^= (np.arange(big) >> 14).astype(np.uint8)      # distinct scalars per tile
+    b = np.roll(a, 5, axis=0)
+    p = np.tile(pts, (big // n, 1))
+    ab = ctx.sc_muladd_batch(a, np.tile(np.frombuffer((1).to_bytes(32, "little"), np.uint8), (big, 1)), b)   # a*1 + b mod L
+    ea, _ = ctx.msm(a, p)
+    eb, _ = ctx.msm(b, p)
+    eab, _ = ctx.msm(ab, p)
+    assert ctx.point_add_batch(np.frombuffer(ea, np.uint8), np.frombuffer(eb, np.uint8))[0][0].tobytes() == eab
+    parts = [ctx.msm(a[k * (big // 4):(k + 1) * (big // 4)], p[k * (big // 4):(k + 1) * (big // 4)], want_partial=True)[1] for k in range(4)]
+    assert ctx.point_sum(np.stack(parts)) == ea
