@@ -152,7 +152,21 @@ def cpu_baseline(C, pk, msg, off, sig, gpu_status, budget_s: float, threads: int
     dt = time.perf_counter() - t0
     if gpu_status is not None and not (st == gpu_status[:m]).all():
         raise SystemExit("bench: GPU statuses differ from the oracle on the CPU-baseline sample")
-    return {"value": m / dt, "unit": "sigs/s", "cores": threads, "kind": "port",
+    sodium = None
+    try:  # independent sanity anchor: libsodium's own verifier, one core, same signatures
+        import nacl.bindings as nb
+
+        k = 0
+        t1 = time.perf_counter()
+        for i in range(min(m, 4000)):
+            if gpu_status is not None and gpu_status[i] != 0:
+                continue
+            nb.crypto_sign_open(sig[i].tobytes() + msg[64 * i:64 * i + 64].tobytes(), pk[i].tobytes())
+            k += 1
+        sodium = k / (time.perf_counter() - t1)
+    except Exception:  # pragma: no cover - optional
+        pass
+    return {"value": m / dt, "unit": "sigs/s", "cores": threads, "kind": "port", "libsodium_single_core_sigs_per_s": sodium,
             "sample": f"first {m} of the 2^20 signatures of the same batch, oracle/ref10_port.c (ref10-style C restatement of the Rust path; no Rust toolchain in this image), {dt:.1f} s"}
 
 

@@ -226,10 +226,14 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
     uint32_t* xyz;
     KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
     const size_t smem = 64 * 8 * 96;
+    // lanes per scalar: enough threads to give every SM ~2048 of them, at most 4
+    const size_t fill = (size_t)ctx->sm_count * 2048;
+    const int split = (n * 4 <= fill) ? 4 : (n * 2 <= fill) ? 2 : 1;
+    const unsigned blocks = kb_blocks(n * split, KB_THREADS);
     if (flags & KB_FLAG_VARTIME)
-        k_mul_base<false><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table);
+        k_mul_base<false><<<blocks, KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table, split);
     else
-        k_mul_base<true><<<kb_blocks(n, KB_THREADS), KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table);
+        k_mul_base<true><<<blocks, KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table, split);
     KB_LAUNCHED();
     k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, nullptr, (uint8_t*)d_out);
     KB_LAUNCHED();
@@ -255,17 +259,17 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
     KB_LAUNCHED();
     return KB_OK;
 }
-static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, const uint8_t* d_sig, uint8_t* d_status, int schnorr, uint32_t* xyz,
-                            uint8_t* fl, cudaStream_t st)
+static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, uint64_t msg_base, const uint8_t* d_sig, uint8_t* d_status, int schnorr,
+                            uint32_t* xyz, uint8_t* fl, cudaStream_t st)
 {
     const unsigned th = kb_item_threads(ctx, n);
     const unsigned g1 = kb_blocks(n, th), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
     if (schnorr) {
-        k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
         k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
     } else {
-        k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, d_sig, xyz, fl, ctx->base128);
+        k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
         k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
     }
@@ -280,7 +284,7 @@ int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_m
     uint8_t* fl;
     KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
     KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
-    return kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, (cudaStream_t)stream);
+    return kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, 0, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, (cudaStream_t)stream);
 }
 // commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel
 static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_commits, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
@@ -545,8 +549,8 @@ static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
         KB_CUDA(cudaMemcpyAsync(d_sig[l], sig + 64 * lo, 64 * cn, cudaMemcpyHostToDevice, st));
         if (mb) KB_CUDA(cudaMemcpyAsync(d_m[l], msg + m0, mb, cudaMemcpyHostToDevice, st));
         KB_CUDA(cudaMemcpyAsync(d_off[l], msg_off + lo, 8 * (cn + 1), cudaMemcpyHostToDevice, st));
-        // offsets stay absolute: hand the kernel a message base shifted back by this chunk's first offset
-        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l] - m0, d_off[l], d_sig[l], d_st[l], schnorr, xyz[l], fl[l], st);
+        // offsets stay absolute; the kernel is told that d_m[l] starts at byte m0 of the caller's array
+        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l], d_off[l], (uint64_t)m0, d_sig[l], d_st[l], schnorr, xyz[l], fl[l], st);
         if (rc != KB_OK) return rc;
         KB_CUDA(cudaMemcpyAsync(status + lo, d_st[l], cn, cudaMemcpyDeviceToHost, st));
     }

@@ -161,21 +161,45 @@ __global__ void __launch_bounds__(KB_THREADS) k_points_from_limbs(size_t n, cons
 }
 
 // ---- Point::mul(s, None): out[i] = compress(s_i * B)   (point.rs:207, ge.rs:442)
+// `split` (1, 2 or 4) adjacent lanes share one scalar: each walks 64/split of the comb windows and the partial
+// points are added with a shuffle butterfly.  The comb has no doublings, so the windows are independent; small
+// batches (config 1 is 2^16 scalars, a fraction of what 148 SMs hold) then occupy 2-4x more lanes.
+__device__ __forceinline__ void kb_shfl_xor_point(ge_p3& q, const ge_p3& p, int off)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        q.X.v[k] = __shfl_xor_sync(0xffffffffu, p.X.v[k], off);
+        q.Y.v[k] = __shfl_xor_sync(0xffffffffu, p.Y.v[k], off);
+        q.Z.v[k] = __shfl_xor_sync(0xffffffffu, p.Z.v[k], off);
+        q.T.v[k] = __shfl_xor_sync(0xffffffffu, p.T.v[k], off);
+    }
+}
 template <bool CT>
-__global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* table)
+__global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* table, int split)
 {
     extern __shared__ uint4 smem4[];
     ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
     kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = gtid / split;
+    const int part = (int)(gtid % split);
+    const bool live = i < n;   // whole warps take part in the shuffles: tail lanes redo the last scalar
+    if (!live) i = n - 1;
     uint32_t s[8];
     int8_t e[64];
     kb_load32(s, scalars, i);
     sc_recode16(e, s);
     ge_p3 h;
-    ge_scalarmult_base<CT>(h, e, base);
-    kb_store_xyz(xyz, i, h);
+    const int per = 64 / split;
+    ge_scalarmult_base<CT>(h, e, base, part * per, (part + 1) * per);
+    for (int off = 1; off < split; off <<= 1) {
+        ge_p3 q;
+        kb_shfl_xor_point(q, h, off);
+        ge_cached qc;
+        ge_to_cached(qc, q);
+        ge_add<true>(h, h, qc);
+    }
+    if (live && part == 0) kb_store_xyz(xyz, i, h);
 }
 
 // ---- Point::mul(s, Some(p)): out[i] = compress(s_i * P_i)   (point.rs:207, ge.rs:508)
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_
 #define KB_VERIFY_MINBLOCKS 3
 #endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
+__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
                                                               const ge_precomp* table128)
 {
     __shared__ uint4 base_raw[128 * 24 / 4];
@@ -325,9 +349,10 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stag
     kb_load32(pw, pk, i);
     kb_load32(sw, sig, 2 * i);
     kb_load32(sw + 8, sig, 2 * i + 1);
+    // msg_off holds offsets into the caller's whole message array; `msg` points at byte msg_base of it
     const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
     ge_p3 Q;
-    const uint32_t f = sig_stage1<SCHNORR>(Q, pw, sw, msg + lo, hi - lo, base128, tbl);
+    const uint32_t f = sig_stage1<SCHNORR>(Q, pw, sw, msg + (lo - msg_base), hi - lo, base128, tbl);
     if (live) {
         kb_store_xyz(xyz, i, Q);
         flags[i] = (uint8_t)f;

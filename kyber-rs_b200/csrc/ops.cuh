@@ -156,12 +156,12 @@ KB_FN void ge_scalarmult(ge_p3& h, const int8_t* e, const ge_cached* tbl)
 // h = a * B, ge_scalar_mult_base (ge.rs:442-486) restated as a 64-window comb:
 // base[w*8 + j] = (j+1) * 16^w * B, so no doublings are needed at all.
 template <bool CT>
-KB_FN void ge_scalarmult_base(ge_p3& h, const int8_t* e, const ge_precomp* base)
+KB_FN void ge_scalarmult_base(ge_p3& h, const int8_t* e, const ge_precomp* base, int w_lo = 0, int w_hi = 64)
 {
     ge_precomp c;
     ge_identity(h);
     KB_NOUNROLL
-    for (int w = 0; w < 64; w++) {
+    for (int w = w_lo; w < w_hi; w++) {
         ge_select_precomp<CT>(c, base + 8 * w, e[w]);
         ge_madd<true>(h, h, c);
     }
