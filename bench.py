@@ -37,7 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 IMAD_EQ_PER_VERIFY = 154_000      # A decompress + Straus s*B - h*A + compress, M=72 S=44
 IMAD_EQ_PER_MSM_POINT = 20_700
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
-VERIFY_STAGE1_DRAM_BYTES_2P20 = 234_627_584 + 667_866_112   # ncu capture, round 1 (profiles/r1_ncu_k_verify_stage1_2p20.txt)
+VERIFY_STAGE1_DRAM_BYTES_2P20 = 204_418_816 + 686_399_744   # ncu capture, round 1 (profiles/r1_ncu_k_verify_stage1_final.txt)
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
 NONCANON = bytes([0xEF]) + b"\xff" * 31
@@ -419,7 +419,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": VERIFY_STAGE1_DRAM_BYTES_2P20 if args.log2n == 20 else None,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of k_verify_stage1 at 2^20 signatures from profiles/r1_ncu_k_verify_stage1_2p20.txt (ncu --set full); algorithmic bytes are 168 MB in + 101 MB out per launch, the rest is the per-thread 1 KiB table of multiples of A (local memory) evicted past L2",
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of k_verify_stage1 at 2^20 signatures from profiles/r1_ncu_k_verify_stage1_final.txt (ncu --set full); algorithmic bytes are 168 MB in + 101 MB out per launch, the rest is the per-thread 1 KiB table of multiples of A (local memory) evicted past L2",
                      "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents per signature (SURVEY 8d) / CUDA-event step time; peak = best IMAD.WIDE.U32 stream measured live by kb_probe_imad (back-to-back field multiplications), ~93% of the architectural 32 lanes/clk/SM of the fmaheavy pipe",
                      "kernel": "k_verify_stage1 (+ k_verify_stage2, ~3% of the step): one step = both launches",
                      "probes_T_per_s": {"imad_lo32": imad_peak_lo / 1e12, "imad_wide_plain": probe_wide_plain / 1e12, "imad_wide_carry_chain": probe_wide_chain / 1e12, "fe_mul_as_imad_wide": fe_mul_rate * 73.0 / 72.0 / 1e12},
