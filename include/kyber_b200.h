@@ -110,6 +110,13 @@ int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
 /* schnorr::verify_with_checks (sign/schnorr/schnorr_sig.rs:53-110) */
 int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);
 
+/* EdDSA::sign (sign/eddsa/eddsa_sig.rs:120-152) for n (seed, message) pairs, with the key derivation of
+ * Curve::new_key_and_seed_with_input (group/edwards25519/curve.rs:74-87): a = clamp(SHA-512(seed)[0..32]),
+ * prefix = SHA-512(seed)[32..64], r = SHA-512(prefix || M) mod L, R = r*B, A = a*B, h = SHA-512(R || A || M) mod L,
+ * s = (r + h*a) mod L.  sig[i] = R || s (64 bytes), pk[i] = A (may be NULL).  Deterministic: reproduces the
+ * reference's golden signatures.  The secret scalars only meet the constant-time table select. */
+int kb_eddsa_sign_batch(kb_ctx* ctx, size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint8_t* sig, uint8_t* pk);
+
 /* ---- committed polynomials (share/poly.rs) -------------------------------------------- */
 /* PubPoly::eval (poly.rs:457-469) for npoly polynomials of t commitments each
  * (commits = npoly*t encodings, coefficient-major inside a polynomial):

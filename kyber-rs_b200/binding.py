@@ -36,7 +36,7 @@ _LIB = None
 EXPORTS = [
     "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
     "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch",
-    "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch",
+    "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
     "kb_probe_imad",
@@ -76,6 +76,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_challenge_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_eddsa_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_schnorr_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.kb_eddsa_sign_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_pubpoly_eval_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
     L.kb_vss_verify_deals_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
     L.kb_dkg_verify_round.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
@@ -229,6 +230,16 @@ class Context:
         fn = self.L.kb_schnorr_verify_batch if schnorr else self.L.kb_eddsa_verify_batch
         self._check(fn(self.h, n, _ptr(pk), _ptr(msg), _ptr(msg_off), _ptr(sig), _ptr(st)), "kb_verify_batch")
         return st
+
+    def eddsa_sign_batch(self, seeds, msg, msg_off):
+        seeds = _u8(seeds, (-1, 32))
+        msg = _u8(msg)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        n = seeds.shape[0]
+        sig = np.empty((n, 64), dtype=np.uint8)
+        pk = np.empty((n, 32), dtype=np.uint8)
+        self._check(self.L.kb_eddsa_sign_batch(self.h, n, _ptr(seeds), _ptr(msg), _ptr(msg_off), _ptr(sig), _ptr(pk)), "kb_eddsa_sign_batch")
+        return sig, pk
 
     def pubpoly_eval_batch(self, commits, t, poly_id, idx):
         c = _u8(commits, (-1, 32))

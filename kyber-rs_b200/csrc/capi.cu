@@ -178,6 +178,7 @@ int kb_ctx_create(int device, kb_ctx** out)
     cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
     cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
     cudaFuncSetAttribute(k_poly_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+    cudaFuncSetAttribute(k_sign_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         cudaFree(ctx->base_table);
         cudaFree(ctx->base128);
@@ -568,6 +569,43 @@ int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint
     return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 1);
 }
 
+int kb_eddsa_sign_batch(kb_ctx* ctx, size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint8_t* sig, uint8_t* pk)
+{
+    KB_ENTER();
+    if (n && (!seeds || !msg_off || !sig)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    const size_t mbytes = (size_t)msg_off[n];
+    if (mbytes && !msg) return KB_ERR_ARG;
+    uint8_t *d_seed, *d_m, *d_a, *d_r, *d_ra, *d_sig, *d_pk;
+    uint64_t* d_off;
+    uint32_t* xyz;
+    KB_SCRATCH(0, 32 * n, d_seed);
+    KB_SCRATCH(4, mbytes, d_m);
+    KB_SCRATCH(5, 8 * (n + 1), d_off);
+    KB_SCRATCH(2, 64 * n, d_sig);
+    KB_SCRATCH(1, 32 * n, d_pk);
+    KB_SCRATCH(6, 32 * n, d_a);
+    KB_SCRATCH(7, 32 * n, d_r);
+    KB_SCRATCH(8, 64 * n, d_ra);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * 2 * n, xyz);
+    KB_H2D(d_seed, seeds, 32 * n);
+    if (mbytes) KB_H2D(d_m, msg, mbytes);
+    KB_H2D(d_off, msg_off, 8 * (n + 1));
+    k_sign_stage1<<<kb_blocks(n, KB_THREADS), KB_THREADS, 64 * 8 * 96, ctx->stream>>>(n, d_seed, d_m, d_off, xyz, d_a, d_r, ctx->base_table);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((2 * n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(2 * n, xyz, nullptr, d_ra);
+    KB_LAUNCHED();
+    k_sign_finish<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_ra, d_m, d_off, d_a, d_r, d_sig, d_pk);
+    KB_LAUNCHED();
+    KB_D2H(sig, d_sig, 64 * n);
+    if (pk) KB_D2H(pk, d_pk, 32 * n);
+    // the secret scalars do not outlive the call
+    KB_CUDA(cudaMemsetAsync(d_a, 0, 32 * n, ctx->stream));
+    KB_CUDA(cudaMemsetAsync(d_r, 0, 32 * n, ctx->stream));
+    KB_CUDA(cudaMemsetAsync(d_seed, 0, 32 * n, ctx->stream));
+    KB_SYNC();
+    return KB_OK;
+}
 static int kb_poly_host(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* out,
                         uint8_t* status)
 {

@@ -330,6 +330,60 @@ __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_
     kb_store32(out, i, h);
 }
 
+// ---- EdDSA::sign (sign/eddsa/eddsa_sig.rs:120-152) with the key derivation of
+// Curve::new_key_and_seed_with_input (group/edwards25519/curve.rs:74-87), three launches:
+//   k_sign_stage1   (a, prefix) = clamp(SHA-512(seed)); r = SHA-512(prefix || M) mod L; r*B and a*B (constant-time comb)
+//   k_compress_batch on the 2n points  ->  R and A encodings
+//   k_sign_finish   h = SHA-512(R || A || M) mod L; s = (r + h*a) mod L; sig = R || s
+// The secret scalars a and r only ever meet the constant-time select (no secret-dependent address or branch).
+__global__ void __launch_bounds__(KB_THREADS) k_sign_stage1(size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint32_t* xyz, uint8_t* a_out, uint8_t* r_out,
+                                                            const ge_precomp* table)
+{
+    extern __shared__ uint4 smem4[];
+    ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
+    kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t seed[8], d[16], a[8], r[8];
+    kb_load32(seed, seeds, i);
+    sha512_prefixed<8>(d, seed, nullptr, 0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = d[k];
+    a[0] &= 0xfffffff8u;                     // digest[0] &= 0xf8
+    a[7] = (a[7] & 0x7fffffffu) | 0x40000000u;  // digest[31] &= 0x7f; |= 0x40   (unreduced scalar)
+    const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+    uint32_t d2[16];
+    sha512_prefixed<8>(d2, d + 8, msg + lo, hi - lo);   // prefix = digest[32..64]
+    sc_reduce512(r, d2);
+    int8_t e[64];
+    ge_p3 h;
+    sc_recode16(e, r);
+    ge_scalarmult_base<true>(h, e, base);
+    kb_store_xyz(xyz, 2 * i, h);
+    sc_recode16(e, a);
+    ge_scalarmult_base<true>(h, e, base);
+    kb_store_xyz(xyz, 2 * i + 1, h);
+    kb_store32(a_out, i, a);
+    kb_store32(r_out, i, r);
+}
+__global__ void __launch_bounds__(KB_THREADS) k_sign_finish(size_t n, const uint8_t* ra, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* a_in, const uint8_t* r_in, uint8_t* sig, uint8_t* pk)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t rw[8], aw[8], d[16], h[8], a[8], r[8], s[8];
+    kb_load32(rw, ra, 2 * i);
+    kb_load32(aw, ra, 2 * i + 1);
+    const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+    sha512_ram(d, rw, aw, msg + lo, hi - lo);
+    sc_reduce512(h, d);
+    kb_load32(a, a_in, i);
+    kb_load32(r, r_in, i);
+    sc_muladd(s, h, a, r);
+    kb_store32(sig, 2 * i, rw);
+    kb_store32(sig, 2 * i + 1, s);
+    if (pk) kb_store32(pk, i, aw);
+}
+
 // ---- eddsa::verify_with_checks / schnorr::verify_with_checks, two launches (ops.cuh: sig_stage1 / sig_finish)
 #ifndef KB_VERIFY_MINBLOCKS
 #define KB_VERIFY_MINBLOCKS 3

@@ -69,28 +69,28 @@ KB_FN uint64_t kb_msg_be64(const uint8_t* msg, uint64_t pos, uint64_t mlen)
     return v;
 }
 
-// digest[0..16) = SHA-512(R || A || msg) as little-endian 32-bit words of the 64 output
-// bytes — i.e. directly the little-endian integer the reference feeds to Scalar::set_bytes.
-// r_w / a_w: the 32-byte encodings as 8 LE words each.
-KB_FN void sha512_ram(uint32_t* digest, const uint32_t* r_w, const uint32_t* a_w, const uint8_t* msg, uint64_t mlen)
+// digest[0..16) = SHA-512(head || msg) as little-endian 32-bit words of the 64 output bytes — i.e. directly the
+// little-endian integer the reference feeds to Scalar::set_bytes.  head = HEAD_WORDS (8 or 16) little-endian
+// words of a 32- or 64-byte prefix held in registers (R || A for the challenge, the key prefix for the EdDSA
+// nonce, the seed for key derivation).
+template <int HEAD_WORDS>
+KB_FN void sha512_prefixed(uint32_t* digest, const uint32_t* head, const uint8_t* msg, uint64_t mlen)
 {
+    constexpr int HB = 4 * HEAD_WORDS;  // prefix bytes: 32 or 64
     uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
                      0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
     uint64_t w[16];
-    const uint64_t total = 64 + mlen;                    // data bytes
+    const uint64_t total = HB + mlen;                    // data bytes
     const uint64_t nblocks = (total + 17 + 127) / 128;   // with 0x80 and the 128-bit length
     KB_NOUNROLL
     for (uint64_t blk = 0; blk < nblocks; blk++) {
         if (blk == 0) {
             KB_UNROLL
-            for (int j = 0; j < 4; j++) {
-                w[j] = ((uint64_t)kb_bswap32(r_w[2 * j]) << 32) | kb_bswap32(r_w[2 * j + 1]);
-                w[4 + j] = ((uint64_t)kb_bswap32(a_w[2 * j]) << 32) | kb_bswap32(a_w[2 * j + 1]);
-            }
+            for (int j = 0; j < HB / 8; j++) w[j] = ((uint64_t)kb_bswap32(head[2 * j]) << 32) | kb_bswap32(head[2 * j + 1]);
             KB_UNROLL
-            for (int j = 8; j < 16; j++) w[j] = kb_msg_be64(msg, (uint64_t)(8 * (j - 8)), mlen);
+            for (int j = HB / 8; j < 16; j++) w[j] = kb_msg_be64(msg, (uint64_t)(8 * j - HB), mlen);
         } else {
-            const uint64_t base = blk * 128 - 64;
+            const uint64_t base = blk * 128 - HB;
             KB_UNROLL
             for (int j = 0; j < 16; j++) w[j] = kb_msg_be64(msg, base + 8 * j, mlen);
         }
@@ -105,4 +105,15 @@ KB_FN void sha512_ram(uint32_t* digest, const uint32_t* r_w, const uint32_t* a_w
         digest[2 * i] = kb_bswap32((uint32_t)(h[i] >> 32));
         digest[2 * i + 1] = kb_bswap32((uint32_t)h[i]);
     }
+}
+// SHA-512(R || A || msg): r_w / a_w are the 32-byte encodings as 8 LE words each
+KB_FN void sha512_ram(uint32_t* digest, const uint32_t* r_w, const uint32_t* a_w, const uint8_t* msg, uint64_t mlen)
+{
+    uint32_t head[16];
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        head[i] = r_w[i];
+        head[8 + i] = a_w[i];
+    }
+    sha512_prefixed<16>(digest, head, msg, mlen);
 }

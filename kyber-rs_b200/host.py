@@ -300,6 +300,12 @@ def schnorr_verify(public: Point, msg: bytes, sig: bytes):
         raise SignatureError(st)
 
 
+def eddsa_sign_batch(seeds, msgs, ctx: Context | None = None):
+    """EdDSA::sign (sign/eddsa/eddsa_sig.rs:120-152) for n (32-byte seed, message) pairs -> (sigs[n,64], pks[n,32])."""
+    flat, off = pack_messages(list(msgs))
+    return (ctx or default_context()).eddsa_sign_batch(np.frombuffer(b"".join(seeds), np.uint8), flat, off)
+
+
 # ---- VSS / DKG / MSM --------------------------------------------------------------------------
 def vss_verify_deal(commits, i: int, share: Scalar) -> bool:
     """Group math of Aggregator::verify_deal (share/vss/pedersen/vss.rs:899-912)."""

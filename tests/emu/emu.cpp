@@ -138,6 +138,33 @@ void emu_sha512_ram(uint8_t* out, const uint8_t* r, const uint8_t* a, const uint
     sha512_ram(d, rw, aw, msg, mlen);
     st(out, d, 16);
 }
+// EdDSA::sign composed exactly as k_sign_stage1 / k_sign_finish do it
+void emu_eddsa_sign(uint8_t* sig, uint8_t* pk, const uint8_t* seed_b, const uint8_t* msg, uint64_t mlen)
+{
+    uint32_t seed[8], d[16], d2[16], a[8], r[8], rw[8], aw[8], h[8], s[8];
+    base_init();
+    ld(seed, seed_b, 8);
+    sha512_prefixed<8>(d, seed, nullptr, 0);
+    for (int k = 0; k < 8; k++) a[k] = d[k];
+    a[0] &= 0xfffffff8u;
+    a[7] = (a[7] & 0x7fffffffu) | 0x40000000u;
+    sha512_prefixed<8>(d2, d + 8, msg, mlen);
+    sc_reduce512(r, d2);
+    int8_t e[64];
+    ge_p3 p;
+    sc_recode16(e, r);
+    ge_scalarmult_base<true>(p, e, g_base);
+    ge_compress(rw, p);
+    sc_recode16(e, a);
+    ge_scalarmult_base<true>(p, e, g_base);
+    ge_compress(aw, p);
+    sha512_ram(d, rw, aw, msg, mlen);
+    sc_reduce512(h, d);
+    sc_muladd(s, h, a, r);
+    st(sig, rw, 8);
+    st(sig + 32, s, 8);
+    st(pk, aw, 8);
+}
 int emu_sig_verify(int schnorr, const uint8_t* pk, const uint8_t* msg, uint64_t mlen, const uint8_t* sig)
 {
     uint32_t pw[8], sw[16];

@@ -27,6 +27,7 @@ def emu():
     E = ctypes.CDLL(so)
     E.emu_sha512_ram.argtypes = [ctypes.c_char_p] * 4 + [ctypes.c_uint64]
     E.emu_sig_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    E.emu_eddsa_sign.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64]
     E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
     return E
@@ -200,3 +201,13 @@ def test_ref10_limb_wire_format(emu, coracle):
             want = bytearray(b32(y))
             want[31] ^= (x & 1) << 7
             assert out.raw == bytes(want)
+
+
+def test_eddsa_sign_golden(emu, golden_records):
+    """EdDSA::sign (eddsa_sig.rs:120-152) + key derivation (curve.rs:74-87) as the signing kernels compose them:
+    reproduces the reference's golden signatures and public keys (tests/sign/eddsa.rs:37-94)."""
+    sig = ctypes.create_string_buffer(64)
+    pk = ctypes.create_string_buffer(32)
+    for seed, want_pk, want_sig, msg in golden_records[::24] + golden_records[:4]:
+        emu.emu_eddsa_sign(sig, pk, seed, msg, len(msg))
+        assert pk.raw == want_pk and sig.raw == want_sig

@@ -471,3 +471,21 @@ def test_cfg5_msm_oracle_2p14_and_linearity_2p20(ctx, coracle, golden_records):
     assert ctx.point_add_batch(np.frombuffer(ea, np.uint8), np.frombuffer(eb, np.uint8))[0][0].tobytes() == eab
     parts = [ctx.msm(a[k * (big // 4):(k + 1) * (big // 4)], p[k * (big // 4):(k + 1) * (big // 4)], want_partial=True)[1] for k in range(4)]
     assert ctx.point_sum(np.stack(parts)) == ea
+
+
+def test_eddsa_sign_golden_file(kb, ctx, golden_records):
+    """kb_eddsa_sign_batch reproduces ALL 1024 golden signatures and public keys of the reference's sign.input
+    (tests/sign/eddsa.rs:37-94: message lengths 0..1023), then 10 000 random sign/verify round trips with the
+    reference's `sig[63] & 0xe0 == 0` property (tests/sign/eddsa.rs:18-33)."""
+    sigs, pks = kb.host.eddsa_sign_batch([r[0] for r in golden_records], [r[3] for r in golden_records])
+    assert sigs.tobytes() == b"".join(r[2] for r in golden_records)
+    assert pks.tobytes() == b"".join(r[1] for r in golden_records)
+    n = 10000
+    seeds = np.frombuffer(xof_bytes("eddsa/10000/seeds", 32 * n), dtype=np.uint8).reshape(n, 32)
+    msgs = [xof_bytes("eddsa/10000/msg%d" % (i % 7), 32 + (i % 100)) for i in range(n)]
+    sigs, pks = kb.host.eddsa_sign_batch([s.tobytes() for s in seeds], msgs)
+    assert not (sigs[:, 63] & 0xE0).any()
+    st = kb.host.eddsa_verify_batch([p.tobytes() for p in pks], msgs, [s.tobytes() for s in sigs])
+    assert not st.any()
+    st = kb.host.schnorr_verify_batch([p.tobytes() for p in pks], msgs, [s.tobytes() for s in sigs])
+    assert not st.any()
