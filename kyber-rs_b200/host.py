@@ -369,3 +369,37 @@ def schnorr_sign_batch(privates, msgs, nonces, ctx: Context | None = None):
     h = ctx.challenge_batch(r, pub, flat, off)
     s = ctx.sc_muladd_batch(x, h, k)
     return np.concatenate([r, s], axis=1), pub
+
+
+def recover_commit(shares, t: int, n: int, ctx: Context | None = None) -> Point:
+    """share::poly::recover_commit (share/poly.rs:566-603): Lagrange interpolation in the exponent of the
+    secret commitment p(0) from public shares [(index, Point), ...] — the first t of them in index order
+    (xy_commit, poly.rs:535-562).  The Lagrange coefficients num/den are built with the batched scalar
+    kernels, the weighted sum is ONE Pippenger MSM (kb_msm) instead of t scalar mults and t additions."""
+    ctx = ctx or default_context()
+    good = sorted(((i, p) for i, p in shares if p is not None), key=lambda s: s[0])[:t]
+    if len(good) < t:
+        raise ValueError("not enough good public shares to reconstruct secret commitment")   # PolyError::NotEnoughtGoodPublics
+    k = len(good)
+    xs = np.zeros((k, 32), dtype=np.uint8)
+    for r, (i, _) in enumerate(good):
+        xs[r] = np.frombuffer((i + 1).to_bytes(32, "little"), dtype=np.uint8)      # set_int64(idx + 1)
+    one = np.zeros((k, 32), dtype=np.uint8)
+    one[:, 0] = 1
+    zero = np.zeros((k, 32), dtype=np.uint8)
+    lm1 = np.tile(np.frombuffer(_L_MINUS_1, dtype=np.uint8), (k, 1))
+    num, den = one.copy(), one.copy()
+    for j in range(k):
+        xj = np.tile(xs[j], (k, 1))
+        diff = ctx.sc_muladd_batch(xs, lm1, xj)          # x_j - x_i  (Scalar::sub, scalar.rs:162)
+        fnum, fden = xj.copy(), diff
+        fnum[j] = one[0]                                  # skip i == j
+        fden[j] = one[0]
+        num = ctx.sc_muladd_batch(num, fnum, zero)
+        den = ctx.sc_muladd_batch(den, fden, zero)
+    lam = ctx.sc_muladd_batch(num, ctx.sc_invert_batch(den), zero)                  # num.div(num, den)
+    pts = np.frombuffer(b"".join(p.b for _, p in good), dtype=np.uint8).reshape(-1, 32)
+    enc, bad = ctx.msm(lam, pts)
+    if bad:
+        raise MarshallingError("invalid Ed25519 curve point")
+    return Point(enc)

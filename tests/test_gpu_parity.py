@@ -489,3 +489,34 @@ def test_eddsa_sign_golden_file(kb, ctx, golden_records):
     assert not st.any()
     st = kb.host.schnorr_verify_batch([p.tobytes() for p in pks], msgs, [s.tobytes() for s in sigs])
     assert not st.any()
+
+
+def test_recover_commit_lagrange_msm(kb, ctx):
+    """share/poly_test.rs recover tests (n = 10, t = 6 there; also a larger one): the secret commitment p(0) is
+    recovered from t public shares by Lagrange interpolation in the exponent — here ONE Pippenger MSM —
+    and equals commit[0]; with fewer than t shares the reference's error is raised."""
+    H = kb.host
+    for n, t, seed in ((10, 6, b"rc1"), (40, 27, b"rc2")):
+        coeffs = _poly(seed, t)
+        commits = O.pripoly_commit(coeffs)
+        pub = H.PubPoly([O.point_encode(c) for c in commits])
+        idx = list(range(n))
+        shares = [(i, p) for i, p in zip(idx, pub.eval_batch(idx))]
+        shares[1] = (1, None)                    # a missing share, as in poly_test.rs
+        shares = shares[::-1]                    # order must not matter (xy_commit sorts)
+        got = H.recover_commit(shares, t, n)
+        assert got.b == O.point_encode(commits[0])
+        # oracle-side Lagrange with the same t shares
+        good = sorted((i for i, p in shares if p is not None))[:t]
+        lam = []
+        for i in good:
+            num = den = 1
+            for j in good:
+                if j != i:
+                    num = num * (j + 1) % O.L
+                    den = den * ((j + 1) - (i + 1)) % O.L
+            lam.append((num * pow(den, O.L - 2, O.L) % O.L).to_bytes(32, "little"))
+        pts = [O.pubpoly_eval(commits, i) for i in good]
+        assert got.b == O.point_encode(O.msm(lam, pts))
+    with pytest.raises(ValueError):
+        H.recover_commit(shares[:3], t, n)
