@@ -115,7 +115,8 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         KB_SCRATCH(20, 128 * nthreads, heads);
         KB_SCRATCH(21, 128 * nthreads, tails);
         KB_SCRATCH(22, nthreads, flags);
-        KB_SCRATCH(23, 128 * (size_t)pl.windows * groups, partial);
+        KB_SCRATCH(23, 2 * 128 * (size_t)pl.windows * groups, partial);
+        uint32_t* part_tot = partial + 32 * (size_t)pl.windows * groups;
         KB_SCRATCH(24, 4 * 2048, tile_sums);
         KB_SCRATCH(25, 16 + 12 * (size_t)pl.nb, long_list);  // at most one long run per bucket
         KB_SCRATCH(26, 128 * (size_t)pl.windows, win_sum);
@@ -141,9 +142,9 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         KB_LAUNCHED();
         k_msm_merge_long<<<ctx->sm_count * 2, KB_THREADS, 0, st>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
         KB_LAUNCHED();
-        k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial);
+        k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial, part_tot);
         KB_LAUNCHED();
-        k_msm_window_sums<<<pl.windows, 256, 0, st>>>(groups, partial, win_sum);
+        k_msm_window_sums<<<pl.windows, 256, 0, st>>>(pl, groups, partial, part_tot, win_sum);
         KB_LAUNCHED();
         const bool last = off + cn >= n;
         k_msm_finish<<<1, 32, 0, st>>>(pl, win_sum, acc128, off == 0 ? 1 : 0, last ? d_out32 : nullptr);

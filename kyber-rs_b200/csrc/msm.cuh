@@ -23,7 +23,7 @@
 #include "sc.cuh"
 
 #define KB_MSM_CHUNK (1u << 22)
-#define KB_MSM_GROUPS 1024  // bucket groups per window in the reduction
+#define KB_MSM_GROUPS 4096  // bucket groups per window in the reduction
 
 #if defined(KB_HOST_EMU)
 KB_FN uint32_t kb_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
@@ -198,18 +198,38 @@ KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* of
     ge_p3 acc;
     ge_identity(acc);
     uint32_t fl = 0;
-    for (uint32_t k = s; k < e; k++) {
-        const uint32_t v = sorted[k];
+    uint32_t v = sorted[s];
+    ge_precomp q;
+    {
         const uint32_t* pp = pts + 24 * (size_t)(v >> 1);
-        ge_precomp q;
         KB_UNROLL
         for (int j = 0; j < 8; j++) {
             q.ypx.v[j] = pp[j];
             q.ymx.v[j] = pp[8 + j];
             q.xy2d.v[j] = pp[16 + j];
         }
-        ge_precomp_cneg(q, v & 1u);
+    }
+    for (uint32_t k = s; k < e; k++) {
+        // fetch the NEXT entry's point before the ~900-instruction addition so the gather overlaps it
+        const uint32_t vcur = v;
+        ge_precomp qn;
+        uint32_t vn = v;
+        if (k + 1 < e) {
+            vn = sorted[k + 1];
+            const uint32_t* pn = pts + 24 * (size_t)(vn >> 1);
+            KB_UNROLL
+            for (int j = 0; j < 8; j++) {
+                qn.ypx.v[j] = pn[j];
+                qn.ymx.v[j] = pn[8 + j];
+                qn.xy2d.v[j] = pn[16 + j];
+            }
+        } else {
+            qn = q;
+        }
+        ge_precomp_cneg(q, vcur & 1u);
         ge_madd<true>(acc, acc, q);
+        q = qn;
+        v = vn;
         const uint32_t bend = offsets[b + 1];
         if (k + 1 == bend || k + 1 == e) {
             // run of bucket b inside this chunk ends here
@@ -272,9 +292,11 @@ KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, c
     kb_store_p3(bucket_sum + 32 * (size_t)b, acc);
 }
 
-// ---- reduce: group g of window w covers buckets [g*gs, (g+1)*gs) (0-based, weight = index+1)
-// partial[w*G + g] = sum_k (k+1) * bucket[w][k] over the group
-KB_FN void kb_msm_reduce_body(const kb_msm_plan& pl, size_t tid, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* partial)
+// ---- reduce: group g of window w covers buckets [g*gs, (g+1)*gs) (0-based, bucket k has weight k+1)
+//   run[w*G + g] = sum_k bucket_k                 over the group
+//   tot[w*G + g] = sum_k (k - g*gs + 1) bucket_k   (running sum of running sums)
+// so that the window sum is  sum_g tot_g + gs * sum_g g * run_g  (k_msm_window_sums).
+KB_FN void kb_msm_reduce_body(const kb_msm_plan& pl, size_t tid, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* part_run, uint32_t* part_tot)
 {
     const uint32_t w = (uint32_t)(tid / groups), g = (uint32_t)(tid % groups);
     if (w >= pl.windows) return;
@@ -285,29 +307,55 @@ KB_FN void kb_msm_reduce_body(const kb_msm_plan& pl, size_t tid, uint32_t groups
     ge_p3 run, tot;
     ge_identity(run);
     ge_identity(tot);
-    if (k0 < k1) {
-        for (uint32_t k = k1; k-- > k0;) {
-            const uint32_t b = w * pl.half + k;
-            if (offsets[b + 1] > offsets[b]) {
-                ge_p3 p;
-                kb_load_p3(p, bucket_sum + 32 * (size_t)b);
-                ge_cached pc;
-                ge_to_cached(pc, p);
-                ge_add<true>(run, run, pc);
-            }
-            ge_cached rc;
-            ge_to_cached(rc, run);
-            ge_add<true>(tot, tot, rc);
+    for (uint32_t k = k1; k-- > k0;) {
+        const uint32_t b = w * pl.half + k;
+        if (offsets[b + 1] > offsets[b]) {
+            ge_p3 p;
+            kb_load_p3(p, bucket_sum + 32 * (size_t)b);
+            ge_cached pc;
+            ge_to_cached(pc, p);
+            ge_add<true>(run, run, pc);
         }
-        // tot = sum (k - k0 + 1) b_k ; add k0 * run
-        if (k0 > 0) {
-            ge_cached tc;
-            ge_to_cached(tc, tot);
-            kb_horner_step(run, (uint64_t)k0, tc);  // run = k0 * run + tot
-            tot = run;
-        }
+        ge_cached rc;
+        ge_to_cached(rc, run);
+        ge_add<true>(tot, tot, rc);
     }
-    kb_store_p3(partial + 32 * tid, tot);
+    kb_store_p3(part_run + 32 * tid, run);
+    kb_store_p3(part_tot + 32 * tid, tot);
+}
+// one thread's share of a window: groups [c0, c1) -> t1 = sum tot_g, t2 = sum g * run_g
+KB_FN void kb_msm_window_chunk(ge_p3& t1, ge_p3& t2, uint32_t c0, uint32_t c1, const uint32_t* run_w, const uint32_t* tot_w)
+{
+    ge_p3 r, ws;
+    ge_identity(r);
+    ge_identity(ws);
+    ge_identity(t1);
+    for (uint32_t g = c1; g-- > c0;) {
+        ge_p3 p;
+        ge_cached pc;
+        kb_load_p3(p, run_w + 32 * (size_t)g);
+        ge_to_cached(pc, p);
+        ge_add<true>(r, r, pc);
+        ge_to_cached(pc, r);
+        ge_add<true>(ws, ws, pc);     // ws = sum (g - c0 + 1) run_g
+        kb_load_p3(p, tot_w + 32 * (size_t)g);
+        ge_to_cached(pc, p);
+        ge_add<true>(t1, t1, pc);
+    }
+    // sum g * run_g = ws + (c0 - 1) * r
+    if (c0 >= 2 && c0 < c1) {
+        ge_cached wc;
+        ge_to_cached(wc, ws);
+        kb_horner_step(r, (uint64_t)(c0 - 1), wc);
+        t2 = r;
+    } else if (c0 == 0 && c0 < c1) {
+        // weights (g + 1): subtract one r
+        ge_cached rc;
+        ge_to_cached(rc, r);
+        ge_addsub_rt(t2, ws, rc, true, true);
+    } else {
+        t2 = ws;
+    }
 }
 
 #if !defined(KB_HOST_EMU)
@@ -421,11 +469,11 @@ __global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t
     if (t >= nthreads) return;
     kb_msm_merge_body(pl, t, nthreads, offsets, 32u, long_count, long_list, bucket_sum, heads, tails, flags);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* partial)
+__global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* part_run, uint32_t* part_tot)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)pl.windows * groups) return;
-    kb_msm_reduce_body(pl, tid, groups, offsets, bucket_sum, partial);
+    kb_msm_reduce_body(pl, tid, groups, offsets, bucket_sum, part_run, part_tot);
 }
 
 // butterfly sum of one point per lane: after the call every lane holds the warp total
@@ -481,41 +529,95 @@ __global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nthreads, 
         }
     }
 }
-// window sums: block w adds the `groups` partials of window w (threads stride, warp-shuffle butterfly,
-// then the 8 warp totals through shared memory)
-__global__ void __launch_bounds__(256) k_msm_window_sums(uint32_t groups, const uint32_t* partial, uint32_t* win_sum)
+// window sums: block w folds the group partials of window w:  S_w = sum_g tot_g + gs * sum_g g * run_g.
+// Each of the 256 threads owns a contiguous run of groups (kb_msm_window_chunk), the two partial points are summed
+// with a warp-shuffle butterfly and then across the 8 warps through shared memory.
+__global__ void __launch_bounds__(256) k_msm_window_sums(kb_msm_plan pl, uint32_t groups, const uint32_t* part_run, const uint32_t* part_tot, uint32_t* win_sum)
 {
-    __shared__ uint32_t wtot[8 * 32];
+    __shared__ uint32_t wtot[2 * 8 * 32];
     const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ge_p3 s;
-    ge_identity(s);
-    for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
-        ge_p3 p;
-        kb_load_p3(p, partial + 32 * ((size_t)w * groups + g));
-        ge_cached pc;
-        ge_to_cached(pc, p);
-        ge_add<true>(s, s, pc);
+    const uint32_t per = (groups + blockDim.x - 1) / blockDim.x;
+    uint32_t c0 = threadIdx.x * per, c1 = c0 + per;
+    if (c0 > groups) c0 = groups;
+    if (c1 > groups) c1 = groups;
+    ge_p3 t1, t2;
+    kb_msm_window_chunk(t1, t2, c0, c1, part_run + 32 * (size_t)w * groups, part_tot + 32 * (size_t)w * groups);
+    kb_warp_sum_point(t1);
+    kb_warp_sum_point(t2);
+    if (lane == 0) {
+        kb_store_p3(wtot + 32 * warp, t1);
+        kb_store_p3(wtot + 32 * (8 + warp), t2);
     }
-    kb_warp_sum_point(s);
-    if (lane == 0) kb_store_p3(wtot + 32 * warp, s);
     __syncthreads();
     if (warp == 0) {
-        ge_p3 p;
-        ge_identity(p);
-        if (lane < 8) kb_load_p3(p, wtot + 32 * lane);
-        kb_warp_sum_point(p);
-        if (lane == 0) kb_store_p3(win_sum + 32 * w, p);
+        ge_p3 a, b;
+        ge_identity(a);
+        ge_identity(b);
+        if (lane < 8) {
+            kb_load_p3(a, wtot + 32 * lane);
+            kb_load_p3(b, wtot + 32 * (8 + lane));
+        }
+        kb_warp_sum_point(a);
+        kb_warp_sum_point(b);
+        if (lane == 0) {
+            const uint32_t gs = (pl.half + groups - 1) / groups;
+            ge_cached ac;
+            ge_to_cached(ac, a);
+            kb_horner_step(b, (uint64_t)gs, ac);   // b = gs * b + a
+            kb_store_p3(win_sum + 32 * w, b);
+        }
     }
 }
-// finish: Horner over the windows (c doublings per window), add to the running total `acc128`
-// (X,Y,Z,T words) and, if out32 != nullptr, write its encoding.
+// One doubling shared by 4 adjacent lanes: the four squarings (X^2, Y^2, Z^2, (X+Y)^2) and then the four
+// products (E*F, G*H, F*G, E*H) of the doubling formula are independent, so each lane of a quad does ONE of
+// them and the results travel by warp shuffle.  The chain of ~270 dependent doublings that closes an MSM
+// (Horner over the windows) is pure latency for a single thread; this cuts it about three-fold.
+// Every lane of the quad enters with the same point and leaves with the same doubled point.
+__device__ __forceinline__ void kb_shfl_fe(fe& out, const fe& in, int src_lane)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) out.v[k] = __shfl_sync(0xffffffffu, in.v[k], src_lane);
+}
+__device__ __forceinline__ void kb_dbl_quad(ge_p3& p)
+{
+    const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+    fe in = p.X, t, sq;
+    fe_add(t, p.X, p.Y);
+    fe_cmov(in, p.Y, (uint32_t)(role == 1));
+    fe_cmov(in, p.Z, (uint32_t)(role == 2));
+    fe_cmov(in, t, (uint32_t)(role == 3));
+    fe_sq(sq, in);
+    fe a, b, c, d, e, f, g, h;
+    kb_shfl_fe(a, sq, base + 0);
+    kb_shfl_fe(b, sq, base + 1);
+    kb_shfl_fe(c, sq, base + 2);
+    kb_shfl_fe(d, sq, base + 3);
+    fe_dbl(c, c);
+    fe_add(h, a, b);
+    fe_sub(e, h, d);
+    fe_sub(g, a, b);
+    fe_add(f, c, g);
+    // role 0: E*F   1: G*H   2: F*G   3: E*H
+    fe l = e, r = f, prod;
+    fe_cmov(l, g, (uint32_t)(role == 1));
+    fe_cmov(l, f, (uint32_t)(role == 2));
+    fe_cmov(r, h, (uint32_t)(role == 1 || role == 3));
+    fe_cmov(r, g, (uint32_t)(role == 2));
+    fe_mul(prod, l, r);
+    kb_shfl_fe(p.X, prod, base + 0);
+    kb_shfl_fe(p.Y, prod, base + 1);
+    kb_shfl_fe(p.Z, prod, base + 2);
+    kb_shfl_fe(p.T, prod, base + 3);
+}
+// finish: Horner over the windows (c quad-doublings per window), add to the running total `acc128`
+// (X,Y,Z,T words) and, if out32 != nullptr, write its encoding.  One warp; all quads compute the same thing.
 __global__ void k_msm_finish(kb_msm_plan pl, const uint32_t* win_sum, uint32_t* acc128, int first_chunk, uint8_t* out32)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     ge_p3 tot;
     ge_identity(tot);
     for (uint32_t w = pl.windows; w-- > 0;) {
-        for (uint32_t k = 0; k < pl.c; k++) ge_dbl<true>(tot, tot);
+        for (uint32_t k = 0; k < pl.c; k++) kb_dbl_quad(tot);
         ge_p3 s;
         kb_load_p3(s, win_sum + 32 * w);
         ge_cached sc;
@@ -529,6 +631,8 @@ __global__ void k_msm_finish(kb_msm_plan pl, const uint32_t* win_sum, uint32_t* 
         ge_to_cached(pc, prev);
         ge_add<true>(tot, tot, pc);
     }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
     kb_store_p3(acc128, tot);
     if (out32) {
         uint32_t o[8];

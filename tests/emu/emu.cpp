@@ -220,18 +220,36 @@ int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* point
     for (size_t i = 0; i < n; i++) kb_msm_scatter_body(pl, i, mags.data(), negs.data(), offsets.data(), cursor.data(), sorted.data());
     for (size_t t = 0; t < nthreads; t++) kb_msm_accum_body(pl, t, offsets.data(), sorted.data(), pts.data(), bucket_sum.data(), heads.data(), tails.data(), flags.data());
     for (size_t t = 0; t < nthreads; t++) kb_msm_merge_body(pl, t, nthreads, offsets.data(), 0xffffffffu, nullptr, nullptr, bucket_sum.data(), heads.data(), tails.data(), flags.data());
-    for (size_t t = 0; t < (size_t)pl.windows * groups; t++) kb_msm_reduce_body(pl, t, groups, offsets.data(), bucket_sum.data(), partial.data());
+    std::vector<uint32_t> part_tot(32 * (size_t)pl.windows * groups);
+    for (size_t t = 0; t < (size_t)pl.windows * groups; t++) kb_msm_reduce_body(pl, t, groups, offsets.data(), bucket_sum.data(), partial.data(), part_tot.data());
+    // window sums as k_msm_window_sums forms them: 256 "threads" per window, chunked groups
+    const uint32_t gs = (pl.half + groups - 1) / groups;
     ge_p3 tot;
     ge_identity(tot);
     for (uint32_t w = pl.windows; w-- > 0;) {
         for (uint32_t k = 0; k < pl.c; k++) ge_dbl<true>(tot, tot);
-        for (uint32_t g = 0; g < groups; g++) {
-            ge_p3 p;
-            kb_load_p3(p, partial.data() + 32 * ((size_t)w * groups + g));
+        ge_p3 a, b;
+        ge_identity(a);
+        ge_identity(b);
+        const uint32_t per = (groups + 255) / 256;
+        for (uint32_t th = 0; th < 256; th++) {
+            uint32_t c0 = th * per, c1 = c0 + per;
+            if (c0 > groups) c0 = groups;
+            if (c1 > groups) c1 = groups;
+            ge_p3 t1, t2;
+            kb_msm_window_chunk(t1, t2, c0, c1, partial.data() + 32 * (size_t)w * groups, part_tot.data() + 32 * (size_t)w * groups);
             ge_cached pc;
-            ge_to_cached(pc, p);
-            ge_add<true>(tot, tot, pc);
+            ge_to_cached(pc, t1);
+            ge_add<true>(a, a, pc);
+            ge_to_cached(pc, t2);
+            ge_add<true>(b, b, pc);
         }
+        ge_cached ac;
+        ge_to_cached(ac, a);
+        kb_horner_step(b, (uint64_t)gs, ac);
+        ge_cached bc;
+        ge_to_cached(bc, b);
+        ge_add<true>(tot, tot, bc);
     }
     uint32_t o[8];
     ge_compress(o, tot);
