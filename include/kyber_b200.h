@@ -63,6 +63,8 @@ typedef enum kb_sig_status {
 /* ---- context ---------------------------------------------------------------------- */
 int kb_ctx_create(int device, kb_ctx** out);
 void kb_ctx_destroy(kb_ctx* ctx);
+/* zero every device scratch buffer of the context (inputs such as secret scalars are staged there) */
+int kb_ctx_wipe(kb_ctx* ctx);
 const char* kb_last_error(const kb_ctx* ctx);
 int kb_device_sm_count(const kb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

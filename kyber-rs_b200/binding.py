@@ -34,7 +34,7 @@ _LIB = None
 
 # every symbol include/kyber_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
+    "kb_ctx_create", "kb_ctx_destroy", "kb_ctx_wipe", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
     "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch",
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
@@ -55,6 +55,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
     L.kb_ctx_destroy.argtypes = [vp]
     L.kb_ctx_destroy.restype = None
+    L.kb_ctx_wipe.argtypes = [vp]
     L.kb_last_error.argtypes = [vp]
     L.kb_last_error.restype = ctypes.c_char_p
     L.kb_device_sm_count.argtypes = [vp]
@@ -140,6 +141,9 @@ class Context:
     def _check(self, rc, what):
         if rc != 0:
             raise KBError(f"{what} failed with {rc}: {self.L.kb_last_error(self.h).decode(errors='replace')}")
+
+    def wipe(self):
+        self._check(self.L.kb_ctx_wipe(self.h), "kb_ctx_wipe")
 
     @property
     def sm_count(self):

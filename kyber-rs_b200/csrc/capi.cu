@@ -165,25 +165,25 @@ int kb_ctx_create(int device, kb_ctx** out)
     kb_ctx* ctx = (kb_ctx*)calloc(1, sizeof(kb_ctx));
     if (!ctx) return KB_ERR_NOMEM;
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
-    ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
-    if (cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) != cudaSuccess) { free(ctx); return KB_ERR_CUDA; }
-    if (cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) != cudaSuccess) { cudaFree(ctx->base_table); free(ctx); return KB_ERR_CUDA; }
-    k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
-    k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
-    ctx->launches += 2;
-    cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-    cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-    cudaFuncSetAttribute(k_poly_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-    cudaFuncSetAttribute(k_sign_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-        cudaFree(ctx->base_table);
-        cudaFree(ctx->base128);
-        free(ctx);
+    bool ok = cudaSetDevice(device) == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok) ctx->sm_count = prop.multiProcessorCount;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
+    if (ok) {
+        k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
+        k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
+        ctx->launches += 2;
+        cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+        cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+        cudaFuncSetAttribute(k_poly_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+        cudaFuncSetAttribute(k_sign_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
+        ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    }
+    if (!ok) {
+        kb_ctx_destroy(ctx);   // releases whatever was created
         return KB_ERR_CUDA;
     }
     *out = ctx;
@@ -194,13 +194,14 @@ void kb_ctx_destroy(kb_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     for (int s = 0; s < KB_NSLOTS; s++)
         if (ctx->slot[s]) cudaFree(ctx->slot[s]);
-    cudaFree(ctx->base_table);
-    cudaFree(ctx->base128);
-    cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->stream2);
+    if (ctx->base_table) cudaFree(ctx->base_table);
+    if (ctx->base128) cudaFree(ctx->base128);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);
 }
 const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err : "no context"; }
@@ -330,6 +331,15 @@ int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, co
     if (!ctx) return KB_ERR_ARG;                    \
     KB_CUDA(cudaSetDevice(ctx->device))
 
+int kb_ctx_wipe(kb_ctx* ctx)
+{
+    KB_ENTER();
+    KB_CUDA(cudaDeviceSynchronize());
+    for (int s = 0; s < KB_NSLOTS; s++)
+        if (ctx->slot[s]) KB_CUDA(cudaMemsetAsync(ctx->slot[s], 0, ctx->slot_bytes[s], ctx->stream));
+    KB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
 int kb_point_mul_base_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, uint8_t* out, uint32_t flags)
 {
     KB_ENTER();

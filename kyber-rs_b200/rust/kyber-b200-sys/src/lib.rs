@@ -20,6 +20,7 @@ pub const KB_FLAG_SHARED_POINT: u32 = 2;
 extern "C" {
     pub fn kb_ctx_create(device: c_int, out: *mut *mut kb_ctx) -> c_int;
     pub fn kb_ctx_destroy(ctx: *mut kb_ctx);
+    pub fn kb_ctx_wipe(ctx: *mut kb_ctx) -> c_int;
     pub fn kb_last_error(ctx: *const kb_ctx) -> *const c_char;
     pub fn kb_device_sm_count(ctx: *const kb_ctx) -> c_int;
     pub fn kb_launch_count(ctx: *const kb_ctx) -> u64;
