@@ -19,7 +19,8 @@ struct kb_ctx {
     cudaStream_t stream;
     cudaStream_t stream2;    // second copy/compute lane of the pipelined host entry points
     ge_precomp* base_table;  // 64 x 8 entries: (j+1) * 16^w * B
-    ge_precomp* base128;     // 128 entries: (j+1) * B
+    ge_precomp* base128;     // 256 entries: (j+1) * B, then (j+1) * 2^128 * B
+    int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     void* slot[KB_NSLOTS];
     size_t slot_bytes[KB_NSLOTS];
     uint64_t launches;
@@ -171,10 +172,12 @@ int kb_ctx_create(int device, kb_ctx** out)
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 256) == cudaSuccess;
     if (ok) {
         k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
-        k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
+        k_base256_init<<<2, 32, 0, ctx->stream>>>(ctx->base128);
+        const char* vf = getenv("KB_VERIFY_FULL");
+        ctx->verify_full = (vf && vf[0] == '1') ? 1 : 0;
         ctx->launches += 2;
         cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
         cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
@@ -263,11 +266,28 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
     KB_LAUNCHED();
     return KB_OK;
 }
+// per-signature scratch of the verifiers: 304-byte records (half-size-scalar path) / 96-byte points (full-length path)
+#define KB_VERIFY_SCRATCH_BYTES (4 * KB_HALF_REC_WORDS)
 static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, uint64_t msg_base, const uint8_t* d_sig, uint8_t* d_status, int schnorr,
                             uint32_t* xyz, uint8_t* fl, cudaStream_t st)
 {
     const unsigned th = kb_item_threads(ctx, n);
     const unsigned g1 = kb_blocks(n, th), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    if (!ctx->verify_full) {
+        // the 96-byte-per-item xyz scratch of the full-length path is not needed; `xyz` carries the 304-byte records
+        const unsigned gp = kb_blocks(n, KB_THREADS);
+        if (schnorr) {
+            k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+            KB_LAUNCHED();
+            k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->base128);
+        } else {
+            k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+            KB_LAUNCHED();
+            k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->base128);
+        }
+        KB_LAUNCHED();
+        return KB_OK;
+    }
     if (schnorr) {
         k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
         KB_LAUNCHED();
@@ -286,7 +306,7 @@ int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_m
     if (n == 0) return KB_OK;
     uint32_t* xyz;
     uint8_t* fl;
-    KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
+    KB_SCRATCH(KB_SLOT_XYZ, KB_VERIFY_SCRATCH_BYTES * n, xyz);
     KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
     return kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, 0, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, (cudaStream_t)stream);
 }
@@ -550,7 +570,7 @@ static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
         KB_SCRATCH(b + 2, max_mbytes, d_m[l]);
         KB_SCRATCH(b + 3, 8 * (cn_max + 1), d_off[l]);
         KB_SCRATCH(b + 4, cn_max, d_st[l]);
-        KB_SCRATCH(b + 5, 96 * cn_max, xyz[l]);
+        KB_SCRATCH(b + 5, KB_VERIFY_SCRATCH_BYTES * cn_max, xyz[l]);
         KB_SCRATCH(b + 6, cn_max, fl[l]);
     }
     int l = 0;

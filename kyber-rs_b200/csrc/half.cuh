@@ -1,0 +1,144 @@
+// half.cuh — half-size scalars for the signature verifiers.
+//
+// The reference checks  s*B == R + h*A  on canonical encodings (eddsa_sig.rs:201-210,
+// schnorr_sig.rs:96-106) with a 253-bit h: 253 doublings per signature.  Here the SAME verdict is
+// obtained from 128 doublings.  Let N = 8L (the order of the whole curve group) and let (u, v) be a
+// short vector of the lattice { (u, v) : v = u*h (mod N) } with u ODD.  With D = s*B - h*A - R:
+//
+//     u*D = (u*s mod L)*B - v*A - u*R            (ord B = L; ord A | N, so u*h*A = v*A exactly —
+//                                                 also for keys that carry a small-order component)
+//     u*D = 0  <=>  D = 0                          (gcd(u, 8L) = 1: u is odd and 0 < u < L)
+//
+// so "u*D is the identity" is equivalent to the reference's equation for EVERY input, not only for
+// honest ones (the lattice is taken modulo 8L, not L, precisely so that torsion cannot slip through).
+// u and |v| are about sqrt(8L) = 2^127.5.  This is the verification trick of Antipa, Brown, Gallant,
+// Lambert, Struik and Vanstone ("Accelerated verification of ECDSA signatures", SAC 2005) restated for a
+// cofactor-8 curve and a cofactorless verifier.
+//
+// sc_half runs the (binary long-division form of the) extended Euclidean algorithm on (N, h) and keeps
+// the best vector with an odd u it meets; (u, v) = (1, h) is the starting candidate, so a result always
+// exists and at worst costs what the full-length path costs.  h is public: nothing here is constant-time.
+#pragma once
+#include "fe.cuh"
+#include "sc.cuh"
+
+// N = 8L
+#define KB_8L_WORDS {0xe7ae9f68u, 0xc09318d2u, 0x17bce6b2u, 0xa6f7cef5u, 0u, 0u, 0u, 0x80000000u}
+
+KB_FN int kb_clz32(uint32_t x)
+{
+#if defined(KB_HOST_EMU)
+    return x ? __builtin_clz(x) : 32;
+#else
+    return __clz((int)x);
+#endif
+}
+// upper word of (hi:lo) << s, s in [0, 32)
+KB_FN uint32_t kb_shf_l(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#if defined(KB_HOST_EMU)
+    return s ? ((hi << s) | (lo >> (32 - s))) : hi;
+#else
+    return __funnelshift_l(lo, hi, s);
+#endif
+}
+// bit length of a 256-bit integer (0 for 0)
+KB_FN int kb_bitlen8(const uint32_t* a)
+{
+    int bl = 0;
+    KB_UNROLL
+    for (int i = 0; i < 8; i++)
+        if (a[i]) bl = 32 * i + 32 - kb_clz32(a[i]);
+    return bl;
+}
+// y = a << s truncated to 256 bits, s in [0, 256)
+KB_FN void kb_shl8(uint32_t* y, const uint32_t* a, int s)
+{
+    const uint32_t bs = (uint32_t)s & 31u;
+    KB_UNROLL
+    for (int i = 7; i >= 1; i--) y[i] = kb_shf_l(a[i - 1], a[i], bs);
+    y[0] = a[0] << bs;
+    // whole words: almost always none (quotients of a Euclidean run are small)
+    KB_NOUNROLL
+    for (int k = s >> 5; k > 0; k--) {
+        KB_UNROLL
+        for (int i = 7; i >= 1; i--) y[i] = y[i - 1];
+        y[0] = 0;
+    }
+}
+KB_FN void kb_shr1_8(uint32_t* y)
+{
+    KB_UNROLL
+    for (int i = 0; i < 7; i++) y[i] = (y[i] >> 1) | (y[i + 1] << 31);
+    y[7] >>= 1;
+}
+
+struct kb_halfsc {
+    uint32_t u[8];   // odd, > 0
+    uint32_t v[8];   // |v|
+    uint32_t vneg;   // v = -|v| when set:   v == u*h (mod 8L)
+    int bits;        // max(bitlen(u), bitlen(|v|))
+};
+
+KB_FN void sc_half(kb_halfsc& o, const uint32_t* h)
+{
+    const uint32_t n8l[8] = KB_8L_WORDS;
+    uint32_t r0[8], r1[8], t0[8], t1[8];
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        r0[i] = n8l[i];
+        r1[i] = h[i];
+        t0[i] = 0;
+        t1[i] = (i == 0) ? 1u : 0u;
+        o.u[i] = t1[i];
+        o.v[i] = h[i];
+    }
+    // invariant: r0 = sg0 * t0 * h, r1 = -sg0 * t1 * h (mod N), r0 >= r1, t's are magnitudes
+    uint32_t sg0neg = 1;
+    int la = 256, lb = kb_bitlen8(h), lt1 = 1;
+    o.vneg = 0;
+    o.bits = lb > 1 ? lb : 1;
+    // every later vector has |u| >= t1, so once bitlen(t1) reaches the best cost nothing can improve
+    KB_NOUNROLL
+    while (lb != 0 && lt1 < o.bits) {
+        int s = la - lb;
+        uint32_t y[8], d[8];
+        kb_shl8(y, r1, s);
+        if (kb_sub8(d, r0, y)) {   // r1 << s overshoots: s >= 1 here because r0 >= r1
+            s -= 1;
+            kb_shr1_8(y);
+            kb_sub8(d, r0, y);
+        }
+        kb_shl8(y, t1, s);
+        kb_add8(t0, t0, y);
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) r0[i] = d[i];
+        la = kb_bitlen8(r0);
+        const int lt0 = kb_bitlen8(t0);
+        const int c = la > lt0 ? la : lt0;
+        if ((t0[0] & 1u) && c < o.bits) {
+            KB_UNROLL
+            for (int i = 0; i < 8; i++) {
+                o.u[i] = t0[i];
+                o.v[i] = r0[i];
+            }
+            o.vneg = sg0neg;
+            o.bits = c;
+        }
+        if (kb_sub8(d, r0, r1)) {   // r0 < r1: the division step is complete, exchange the rows
+            KB_UNROLL
+            for (int i = 0; i < 8; i++) {
+                const uint32_t a = r0[i], b = t0[i];
+                r0[i] = r1[i];
+                r1[i] = a;
+                t0[i] = t1[i];
+                t1[i] = b;
+            }
+            const int l = la;
+            la = lb;
+            lb = l;
+            lt1 = lt0;
+            sg0neg ^= 1u;
+        }
+    }
+}

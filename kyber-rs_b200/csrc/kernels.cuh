@@ -57,15 +57,18 @@ __global__ void k_base_init(ge_precomp* table)
     kb_base_window(table + 8 * w, pos);
 }
 
-// base128[j] = (j+1) * B, j = 0..127: the radix-256 fixed-base table of the verifiers
-__global__ void k_base128_init(ge_precomp* table)
+// base256[j] = (j+1) * B, base256[128 + j] = (j+1) * 2^128 * B, j = 0..127: the radix-256 fixed-base tables of
+// the verifiers (the full-length path only uses the first half).  One block per half.
+__global__ void k_base256_init(ge_precomp* table)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x != 0 || blockIdx.x > 1) return;
     ge_p3 pos;
     const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
     pos.X = bx; pos.Y = by; pos.T = bt;
     fe_set(pos.Z, 1);
-    kb_base_window(table, pos, 128);
+    if (blockIdx.x == 1)
+        for (int k = 0; k < 128; k++) ge_dbl<true>(pos, pos);
+    kb_base_window(table + 128 * blockIdx.x, pos, 128);
 }
 
 // ---- shared tail of every point-producing kernel: Montgomery's trick over KB_INV_K results -----
@@ -420,6 +423,91 @@ __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const ui
         kb_load32(rw, sig, 2 * i);
         status[i] = (uint8_t)sig_finish<SCHNORR>(flags[i], enc, rw);
     });
+}
+
+// ---- the same verifiers with half-size scalars (ops.cuh sig_half_*, half.cuh): 128 doublings per signature,
+// verdict from a projective identity test (no inversion).  Two launches so that the two phases — which have
+// very different code (decompression / SHA-512 / Euclid vs. the doubling loop) and register needs — do not
+// compete for the instruction cache on one SM:
+//   k_verify_half_prep   checks, decompress A and R, h, (u, v), u*s mod L   -> 304-byte record per signature
+//   k_verify_half_main   digit strings, two tables, the 33-window loop        -> status
+#define KB_HALF_REC_WORDS 76
+template <bool SCHNORR>
+__global__ void __launch_bounds__(KB_THREADS, 4) k_verify_half_prep(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t pw[8], sw[16];
+    kb_load32(pw, pk, i);
+    kb_load32(sw, sig, 2 * i);
+    kb_load32(sw + 8, sig, 2 * i + 1);
+    // msg_off holds offsets into the caller's whole message array; `msg` points at byte msg_base of it
+    const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+    kb_half_rec rec;
+    sig_half_prep<SCHNORR>(rec, pw, sw, msg + (lo - msg_base), hi - lo);
+    uint32_t* o = recs + KB_HALF_REC_WORDS * i;
+    kb_store_fe(o, rec.ax);
+    kb_store_fe(o + 8, rec.ay);
+    kb_store_fe(o + 16, rec.at);
+    kb_store_fe(o + 24, rec.rx);
+    kb_store_fe(o + 32, rec.ry);
+    kb_store_fe(o + 40, rec.rt);
+    uint4* q = reinterpret_cast<uint4*>(o + 48);
+    q[0] = make_uint4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]);
+    q[1] = make_uint4(rec.w[4], rec.w[5], rec.w[6], rec.w[7]);
+    q[2] = make_uint4(rec.u[0], rec.u[1], rec.u[2], rec.u[3]);
+    q[3] = make_uint4(rec.u[4], rec.u[5], rec.u[6], rec.u[7]);
+    q[4] = make_uint4(rec.v[0], rec.v[1], rec.v[2], rec.v[3]);
+    q[5] = make_uint4(rec.v[4], rec.v[5], rec.v[6], rec.v[7]);
+    q[6] = make_uint4(rec.f | ((uint32_t)rec.nwin << 8), 0u, 0u, 0u);
+}
+#ifndef KB_VERIFY_HALF_MINBLOCKS
+#define KB_VERIFY_HALF_MINBLOCKS 3
+#endif
+template <bool SCHNORR>
+__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* table256)
+{
+    __shared__ uint4 base_raw[256 * 24 / 4];
+    __shared__ int s_nwin;
+    ge_precomp* base256 = reinterpret_cast<ge_precomp*>(base_raw);
+    if (threadIdx.x == 0) s_nwin = KB_HALF_MIN_WINDOWS;
+    kb_stage(reinterpret_cast<uint32_t*>(base256), reinterpret_cast<const uint32_t*>(table256), 256 * 24);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;   // tail threads redo the last item so that they reach the block barriers
+    if (!live) i = n - 1;
+    kb_half_rec rec;
+    {
+        const uint32_t* o = recs + KB_HALF_REC_WORDS * i;
+        kb_load_fe(rec.ax, o);
+        kb_load_fe(rec.ay, o + 8);
+        kb_load_fe(rec.at, o + 16);
+        kb_load_fe(rec.rx, o + 24);
+        kb_load_fe(rec.ry, o + 32);
+        kb_load_fe(rec.rt, o + 40);
+        const uint4* q = reinterpret_cast<const uint4*>(o + 48);
+        uint4 a;
+        a = q[0]; rec.w[0] = a.x; rec.w[1] = a.y; rec.w[2] = a.z; rec.w[3] = a.w;
+        a = q[1]; rec.w[4] = a.x; rec.w[5] = a.y; rec.w[6] = a.z; rec.w[7] = a.w;
+        a = q[2]; rec.u[0] = a.x; rec.u[1] = a.y; rec.u[2] = a.z; rec.u[3] = a.w;
+        a = q[3]; rec.u[4] = a.x; rec.u[5] = a.y; rec.u[6] = a.z; rec.u[7] = a.w;
+        a = q[4]; rec.v[0] = a.x; rec.v[1] = a.y; rec.v[2] = a.z; rec.v[3] = a.w;
+        a = q[5]; rec.v[4] = a.x; rec.v[5] = a.y; rec.v[6] = a.z; rec.v[7] = a.w;
+        a = q[6];
+        rec.f = a.x & 0xffu;
+        rec.nwin = (int)(a.x >> 8);
+    }
+    ge_cached tbl[16];
+    int16_t dw[32];
+    int8_t eu[64], ev[64];
+    sig_half_setup(dw, eu, ev, tbl, rec);
+    // the window count of the block = the longest any of its signatures needs
+    int nwin = __reduce_max_sync(0xffffffffu, rec.nwin);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_nwin, nwin);
+    __syncthreads();
+    nwin = s_nwin;
+    ge_p3 W;
+    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, base256);
+    if (live) status[i] = (uint8_t)sig_half_finish<SCHNORR>(rec.f, W);
 }
 
 // ---- committed polynomials

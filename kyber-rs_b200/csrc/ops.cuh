@@ -8,6 +8,7 @@
 #include "ge.cuh"
 #include "sc.cuh"
 #include "sha512.cuh"
+#include "half.cuh"
 
 // kb_sig_status (include/kyber_b200.h) — sign/error.rs:6-25
 #define KB_SIG_OK 0
@@ -285,26 +286,15 @@ KB_FN uint32_t sig_stage1(ge_p3& Q, const uint32_t* pk_w, const uint32_t* sig_w,
     }
     return f | KB_F_FAST;
 }
-// enc = compress(Q) (only meaningful with KB_F_FAST)
+// The first failing check in the reference's order (the signature is known not to verify).  r_ok = "R decodes"
+// (ge.rs:124) is only looked at where the reference would have reached the decode.
 template <bool SCHNORR>
-KB_FN uint32_t sig_finish(uint32_t f, const uint32_t* enc, const uint32_t* r_w)
+KB_FN uint32_t sig_classify(uint32_t f, uint32_t r_ok)
 {
-    if (f & KB_F_FAST) {
-        uint32_t diff = 0;
-        KB_UNROLL
-        for (int i = 0; i < 8; i++) diff |= enc[i] ^ r_w[i];
-        if (diff == 0) return KB_SIG_OK;
-    }
-    // report the FIRST failing check in the reference's order
     if (!SCHNORR) {
         if (!(f & KB_F_SC)) return KB_SIG_NOT_CANONICAL;
         if (!(f & KB_F_RC)) return KB_SIG_R_NOT_CANONICAL;
         if (f & KB_F_RS) return KB_SIG_R_SMALL_ORDER;  // weak encodings are on the curve
-    }
-    uint32_t r_ok = 1;
-    if (!(f & KB_F_RS)) {
-        ge_p3 R;
-        r_ok = ge_decompress(R, r_w);
     }
     if (!r_ok) return KB_SIG_MARSHALLING;
     if (SCHNORR) {
@@ -320,6 +310,24 @@ KB_FN uint32_t sig_finish(uint32_t f, const uint32_t* enc, const uint32_t* r_w)
     if (f & KB_F_AS) return KB_SIG_PK_SMALL_ORDER;
     return KB_SIG_INVALID;
 }
+// enc = compress(Q) (only meaningful with KB_F_FAST)
+template <bool SCHNORR>
+KB_FN uint32_t sig_finish(uint32_t f, const uint32_t* enc, const uint32_t* r_w)
+{
+    if (f & KB_F_FAST) {
+        uint32_t diff = 0;
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) diff |= enc[i] ^ r_w[i];
+        if (diff == 0) return KB_SIG_OK;
+    }
+    uint32_t r_ok = 1;
+    const bool r_reached = SCHNORR || (f & (KB_F_SC | KB_F_RC | KB_F_RS)) == (KB_F_SC | KB_F_RC);
+    if (r_reached && !(f & KB_F_RS)) {
+        ge_p3 R;
+        r_ok = ge_decompress(R, r_w);
+    }
+    return sig_classify<SCHNORR>(f, r_ok);
+}
 // one signature start to finish (own inversion) — the composition the two-stage kernels implement
 template <bool SCHNORR>
 KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base128, ge_cached* tbl)
@@ -329,6 +337,168 @@ KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uin
     uint32_t enc[8];
     ge_compress(enc, Q);
     return sig_finish<SCHNORR>(f, enc, sig_w);
+}
+
+// ---------------------------------------------------------------------------------------
+// the same verifiers with half-size scalars (half.cuh): 128 doublings instead of 253
+// ---------------------------------------------------------------------------------------
+//   W = (u*s mod L)*B + |v|*A' + u*R',   A' = -sign(v)*A,  R' = -R,   accept <=> W is the identity
+// with (u, v) = sc_half(h).  One signed radix-16 table each for A' and R' (tbl[0..7], tbl[8..15]); the
+// 253-bit multiple of B is split at 2^128 and walks two radix-256 tables, base256[j] = (j+1) B and
+// base256[128 + j] = (j+1) 2^128 B.  The number of windows is BLOCK-uniform (the loop holds a block
+// barrier): the kernel takes the maximum over its threads, 33 for almost every block of honest input.
+#define KB_F_ROK 128u  // R decodes            (ge.rs:124)
+#define KB_HALF_MIN_WINDOWS 31   // the fixed-base digits sit at windows 0, 2, ..., 30
+
+// What the preparation hands to the main loop: the two operand points (affine, Z = 1), the three scalars.
+struct kb_half_rec {
+    fe ax, ay, at;    // A' = -sign(v) * A
+    fe rx, ry, rt;    // R' = -R
+    uint32_t w[8];    // u*s mod L
+    uint32_t u[8];    // odd, > 0
+    uint32_t v[8];    // |v|
+    uint32_t f;       // KB_F_* flags
+    int nwin;         // windows this signature needs (0 when it is off the fast path)
+};
+// byte-level checks, both decompressions, challenge hash, lattice step
+template <bool SCHNORR>
+KB_FN void sig_half_prep(kb_half_rec& rec, const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen)
+{
+    const uint32_t* r_w = sig_w;
+    const uint32_t* s_w = sig_w + 8;
+    uint32_t f = 0;
+    f |= sc_is_canonical(s_w) ? KB_F_SC : 0u;
+    f |= pt_is_canonical(r_w) ? KB_F_RC : 0u;
+    f |= pt_is_small_order_bytes(r_w) ? KB_F_RS : 0u;
+    f |= pt_is_canonical(pk_w) ? KB_F_AC : 0u;
+    f |= pt_is_small_order_bytes(pk_w) ? KB_F_AS : 0u;
+    const uint32_t pre_ok = (f & (KB_F_SC | KB_F_RC | KB_F_RS)) == (KB_F_SC | KB_F_RC);
+    // one copy of the decompression code for both points (the kernel is instruction-cache bound)
+    uint32_t dec = 0;
+    KB_NOUNROLL
+    for (int k = 0; k < 2; k++) {
+        ge_p3 p;
+        dec |= ge_decompress(p, k ? r_w : pk_w) << k;
+        fe_neg(p.X, p.X);
+        fe_neg(p.T, p.T);
+        if (k) { rec.rx = p.X; rec.ry = p.Y; rec.rt = p.T; }
+        else { rec.ax = p.X; rec.ay = p.Y; rec.at = p.T; }
+    }
+    f |= (dec & 2u) ? KB_F_ROK : 0u;
+    // EdDSA never looks at A when an earlier check fails; Schnorr decodes A before is_canonical(A)
+    if (SCHNORR || (pre_ok && (f & KB_F_AC))) f |= (dec & 1u) ? KB_F_AOK : 0u;
+    const bool fast = pre_ok && (dec & 2u) && (f & (KB_F_AC | KB_F_AS | KB_F_AOK)) == (KB_F_AC | KB_F_AOK);
+    if (fast) {
+        uint32_t digest[16], hk[8];
+        const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        sha512_ram(digest, r_w, pk_w, msg, mlen);
+        sc_reduce512(hk, digest);
+        kb_halfsc hs;
+        sc_half(hs, hk);
+        sc_muladd(rec.w, hs.u, s_w, zero);
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) {
+            rec.u[i] = hs.u[i];
+            rec.v[i] = hs.v[i];
+        }
+        fe nx, nt;   // A' = +A when v is negative
+        fe_neg(nx, rec.ax);
+        fe_neg(nt, rec.at);
+        fe_cmov(rec.ax, nx, hs.vneg);
+        fe_cmov(rec.at, nt, hs.vneg);
+        rec.nwin = hs.bits / 4 + 1;
+        f |= KB_F_FAST;
+    } else {
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) rec.w[i] = rec.u[i] = rec.v[i] = 0;
+        fe_set(rec.ax, 0); fe_set(rec.ay, 1); fe_set(rec.at, 0);
+        fe_set(rec.rx, 0); fe_set(rec.ry, 1); fe_set(rec.rt, 0);
+        rec.nwin = 0;
+    }
+    rec.f = f;
+}
+// digit strings and the two per-signature tables: tbl[0..7] = 1..8 A', tbl[8..15] = 1..8 R'
+KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, const kb_half_rec& rec)
+{
+    sc_recode256(dw, rec.w);
+    sc_recode16(eu, rec.u);
+    sc_recode16(ev, rec.v);
+    // A magnitude below 2^(4k - 1) fits k signed radix-16 digits if the top one may be +8 (the tables hold
+    // 1P..8P): the standard recoding turns a top digit of 8 into (-8, carry 1); undo exactly that.
+    const int k = rec.nwin;
+    if (k > 0 && k < 64) {
+        if (eu[k] == 1) { eu[k] = 0; eu[k - 1] = 8; }
+        if (ev[k] == 1) { ev[k] = 0; ev[k - 1] = 8; }
+    }
+    KB_NOUNROLL
+    for (int q = 0; q < 2; q++) {
+        ge_p3 p;
+        p.X = q ? rec.rx : rec.ax;
+        p.Y = q ? rec.ry : rec.ay;
+        p.T = q ? rec.rt : rec.at;
+        fe_set(p.Z, 1);
+        ge_build_table8(tbl + 8 * q, p);
+    }
+}
+// W = sum over the three digit strings; every thread of the block runs `nwin` windows (>= KB_HALF_MIN_WINDOWS).
+KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* base256)
+{
+    ge_cached c;
+    ge_identity(h);
+    KB_NOUNROLL
+    for (int i = nwin - 1; i >= 0; i--) {
+        KB_LOCKSTEP();
+        if (i != nwin - 1) {
+            KB_NOUNROLL
+            for (int k = 0; k < 4; k++) ge_dbl_rt(h, h, k == 3);
+        }
+        // one addition body for all four operands (the fixed-base entries are widened to the cached form, Z = 1)
+        const int nadd = (!(i & 1) && i <= 30) ? 4 : 2;
+        KB_NOUNROLL
+        for (int a = 0; a < nadd; a++) {
+            if (a < 2) {
+                ge_select_cached<false>(c, tbl + 8 * a, a ? eu[i] : ev[i]);
+            } else {
+                const int d = dw[(i >> 1) + 16 * (a - 2)];
+                const uint32_t neg = (uint32_t)d >> 31;
+                const int babs = (d ^ -(int)neg) + (int)neg;
+                ge_cached_identity(c);
+                if (babs != 0) {
+                    const ge_precomp* e = base256 + 128 * (a - 2) + (babs - 1);
+                    c.YpX = e->ypx;
+                    c.YmX = e->ymx;
+                    c.T2d = e->xy2d;
+                }
+                ge_cached_cneg(c, neg);
+            }
+            ge_add_rt(h, h, c, a + 1 < nadd);   // T is dead after the last addition of a window (a doubling or the end follows)
+        }
+    }
+}
+// the identity is (0 : Z : Z)
+template <bool SCHNORR>
+KB_FN uint32_t sig_half_finish(uint32_t f, const ge_p3& W)
+{
+    if (f & KB_F_FAST) {
+        fe d;
+        fe_sub(d, W.Y, W.Z);
+        if (fe_is_zero(W.X) & fe_is_zero(d)) return KB_SIG_OK;
+    }
+    return sig_classify<SCHNORR>(f, (f & KB_F_ROK) ? 1u : 0u);
+}
+// one signature start to finish — the composition k_verify_half implements
+template <bool SCHNORR>
+KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base256, ge_cached* tbl, int min_windows = KB_HALF_MIN_WINDOWS)
+{
+    kb_half_rec rec;
+    sig_half_prep<SCHNORR>(rec, pk_w, sig_w, msg, mlen);
+    int16_t dw[32];
+    int8_t eu[64], ev[64];
+    sig_half_setup(dw, eu, ev, tbl, rec);
+    const int nwin = rec.nwin < min_windows ? min_windows : rec.nwin;
+    ge_p3 W;
+    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, base256);
+    return sig_half_finish<SCHNORR>(rec.f, W);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ static void ld(uint32_t* w, const uint8_t* b, int nwords) { memcpy(w, b, 4 * nwo
 static void st(uint8_t* b, const uint32_t* w, int nwords) { memcpy(b, w, 4 * nwords); }
 
 static ge_precomp g_base[64 * 8];
-static ge_precomp g_base128[128];
+static ge_precomp g_base128[256];   // (j+1) B, then (j+1) 2^128 B
 static int g_base_ready = 0;
 static void base_init()
 {
@@ -25,6 +25,11 @@ static void base_init()
     const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
     pos.X = bx; pos.Y = by; pos.T = bt; fe_set(pos.Z, 1);
     kb_base_window(g_base128, pos, 128);
+    {
+        ge_p3 hi = pos;
+        for (int k = 0; k < 128; k++) ge_dbl<true>(hi, hi);
+        kb_base_window(g_base128 + 128, hi, 128);
+    }
     for (int w = 0; w < 64; w++) {
         kb_base_window(g_base + 8 * w, pos);
         for (int k = 0; k < 4; k++) ge_dbl<true>(pos, pos);
@@ -172,6 +177,27 @@ int emu_sig_verify(int schnorr, const uint8_t* pk, const uint8_t* msg, uint64_t 
     base_init();
     ld(pw, pk, 8); ld(sw, sig, 16);
     return schnorr ? (int)sig_verify<true>(pw, sw, msg, mlen, g_base128, tbl) : (int)sig_verify<false>(pw, sw, msg, mlen, g_base128, tbl);
+}
+// the half-size-scalar verifier (ops.cuh sig_verify_half); min_windows lets a test force longer loops
+int emu_sig_verify_half(int schnorr, const uint8_t* pk, const uint8_t* msg, uint64_t mlen, const uint8_t* sig, int min_windows)
+{
+    uint32_t pw[8], sw[16];
+    ge_cached tbl[16];
+    base_init();
+    ld(pw, pk, 8); ld(sw, sig, 16);
+    if (min_windows < KB_HALF_MIN_WINDOWS) min_windows = KB_HALF_MIN_WINDOWS;
+    return schnorr ? (int)sig_verify_half<true>(pw, sw, msg, mlen, g_base128, tbl, min_windows) : (int)sig_verify_half<false>(pw, sw, msg, mlen, g_base128, tbl, min_windows);
+}
+// sc_half: out = u (32 bytes) || |v| (32 bytes); returns bits | vneg << 16
+int emu_sc_half(uint8_t* out, const uint8_t* h)
+{
+    uint32_t hw[8];
+    kb_halfsc hs;
+    ld(hw, h, 8);
+    sc_half(hs, hw);
+    st(out, hs.u, 8);
+    st(out + 32, hs.v, 8);
+    return hs.bits | (int)(hs.vneg << 16);
 }
 // PubPoly::eval via the short-scalar Horner used by the eval kernel
 int emu_pubpoly_eval(uint8_t* out, const uint8_t* commits, int t, uint32_t idx)

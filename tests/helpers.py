@@ -303,3 +303,38 @@ def pack_batch(pks, msgs, sigs):
     pk = np.frombuffer(b"".join(pks), dtype=np.uint8).reshape(-1, 32).copy()
     sg = np.frombuffer(b"".join(sigs), dtype=np.uint8).reshape(-1, 64).copy()
     return pk, flat, off, sg
+
+
+def make_mixed_order_sigs(count: int, seed: int = 1):
+    """Signatures whose public key AND R carry a small-order component (both pass the reference's small-order
+    filter, which only rejects points that are ENTIRELY of small order).  With A = a*B + T, R = r*B + T' the
+    reference's cofactorless equation s*B == R + h*A holds iff T' + h*T == 0.  Returns `count` triples
+    (pk, msg, sig) for which it holds ("accept") and `count` near misses for which it fails ("reject") although
+    8*(s*B - R - h*A) == 0 — the inputs on which a cofactored, a batched or a mod-L-shortened verifier would
+    disagree with the reference."""
+    import random
+
+    from oracle import ed25519_bigint as O
+
+    rnd = random.Random(seed)
+    tors = [O.point_decode(k) for k in O.WEAK_KEYS[2:4]]          # the two encodings of order-8 points
+    t8 = tors[0]
+    torsion = [O.IDENTITY]
+    for _ in range(7):
+        torsion.append(O.point_add(torsion[-1], t8))
+    good, bad = [], []
+    while len(good) < count or len(bad) < count:
+        a = rnd.randrange(1, O.L)
+        r = rnd.randrange(1, O.L)
+        T = torsion[rnd.randrange(1, 8)]
+        Tp = torsion[rnd.randrange(0, 8)]
+        A = O.point_add(O._mul_int(a, O.BASE), T)
+        R = O.point_add(O._mul_int(r, O.BASE), Tp)
+        pk, rb = O.point_encode(A), O.point_encode(R)
+        msg = rnd.randbytes(rnd.randrange(0, 100))
+        h = int.from_bytes(O.challenge(rb, pk, msg), "little")
+        s = (r + h * a) % O.L
+        sig = rb + s.to_bytes(32, "little")
+        holds = O.point_eq(O.point_add(Tp, O._mul_int(h, T)), O.IDENTITY)
+        (good if holds else bad).append((pk, msg, sig))
+    return good[:count], bad[:count]

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import ROOT, load_c_oracle, load_sign_input, make_sig_batch
+from helpers import ROOT, load_c_oracle, load_sign_input, make_mixed_order_sigs, make_sig_batch
 from oracle import ed25519_bigint as O
 
 P = O.P
@@ -27,6 +27,8 @@ def emu():
     E = ctypes.CDLL(so)
     E.emu_sha512_ram.argtypes = [ctypes.c_char_p] * 4 + [ctypes.c_uint64]
     E.emu_sig_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    E.emu_sig_verify_half.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_int]
+    E.emu_sc_half.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
     E.emu_eddsa_sign.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64]
     E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
@@ -129,6 +131,55 @@ def test_verify_state_machine(emu, coracle, golden_records):
     for _, pk, sig, msg in golden_records[::32]:
         assert emu.emu_sig_verify(0, pk, msg, len(msg), sig) == 0
         assert emu.emu_sig_verify(1, pk, msg, len(msg), sig) == 0
+
+
+def test_half_size_lattice_step(emu):
+    """sc_half (csrc/half.cuh): u odd and positive, v == u*h (mod 8L), bits = max bit length; about 128 bits
+    for hash-like h, and still a valid (if long) vector for adversarial h."""
+    rnd = random.Random(23)
+    out = ctypes.create_string_buffer(64)
+    N = 8 * O.L
+    special = [0, 1, 2, 3, 7, 8, O.L - 1, O.L - 2, O.L // 2, O.L // 3, 2**128, 2**127 + 1, 2**64, 2**200 + 5, (N // 3) % O.L, (N // 5 + 1) % O.L]
+    worst = 0
+    for k in range(1200):
+        h = special[k] if k < len(special) else rnd.randrange(O.L)
+        r = emu.emu_sc_half(out, b32(h))
+        bits, vneg = r & 0xFFFF, r >> 16
+        u = int.from_bytes(out.raw[:32], "little")
+        v = int.from_bytes(out.raw[32:], "little")
+        assert u & 1 and u > 0
+        assert (u * h - (-v if vneg else v)) % N == 0
+        assert bits == max(u.bit_length(), v.bit_length(), 1) and bits <= 253
+        if k >= len(special):
+            worst = max(worst, bits)
+    assert worst <= 140   # 33 or 34 radix-16 windows for honest challenges
+
+
+def test_verify_half_state_machine(emu, coracle, golden_records):
+    """The half-size-scalar verifier returns the reference's status for every mutation class, for valid and
+    near-miss signatures under keys with a small-order component, and independently of how many windows the
+    block-uniform loop is forced to run."""
+    pks, msgs, sigs = make_sig_batch(golden_records[1:256:3], 24 * 4, bad_every=1)
+    seen = set()
+    for pk, msg, sig in zip(pks, msgs, sigs):
+        for sch in (0, 1):
+            want = coracle.schnorr_verify(pk, msg, sig) if sch else coracle.eddsa_verify(pk, msg, sig)
+            assert emu.emu_sig_verify_half(sch, pk, msg, len(msg), sig, 0) == want
+            seen.add(want)
+    assert seen == {0, 2, 3, 4, 5, 6, 7, 8}
+    for k, (_, pk, sig, msg) in enumerate(golden_records[::16]):
+        for sch in (0, 1):
+            assert emu.emu_sig_verify_half(sch, pk, msg, len(msg), sig, (0, 34, 40, 64)[k % 4]) == 0
+    good, bad = make_mixed_order_sigs(12)
+    for sch in (0, 1):
+        for pk, msg, sig in good:
+            assert O.eddsa_verify(pk, msg, sig) == 0 and coracle.eddsa_verify(pk, msg, sig) == 0
+            assert emu.emu_sig_verify_half(sch, pk, msg, len(msg), sig, 0) == 0
+            assert emu.emu_sig_verify(sch, pk, msg, len(msg), sig) == 0
+        for pk, msg, sig in bad:
+            assert O.schnorr_verify(pk, msg, sig) == 8 and coracle.schnorr_verify(pk, msg, sig) == 8
+            assert emu.emu_sig_verify_half(sch, pk, msg, len(msg), sig, 0) == 8
+            assert emu.emu_sig_verify(sch, pk, msg, len(msg), sig) == 8
 
 
 def test_verify_oracles_agree_on_mutations(coracle, golden_records):

@@ -6,7 +6,9 @@ import importlib
 import numpy as np
 import pytest
 
-from helpers import load_sign_input, make_sig_batch, pack_batch, random_scalars, xof_bytes
+import os
+
+from helpers import load_sign_input, make_mixed_order_sigs, make_sig_batch, pack_batch, random_scalars, xof_bytes
 from oracle import ed25519_bigint as O
 
 pytestmark = pytest.mark.gpu
@@ -22,6 +24,19 @@ def ctx(kb):
     c = kb.Context(0)
     kb.host.set_default_context(c)
     yield c
+
+
+@pytest.fixture(scope="module")
+def ctx_full(kb):
+    """A context that runs the full-length (253-doubling, two-launch) verify kernels instead of the default
+    half-size-scalar kernel (csrc/half.cuh): both must give the reference's statuses."""
+    os.environ["KB_VERIFY_FULL"] = "1"
+    try:
+        c = kb.Context(0)
+    finally:
+        del os.environ["KB_VERIFY_FULL"]
+    yield c
+    c.close()
 
 
 def _golden_pks(records, n):
@@ -139,16 +154,65 @@ def test_verify_golden_file(ctx, golden_records, schnorr):
     assert not st.any()
 
 
+@pytest.mark.parametrize("path", ["half", "full"])
 @pytest.mark.parametrize("schnorr", [False, True])
-def test_verify_reject_classes(ctx, coracle, golden_records, schnorr):
+def test_verify_reject_classes(ctx, ctx_full, coracle, golden_records, schnorr, path):
     """Every mutation class (eddsa_test.rs:111-272, schnorr_test.rs:6-110 and SURVEY §A cases):
     status must equal the oracle's, i.e. the reference's error variant in ITS check order."""
+    c = ctx if path == "half" else ctx_full
     pks, msgs, sigs = make_sig_batch(golden_records, 4096, bad_every=2)
     pk, flat, off, sg = pack_batch(pks, msgs, sigs)
-    got = ctx.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+    got = c.verify_batch(pk, flat, off, sg, schnorr=schnorr)
     want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
     assert (got == want).all(), np.nonzero(got != want)[0][:10]
     assert set(np.unique(want)) == {0, 2, 3, 4, 5, 6, 7, 8}
+
+
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_verify_mixed_order_keys(ctx, ctx_full, coracle, golden_records, schnorr):
+    """Keys and R values that carry a small-order component (they pass the reference's small-order filter): the
+    reference's cofactorless equation accepts exactly those with T' + h*T = 0.  Both kernels must agree with
+    the oracle on the accepted ones AND on the near misses (8*defect = 0), which is where a shortened-scalar
+    verifier that reduced modulo L instead of 8L would go wrong."""
+    good, bad = make_mixed_order_sigs(96, seed=5)
+    items = []
+    for k in range(96):
+        items += [good[k], bad[k], (golden_records[k][1], golden_records[k][3], golden_records[k][2])]
+    pk, flat, off, sg = pack_batch([x[0] for x in items], [x[1] for x in items], [x[2] for x in items])
+    want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
+    assert (want.reshape(-1, 3) == np.array([0, 8, 0])).all()
+    for c in (ctx, ctx_full):
+        got = c.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+        assert (got == want).all(), np.nonzero(got != want)[0][:10]
+
+
+def test_verify_paths_agree_on_random_batch(kb, ctx, ctx_full, coracle):
+    """2^16 fresh signatures (signed on the GPU), 1/8 damaged in s, R, A or the message: the half-size-scalar
+    kernel, the full-length kernels and (on a slice) the oracle give the same statuses."""
+    n = 1 << 16
+    seeds = np.frombuffer(xof_bytes("kyber-b200/test/half/seed", 32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    flat = np.frombuffer(xof_bytes("kyber-b200/test/half/msg", 64 * n), dtype=np.uint8).copy()
+    off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(64))
+    sigs, pks = ctx.eddsa_sign_batch(seeds, flat, off)
+    sigs, pks, flat = sigs.copy(), pks.copy(), flat.copy()
+    rng = np.random.default_rng(9)
+    for i in range(0, n, 8):
+        kind = (i // 8) % 4
+        if kind == 0:
+            sigs[i, 32 + rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+        elif kind == 1:
+            sigs[i, rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+        elif kind == 2:
+            pks[i, rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+        else:
+            flat[64 * i + rng.integers(0, 64)] ^= 1
+    a = ctx.verify_batch(pks, flat, off, sigs)
+    b = ctx_full.verify_batch(pks, flat, off, sigs)
+    assert (a == b).all(), np.nonzero(a != b)[0][:10]
+    assert (a.reshape(-1, 8)[:, 1:] == 0).all() and a.reshape(-1, 8)[:, 0].all()
+    m = 4096
+    want = coracle.verify_batch(pks[:m], flat[:64 * m], off[:m + 1], sigs[:m], nthreads=8)
+    assert (a[:m] == want).all()
 
 
 def test_verify_host_mirror_errors(kb, ctx, golden_records):
