@@ -19,7 +19,8 @@ struct kb_ctx {
     cudaStream_t stream;
     cudaStream_t stream2;    // second copy/compute lane of the pipelined host entry points
     ge_precomp* base_table;  // 64 x 8 entries: (j+1) * 16^w * B
-    ge_precomp* base128;     // 256 entries: (j+1) * B, then (j+1) * 2^128 * B
+    ge_precomp* base128;     // 128 entries: (j+1) * B
+    ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     void* slot[KB_NSLOTS];
     size_t slot_bytes[KB_NSLOTS];
@@ -172,10 +173,13 @@ int kb_ctx_create(int device, kb_ctx** out)
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 256) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->comb, sizeof(ge_precomp) * KB_COMB_POS * KB_COMB_HALF) == cudaSuccess;
     if (ok) {
         k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
-        k_base256_init<<<2, 32, 0, ctx->stream>>>(ctx->base128);
+        k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
+        k_comb_init<<<kb_blocks((size_t)KB_COMB_POS * KB_COMB_HALF, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(ctx->comb, ctx->base_table);
+        ctx->launches++;
         const char* vf = getenv("KB_VERIFY_FULL");
         ctx->verify_full = (vf && vf[0] == '1') ? 1 : 0;
         ctx->launches += 2;
@@ -203,6 +207,7 @@ void kb_ctx_destroy(kb_ctx* ctx)
         if (ctx->slot[s]) cudaFree(ctx->slot[s]);
     if (ctx->base_table) cudaFree(ctx->base_table);
     if (ctx->base128) cudaFree(ctx->base128);
+    if (ctx->comb) cudaFree(ctx->comb);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);
@@ -279,11 +284,11 @@ static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const ui
         if (schnorr) {
             k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
             KB_LAUNCHED();
-            k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->base128);
+            k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
         } else {
             k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
             KB_LAUNCHED();
-            k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->base128);
+            k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
         }
         KB_LAUNCHED();
         return KB_OK;

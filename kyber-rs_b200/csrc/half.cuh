@@ -42,14 +42,18 @@ KB_FN uint32_t kb_shf_l(uint32_t lo, uint32_t hi, uint32_t s)
     return __funnelshift_l(lo, hi, s);
 #endif
 }
-// bit length of a 256-bit integer (0 for 0)
+// bit length of a 256-bit integer (0 for 0): binary search over the words
 KB_FN int kb_bitlen8(const uint32_t* a)
 {
-    int bl = 0;
-    KB_UNROLL
-    for (int i = 0; i < 8; i++)
-        if (a[i]) bl = 32 * i + 32 - kb_clz32(a[i]);
-    return bl;
+    const uint32_t hi4 = a[4] | a[5] | a[6] | a[7];
+    const bool h = hi4 != 0;
+    const uint32_t b0 = h ? a[4] : a[0], b1 = h ? a[5] : a[1], b2 = h ? a[6] : a[2], b3 = h ? a[7] : a[3];
+    const bool m = (b2 | b3) != 0;
+    const uint32_t c0 = m ? b2 : b0, c1 = m ? b3 : b1;
+    const bool l = c1 != 0;
+    const uint32_t w = l ? c1 : c0;
+    const int base = (h ? 128 : 0) + (m ? 64 : 0) + (l ? 32 : 0);
+    return w ? base + 32 - kb_clz32(w) : 0;
 }
 // y = a << s truncated to 256 bits, s in [0, 256)
 KB_FN void kb_shl8(uint32_t* y, const uint32_t* a, int s)
@@ -80,6 +84,15 @@ struct kb_halfsc {
     int bits;        // max(bitlen(u), bitlen(|v|))
 };
 
+// Candidates are only looked at once the remainders are below 2^KB_HALF_TRACK: the short vectors live where
+// both coordinates are near 2^128, and the first hundred iterations then carry no bookkeeping at all.
+#define KB_HALF_TRACK 144
+
+// The run is ONE loop whose body is a single binary long-division step followed by a predicated exchange of
+// the two rows: the lanes of a warp are at different places of their Euclidean sequences, and a loop nest (or
+// two role-swapped copies of the body) would make every lane pay for the slowest one.
+// Invariants: r0 >= r1; r0 = -/+ t0 * h, r1 = +/- t1 * h (mod 8L), the t's are magnitudes and the signs
+// alternate from row to row.  Every intermediate row is a lattice vector, hence a candidate.
 KB_FN void sc_half(kb_halfsc& o, const uint32_t* h)
 {
     const uint32_t n8l[8] = KB_8L_WORDS;
@@ -93,14 +106,16 @@ KB_FN void sc_half(kb_halfsc& o, const uint32_t* h)
         o.u[i] = t1[i];
         o.v[i] = h[i];
     }
-    // invariant: r0 = sg0 * t0 * h, r1 = -sg0 * t1 * h (mod N), r0 >= r1, t's are magnitudes
+    // row 0 starts as (8L, 0): 8L = -0*h;  row 1 as (h, 1): h = +1*h
     uint32_t sg0neg = 1;
     int la = 256, lb = kb_bitlen8(h), lt1 = 1;
     o.vneg = 0;
     o.bits = lb > 1 ? lb : 1;
-    // every later vector has |u| >= t1, so once bitlen(t1) reaches the best cost nothing can improve
     KB_NOUNROLL
-    while (lb != 0 && lt1 < o.bits) {
+    while (lb != 0) {
+        // every later vector has |u| >= t1: once bitlen(t1) reaches the best cost nothing can improve
+        // (lt1 may lag behind while the rows are not tracked, which only delays the exit)
+        if (la <= KB_HALF_TRACK && lt1 >= o.bits) break;
         int s = la - lb;
         uint32_t y[8], d[8];
         kb_shl8(y, r1, s);
@@ -114,18 +129,23 @@ KB_FN void sc_half(kb_halfsc& o, const uint32_t* h)
         KB_UNROLL
         for (int i = 0; i < 8; i++) r0[i] = d[i];
         la = kb_bitlen8(r0);
-        const int lt0 = kb_bitlen8(t0);
-        const int c = la > lt0 ? la : lt0;
-        if ((t0[0] & 1u) && c < o.bits) {
-            KB_UNROLL
-            for (int i = 0; i < 8; i++) {
-                o.u[i] = t0[i];
-                o.v[i] = r0[i];
+        int lt0 = 0;
+        if (la <= KB_HALF_TRACK) {
+            lt0 = kb_bitlen8(t0);
+            const int c = la > lt0 ? la : lt0;
+            if ((t0[0] & 1u) && c < o.bits) {
+                KB_UNROLL
+                for (int i = 0; i < 8; i++) {
+                    o.u[i] = t0[i];
+                    o.v[i] = r0[i];
+                }
+                o.vneg = sg0neg;
+                o.bits = c;
             }
-            o.vneg = sg0neg;
-            o.bits = c;
         }
-        if (kb_sub8(d, r0, r1)) {   // r0 < r1: the division step is complete, exchange the rows
+        bool swap = la < lb;
+        if (la == lb) swap = kb_sub8(d, r0, r1) != 0;
+        if (swap) {   // the division step is complete: exchange the rows
             KB_UNROLL
             for (int i = 0; i < 8; i++) {
                 const uint32_t a = r0[i], b = t0[i];

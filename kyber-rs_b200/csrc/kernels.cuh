@@ -57,18 +57,24 @@ __global__ void k_base_init(ge_precomp* table)
     kb_base_window(table + 8 * w, pos);
 }
 
-// base256[j] = (j+1) * B, base256[128 + j] = (j+1) * 2^128 * B, j = 0..127: the radix-256 fixed-base tables of
-// the verifiers (the full-length path only uses the first half).  One block per half.
-__global__ void k_base256_init(ge_precomp* table)
+// base128[j] = (j+1) * B, j = 0..127: the radix-256 fixed-base table of the full-length verifiers
+__global__ void k_base128_init(ge_precomp* table)
 {
-    if (threadIdx.x != 0 || blockIdx.x > 1) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ge_p3 pos;
     const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
     pos.X = bx; pos.Y = by; pos.T = bt;
     fe_set(pos.Z, 1);
-    if (blockIdx.x == 1)
-        for (int k = 0; k < 128; k++) ge_dbl<true>(pos, pos);
-    kb_base_window(table + 128 * blockIdx.x, pos, 128);
+    kb_base_window(table, pos, 128);
+}
+// comb[p][j] = (j+1) * 2^(13 p) * B: the fixed-base comb of the half-size-scalar verifiers (ops.cuh)
+__global__ void __launch_bounds__(KB_THREADS) k_comb_init(ge_precomp* comb, const ge_precomp* base_table)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= KB_COMB_POS * KB_COMB_HALF) return;
+    ge_precomp e;
+    kb_comb_entry(e, k / KB_COMB_HALF, k % KB_COMB_HALF, base_table);
+    comb[k] = e;
 }
 
 // ---- shared tail of every point-producing kernel: Montgomery's trick over KB_INV_K results -----
@@ -465,13 +471,11 @@ __global__ void __launch_bounds__(KB_THREADS, 4) k_verify_half_prep(size_t n, co
 #define KB_VERIFY_HALF_MINBLOCKS 3
 #endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* table256)
+__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb)
 {
-    __shared__ uint4 base_raw[256 * 24 / 4];
     __shared__ int s_nwin;
-    ge_precomp* base256 = reinterpret_cast<ge_precomp*>(base_raw);
     if (threadIdx.x == 0) s_nwin = KB_HALF_MIN_WINDOWS;
-    kb_stage(reinterpret_cast<uint32_t*>(base256), reinterpret_cast<const uint32_t*>(table256), 256 * 24);
+    __syncthreads();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;   // tail threads redo the last item so that they reach the block barriers
     if (!live) i = n - 1;
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify
         rec.nwin = (int)(a.x >> 8);
     }
     ge_cached tbl[16];
-    int16_t dw[32];
+    int16_t dw[KB_COMB_POS];
     int8_t eu[64], ev[64];
     sig_half_setup(dw, eu, ev, tbl, rec);
     // the window count of the block = the longest any of its signatures needs
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify
     __syncthreads();
     nwin = s_nwin;
     ge_p3 W;
-    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, base256);
+    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, comb);
     if (live) status[i] = (uint8_t)sig_half_finish<SCHNORR>(rec.f, W);
 }
 

@@ -343,12 +343,49 @@ KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uin
 // the same verifiers with half-size scalars (half.cuh): 128 doublings instead of 253
 // ---------------------------------------------------------------------------------------
 //   W = (u*s mod L)*B + |v|*A' + u*R',   A' = -sign(v)*A,  R' = -R,   accept <=> W is the identity
-// with (u, v) = sc_half(h).  One signed radix-16 table each for A' and R' (tbl[0..7], tbl[8..15]); the
-// 253-bit multiple of B is split at 2^128 and walks two radix-256 tables, base256[j] = (j+1) B and
-// base256[128 + j] = (j+1) 2^128 B.  The number of windows is BLOCK-uniform (the loop holds a block
-// barrier): the kernel takes the maximum over its threads, 33 for almost every block of honest input.
+// with (u, v) = sc_half(h).  One signed radix-16 table each for A' and R' (tbl[0..7], tbl[8..15]) inside the
+// doubling loop.  The multiple of B needs no doublings at all: it is a comb over a table that is computed once
+// per context and shared by every signature, comb[p][j] = (j+1) * 2^(13 p) * B, p = 0..19, j = 0..4095 (7.9 MB,
+// L2-resident): 20 additions after the loop instead of 32 inside it.  The number of windows is BLOCK-uniform
+// (the loop holds a block barrier): the kernel takes the maximum over its threads, 33 for almost every block
+// of honest input.
 #define KB_F_ROK 128u  // R decodes            (ge.rs:124)
-#define KB_HALF_MIN_WINDOWS 31   // the fixed-base digits sit at windows 0, 2, ..., 30
+#define KB_HALF_MIN_WINDOWS 1
+#define KB_COMB_BITS 13
+#define KB_COMB_POS 20
+#define KB_COMB_HALF (1 << (KB_COMB_BITS - 1))
+
+// signed radix-2^13 digits of a scalar < 2^253: d[0..19] in (-4096, 4096]
+KB_FN void sc_recode_comb(int16_t* d, const uint32_t* s)
+{
+    int carry = 0;
+    KB_UNROLL
+    for (int p = 0; p < KB_COMB_POS; p++) {
+        const int bit = KB_COMB_BITS * p, wi = bit >> 5, sh = bit & 31;
+        uint32_t x = s[wi] >> sh;
+        if (sh + KB_COMB_BITS > 32 && wi + 1 < 8) x |= s[wi + 1] << (32 - sh);
+        int v = (int)(x & ((1u << KB_COMB_BITS) - 1u)) + carry;
+        carry = v > KB_COMB_HALF;
+        d[p] = (int16_t)(v - (carry << KB_COMB_BITS));
+    }
+}
+KB_FN void kb_ld_precomp(ge_cached& c, const ge_precomp* e)
+{
+#if defined(KB_HOST_EMU)
+    c.YpX = e->ypx;
+    c.YmX = e->ymx;
+    c.T2d = e->xy2d;
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(e);
+    uint4 a;
+    a = __ldg(q + 0); c.YpX.v[0] = a.x; c.YpX.v[1] = a.y; c.YpX.v[2] = a.z; c.YpX.v[3] = a.w;
+    a = __ldg(q + 1); c.YpX.v[4] = a.x; c.YpX.v[5] = a.y; c.YpX.v[6] = a.z; c.YpX.v[7] = a.w;
+    a = __ldg(q + 2); c.YmX.v[0] = a.x; c.YmX.v[1] = a.y; c.YmX.v[2] = a.z; c.YmX.v[3] = a.w;
+    a = __ldg(q + 3); c.YmX.v[4] = a.x; c.YmX.v[5] = a.y; c.YmX.v[6] = a.z; c.YmX.v[7] = a.w;
+    a = __ldg(q + 4); c.T2d.v[0] = a.x; c.T2d.v[1] = a.y; c.T2d.v[2] = a.z; c.T2d.v[3] = a.w;
+    a = __ldg(q + 5); c.T2d.v[4] = a.x; c.T2d.v[5] = a.y; c.T2d.v[6] = a.z; c.T2d.v[7] = a.w;
+#endif
+}
 
 // What the preparation hands to the main loop: the two operand points (affine, Z = 1), the three scalars.
 struct kb_half_rec {
@@ -420,7 +457,7 @@ KB_FN void sig_half_prep(kb_half_rec& rec, const uint32_t* pk_w, const uint32_t*
 // digit strings and the two per-signature tables: tbl[0..7] = 1..8 A', tbl[8..15] = 1..8 R'
 KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, const kb_half_rec& rec)
 {
-    sc_recode256(dw, rec.w);
+    sc_recode_comb(dw, rec.w);
     sc_recode16(eu, rec.u);
     sc_recode16(ev, rec.v);
     // A magnitude below 2^(4k - 1) fits k signed radix-16 digits if the top one may be +8 (the tables hold
@@ -440,40 +477,64 @@ KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, c
         ge_build_table8(tbl + 8 * q, p);
     }
 }
-// W = sum over the three digit strings; every thread of the block runs `nwin` windows (>= KB_HALF_MIN_WINDOWS).
-KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* base256)
+// W = |v|*A' + u*R' by `nwin` shared windows of four doublings, then the comb for the multiple of B.  Every thread
+// of the block runs the same trip count; one addition body serves all three operands (the comb entries are widened
+// to the cached form, Z = 1).
+KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
 {
     ge_cached c;
     ge_identity(h);
     KB_NOUNROLL
-    for (int i = nwin - 1; i >= 0; i--) {
+    for (int i = nwin - 1; i >= -KB_COMB_POS; i--) {
         KB_LOCKSTEP();
-        if (i != nwin - 1) {
+        if (i >= 0 && i != nwin - 1) {
             KB_NOUNROLL
             for (int k = 0; k < 4; k++) ge_dbl_rt(h, h, k == 3);
         }
-        // one addition body for all four operands (the fixed-base entries are widened to the cached form, Z = 1)
-        const int nadd = (!(i & 1) && i <= 30) ? 4 : 2;
+        const int nadd = i >= 0 ? 2 : 1;
         KB_NOUNROLL
         for (int a = 0; a < nadd; a++) {
-            if (a < 2) {
+            if (i >= 0) {
                 ge_select_cached<false>(c, tbl + 8 * a, a ? eu[i] : ev[i]);
             } else {
-                const int d = dw[(i >> 1) + 16 * (a - 2)];
+                const int p = -1 - i;
+                const int d = dw[p];
                 const uint32_t neg = (uint32_t)d >> 31;
                 const int babs = (d ^ -(int)neg) + (int)neg;
                 ge_cached_identity(c);
-                if (babs != 0) {
-                    const ge_precomp* e = base256 + 128 * (a - 2) + (babs - 1);
-                    c.YpX = e->ypx;
-                    c.YmX = e->ymx;
-                    c.T2d = e->xy2d;
-                }
+                if (babs != 0) kb_ld_precomp(c, comb + (size_t)p * KB_COMB_HALF + (babs - 1));
                 ge_cached_cneg(c, neg);
             }
-            ge_add_rt(h, h, c, a + 1 < nadd);   // T is dead after the last addition of a window (a doubling or the end follows)
+            // T is dead when a doubling (or the end) follows
+            const bool dead = (i > 0 && a + 1 == nadd) || i == -KB_COMB_POS;
+            ge_add_rt(h, h, c, !dead);
         }
     }
+}
+// comb[p][j] = (j+1) * 2^(13 p) * B in affine (y+x, y-x, 2dxy) form; entries whose multiplier does not fit 255 bits are
+// never addressed by a scalar below 2^253 and hold the identity.  `base` = the 64 x 8 fixed-base table (kb_base_window).
+KB_FN void kb_comb_entry(ge_precomp& out, int p, int j, const ge_precomp* base)
+{
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int bit = KB_COMB_BITS * p, wi = bit >> 5, sh = bit & 31;
+    const uint64_t m = (uint64_t)(j + 1) << sh;
+    ge_precomp_identity(out);
+    if (bit + KB_COMB_BITS + 1 > 255 && ((uint64_t)(j + 1) >> (255 - bit)) != 0) return;
+    s[wi] = (uint32_t)m;
+    if (wi + 1 < 8) s[wi + 1] = (uint32_t)(m >> 32);
+    int8_t e[64];
+    sc_recode16(e, s);
+    ge_p3 h;
+    ge_scalarmult_base<false>(h, e, base);
+    const fe d2 = KB_FE_D2;
+    fe zinv, x, y, xy;
+    fe_invert(zinv, h.Z);
+    fe_mul(x, h.X, zinv);
+    fe_mul(y, h.Y, zinv);
+    fe_add(out.ypx, y, x);
+    fe_sub(out.ymx, y, x);
+    fe_mul(xy, x, y);
+    fe_mul(out.xy2d, xy, d2);
 }
 // the identity is (0 : Z : Z)
 template <bool SCHNORR>
@@ -488,16 +549,16 @@ KB_FN uint32_t sig_half_finish(uint32_t f, const ge_p3& W)
 }
 // one signature start to finish — the composition k_verify_half implements
 template <bool SCHNORR>
-KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* base256, ge_cached* tbl, int min_windows = KB_HALF_MIN_WINDOWS)
+KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen, const ge_precomp* comb, ge_cached* tbl, int min_windows = KB_HALF_MIN_WINDOWS)
 {
     kb_half_rec rec;
     sig_half_prep<SCHNORR>(rec, pk_w, sig_w, msg, mlen);
-    int16_t dw[32];
+    int16_t dw[KB_COMB_POS];
     int8_t eu[64], ev[64];
     sig_half_setup(dw, eu, ev, tbl, rec);
     const int nwin = rec.nwin < min_windows ? min_windows : rec.nwin;
     ge_p3 W;
-    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, base256);
+    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, comb);
     return sig_half_finish<SCHNORR>(rec.f, W);
 }
 

@@ -7,16 +7,17 @@
 // library has no host compute path.
 #define KB_HOST_EMU 1
 #include <string.h>
+#include <vector>
 #include "../../kyber-rs_b200/csrc/ops.cuh"
 #include "../../kyber-rs_b200/csrc/poly.cuh"
 #include "../../kyber-rs_b200/csrc/msm.cuh"
-#include <vector>
 
 static void ld(uint32_t* w, const uint8_t* b, int nwords) { memcpy(w, b, 4 * nwords); }
 static void st(uint8_t* b, const uint32_t* w, int nwords) { memcpy(b, w, 4 * nwords); }
 
 static ge_precomp g_base[64 * 8];
-static ge_precomp g_base128[256];   // (j+1) B, then (j+1) 2^128 B
+static ge_precomp g_base128[128];
+static std::vector<ge_precomp> g_comb;   // fixed-base comb of the half-size-scalar verifiers
 static int g_base_ready = 0;
 static void base_init()
 {
@@ -25,11 +26,6 @@ static void base_init()
     const fe bx = KB_FE_BX, by = KB_FE_BY, bt = KB_FE_BT;
     pos.X = bx; pos.Y = by; pos.T = bt; fe_set(pos.Z, 1);
     kb_base_window(g_base128, pos, 128);
-    {
-        ge_p3 hi = pos;
-        for (int k = 0; k < 128; k++) ge_dbl<true>(hi, hi);
-        kb_base_window(g_base128 + 128, hi, 128);
-    }
     for (int w = 0; w < 64; w++) {
         kb_base_window(g_base + 8 * w, pos);
         for (int k = 0; k < 4; k++) ge_dbl<true>(pos, pos);
@@ -186,7 +182,11 @@ int emu_sig_verify_half(int schnorr, const uint8_t* pk, const uint8_t* msg, uint
     base_init();
     ld(pw, pk, 8); ld(sw, sig, 16);
     if (min_windows < KB_HALF_MIN_WINDOWS) min_windows = KB_HALF_MIN_WINDOWS;
-    return schnorr ? (int)sig_verify_half<true>(pw, sw, msg, mlen, g_base128, tbl, min_windows) : (int)sig_verify_half<false>(pw, sw, msg, mlen, g_base128, tbl, min_windows);
+    if (g_comb.empty()) {
+        g_comb.resize((size_t)KB_COMB_POS * KB_COMB_HALF);
+        for (int k = 0; k < KB_COMB_POS * KB_COMB_HALF; k++) kb_comb_entry(g_comb[k], k / KB_COMB_HALF, k % KB_COMB_HALF, g_base);
+    }
+    return schnorr ? (int)sig_verify_half<true>(pw, sw, msg, mlen, g_comb.data(), tbl, min_windows) : (int)sig_verify_half<false>(pw, sw, msg, mlen, g_comb.data(), tbl, min_windows);
 }
 // sc_half: out = u (32 bytes) || |v| (32 bytes); returns bits | vneg << 16
 int emu_sc_half(uint8_t* out, const uint8_t* h)
