@@ -86,11 +86,53 @@ struct kb_halfsc {
 
 // Candidates are only looked at once the remainders are below 2^KB_HALF_TRACK: the short vectors live where
 // both coordinates are near 2^128, and the first hundred iterations then carry no bookkeeping at all.
+#ifndef KB_HALF_TRACK
 #define KB_HALF_TRACK 144
+#endif
 
-// The run is ONE loop whose body is a single binary long-division step followed by a predicated exchange of
-// the two rows: the lanes of a warp are at different places of their Euclidean sequences, and a loop nest (or
-// two role-swapped copies of the body) would make every lane pay for the slowest one.
+// Lehmer acceleration: while the remainders are far above 2^128 nothing has to be looked at, so the leading 63
+// bits of both rows are reduced on their own (64-bit arithmetic, a few instructions per quotient bit) while a
+// 2x2 cofactor matrix with entries below 2^31 is accumulated; the matrix is then applied to the full rows at
+// once.  Quotient bits are only taken when they are provably not too large for the FULL rows (interval bounds
+// from the cofactors), so the rows stay non-negative and every row remains a lattice vector whatever the
+// truncation does; an under-estimated quotient merely leaves work for the next step.
+#ifndef KB_HALF_LEHMER_MIN
+#define KB_HALF_LEHMER_MIN 152   // batches stop before the rows enter the tracked range
+#endif
+
+KB_FN int kb_clz64(uint64_t x) { return (x >> 32) ? kb_clz32((uint32_t)(x >> 32)) : 32 + kb_clz32((uint32_t)x); }
+// out = a*x - b*y (mod 2^256); the caller guarantees the true value lies in [0, 2^256)
+KB_FN void kb_mulsub8(uint32_t* out, uint32_t a, const uint32_t* x, uint32_t b, const uint32_t* y)
+{
+    uint64_t cp = 0, cq = 0, br = 0;
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        const uint64_t p = (uint64_t)a * x[i] + cp;
+        const uint64_t q = (uint64_t)b * y[i] + cq;
+        cp = p >> 32;
+        cq = q >> 32;
+        const uint64_t d = (uint64_t)(uint32_t)p - (uint32_t)q - br;
+        out[i] = (uint32_t)d;
+        br = (d >> 32) & 1u;
+    }
+}
+// out = a*x + b*y (mod 2^256)
+KB_FN void kb_muladd8(uint32_t* out, uint32_t a, const uint32_t* x, uint32_t b, const uint32_t* y)
+{
+    uint64_t c = 0;
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        const uint64_t p = (uint64_t)a * x[i] + (uint32_t)c;
+        const uint64_t q = (uint64_t)b * y[i] + (c >> 32);
+        const uint64_t s = (p & 0xffffffffu) + (q & 0xffffffffu);
+        out[i] = (uint32_t)s;
+        c = (p >> 32) + (q >> 32) + (s >> 32);   // < 2^33: low word and a small high part, re-split above
+    }
+}
+
+// The run is ONE loop whose body is either a Lehmer batch or a single binary long-division step followed by a
+// predicated exchange of the two rows: the lanes of a warp are at different places of their Euclidean
+// sequences, and a loop nest would make every lane pay for the slowest one.
 // Invariants: r0 >= r1; r0 = -/+ t0 * h, r1 = +/- t1 * h (mod 8L), the t's are magnitudes and the signs
 // alternate from row to row.  Every intermediate row is a lattice vector, hence a candidate.
 KB_FN void sc_half(kb_halfsc& o, const uint32_t* h)
@@ -116,8 +158,79 @@ KB_FN void sc_half(kb_halfsc& o, const uint32_t* h)
         // every later vector has |u| >= t1: once bitlen(t1) reaches the best cost nothing can improve
         // (lt1 may lag behind while the rows are not tracked, which only delays the exit)
         if (la <= KB_HALF_TRACK && lt1 >= o.bits) break;
-        int s = la - lb;
         uint32_t y[8], d[8];
+        if (la > KB_HALF_LEHMER_MIN && la - lb < 24) {
+            // ---- Lehmer batch on the leading 63 bits (x0 < 2^63, so the bounds below cannot overflow)
+            kb_shl8(y, r0, 256 - la);
+            uint64_t x0 = (((uint64_t)y[7] << 32) | y[6]) >> 1;
+            kb_shl8(y, r1, 256 - la);
+            uint64_t x1 = (((uint64_t)y[7] << 32) | y[6]) >> 1;
+            // current row0 = a*r0 - b*r1, row1 = d*r1 - c*r0 (par = 0) or the negatives of both forms (par = 1);
+            // true row / 2^(la-63) lies within (x - (sum of its cofactors), x + (sum of its cofactors))
+            uint32_t ca = 1, cb = 0, cc = 0, cd = 1, par = 0;
+            int steps = 0;
+            const int xstop = KB_HALF_LEHMER_MIN - (la - 63);   // keep row0 above 2^KB_HALF_LEHMER_MIN
+            KB_NOUNROLL
+            for (;;) {
+                const uint64_t e0 = (uint64_t)ca + cb, e1 = (uint64_t)cc + cd;
+                if (x0 <= e0) break;
+                const uint64_t lo0 = x0 - e0, hi1 = x1 + e1;
+                if (hi1 > lo0) break;
+                if (64 - kb_clz64(lo0) <= xstop) break;
+                int s = kb_clz64(hi1) - kb_clz64(lo0);
+                if ((hi1 << s) > lo0) s -= 1;
+                if (s > 30) break;
+                const uint64_t na = (uint64_t)ca + ((uint64_t)cc << s), nb = (uint64_t)cb + ((uint64_t)cd << s);
+                if ((na | nb) >> 31) break;
+                x0 -= x1 << s;
+                ca = (uint32_t)na;
+                cb = (uint32_t)nb;
+                steps++;
+                if (x0 < x1) {
+                    const uint64_t tx = x0; x0 = x1; x1 = tx;
+                    uint32_t tc = ca; ca = cc; cc = tc;
+                    tc = cb; cb = cd; cd = tc;
+                    par ^= 1u;
+                }
+            }
+            if (steps != 0) {
+                if (par == 0) {
+                    kb_mulsub8(y, ca, r0, cb, r1);
+                    kb_mulsub8(d, cd, r1, cc, r0);
+                } else {
+                    kb_mulsub8(y, cb, r1, ca, r0);
+                    kb_mulsub8(d, cc, r0, cd, r1);
+                }
+                KB_UNROLL
+                for (int i = 0; i < 8; i++) { r0[i] = y[i]; r1[i] = d[i]; }
+                kb_muladd8(y, ca, t0, cb, t1);
+                kb_muladd8(d, cc, t0, cd, t1);
+                KB_UNROLL
+                for (int i = 0; i < 8; i++) { t0[i] = y[i]; t1[i] = d[i]; }
+                sg0neg ^= par;
+                la = kb_bitlen8(r0);
+                lb = kb_bitlen8(r1);
+                bool swap = la < lb;
+                if (la == lb) swap = kb_sub8(d, r0, r1) != 0;
+                if (swap) {
+                    KB_UNROLL
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t a = r0[i], b = t0[i];
+                        r0[i] = r1[i];
+                        r1[i] = a;
+                        t0[i] = t1[i];
+                        t1[i] = b;
+                    }
+                    const int l = la;
+                    la = lb;
+                    lb = l;
+                    sg0neg ^= 1u;
+                }
+                continue;
+            }
+        }
+        // ---- one exact binary long-division step
+        int s = la - lb;
         kb_shl8(y, r1, s);
         if (kb_sub8(d, r0, y)) {   // r1 << s overshoots: s >= 1 here because r0 >= r1
             s -= 1;

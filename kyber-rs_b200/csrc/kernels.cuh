@@ -438,8 +438,11 @@ __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const ui
 //   k_verify_half_prep   checks, decompress A and R, h, (u, v), u*s mod L   -> 304-byte record per signature
 //   k_verify_half_main   digit strings, two tables, the 33-window loop        -> status
 #define KB_HALF_REC_WORDS 76
+#ifndef KB_VERIFY_PREP_MINBLOCKS
+#define KB_VERIFY_PREP_MINBLOCKS 5
+#endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, 4) k_verify_half_prep(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs)
+__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify_half_prep(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
