@@ -11,8 +11,10 @@ its own 2^20 signatures (independent shards, no data-path collective).
 
   value     verified signatures / s, inputs resident in HBM (CUDA events on the launch stream)
   e2e       same metric through the host-buffer C-ABI call (pinned host buffers; H2D + D2H inside)
-  roofline  integer-multiply roofline of the verify kernel: 154 k IMAD-eq per signature
-             / measured time, against the IMAD.WIDE peak measured live by kb_probe_imad
+  roofline  integer-multiply roofline of the verify step (k_verify_half_prep + k_verify_half_main):
+            154 k IMAD-eq CHARGED per signature / measured time, against the IMAD.WIDE peak
+            measured live by kb_probe_imad; the two kernels are also timed one by one (CUDA events on the
+            launch stream, recorded inside the library around each launch)
   cpu_baseline  the oracle's ref10-style C port (oracle/ref10_port.c) on the host cores
 
 --impl reference times that same CPU port on all host cores (the reference is Rust; no Rust
@@ -34,10 +36,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-IMAD_EQ_PER_VERIFY = 154_000      # A decompress + Straus s*B - h*A + compress, M=72 S=44
+IMAD_EQ_PER_VERIFY = 154_000      # A decompress + Straus s*B - h*A + compress, M=72 S=44 (the CHARGED figure)
+# what the half-size-scalar kernels execute per signature (IMAD.WIDE, M=73 S=44):
+EXEC_PREP_PER_VERIFY = 25_600     # two decompressions (2 x (251+4 S + 22 M))
+EXEC_MAIN_PER_VERIFY = 110_000    # 128 doublings, 66 + 20 additions, two 8-entry tables
 IMAD_EQ_PER_MSM_POINT = 20_700
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
-VERIFY_STAGE1_DRAM_BYTES_2P20 = 204_418_816 + 686_399_744   # ncu capture, round 1 (profiles/r1_ncu_k_verify_stage1_final.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum at 2^20 signatures, ncu --set full (profiles/r1_ncu_k_verify_half.txt)
+VERIFY_DRAM_BYTES_2P20 = {"k_verify_half_prep": None, "k_verify_half_main": None}
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
 NONCANON = bytes([0xEF]) + b"\xff" * 31
@@ -308,6 +314,16 @@ def main():
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    # the two launches of a step one by one: events recorded by the library around each launch, read back after
+    # every step (a second pass, so that the read-back's synchronisation stays out of the timed region above)
+    ctx.verify_kernel_timing(True)
+    k_prep_ms, k_main_ms = [], []
+    for _ in range(args.steps):
+        step_dev()
+        a_ms, b_ms = ctx.last_verify_kernel_ms()
+        k_prep_ms.append(a_ms)
+        k_main_ms.append(b_ms)
+    ctx.verify_kernel_timing(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -410,6 +426,10 @@ def main():
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    prep_s, main_s = statistics.mean(k_prep_ms) * 1e-3, statistics.mean(k_main_ms) * 1e-3
+    traffic = None
+    if args.log2n == 20 and all(VERIFY_DRAM_BYTES_2P20.values()):
+        traffic = sum(VERIFY_DRAM_BYTES_2P20.values())
     out = {
         "metric": "verified Ed25519 sigs/sec", "value": value, "unit": "sigs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -418,10 +438,20 @@ def main():
         "e2e": {"value": e2e_value, "unit": "sigs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": VERIFY_STAGE1_DRAM_BYTES_2P20 if args.log2n == 20 else None,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of k_verify_stage1 at 2^20 signatures from profiles/r1_ncu_k_verify_stage1_final.txt (ncu --set full); algorithmic bytes are 168 MB in + 101 MB out per launch, the rest is the per-thread 1 KiB table of multiples of A (local memory) evicted past L2",
-                     "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents per signature (SURVEY 8d) / CUDA-event step time; peak = best IMAD.WIDE.U32 stream measured live by kb_probe_imad (back-to-back field multiplications), ~93% of the architectural 32 lanes/clk/SM of the fmaheavy pipe",
-                     "kernel": "k_verify_stage1 (+ k_verify_stage2, ~3% of the step): one step = both launches",
+        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one step at 2^20 signatures (ncu --set full, profiles/r1_ncu_k_verify_half.txt): "
+                                     + json.dumps(VERIFY_DRAM_BYTES_2P20) + "; algorithmic bytes are 168 MB in + 1 MB out per step plus the 319 MB of records written by the first launch and read by the second; "
+                                     "the rest is the two per-thread 1 KiB tables (multiples of A and of R, local memory) that do not all fit the 126 MB L2; DRAM runs at 3 % of its peak",
+                     "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents CHARGED per signature (SURVEY 8d: decompress A + 253-doubling Straus + compress) / CUDA-event step time; "
+                             "peak = best IMAD.WIDE.U32 stream measured live by kb_probe_imad (back-to-back field multiplications), ~93% of the architectural 32 lanes/clk/SM of the fmaheavy pipe. "
+                             "The kernels EXECUTE fewer multiplies than charged (half-size scalars: 128 doublings, csrc/half.cuh): see `executed`",
+                     "kernel": "one step = k_verify_half_prep (checks, decompress A and R, SHA-512, lattice step) + k_verify_half_main (tables, 33-window loop, comb, verdict)",
+                     "kernels_ms": {"k_verify_half_prep": prep_s * 1e3, "k_verify_half_main": main_s * 1e3, "timed_steps": len(k_main_ms),
+                                    "how": "cudaEventRecord on the launch stream around each launch (kb_verify_kernel_times), averaged over a second pass of the same steps"},
+                     "executed": {"imad_wide_per_sig": {"k_verify_half_prep": EXEC_PREP_PER_VERIFY, "k_verify_half_main": EXEC_MAIN_PER_VERIFY},
+                                  "frac_step": n * (EXEC_PREP_PER_VERIFY + EXEC_MAIN_PER_VERIFY) / kernel_s / imad_peak,
+                                  "frac_k_verify_half_main": n * EXEC_MAIN_PER_VERIFY / main_s / imad_peak,
+                                  "frac_k_verify_half_prep": n * EXEC_PREP_PER_VERIFY / prep_s / imad_peak},
                      "probes_T_per_s": {"imad_lo32": imad_peak_lo / 1e12, "imad_wide_plain": probe_wide_plain / 1e12, "imad_wide_carry_chain": probe_wide_chain / 1e12, "fe_mul_as_imad_wide": fe_mul_rate * 73.0 / 72.0 / 1e12},
                      "architectural_imad_wide_T_per_s": 32 * ctx.sm_count * 1.965e9 / 1e12},
         "roofline_hbm": {"bound": "hbm", "achieved": n * ALG_BYTES_PER_SIG / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": n * ALG_BYTES_PER_SIG / kernel_s / 1e9 / hbm_peak,

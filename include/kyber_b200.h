@@ -162,6 +162,11 @@ int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_o
  * kind: 0 = IMAD.WIDE.U32 (64-bit accumulate), 1 = IMAD (32-bit lo), 2 = IMAD.WIDE.U32.X carry chains,
  * 3 = the library's own fe_mul (reported in IMAD-eq at 72 per multiplication). */
 int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double* elapsed_ms);
+/* Per-kernel timing of the verifiers.  enable = 1/0 switches CUDA-event recording (on the launch stream, around
+ * each of the two launches of a verify call) on or off; with ms_out != NULL the call then waits for the most recent
+ * kb_dev_eddsa_verify and returns ms_out[0] = first launch (k_verify_half_prep / k_verify_stage1), ms_out[1] =
+ * second launch (k_verify_half_main / k_verify_stage2).  This is how bench.py times the dominant kernel live. */
+int kb_verify_kernel_times(kb_ctx* ctx, int enable, float* ms_out);
 
 #ifdef __cplusplus
 }

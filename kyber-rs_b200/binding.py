@@ -39,7 +39,7 @@ EXPORTS = [
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
-    "kb_probe_imad",
+    "kb_probe_imad", "kb_verify_kernel_times",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_dev_dkg_verify_round.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_point_sum.argtypes = [vp, sz, vp, vp, vp]
     L.kb_probe_imad.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.kb_verify_kernel_times.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     _LIB = L
     return L
 
@@ -310,6 +311,16 @@ class Context:
         rate, ms = ctypes.c_double(), ctypes.c_double()
         self._check(self.L.kb_probe_imad(self.h, kind, iters, ctypes.byref(rate), ctypes.byref(ms)), "kb_probe_imad")
         return rate.value, ms.value
+
+    def verify_kernel_timing(self, enable=True):
+        """Switch per-kernel CUDA-event timing of dev_verify on or off."""
+        self._check(self.L.kb_verify_kernel_times(self.h, 1 if enable else 0, None), "kb_verify_kernel_times")
+
+    def last_verify_kernel_ms(self):
+        """(first launch ms, second launch ms) of the most recent dev_verify; waits for it."""
+        ms = (ctypes.c_float * 2)()
+        self._check(self.L.kb_verify_kernel_times(self.h, 1, ms), "kb_verify_kernel_times")
+        return float(ms[0]), float(ms[1])
 
     # ---- device-pointer API (torch CUDA tensors; enqueues on torch's current stream) --------
     @staticmethod

@@ -10,6 +10,7 @@
 #include "msm.cuh"
 
 #define KB_NSLOTS 48
+#define KB_VERIFY_CHUNK (1u << 18)   // largest signatures-per-chunk of the pipelined host-buffer verify calls
 #define KB_SLOT_XYZ 28
 #define KB_SLOT_FLAGS 29
 
@@ -22,6 +23,10 @@ struct kb_ctx {
     ge_precomp* base128;     // 128 entries: (j+1) * B
     ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
+    size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
+    int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
+    int timing_valid;
+    cudaEvent_t tev[3];
     void* slot[KB_NSLOTS];
     size_t slot_bytes[KB_NSLOTS];
     uint64_t launches;
@@ -180,6 +185,10 @@ int kb_ctx_create(int device, kb_ctx** out)
         k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
         k_comb_init<<<kb_blocks((size_t)KB_COMB_POS * KB_COMB_HALF, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(ctx->comb, ctx->base_table);
         ctx->launches++;
+        for (int k = 0; k < 3; k++) ok = ok && cudaEventCreate(&ctx->tev[k]) == cudaSuccess;
+        const char* vc = getenv("KB_VERIFY_CHUNK_LOG2");
+        const int vcl = vc ? atoi(vc) : 0;
+        ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
         const char* vf = getenv("KB_VERIFY_FULL");
         ctx->verify_full = (vf && vf[0] == '1') ? 1 : 0;
         ctx->launches += 2;
@@ -208,6 +217,8 @@ void kb_ctx_destroy(kb_ctx* ctx)
     if (ctx->base_table) cudaFree(ctx->base_table);
     if (ctx->base128) cudaFree(ctx->base128);
     if (ctx->comb) cudaFree(ctx->comb);
+    for (int k = 0; k < 3; k++)
+        if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);
@@ -278,31 +289,36 @@ static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const ui
 {
     const unsigned th = kb_item_threads(ctx, n);
     const unsigned g1 = kb_blocks(n, th), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    const bool tm = ctx->timing != 0;
     if (!ctx->verify_full) {
         // the 96-byte-per-item xyz scratch of the full-length path is not needed; `xyz` carries the 304-byte records
         const unsigned gp = kb_blocks(n, KB_THREADS);
-        if (schnorr) {
-            k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
-            KB_LAUNCHED();
-            k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
-        } else {
-            k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
-            KB_LAUNCHED();
-            k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
-        }
+        if (tm) cudaEventRecord(ctx->tev[0], st);
+        if (schnorr) k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+        else k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
         KB_LAUNCHED();
+        if (tm) cudaEventRecord(ctx->tev[1], st);
+        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
+        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
+        KB_LAUNCHED();
+        if (tm) {
+            cudaEventRecord(ctx->tev[2], st);
+            ctx->timing_valid = 1;
+        }
         return KB_OK;
     }
-    if (schnorr) {
-        k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
-        KB_LAUNCHED();
-        k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
-    } else {
-        k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
-        KB_LAUNCHED();
-        k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
-    }
+    if (tm) cudaEventRecord(ctx->tev[0], st);
+    if (schnorr) k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
+    else k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
     KB_LAUNCHED();
+    if (tm) cudaEventRecord(ctx->tev[1], st);
+    if (schnorr) k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
+    else k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
+    KB_LAUNCHED();
+    if (tm) {
+        cudaEventRecord(ctx->tev[2], st);
+        ctx->timing_valid = 1;
+    }
     return KB_OK;
 }
 int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream)
@@ -548,14 +564,18 @@ int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t*
 // Host-buffer verification, pipelined: the batch is cut into chunks of KB_VERIFY_CHUNK signatures that
 // alternate between two streams, so the H2D copy of chunk k+1 and the D2H of chunk k-1 overlap the
 // kernels of chunk k (each stream owns its own staging and scratch buffers).
-#define KB_VERIFY_CHUNK (1u << 17)
 static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr)
 {
     KB_ENTER();
     if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     if (msg_off[n] && !msg) return KB_ERR_ARG;
-    const size_t chunk = KB_VERIFY_CHUNK;
+    // measured on a 2^20 batch (tools/e2e_sweep.py): 2^18-signature chunks give the best overlap of copies and kernels
+    size_t chunk = ctx->verify_chunk;
+    if (chunk == 0) {
+        chunk = (size_t)1 << 15;
+        while (chunk < KB_VERIFY_CHUNK && chunk * 4 < n) chunk <<= 1;
+    }
     size_t max_mbytes = 0;
     for (size_t lo = 0; lo < n; lo += chunk) {
         const size_t hi = (lo + chunk < n) ? lo + chunk : n;
@@ -779,6 +799,19 @@ int kb_point_sum(kb_ctx* ctx, size_t k, const uint8_t* partials128, uint8_t* out
 // ------------------------------------------------------------------------------------
 // measurement
 // ------------------------------------------------------------------------------------
+int kb_verify_kernel_times(kb_ctx* ctx, int enable, float* ms_out)
+{
+    KB_ENTER();
+    if (ms_out) {
+        if (!ctx->timing || !ctx->timing_valid) return KB_ERR_ARG;
+        KB_CUDA(cudaEventSynchronize(ctx->tev[2]));
+        KB_CUDA(cudaEventElapsedTime(&ms_out[0], ctx->tev[0], ctx->tev[1]));
+        KB_CUDA(cudaEventElapsedTime(&ms_out[1], ctx->tev[1], ctx->tev[2]));
+    }
+    ctx->timing = enable ? 1 : 0;
+    if (!enable) ctx->timing_valid = 0;
+    return KB_OK;
+}
 int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double* elapsed_ms)
 {
     KB_ENTER();

@@ -35,6 +35,21 @@ __device__ __forceinline__ void kb_store_fe(uint32_t* p, const fe& f)
     q[0] = make_uint4(f.v[0], f.v[1], f.v[2], f.v[3]);
     q[1] = make_uint4(f.v[4], f.v[5], f.v[6], f.v[7]);
 }
+// streaming (evict-first) variants for data that crosses HBM exactly once — the records between the two verify
+// launches — so that it does not push the per-thread tables out of L2
+__device__ __forceinline__ void kb_load_fe_cs(fe& f, const uint32_t* p)
+{
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldcs(q), b = __ldcs(q + 1);
+    f.v[0] = a.x; f.v[1] = a.y; f.v[2] = a.z; f.v[3] = a.w;
+    f.v[4] = b.x; f.v[5] = b.y; f.v[6] = b.z; f.v[7] = b.w;
+}
+__device__ __forceinline__ void kb_store_fe_cs(uint32_t* p, const fe& f)
+{
+    uint4* q = reinterpret_cast<uint4*>(p);
+    __stcs(q, make_uint4(f.v[0], f.v[1], f.v[2], f.v[3]));
+    __stcs(q + 1, make_uint4(f.v[4], f.v[5], f.v[6], f.v[7]));
+}
 // cooperative copy of `words` 32-bit words from global to shared
 __device__ __forceinline__ void kb_stage(uint32_t* dst, const uint32_t* src, int words)
 {
@@ -455,20 +470,20 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify
     kb_half_rec rec;
     sig_half_prep<SCHNORR>(rec, pw, sw, msg + (lo - msg_base), hi - lo);
     uint32_t* o = recs + KB_HALF_REC_WORDS * i;
-    kb_store_fe(o, rec.ax);
-    kb_store_fe(o + 8, rec.ay);
-    kb_store_fe(o + 16, rec.at);
-    kb_store_fe(o + 24, rec.rx);
-    kb_store_fe(o + 32, rec.ry);
-    kb_store_fe(o + 40, rec.rt);
+    kb_store_fe_cs(o, rec.ax);
+    kb_store_fe_cs(o + 8, rec.ay);
+    kb_store_fe_cs(o + 16, rec.at);
+    kb_store_fe_cs(o + 24, rec.rx);
+    kb_store_fe_cs(o + 32, rec.ry);
+    kb_store_fe_cs(o + 40, rec.rt);
     uint4* q = reinterpret_cast<uint4*>(o + 48);
-    q[0] = make_uint4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]);
-    q[1] = make_uint4(rec.w[4], rec.w[5], rec.w[6], rec.w[7]);
-    q[2] = make_uint4(rec.u[0], rec.u[1], rec.u[2], rec.u[3]);
-    q[3] = make_uint4(rec.u[4], rec.u[5], rec.u[6], rec.u[7]);
-    q[4] = make_uint4(rec.v[0], rec.v[1], rec.v[2], rec.v[3]);
-    q[5] = make_uint4(rec.v[4], rec.v[5], rec.v[6], rec.v[7]);
-    q[6] = make_uint4(rec.f | ((uint32_t)rec.nwin << 8), 0u, 0u, 0u);
+    __stcs(q + 0, make_uint4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]));
+    __stcs(q + 1, make_uint4(rec.w[4], rec.w[5], rec.w[6], rec.w[7]));
+    __stcs(q + 2, make_uint4(rec.u[0], rec.u[1], rec.u[2], rec.u[3]));
+    __stcs(q + 3, make_uint4(rec.u[4], rec.u[5], rec.u[6], rec.u[7]));
+    __stcs(q + 4, make_uint4(rec.v[0], rec.v[1], rec.v[2], rec.v[3]));
+    __stcs(q + 5, make_uint4(rec.v[4], rec.v[5], rec.v[6], rec.v[7]));
+    __stcs(q + 6, make_uint4(rec.f | ((uint32_t)rec.nwin << 8), 0u, 0u, 0u));
 }
 #ifndef KB_VERIFY_HALF_MINBLOCKS
 #define KB_VERIFY_HALF_MINBLOCKS 3
@@ -485,21 +500,21 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify
     kb_half_rec rec;
     {
         const uint32_t* o = recs + KB_HALF_REC_WORDS * i;
-        kb_load_fe(rec.ax, o);
-        kb_load_fe(rec.ay, o + 8);
-        kb_load_fe(rec.at, o + 16);
-        kb_load_fe(rec.rx, o + 24);
-        kb_load_fe(rec.ry, o + 32);
-        kb_load_fe(rec.rt, o + 40);
+        kb_load_fe_cs(rec.ax, o);
+        kb_load_fe_cs(rec.ay, o + 8);
+        kb_load_fe_cs(rec.at, o + 16);
+        kb_load_fe_cs(rec.rx, o + 24);
+        kb_load_fe_cs(rec.ry, o + 32);
+        kb_load_fe_cs(rec.rt, o + 40);
         const uint4* q = reinterpret_cast<const uint4*>(o + 48);
         uint4 a;
-        a = q[0]; rec.w[0] = a.x; rec.w[1] = a.y; rec.w[2] = a.z; rec.w[3] = a.w;
-        a = q[1]; rec.w[4] = a.x; rec.w[5] = a.y; rec.w[6] = a.z; rec.w[7] = a.w;
-        a = q[2]; rec.u[0] = a.x; rec.u[1] = a.y; rec.u[2] = a.z; rec.u[3] = a.w;
-        a = q[3]; rec.u[4] = a.x; rec.u[5] = a.y; rec.u[6] = a.z; rec.u[7] = a.w;
-        a = q[4]; rec.v[0] = a.x; rec.v[1] = a.y; rec.v[2] = a.z; rec.v[3] = a.w;
-        a = q[5]; rec.v[4] = a.x; rec.v[5] = a.y; rec.v[6] = a.z; rec.v[7] = a.w;
-        a = q[6];
+        a = __ldcs(q + 0); rec.w[0] = a.x; rec.w[1] = a.y; rec.w[2] = a.z; rec.w[3] = a.w;
+        a = __ldcs(q + 1); rec.w[4] = a.x; rec.w[5] = a.y; rec.w[6] = a.z; rec.w[7] = a.w;
+        a = __ldcs(q + 2); rec.u[0] = a.x; rec.u[1] = a.y; rec.u[2] = a.z; rec.u[3] = a.w;
+        a = __ldcs(q + 3); rec.u[4] = a.x; rec.u[5] = a.y; rec.u[6] = a.z; rec.u[7] = a.w;
+        a = __ldcs(q + 4); rec.v[0] = a.x; rec.v[1] = a.y; rec.v[2] = a.z; rec.v[3] = a.w;
+        a = __ldcs(q + 5); rec.v[4] = a.x; rec.v[5] = a.y; rec.v[6] = a.z; rec.v[7] = a.w;
+        a = __ldcs(q + 6);
         rec.f = a.x & 0xffu;
         rec.nwin = (int)(a.x >> 8);
     }

@@ -61,4 +61,5 @@ extern "C" {
     pub fn kb_dev_point_sum(ctx: *mut kb_ctx, k: usize, d_partials128: *const c_void, d_out32: *mut c_void, stream: *mut c_void) -> c_int;
 
     pub fn kb_probe_imad(ctx: *mut kb_ctx, kind: c_int, iters: c_int, macs_per_sec: *mut c_double, elapsed_ms: *mut c_double) -> c_int;
+    pub fn kb_verify_kernel_times(ctx: *mut kb_ctx, enable: c_int, ms_out: *mut f32) -> c_int;
 }
