@@ -253,9 +253,11 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
     // lane per scalar — the 0.43 ms launch is already within ~25 % of the multiplier bound — so it stays 1.
     const int split = 1;
     const unsigned blocks = kb_blocks(n * split, KB_THREADS);
-    if (flags & KB_FLAG_VARTIME)
-        k_mul_base<false><<<blocks, KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table, split);
-    else
+    if (flags & KB_FLAG_VARTIME) {
+        // public scalars: the shared 20-position comb (ops.cuh ge_scalarmult_base_comb), 3x fewer additions
+        const unsigned th = kb_item_threads(ctx, n);
+        k_mul_base_comb<<<kb_blocks(n, th), th, 0, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->comb);
+    } else
         k_mul_base<true><<<blocks, KB_THREADS, smem, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->base_table, split);
     KB_LAUNCHED();
     k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, nullptr, (uint8_t*)d_out);

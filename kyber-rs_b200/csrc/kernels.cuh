@@ -226,6 +226,18 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t
     if (live && part == 0) kb_store_xyz(xyz, i, h);
 }
 
+// public scalars (KB_FLAG_VARTIME): the shared comb, 20 mixed additions per scalar, nothing staged in shared memory
+__global__ void __launch_bounds__(KB_THREADS) k_mul_base_comb(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* comb)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    kb_load32(s, scalars, i);
+    ge_p3 h;
+    ge_scalarmult_base_comb(h, s, comb);
+    kb_store_xyz(xyz, i, h);
+}
+
 // ---- Point::mul(s, Some(p)): out[i] = compress(s_i * P_i)   (point.rs:207, ge.rs:508)
 template <bool CT>
 __global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint32_t* xyz, uint8_t* status)

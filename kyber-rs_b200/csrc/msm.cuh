@@ -60,32 +60,6 @@ static inline uint32_t kb_msm_window_bits_host(size_t n)
     return (uint32_t)c;
 }
 
-// The integer Point::mul multiplies by: a itself when a[31] <= 127; otherwise the
-// reference's top radix-16 digit (nibble 63 + carry) may exceed 8, then matches no table
-// entry and is dropped, leaving low252 - carry * 2^252 (possibly negative).
-KB_FN void sc_effective(uint32_t* mag, uint32_t& neg, const uint32_t* s)
-{
-    const uint32_t c8[8] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u, 0x08888888u};
-    uint32_t low[8], t[8];
-    KB_UNROLL
-    for (int i = 0; i < 8; i++) low[i] = s[i];
-    low[7] &= 0x0fffffffu;
-    kb_add8(t, low, c8);
-    const uint32_t carry = t[7] >> 28;  // carry out of the 63 low digits
-    const uint32_t top = (s[7] >> 28) + carry;
-    neg = 0;
-    if (top <= 8) {
-        KB_UNROLL
-        for (int i = 0; i < 8; i++) mag[i] = s[i];
-    } else if (carry == 0) {
-        KB_UNROLL
-        for (int i = 0; i < 8; i++) mag[i] = low[i];
-    } else {
-        const uint32_t p252[8] = {0, 0, 0, 0, 0, 0, 0, 0x10000000u};
-        kb_sub8(mag, p252, low);
-        neg = 1;
-    }
-}
 // bits [pos, pos + c) of the 256-bit magnitude (zero beyond bit 255), c <= 16
 KB_FN uint32_t sc_bits(const uint32_t* mag, uint32_t pos, uint32_t c)
 {

@@ -511,6 +511,35 @@ KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, c
         }
     }
 }
+// h = a * B for a PUBLIC scalar through the comb: 20 mixed additions instead of 64 (ge_scalarmult_base), no doublings.
+// Any 32-byte scalar gives the reference's result: sc_effective is the integer the reference's digit loop
+// multiplies by, and B has order L, so that integer may be reduced mod L first.
+KB_FN void ge_scalarmult_base_comb(ge_p3& h, const uint32_t* s, const ge_precomp* comb)
+{
+    uint32_t x[16], r[8], neg;
+    sc_effective(x, neg, s);
+    KB_UNROLL
+    for (int i = 8; i < 16; i++) x[i] = 0;
+    sc_reduce512(r, x);
+    int16_t dw[KB_COMB_POS];
+    sc_recode_comb(dw, r);
+    ge_identity(h);
+    KB_NOUNROLL
+    for (int p = 0; p < KB_COMB_POS; p++) {
+        const int d = dw[p];
+        const uint32_t dn = (uint32_t)d >> 31;
+        const int babs = (d ^ -(int)dn) + (int)dn;
+        ge_cached c;
+        ge_cached_identity(c);
+        if (babs != 0) kb_ld_precomp(c, comb + (size_t)p * KB_COMB_HALF + (babs - 1));
+        ge_precomp q;
+        q.ypx = c.YpX;
+        q.ymx = c.YmX;
+        q.xy2d = c.T2d;
+        ge_precomp_cneg(q, dn ^ neg);   // a negative multiplier negates every term
+        ge_madd<true>(h, h, q);
+    }
+}
 // comb[p][j] = (j+1) * 2^(13 p) * B in affine (y+x, y-x, 2dxy) form; entries whose multiplier does not fit 255 bits are
 // never addressed by a scalar below 2^253 and hold the identity.  `base` = the 64 x 8 fixed-base table (kb_base_window).
 KB_FN void kb_comb_entry(ge_precomp& out, int p, int j, const ge_precomp* base)

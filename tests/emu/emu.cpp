@@ -105,6 +105,24 @@ void emu_mul_base(uint8_t* out, const uint8_t* scalar, int ct)
     ge_compress(o, h);
     st(out, o, 8);
 }
+static void comb_init()
+{
+    base_init();
+    if (!g_comb.empty()) return;
+    g_comb.resize((size_t)KB_COMB_POS * KB_COMB_HALF);
+    for (int k = 0; k < KB_COMB_POS * KB_COMB_HALF; k++) kb_comb_entry(g_comb[k], k / KB_COMB_HALF, k % KB_COMB_HALF, g_base);
+}
+// Point::mul(s, None) for public scalars through the shared comb
+void emu_mul_base_comb(uint8_t* out, const uint8_t* scalar)
+{
+    uint32_t s[8], o[8];
+    ge_p3 h;
+    comb_init();
+    ld(s, scalar, 8);
+    ge_scalarmult_base_comb(h, s, g_comb.data());
+    ge_compress(o, h);
+    st(out, o, 8);
+}
 void emu_sc_reduce512(uint8_t* out, const uint8_t* in)
 {
     uint32_t x[16], r[8];
@@ -182,10 +200,7 @@ int emu_sig_verify_half(int schnorr, const uint8_t* pk, const uint8_t* msg, uint
     base_init();
     ld(pw, pk, 8); ld(sw, sig, 16);
     if (min_windows < KB_HALF_MIN_WINDOWS) min_windows = KB_HALF_MIN_WINDOWS;
-    if (g_comb.empty()) {
-        g_comb.resize((size_t)KB_COMB_POS * KB_COMB_HALF);
-        for (int k = 0; k < KB_COMB_POS * KB_COMB_HALF; k++) kb_comb_entry(g_comb[k], k / KB_COMB_HALF, k % KB_COMB_HALF, g_base);
-    }
+    comb_init();
     return schnorr ? (int)sig_verify_half<true>(pw, sw, msg, mlen, g_comb.data(), tbl, min_windows) : (int)sig_verify_half<false>(pw, sw, msg, mlen, g_comb.data(), tbl, min_windows);
 }
 // sc_half: out = u (32 bytes) || |v| (32 bytes); returns bits | vneg << 16

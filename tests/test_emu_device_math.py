@@ -115,6 +115,11 @@ def test_scalar_mults(emu, coracle, golden_records):
                 assert out.raw == coracle.mul(s, pk)
                 emu.emu_mul_base(out, s, ct)
                 assert out.raw == coracle.mul_base(s)
+    # public scalars through the shared comb, including every out-of-domain shape of the top digit
+    edge = [bytes(32), b"\xff" * 32, b32(O.L), b32(O.L - 1), b32(2**252), b32(2**253 - 1), b32(2**255 - 1), b32(2**255), b"\x88" * 31 + b"\x08", b"\x88" * 32, b"\x77" * 31 + b"\xf7"]
+    for s in edge + [rnd.randbytes(32) for _ in range(300)] + [rnd.randbytes(31) + bytes([t]) for t in range(0, 256, 5)]:
+        emu.emu_mul_base_comb(out, s)
+        assert out.raw == coracle.mul_base(s), s.hex()
 
 
 def test_verify_state_machine(emu, coracle, golden_records):
