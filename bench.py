@@ -43,7 +43,7 @@ EXEC_MAIN_PER_VERIFY = 110_000    # 128 doublings, 66 + 20 additions, two 8-entr
 IMAD_EQ_PER_MSM_POINT = 20_700
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
 # dram__bytes_read.sum + dram__bytes_write.sum at 2^20 signatures, ncu --set full (profiles/r1_ncu_k_verify_half.txt)
-VERIFY_DRAM_BYTES_2P20 = {"k_verify_half_prep": None, "k_verify_half_main": None}
+VERIFY_DRAM_BYTES_2P20 = {"k_verify_half_prep": 197_185_000 + 305_416_000, "k_verify_half_main": 12_329_228_000 + 2_203_952_000}
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
 NONCANON = bytes([0xEF]) + b"\xff" * 31
