@@ -441,7 +441,7 @@ def main():
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one step at 2^20 signatures (ncu --set full, profiles/r1_ncu_k_verify_half.txt): "
                                      + json.dumps(VERIFY_DRAM_BYTES_2P20) + "; algorithmic bytes are 168 MB in + 1 MB out per step plus the 319 MB of records written by the first launch and read by the second; "
-                                     "the rest is the two per-thread 1 KiB tables (multiples of A and of R, local memory) that do not all fit the 126 MB L2; DRAM runs at 3 % of its peak",
+                                     "the rest is the two per-thread 1 KiB tables (multiples of A and of R, local memory) that do not all fit the 126 MB L2 (DESIGN.md 6); DRAM runs at about 10 % of its peak, the step is bound by the multiplier pipe",
                      "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents CHARGED per signature (SURVEY 8d: decompress A + 253-doubling Straus + compress) / CUDA-event step time; "
                              "peak = best IMAD.WIDE.U32 stream measured live by kb_probe_imad (back-to-back field multiplications), ~93% of the architectural 32 lanes/clk/SM of the fmaheavy pipe. "
                              "The kernels EXECUTE fewer multiplies than charged (half-size scalars: 128 doublings, csrc/half.cuh): see `executed`",
