@@ -91,6 +91,16 @@ int kb_point_recode_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out
 int kb_point_from_limbs_batch(kb_ctx* ctx, size_t n, const int32_t* limbs, uint8_t* out);
 /* Point::add / Point::sub (point.rs:179,190) on encodings; status[i] = 1 if either fails to decode */
 int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* out, uint8_t* status, int subtract);
+/* ExtendedGroupElement::set_bytes (ge.rs:124-179) into the uncompressed device-friendly form used for chaining:
+ * out128[i] = X, Y, Z, T as 4 x 8 little-endian 32-bit words (the form of kb_msm's partial128); status[i] = 1 and the
+ * identity where the encoding does not decode. */
+int kb_point_decompress_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out128, uint8_t* status);
+/* ExtendedGroupElement::write_bytes (ge.rs:112-122) from that form (any Z; one shared inversion per 8 points;
+ * Z = 0 gives 32 zero bytes like the reference's fe_invert(0) = 0). */
+int kb_point_compress_batch(kb_ctx* ctx, size_t n, const uint8_t* in128, uint8_t* out);
+/* Point::eq (point.rs:227-241): equal_out[i] bit 0 = the two encodings decode to the same point (the reference
+ * compares re-encodings, so a non-canonical y >= p equals its reduced twin); bit 1 = an operand does not decode. */
+int kb_point_eq_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* equal_out);
 /* byte-level checks: bit0 = Point::is_canonical (point.rs:322, bug-compatible),
  * bit1 = Point::has_small_order (point.rs:286), bit2 = decodes (ge.rs:124) */
 int kb_point_check_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* flags_out);

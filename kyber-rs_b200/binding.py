@@ -35,7 +35,7 @@ _LIB = None
 # every symbol include/kyber_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "kb_ctx_create", "kb_ctx_destroy", "kb_ctx_wipe", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
-    "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch",
+    "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch", "kb_point_decompress_batch", "kb_point_compress_batch", "kb_point_eq_batch",
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
@@ -71,6 +71,9 @@ def load_library(path: str = LIB_PATH):
     L.kb_point_from_limbs_batch.argtypes = [vp, sz, vp, vp]
     L.kb_point_add_batch.argtypes = [vp, sz, vp, vp, vp, vp, i32]
     L.kb_point_check_batch.argtypes = [vp, sz, vp, vp]
+    L.kb_point_decompress_batch.argtypes = [vp, sz, vp, vp, vp]
+    L.kb_point_compress_batch.argtypes = [vp, sz, vp, vp]
+    L.kb_point_eq_batch.argtypes = [vp, sz, vp, vp, vp]
     L.kb_sc_reduce64_batch.argtypes = [vp, sz, vp, vp]
     L.kb_sc_muladd_batch.argtypes = [vp, sz, vp, vp, vp, vp]
     L.kb_sc_invert_batch.argtypes = [vp, sz, vp, vp]
@@ -198,6 +201,27 @@ class Context:
         fl = np.empty(p.shape[0], dtype=np.uint8)
         self._check(self.L.kb_point_check_batch(self.h, p.shape[0], _ptr(p), _ptr(fl)), "kb_point_check_batch")
         return fl
+
+    def point_decompress_batch(self, pts):
+        """32-byte encodings -> (n, 32) uint32 words X, Y, Z, T (8 words each); status 1 = does not decode."""
+        p = _u8(pts, (-1, 32))
+        out = np.empty((p.shape[0], 32), dtype=np.uint32)
+        st = np.empty(p.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_point_decompress_batch(self.h, p.shape[0], _ptr(p), _ptr(out), _ptr(st)), "kb_point_decompress_batch")
+        return out, st
+
+    def point_compress_batch(self, raw):
+        r = np.ascontiguousarray(raw, dtype=np.uint32).reshape(-1, 32)
+        out = np.empty((r.shape[0], 32), dtype=np.uint8)
+        self._check(self.L.kb_point_compress_batch(self.h, r.shape[0], _ptr(r), _ptr(out)), "kb_point_compress_batch")
+        return out
+
+    def point_eq_batch(self, p, q):
+        """Point::eq per pair: bit 0 = equal, bit 1 = an operand does not decode."""
+        p, q = _u8(p, (-1, 32)), _u8(q, (-1, 32))
+        out = np.empty(p.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_point_eq_batch(self.h, p.shape[0], _ptr(p), _ptr(q), _ptr(out)), "kb_point_eq_batch")
+        return out
 
     def sc_reduce64_batch(self, digests):
         d = _u8(digests, (-1, 64))

@@ -475,6 +475,61 @@ int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q
     KB_SYNC();
     return KB_OK;
 }
+int kb_point_decompress_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out128, uint8_t* status)
+{
+    KB_ENTER();
+    if (n && (!in || !out128)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_i, *d_st;
+    uint32_t* d_o;
+    KB_SCRATCH(0, 32 * n, d_i);
+    KB_SCRATCH(KB_SLOT_XYZ, 128 * n, d_o);
+    KB_SCRATCH(3, n, d_st);
+    KB_H2D(d_i, in, 32 * n);
+    k_point_decompress<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_i, d_o, d_st);
+    KB_LAUNCHED();
+    KB_D2H(out128, d_o, 128 * n);
+    if (status) KB_D2H(status, d_st, n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_point_compress_batch(kb_ctx* ctx, size_t n, const uint8_t* in128, uint8_t* out)
+{
+    KB_ENTER();
+    if (n && (!in128 || !out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint32_t *d_i, *xyz;
+    uint8_t *d_o, *zero;
+    KB_SCRATCH(0, 128 * n, d_i);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
+    KB_SCRATCH(1, 32 * n, d_o);
+    KB_SCRATCH(3, n, zero);
+    KB_H2D(d_i, in128, 128 * n);
+    k_points_from_raw<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_i, xyz, zero);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, xyz, zero, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_point_eq_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q, uint8_t* equal_out)
+{
+    KB_ENTER();
+    if (n && (!p || !q || !equal_out)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    uint8_t *d_p, *d_q, *d_o;
+    KB_SCRATCH(0, 32 * n, d_p);
+    KB_SCRATCH(2, 32 * n, d_q);
+    KB_SCRATCH(3, n, d_o);
+    KB_H2D(d_p, p, 32 * n);
+    KB_H2D(d_q, q, 32 * n);
+    k_point_eq<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_p, d_q, d_o);
+    KB_LAUNCHED();
+    KB_D2H(equal_out, d_o, n);
+    KB_SYNC();
+    return KB_OK;
+}
 int kb_point_check_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* flags_out)
 {
     KB_ENTER();

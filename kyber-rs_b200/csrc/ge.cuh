@@ -168,6 +168,46 @@ KB_FN void ge_dbl_rt(ge_p3& r, const ge_p3& p, bool WITH_T)
     if (WITH_T) fe_mul(r.T, e, h);
 }
 
+// The unified addition and the doubling END in the same four products (X3 = E F, Y3 = G H, Z3 = F G, T3 = E H):
+// split into front ends and ONE shared tail, a loop over "steps" holds the tail's code once (the long
+// scalar-multiplication kernels are bound by the instruction cache as much as by the multiplier).
+KB_FN void ge_add_front(fe& e, fe& f, fe& g, fe& h, const ge_p3& p, const ge_cached& q)
+{
+    fe a, b, c, d;
+    fe_sub(a, p.Y, p.X);
+    fe_add(b, p.Y, p.X);
+    fe_mul(a, a, q.YmX);
+    fe_mul(b, b, q.YpX);
+    fe_mul(c, p.T, q.T2d);
+    fe_mul(d, p.Z, q.Z);
+    fe_dbl(d, d);
+    fe_sub(e, b, a);
+    fe_sub(f, d, c);
+    fe_add(g, d, c);
+    fe_add(h, b, a);
+}
+KB_FN void ge_dbl_front(fe& e, fe& f, fe& g, fe& h, const ge_p3& p)
+{
+    fe a, b, c;
+    fe_sq(a, p.X);
+    fe_sq(b, p.Y);
+    fe_sq(c, p.Z);
+    fe_dbl(c, c);
+    fe_add(h, a, b);
+    fe_add(e, p.X, p.Y);
+    fe_sq(e, e);
+    fe_sub(e, h, e);
+    fe_sub(g, a, b);
+    fe_add(f, c, g);
+}
+KB_FN void ge_tail(ge_p3& r, const fe& e, const fe& f, const fe& g, const fe& h, bool WITH_T)
+{
+    fe_mul(r.X, e, f);
+    fe_mul(r.Y, g, h);
+    fe_mul(r.Z, f, g);
+    if (WITH_T) fe_mul(r.T, e, h);
+}
+
 // compile-time flavours (the flag folds away when the call is inlined with a constant)
 template <bool WITH_T = true>
 KB_FN void ge_add(ge_p3& r, const ge_p3& p, const ge_cached& q) { ge_add_rt(r, p, q, WITH_T); }

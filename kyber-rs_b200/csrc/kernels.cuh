@@ -303,6 +303,59 @@ __global__ void __launch_bounds__(KB_THREADS) k_point_add(size_t n, const uint8_
     if (status) status[i] = (uint8_t)(ok ^ 1u);
 }
 
+// ---- the uncompressed, device-friendly form for chaining: X, Y, Z, T as 4 x 8 little-endian words (128 bytes per
+// point, the form kb_msm's partial sums use).  ExtendedGroupElement::set_bytes / write_bytes (ge.rs:124, :112).
+__global__ void __launch_bounds__(KB_THREADS) k_point_decompress(size_t n, const uint8_t* in, uint32_t* out128, uint8_t* status)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    kb_load32(w, in, i);
+    ge_p3 p;
+    const uint32_t ok = ge_decompress(p, w);
+    if (!ok) ge_identity(p);
+    uint32_t* o = out128 + 32 * i;
+    kb_store_fe(o, p.X);
+    kb_store_fe(o + 8, p.Y);
+    kb_store_fe(o + 16, p.Z);
+    kb_store_fe(o + 24, p.T);
+    if (status) status[i] = (uint8_t)(ok ^ 1u);
+}
+// 128-byte form -> (X, Y, Z) for the batch compressor; Z = 0 encodes as 32 zero bytes (fe_invert(0) = 0, ge.rs:112-122)
+__global__ void __launch_bounds__(KB_THREADS) k_points_from_raw(size_t n, const uint32_t* in128, uint32_t* xyz, uint8_t* zero_out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_p3 p;
+    const uint32_t* o = in128 + 32 * i;
+    kb_load_fe(p.X, o);
+    kb_load_fe(p.Y, o + 8);
+    kb_load_fe(p.Z, o + 16);
+    const uint32_t z0 = fe_is_zero(p.Z);
+    if (z0) ge_identity(p);
+    kb_store_xyz(xyz, i, p);
+    zero_out[i] = (uint8_t)z0;
+}
+// ---- Point::eq (point.rs:227-241): equality of the canonical encodings of two decoded points; bit 1 of the
+// result flags an operand that does not decode (the reference cannot even construct such a Point)
+__global__ void __launch_bounds__(KB_THREADS) k_point_eq(size_t n, const uint8_t* pa, const uint8_t* pb, uint8_t* out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    ge_p3 p, q;
+    kb_load32(w, pa, i);
+    uint32_t ok = ge_decompress(p, w);
+    kb_load32(w, pb, i);
+    ok &= ge_decompress(q, w);
+    fe d;   // both have Z = 1
+    fe_sub(d, p.X, q.X);
+    uint32_t same = fe_is_zero(d);
+    fe_sub(d, p.Y, q.Y);
+    same &= fe_is_zero(d);
+    out[i] = (uint8_t)((same & ok) | ((ok ^ 1u) << 1));
+}
+
 // ---- Point::is_canonical / has_small_order / decodes   (point.rs:322, :286; ge.rs:124)
 __global__ void __launch_bounds__(KB_THREADS) k_point_check(size_t n, const uint8_t* in, uint8_t* flags)
 {

@@ -482,32 +482,39 @@ KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, c
 // to the cached form, Z = 1).
 KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
 {
-    ge_cached c;
     ge_identity(h);
     KB_NOUNROLL
     for (int i = nwin - 1; i >= -KB_COMB_POS; i--) {
         KB_LOCKSTEP();
-        if (i >= 0 && i != nwin - 1) {
-            KB_NOUNROLL
-            for (int k = 0; k < 4; k++) ge_dbl_rt(h, h, k == 3);
-        }
-        const int nadd = i >= 0 ? 2 : 1;
+        // a window = up to four doublings, then its additions; every step ends in the same four products
+        const int ndbl = (i >= 0 && i != nwin - 1) ? 4 : 0;
+        const int nstep = ndbl + (i >= 0 ? 2 : 1);
         KB_NOUNROLL
-        for (int a = 0; a < nadd; a++) {
-            if (i >= 0) {
-                ge_select_cached<false>(c, tbl + 8 * a, a ? eu[i] : ev[i]);
+        for (int step = 0; step < nstep; step++) {
+            fe e, f, g, hh;
+            bool with_t;
+            if (step < ndbl) {
+                ge_dbl_front(e, f, g, hh, h);
+                with_t = step == ndbl - 1;
             } else {
-                const int p = -1 - i;
-                const int d = dw[p];
-                const uint32_t neg = (uint32_t)d >> 31;
-                const int babs = (d ^ -(int)neg) + (int)neg;
-                ge_cached_identity(c);
-                if (babs != 0) kb_ld_precomp(c, comb + (size_t)p * KB_COMB_HALF + (babs - 1));
-                ge_cached_cneg(c, neg);
+                const int a = step - ndbl;
+                ge_cached c;
+                if (i >= 0) {
+                    ge_select_cached<false>(c, tbl + 8 * a, a ? eu[i] : ev[i]);
+                } else {
+                    const int p = -1 - i;
+                    const int d = dw[p];
+                    const uint32_t neg = (uint32_t)d >> 31;
+                    const int babs = (d ^ -(int)neg) + (int)neg;
+                    ge_cached_identity(c);
+                    if (babs != 0) kb_ld_precomp(c, comb + (size_t)p * KB_COMB_HALF + (babs - 1));
+                    ge_cached_cneg(c, neg);
+                }
+                ge_add_front(e, f, g, hh, h, c);
+                // T is dead when a doubling (or the end) follows
+                with_t = !((i > 0 && step + 1 == nstep) || i == -KB_COMB_POS);
             }
-            // T is dead when a doubling (or the end) follows
-            const bool dead = (i > 0 && a + 1 == nadd) || i == -KB_COMB_POS;
-            ge_add_rt(h, h, c, !dead);
+            ge_tail(h, e, f, g, hh, with_t);
         }
     }
 }

@@ -33,6 +33,9 @@ extern "C" {
     pub fn kb_point_from_limbs_batch(ctx: *mut kb_ctx, n: usize, limbs: *const i32, out: *mut u8) -> c_int;
     pub fn kb_point_add_batch(ctx: *mut kb_ctx, n: usize, p: *const u8, q: *const u8, out: *mut u8, status: *mut u8, subtract: c_int) -> c_int;
     pub fn kb_point_check_batch(ctx: *mut kb_ctx, n: usize, input: *const u8, flags_out: *mut u8) -> c_int;
+    pub fn kb_point_decompress_batch(ctx: *mut kb_ctx, n: usize, input: *const u8, out128: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_point_compress_batch(ctx: *mut kb_ctx, n: usize, in128: *const u8, out: *mut u8) -> c_int;
+    pub fn kb_point_eq_batch(ctx: *mut kb_ctx, n: usize, p: *const u8, q: *const u8, equal_out: *mut u8) -> c_int;
 
     pub fn kb_sc_reduce64_batch(ctx: *mut kb_ctx, n: usize, in64: *const u8, out32: *mut u8) -> c_int;
     pub fn kb_sc_muladd_batch(ctx: *mut kb_ctx, n: usize, a: *const u8, b: *const u8, c: *const u8, out: *mut u8) -> c_int;

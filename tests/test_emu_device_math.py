@@ -145,8 +145,19 @@ def test_half_size_lattice_step(emu):
     out = ctypes.create_string_buffer(64)
     N = 8 * O.L
     special = [0, 1, 2, 3, 7, 8, O.L - 1, O.L - 2, O.L // 2, O.L // 3, 2**128, 2**127 + 1, 2**64, 2**200 + 5, (N // 3) % O.L, (N // 5 + 1) % O.L]
+    # rationals k/m of the modulus (short vectors with tiny u, the Lehmer batches' awkward cases), powers of two,
+    # Fibonacci numbers (all quotients 1)
+    for m in range(1, 400):
+        for k in (1, 2, m // 2 + 1, m - 1):
+            for d in (-2, -1, 0, 1, 2, 2**64, 2**128 + 1):
+                special.append(((N * k) // m + d) % O.L)
+    special += [(mul << e) % O.L for e in range(1, 253, 3) for mul in (1, 3, 5)]
+    fa, fb = 1, 1
+    while fb < O.L:
+        special.append(fb)
+        fa, fb = fb, fa + fb
     worst = 0
-    for k in range(1200):
+    for k in range(len(special) + 20000):
         h = special[k] if k < len(special) else rnd.randrange(O.L)
         r = emu.emu_sc_half(out, b32(h))
         bits, vneg = r & 0xFFFF, r >> 16

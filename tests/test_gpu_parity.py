@@ -126,6 +126,46 @@ def test_recode_add_check(ctx, coracle, golden_records):
 
 
 # ---- scalars and the challenge hash ---------------------------------------------------------------
+def test_decompress_compress_eq(ctx, coracle, golden_records):
+    """The uncompressed chaining form: decompress -> compress is the reference's unmarshal -> marshal (re-encoding,
+    so y >= p comes back reduced); Point::eq (point.rs:227-241) compares re-encodings."""
+    rnd = np.random.default_rng(21)
+    pts = [r[1] for r in golden_records[:300]] + list(O.WEAK_KEYS)
+    pts += [bytes([0xEE]) + b"\xff" * 30 + b"\x7f", bytes([0xF0]) + b"\xff" * 30 + b"\xff", bytes([1]) + bytes(30) + b"\x80"]   # y >= p twice, identity with sign bit
+    pts += [rnd.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(200)]
+    arr = np.frombuffer(b"".join(pts), dtype=np.uint8).reshape(-1, 32)
+    raw, st = ctx.point_decompress_batch(arr)
+    enc = ctx.point_compress_batch(raw)
+    for k, p in enumerate(pts):
+        want = coracle.point_recode(p)
+        assert (st[k] == 0) == (want is not None)
+        if want is not None:
+            assert enc[k].tobytes() == want
+        else:
+            assert enc[k].tobytes() == O.point_encode(O.IDENTITY)
+    # Z = 0 (Point::default()) encodes as zeros; a scaled representative compresses to the same bytes
+    z = raw[:4].copy()
+    z[0, 16:24] = 0
+    for c in range(4):   # multiply X, Y, Z, T of item 1 by 2 (still < 2^256 for these small limbs? use doubling via add mod p on host)
+        v = int.from_bytes(z[1, 8 * c:8 * c + 8].tobytes(), "little") * 2 % O.P
+        z[1, 8 * c:8 * c + 8] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint32)
+    ez = ctx.point_compress_batch(z)
+    assert ez[0].tobytes() == bytes(32) and ez[1].tobytes() == enc[1].tobytes() and ez[2].tobytes() == enc[2].tobytes()
+    # eq: same point through a different encoding, different points, undecodable operand
+    a = arr.copy()
+    b = arr.copy()
+    b[1] = arr[2]
+    noncanon = np.frombuffer(bytes([0xEE]) + b"\xff" * 30 + b"\x7f", dtype=np.uint8)   # y = p + 1 -> the point y = 1
+    a[3] = noncanon
+    b[3] = np.frombuffer(O.point_encode(O.IDENTITY), dtype=np.uint8)
+    got = ctx.point_eq_batch(a, b)
+    for k in range(len(pts)):
+        pa, pb = coracle.point_recode(a[k].tobytes()), coracle.point_recode(b[k].tobytes())
+        want = (2 if (pa is None or pb is None) else 0) | (1 if (pa is not None and pa == pb) else 0)
+        assert got[k] == want, k
+    assert got[1] == 0 and got[3] == 1
+
+
 def test_scalar_ops_and_challenge(ctx, coracle, golden_records):
     d = np.frombuffer(xof_bytes("digests", 1000 * 64), dtype=np.uint8).reshape(-1, 64).copy()
     d[0] = 255
