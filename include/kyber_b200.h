@@ -117,7 +117,11 @@ int kb_sc_invert_batch(kb_ctx* ctx, size_t n, const uint8_t* a, uint8_t* out);
 int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out32);
 
 /* ---- signatures ----------------------------------------------------------------------- */
-/* eddsa::verify_with_checks (sign/eddsa/eddsa_sig.rs:159-212); sig is n x 64 bytes */
+/* eddsa::verify_with_checks (sign/eddsa/eddsa_sig.rs:159-212); sig is n x 64 bytes.
+ * Two independent kernel families return the reference's status: the default multiplies the reference's equation by
+ * an odd u with u*h = v (mod 8L), |u|, |v| ~ 2^128 (128 doublings instead of 253; equivalent for every input because the
+ * whole curve group has order 8L — csrc/half.cuh); KB_VERIFY_FULL=1 in the environment of kb_ctx_create selects the
+ * full-length kernels.  KB_VERIFY_CHUNK_LOG2=k fixes the chunk size of the pipelined host-buffer calls to 2^k signatures. */
 int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);
 /* schnorr::verify_with_checks (sign/schnorr/schnorr_sig.rs:53-110) */
 int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);

@@ -255,6 +255,30 @@ def test_verify_paths_agree_on_random_batch(kb, ctx, ctx_full, coracle):
     assert (a[:m] == want).all()
 
 
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_device_resident_verify_and_kernel_timing(ctx, ctx_full, coracle, golden_records, schnorr):
+    """kb_dev_eddsa_verify on torch tensors (the path bench.py times) gives the oracle's statuses on both kernel
+    families, for batch sizes around the block / warp boundaries, and kb_verify_kernel_times reports both launches."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    for n in (1, 31, 64, 129, 1000):
+        pks, msgs, sigs = make_sig_batch(golden_records[5:], n, bad_every=3)
+        pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+        want = coracle.verify_batch(pk, flat, off, sg, nthreads=4, schnorr=schnorr)
+        d_pk, d_sig = torch.from_numpy(pk).to(dev), torch.from_numpy(sg).to(dev)
+        d_msg = torch.from_numpy(flat if flat.size else np.zeros(1, dtype=np.uint8)).to(dev)
+        d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+        for c in (ctx, ctx_full):
+            d_st = torch.full((n,), 99, dtype=torch.uint8, device=dev)
+            c.verify_kernel_timing(True)
+            c.dev_verify(n, d_pk, d_msg, d_off, d_sig, d_st, schnorr=schnorr)
+            a_ms, b_ms = c.last_verify_kernel_ms()
+            c.verify_kernel_timing(False)
+            assert a_ms > 0 and b_ms > 0
+            assert (d_st.cpu().numpy() == want).all()
+
+
 def test_verify_host_mirror_errors(kb, ctx, golden_records):
     """Reads like sign/eddsa/eddsa_test.rs: error strings are the reference's."""
     H = kb.host
