@@ -103,6 +103,10 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         kb_msm_plan pl;
         pl.n = (uint32_t)cn;
         pl.c = kb_msm_window_bits_host(cn);
+        if (const char* ce = getenv("KB_MSM_C")) {   // tuning override (tools/bench_msm.py sweeps)
+            const int cv = atoi(ce);
+            if (cv >= 4 && cv <= 16) pl.c = (uint32_t)cv;   // measured at 2^22: c = 15 / 16 / 17 -> 15.6 / 15.3 / 15.6 ms
+        }
         pl.windows = (257 + pl.c - 1) / pl.c;
         pl.half = 1u << (pl.c - 1);
         pl.nb = pl.windows * pl.half;
