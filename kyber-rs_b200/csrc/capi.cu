@@ -24,6 +24,7 @@ struct kb_ctx {
     ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
+    int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
     int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
     int timing_valid;
     cudaEvent_t tev[3];
@@ -193,6 +194,9 @@ int kb_ctx_create(int device, kb_ctx** out)
         const char* vc = getenv("KB_VERIFY_CHUNK_LOG2");
         const int vcl = vc ? atoi(vc) : 0;
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
+        const char* vw = getenv("KB_VERIFY_MIN_WINDOWS");
+        const int vwn = vw ? atoi(vw) : 0;
+        ctx->verify_min_windows = (vwn > KB_HALF_MIN_WINDOWS && vwn <= 64) ? vwn : KB_HALF_MIN_WINDOWS;
         const char* vf = getenv("KB_VERIFY_FULL");
         ctx->verify_full = (vf && vf[0] == '1') ? 1 : 0;
         ctx->launches += 2;
@@ -304,8 +308,8 @@ static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const ui
         else k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
         KB_LAUNCHED();
         if (tm) cudaEventRecord(ctx->tev[1], st);
-        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
-        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb);
+        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
+        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
         KB_LAUNCHED();
         if (tm) {
             cudaEventRecord(ctx->tev[2], st);

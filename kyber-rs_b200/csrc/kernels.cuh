@@ -554,10 +554,10 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify
 #define KB_VERIFY_HALF_MINBLOCKS 3
 #endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb)
+__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb, int min_windows)
 {
     __shared__ int s_nwin;
-    if (threadIdx.x == 0) s_nwin = KB_HALF_MIN_WINDOWS;
+    if (threadIdx.x == 0) s_nwin = min_windows;   // KB_HALF_MIN_WINDOWS, or more when a test forces long loops
     __syncthreads();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;   // tail threads redo the last item so that they reach the block barriers

@@ -39,6 +39,19 @@ def ctx_full(kb):
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_long(kb):
+    """The half-size-scalar kernel forced to run 64 windows in every block — what an adversarial challenge whose
+    lattice has no short vector with an odd u would make it do (never a hash output)."""
+    os.environ["KB_VERIFY_MIN_WINDOWS"] = "64"
+    try:
+        c = kb.Context(0)
+    finally:
+        del os.environ["KB_VERIFY_MIN_WINDOWS"]
+    yield c
+    c.close()
+
+
 def _golden_pks(records, n):
     return np.frombuffer(b"".join(r[1] for r in records[:n]), dtype=np.uint8).reshape(-1, 32).copy()
 
@@ -224,6 +237,21 @@ def test_verify_mixed_order_keys(ctx, ctx_full, coracle, golden_records, schnorr
     for c in (ctx, ctx_full):
         got = c.verify_batch(pk, flat, off, sg, schnorr=schnorr)
         assert (got == want).all(), np.nonzero(got != want)[0][:10]
+
+
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_verify_long_window_loops(ctx_long, coracle, golden_records, schnorr):
+    """Same verdicts when every block runs the maximum number of windows (block-uniform trip count above what its
+    own signatures need: the extra windows only add identities)."""
+    good, bad = make_mixed_order_sigs(16, seed=11)
+    pks, msgs, sigs = make_sig_batch(golden_records[300:], 700, bad_every=2)
+    pks += [x[0] for x in good + bad]
+    msgs += [x[1] for x in good + bad]
+    sigs += [x[2] for x in good + bad]
+    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+    got = ctx_long.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+    want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
 
 
 def test_verify_paths_agree_on_random_batch(kb, ctx, ctx_full, coracle):
