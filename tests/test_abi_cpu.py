@@ -29,6 +29,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, sym), sym
 
 
+def test_header_is_plain_c_and_the_c_harness_compiles(tmp_path):
+    """include/kyber_b200.h is valid C99 and C++17 on its own, and the plain-C caller of tests/c compiles against it
+    (it is linked and run by the -m gpu suite)."""
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "kyber_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", hdr])
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-c", os.path.join(ROOT, "tests", "c", "abi_check.c"),
+                           "-o", str(tmp_path / "abi_check.o")])
+
+
 def test_no_cpu_fallback():
     import torch
 

@@ -307,6 +307,33 @@ def test_device_resident_verify_and_kernel_timing(ctx, ctx_full, coracle, golden
             assert (d_st.cpu().numpy() == want).all()
 
 
+def test_c_abi_from_plain_c(kb, coracle, golden_records, tmp_path):
+    """tests/c/abi_check.c: the boundary called from plain C (gcc, -lkyber_b200) — no Python, no torch in the
+    process — on a fixture whose expected bytes come from the oracle."""
+    import subprocess
+
+    from helpers import ROOT
+
+    n = 1500
+    pks, msgs, sigs = make_sig_batch(golden_records, n, bad_every=4)
+    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+    want = coracle.verify_batch(pk, flat, off, sg, nthreads=8)
+    scalars = np.frombuffer(xof_bytes("kyber-b200/test/c-abi", 32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    want_mul = coracle.mul_base_batch(scalars)
+    fx = tmp_path / "fixture.bin"
+    with open(fx, "wb") as f:
+        f.write(np.array([n, flat.size], dtype=np.uint64).tobytes())
+        for a in (pk, sg, off, flat, want.astype(np.uint8), scalars, want_mul):
+            f.write(np.ascontiguousarray(a).tobytes())
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(kb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_check.c"),
+                           "-L", libdir, "-lkyber_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    r = subprocess.run([str(exe), str(fx)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches=0" in r.stdout
+
+
 def test_verify_host_mirror_errors(kb, ctx, golden_records):
     """Reads like sign/eddsa/eddsa_test.rs: error strings are the reference's."""
     H = kb.host
