@@ -8,6 +8,7 @@
 #include "../../include/kyber_b200.h"
 #include "kernels.cuh"
 #include "msm.cuh"
+#include "dkgfd.cuh"
 
 #define KB_NSLOTS 48
 #define KB_VERIFY_CHUNK (1u << 18)   // largest signatures-per-chunk of the pipelined host-buffer verify calls
@@ -24,6 +25,7 @@ struct kb_ctx {
     ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
+    int dkg_fd;              // KB_DKG_FD: 1 = always / 0 = never use the forward-difference DKG round (default: by cost)
     int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
     int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
     int timing_valid;
@@ -194,6 +196,8 @@ int kb_ctx_create(int device, kb_ctx** out)
         const char* vc = getenv("KB_VERIFY_CHUNK_LOG2");
         const int vcl = vc ? atoi(vc) : 0;
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
+        const char* fd = getenv("KB_DKG_FD");
+        ctx->dkg_fd = fd ? atoi(fd) : -1;
         const char* vw = getenv("KB_VERIFY_MIN_WINDOWS");
         const int vwn = vw ? atoi(vw) : 0;
         ctx->verify_min_windows = (vwn > KB_HALF_MIN_WINDOWS && vwn <= 64) ? vwn : KB_HALF_MIN_WINDOWS;
@@ -365,10 +369,133 @@ static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_com
     }
     return KB_OK;
 }
+// fact[k] = k! mod 8L in signed form: 8 words of magnitude (<= 4L, inside the domain of the radix-16 recoding) + 1 word
+// of sign.  Host integers only (this is table construction, like the window counts of the MSM plan).
+static void kb_factorials_mod_8l(size_t t, uint32_t* out)
+{
+    const uint64_t N[4] = {0xc09318d2e7ae9f68ull, 0xa6f7cef517bce6b2ull, 0ull, 0x8000000000000000ull};
+    const uint64_t H[4] = {0x60498c6973d74fb4ull, 0x537be77a8bde7359ull, 0ull, 0x4000000000000000ull};   // N / 2 = 4L
+    uint64_t x[4] = {1, 0, 0, 0};
+    for (size_t k = 0; k < t; k++) {
+        if (k >= 2) {
+            uint64_t y[5];
+            unsigned __int128 c = 0;
+            for (int i = 0; i < 4; i++) {
+                c += (unsigned __int128)x[i] * (uint64_t)k;
+                y[i] = (uint64_t)c;
+                c >>= 64;
+            }
+            y[4] = (uint64_t)c;
+            // N = 2^255 + (a 128-bit number): floor(y / 2^255) is the quotient or one more
+            const uint64_t q = (y[4] << 1) | (y[3] >> 63);
+            unsigned __int128 mc = 0;
+            uint64_t qn[5];
+            for (int i = 0; i < 4; i++) {
+                mc += (unsigned __int128)N[i] * q;
+                qn[i] = (uint64_t)mc;
+                mc >>= 64;
+            }
+            qn[4] = (uint64_t)mc;
+            uint64_t borrow = 0;
+            for (int i = 0; i < 5; i++) {
+                const unsigned __int128 dd = (unsigned __int128)y[i] - qn[i] - borrow;
+                y[i] = (uint64_t)dd;
+                borrow = (uint64_t)(dd >> 64) & 1u;
+            }
+            if (borrow) {   // one N too many: add it back
+                unsigned __int128 a = 0;
+                for (int i = 0; i < 5; i++) {
+                    a += (unsigned __int128)y[i] + (i < 4 ? N[i] : 0);
+                    y[i] = (uint64_t)a;
+                    a >>= 64;
+                }
+            }
+            for (int i = 0; i < 4; i++) x[i] = y[i];
+        }
+        // signed representative
+        bool big = false;
+        for (int i = 3; i >= 0; i--) {
+            if (x[i] != H[i]) {
+                big = x[i] > H[i];
+                break;
+            }
+        }
+        uint64_t m[4];
+        if (big) {
+            uint64_t borrow = 0;
+            for (int i = 0; i < 4; i++) {
+                const unsigned __int128 dd = (unsigned __int128)N[i] - x[i] - borrow;
+                m[i] = (uint64_t)dd;
+                borrow = (uint64_t)(dd >> 64) & 1u;
+            }
+        } else {
+            for (int i = 0; i < 4; i++) m[i] = x[i];
+        }
+        for (int i = 0; i < 4; i++) {
+            out[9 * k + 2 * i] = (uint32_t)m[i];
+            out[9 * k + 2 * i + 1] = (uint32_t)(m[i] >> 32);
+        }
+        out[9 * k + 8] = big ? 1u : 0u;
+    }
+}
+// The whole round by forward differences (dkgfd.cuh): t - 1 wavefront launches, one scaling launch, n step launches,
+// one check launch.
+static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, const uint8_t* d_commits, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
+{
+    uint32_t *q0, *q1, *q2, *evals, *dbad, *fact;
+    const size_t cells = nd * t;
+    KB_SCRATCH(8, 128 * cells, q0);
+    KB_SCRATCH(30, 128 * cells, q1);
+    KB_SCRATCH(31, 128 * cells, q2);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * nd * n, evals);
+    KB_SCRATCH(9, 4 * nd, dbad);
+    KB_SCRATCH(27, 36 * t, fact);
+    {
+        uint32_t* hf = (uint32_t*)malloc(36 * t);
+        if (!hf) return KB_ERR_NOMEM;
+        kb_factorials_mod_8l(t, hf);
+        cudaError_t e = cudaMemcpyAsync(fact, hf, 36 * t, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // hf is pageable: the copy is staged, but keep it simple
+        free(hf);
+        if (e != cudaSuccess) return kb_fail(ctx, e, "factorial table");
+    }
+    KB_CUDA(cudaMemsetAsync(dbad, 0, 4 * nd, st));
+    k_fd_init<<<kb_blocks(cells, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, d_commits, q0, q1, dbad);
+    KB_LAUNCHED();
+    for (size_t w = 1; w + 1 <= t; w++) {
+        k_fd_newton<<<kb_blocks(nd * w, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, w, q0, q1);
+        KB_LAUNCHED();
+    }
+    k_fd_scale<<<kb_blocks(cells, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, q0, q1, fact, q2);
+    KB_LAUNCHED();
+    uint32_t *src = q2, *dst = q0;
+    for (size_t i = 0; i < n; i++) {
+        k_fd_step<<<kb_blocks(cells, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, n, i, src, dst, evals);
+        KB_LAUNCHED();
+        uint32_t* tmp = src;
+        src = dst;
+        dst = tmp;
+    }
+    k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 0, st>>>(nd, n, evals, d_shares, dbad, ctx->comb, d_verdict);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+// multiplies (IMAD-eq) per dealer: Horner per share check against Newton conversion + scaling + difference steps
+static bool kb_dkg_use_fd(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
+{
+    if (ctx->dkg_fd == 0) return false;
+    if (ctx->dkg_fd == 1) return true;
+    const double horner = (double)n * t * 6800.0;
+    const double fd = 0.5 * t * t * 4600.0 + t * 138300.0 + (double)n * t * 660.0 + n * 11000.0;
+    // every wavefront / step is a launch of nd * (up to t) threads: it needs a GPU's worth of them to pay
+    return nd * t >= 65536 && fd * 1.25 < horner;
+}
 int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream)
 {
     if (!ctx || !t || (n && ndealers && (!d_commits || !d_shares || !d_verdict))) return KB_ERR_ARG;
     if (n == 0 || ndealers == 0) return KB_OK;
+    if (kb_dkg_use_fd(ctx, n, t, ndealers))
+        return kb_dkg_fd_run(ctx, n, t, ndealers, (const uint8_t*)d_commits, (const uint8_t*)d_shares, (uint8_t*)d_verdict, (cudaStream_t)stream);
     return kb_poly_run(ctx, ndealers, t, (const uint8_t*)d_commits, n * ndealers, nullptr, nullptr, n, (const uint8_t*)d_shares, (uint8_t*)d_verdict, nullptr, (cudaStream_t)stream);
 }
 

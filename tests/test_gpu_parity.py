@@ -437,6 +437,48 @@ def test_dkg_round_small(ctx, coracle):
     assert (part.reshape(n, n)[8:16] == want[8:16]).all()
 
 
+@pytest.fixture(scope="module")
+def ctx_fd(kb):
+    """A context that always runs DKG rounds by forward differences (csrc/dkgfd.cuh); the default picks by cost."""
+    os.environ["KB_DKG_FD"] = "1"
+    try:
+        c = kb.Context(0)
+    finally:
+        del os.environ["KB_DKG_FD"]
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n,t,nd", [(24, 16, 24), (5, 1, 3), (7, 2, 4), (9, 3, 33), (40, 40, 5), (12, 30, 7), (130, 67, 40)])
+def test_dkg_round_forward_differences(ctx, ctx_fd, coracle, n, t, nd):
+    """The forward-difference round (Newton conversion, k! scaling, difference steps) gives the verdicts of the
+    per-share Horner kernel and of the oracle: honest and corrupted shares, a dealer whose commitment carries a
+    small-order component (integer identities only: exact there too), a dealer with an undecodable commitment."""
+    polys = [_poly(b"fd%d" % d, t) for d in range(nd)]
+    commits = ctx.point_mul_base_batch(np.frombuffer(b"".join(b"".join(p) for p in polys), dtype=np.uint8).reshape(-1, 32)).copy()
+    shares = np.frombuffer(b"".join(O.pripoly_eval(polys[d], i) for d in range(nd) for i in range(n)), dtype=np.uint8).reshape(-1, 32).copy()
+    rng = np.random.default_rng(n * 1000 + t)
+    for _ in range(max(2, nd * n // 10)):
+        shares[rng.integers(0, nd * n), rng.integers(0, 31)] ^= 1 << rng.integers(0, 8)
+    if nd > 2:   # dealer 1: torsion-contaminated commitment; dealer 2: undecodable commitment
+        j = min(1, t - 1)
+        c = O.point_add(O.point_decode(commits[1 * t + j].tobytes()), O.point_decode(O.WEAK_KEYS[2]))
+        commits[1 * t + j] = np.frombuffer(O.point_encode(c), dtype=np.uint8)
+        k = 0
+        while coracle.point_decode_ok(bytes([k]) + b"\x13" * 31):
+            k += 1
+        commits[2 * t + (t - 1)] = np.frombuffer(bytes([k]) + b"\x13" * 31, dtype=np.uint8)
+    a = ctx.dkg_verify_round(n, t, commits, shares, dealer_lo=0, dealer_hi=nd).reshape(-1)[:nd * n]
+    b = ctx_fd.dkg_verify_round(n, t, commits, shares, dealer_lo=0, dealer_hi=nd).reshape(-1)[:nd * n]
+    assert (a == b).all(), np.nonzero(a != b)[0][:10]
+    for d in range(min(nd, 4)):
+        if nd > 2 and d == 2:
+            assert not b[d * n:(d + 1) * n].any()
+            continue
+        row = coracle.vss_verify_batch(commits[d * t:(d + 1) * t], np.arange(n, dtype=np.uint32), shares[d * n:(d + 1) * n], nthreads=4)
+        assert (row == b[d * n:(d + 1) * n]).all()
+
+
 # ---- MSM -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [0, 1, 2, 33, 1000, 5000])
 def test_msm_matches_oracle(ctx, coracle, golden_records, n):
