@@ -25,6 +25,9 @@ struct kb_ctx {
     ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
+    int fd_groups;           // KB_FD_GROUPS: independent dealer groups (streams) of the forward-difference round
+    cudaStream_t fd_stream[4];
+    cudaEvent_t fd_event[4];
     int dkg_fd;              // KB_DKG_FD: 1 = always / 0 = never use the forward-difference DKG round (default: by cost)
     int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
     int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
@@ -198,6 +201,10 @@ int kb_ctx_create(int device, kb_ctx** out)
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
         const char* fd = getenv("KB_DKG_FD");
         ctx->dkg_fd = fd ? atoi(fd) : -1;
+        const char* fg = getenv("KB_FD_GROUPS");
+        ctx->fd_groups = fg ? atoi(fg) : 2;
+        if (ctx->fd_groups < 1) ctx->fd_groups = 1;
+        if (ctx->fd_groups > 4) ctx->fd_groups = 4;
         const char* vw = getenv("KB_VERIFY_MIN_WINDOWS");
         const int vwn = vw ? atoi(vw) : 0;
         ctx->verify_min_windows = (vwn > KB_HALF_MIN_WINDOWS && vwn <= 64) ? vwn : KB_HALF_MIN_WINDOWS;
@@ -231,6 +238,10 @@ void kb_ctx_destroy(kb_ctx* ctx)
     if (ctx->comb) cudaFree(ctx->comb);
     for (int k = 0; k < 3; k++)
         if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
+    for (int k = 0; k < 4; k++) {
+        if (ctx->fd_stream[k]) cudaStreamDestroy(ctx->fd_stream[k]);
+        if (ctx->fd_event[k]) cudaEventDestroy(ctx->fd_event[k]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);
@@ -439,7 +450,10 @@ static void kb_factorials_mod_8l(size_t t, uint32_t* out)
     }
 }
 // The whole round by forward differences (dkgfd.cuh): t - 1 wavefront launches, one scaling launch, n step launches,
-// one check launch.
+// one check launch — per GROUP of dealers.  Every launch waits for the previous one of its group, so its tail (the
+// last blocks running on a mostly idle GPU) is lost time; KB_FD_GROUPS independent groups on their own streams fill
+// each other's tails.
+#define KB_FD_MAX_GROUPS 4
 static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, const uint8_t* d_commits, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
 {
     uint32_t *q0, *q1, *q2, *evals, *dbad, *fact;
@@ -460,24 +474,64 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, const uint8
         if (e != cudaSuccess) return kb_fail(ctx, e, "factorial table");
     }
     KB_CUDA(cudaMemsetAsync(dbad, 0, 4 * nd, st));
-    k_fd_init<<<kb_blocks(cells, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, d_commits, q0, q1, dbad);
-    KB_LAUNCHED();
+    // groups of dealers (multiples of 32 so that warps stay uniform), each a contiguous slice of every array
+    int ng = ctx->fd_groups;
+    while (ng > 1 && nd / ng < 64) ng--;
+    size_t g0[KB_FD_MAX_GROUPS + 1];
+    for (int g = 0; g <= ng; g++) g0[g] = (g == ng) ? nd : (nd * g / ng) / 32 * 32;
+    cudaStream_t gs[KB_FD_MAX_GROUPS];
+    gs[0] = st;
+    for (int g = 1; g < ng; g++) {
+        if (!ctx->fd_stream[g]) {
+            KB_CUDA(cudaStreamCreateWithFlags(&ctx->fd_stream[g], cudaStreamNonBlocking));
+            KB_CUDA(cudaEventCreateWithFlags(&ctx->fd_event[g], cudaEventDisableTiming));
+        }
+        gs[g] = ctx->fd_stream[g];
+    }
+    if (ng > 1) {
+        if (!ctx->fd_event[0]) KB_CUDA(cudaEventCreateWithFlags(&ctx->fd_event[0], cudaEventDisableTiming));
+        KB_CUDA(cudaEventRecord(ctx->fd_event[0], st));
+        for (int g = 1; g < ng; g++) KB_CUDA(cudaStreamWaitEvent(gs[g], ctx->fd_event[0], 0));
+    }
+#define KB_FD_G(ptr, words_per_dealer) ((ptr) + (size_t)(words_per_dealer) * g0[g])
+    for (int g = 0; g < ng; g++) {
+        const size_t dn = g0[g + 1] - g0[g];
+        k_fd_init<<<kb_blocks(dn * t, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, d_commits + 32 * t * g0[g], KB_FD_G(q0, 32 * t), KB_FD_G(q1, 32 * t), dbad + g0[g]);
+        KB_LAUNCHED();
+    }
     for (size_t w = 1; w + 1 <= t; w++) {
-        k_fd_newton<<<kb_blocks(nd * w, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, w, q0, q1);
+        for (int g = 0; g < ng; g++) {
+            const size_t dn = g0[g + 1] - g0[g];
+            k_fd_newton<<<kb_blocks(dn * w, KB_FD_NEWTON_THREADS), KB_FD_NEWTON_THREADS, 0, gs[g]>>>(dn, t, w, KB_FD_G(q0, 32 * t), KB_FD_G(q1, 32 * t));
+            KB_LAUNCHED();
+        }
+    }
+    for (int g = 0; g < ng; g++) {
+        const size_t dn = g0[g + 1] - g0[g];
+        k_fd_scale<<<kb_blocks(dn * t, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, KB_FD_G(q0, 32 * t), KB_FD_G(q1, 32 * t), fact, KB_FD_G(q2, 32 * t));
         KB_LAUNCHED();
     }
-    k_fd_scale<<<kb_blocks(cells, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, q0, q1, fact, q2);
-    KB_LAUNCHED();
-    uint32_t *src = q2, *dst = q0;
+    // difference steps.  (Walking the dealers in sequential groups whose two arrays fit the L2 was measured SLOWER —
+    // the steps are bound by the additions and by the per-launch tail, not by memory.)
     for (size_t i = 0; i < n; i++) {
-        k_fd_step<<<kb_blocks(cells, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, n, i, src, dst, evals);
-        KB_LAUNCHED();
-        uint32_t* tmp = src;
-        src = dst;
-        dst = tmp;
+        for (int g = 0; g < ng; g++) {
+            const size_t dn = g0[g + 1] - g0[g];
+            uint32_t* a = (i & 1) ? KB_FD_G(q0, 32 * t) : KB_FD_G(q2, 32 * t);
+            uint32_t* b2 = (i & 1) ? KB_FD_G(q2, 32 * t) : KB_FD_G(q0, 32 * t);
+            k_fd_step<<<kb_blocks(dn * t, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, n, i, a, b2, KB_FD_G(evals, 24 * n));
+            KB_LAUNCHED();
+        }
     }
-    k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 0, st>>>(nd, n, evals, d_shares, dbad, ctx->comb, d_verdict);
-    KB_LAUNCHED();
+    for (int g = 0; g < ng; g++) {
+        const size_t dn = g0[g + 1] - g0[g];
+        k_fd_check<<<kb_blocks(dn * n, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, n, KB_FD_G(evals, 24 * n), d_shares + 32 * n * g0[g], dbad + g0[g], ctx->comb, d_verdict + n * g0[g]);
+        KB_LAUNCHED();
+    }
+#undef KB_FD_G
+    for (int g = 1; g < ng; g++) {
+        KB_CUDA(cudaEventRecord(ctx->fd_event[g], gs[g]));
+        KB_CUDA(cudaStreamWaitEvent(st, ctx->fd_event[g], 0));
+    }
     return KB_OK;
 }
 // multiplies (IMAD-eq) per dealer: Horner per share check against Newton conversion + scaling + difference steps

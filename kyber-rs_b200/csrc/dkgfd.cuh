@@ -25,6 +25,12 @@
 #include "kernels.cuh"
 
 #define KB_FD_AT(arr, k, d, nd) ((arr) + (((size_t)(k) * (nd) + (d)) * 32))
+#ifndef KB_FD_NEWTON_THREADS
+#define KB_FD_NEWTON_THREADS 128
+#endif
+#ifndef KB_FD_NEWTON_MINBLOCKS
+#define KB_FD_NEWTON_MINBLOCKS 3
+#endif
 
 __device__ __forceinline__ void kb_fd_load(ge_p3& p, const uint32_t* o)
 {
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_init(size_t nd, size_t t, con
 }
 
 // wavefront w of the Newton conversion: cells m = 1..w, j = m + t - 2 - w
-__global__ void __launch_bounds__(KB_THREADS) k_fd_newton(size_t nd, size_t t, size_t w, uint32_t* q0, uint32_t* q1)
+__global__ void __launch_bounds__(KB_FD_NEWTON_THREADS, KB_FD_NEWTON_MINBLOCKS) k_fd_newton(size_t nd, size_t t, size_t w, uint32_t* q0, uint32_t* q1)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nd * w) return;

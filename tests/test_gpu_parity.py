@@ -449,7 +449,7 @@ def ctx_fd(kb):
     c.close()
 
 
-@pytest.mark.parametrize("n,t,nd", [(24, 16, 24), (5, 1, 3), (7, 2, 4), (9, 3, 33), (40, 40, 5), (12, 30, 7), (130, 67, 40)])
+@pytest.mark.parametrize("n,t,nd", [(24, 16, 24), (5, 1, 3), (7, 2, 4), (9, 3, 33), (40, 40, 5), (12, 30, 7), (130, 67, 40), (20, 9, 200)])
 def test_dkg_round_forward_differences(ctx, ctx_fd, coracle, n, t, nd):
     """The forward-difference round (Newton conversion, k! scaling, difference steps) gives the verdicts of the
     per-share Horner kernel and of the oracle: honest and corrupted shares, a dealer whose commitment carries a

@@ -1,4 +1,5 @@
-"""ncu target: one deal-verification round n=256, t=171 (65 536 share checks) after a warm-up one."""
+"""ncu target: one deal-verification round (default n=256, t=171: 65 536 share checks) after a warm-up one.
+Usage: python tools/profile_dkg.py [n t]"""
 import importlib
 import os
 import sys
@@ -10,7 +11,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 kb = importlib.import_module("kyber-rs_b200")
-n, t = 256, 171
+n, t = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (256, 171)
 ctx = kb.Context(0)
 dev = torch.device("cuda", 0)
 coeff = bench.xof("kyber-b200/profile-dkg", 32 * n * t).reshape(-1, 32).copy()
