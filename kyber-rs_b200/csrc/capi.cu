@@ -513,12 +513,16 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, const uint8
     }
     // difference steps.  (Walking the dealers in sequential groups whose two arrays fit the L2 was measured SLOWER —
     // the steps are bound by the additions and by the per-launch tail, not by memory.)
+    // A difference of order k only reaches the value k steps later: with R = n - i points still to produce, the orders
+    // >= R are dead and are not updated any more (the last live order reads its neighbour from the array that
+    // neighbour was last written to, which is this step's source).  Saves the final triangle, t^2/2 of the n*t additions.
     for (size_t i = 0; i < n; i++) {
+        const size_t live = (n - i < t) ? n - i : t;
         for (int g = 0; g < ng; g++) {
             const size_t dn = g0[g + 1] - g0[g];
             uint32_t* a = (i & 1) ? KB_FD_G(q0, 32 * t) : KB_FD_G(q2, 32 * t);
             uint32_t* b2 = (i & 1) ? KB_FD_G(q2, 32 * t) : KB_FD_G(q0, 32 * t);
-            k_fd_step<<<kb_blocks(dn * t, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, n, i, a, b2, KB_FD_G(evals, 24 * n));
+            k_fd_step<<<kb_blocks(dn * live, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, live, n, i, a, b2, KB_FD_G(evals, 24 * n));
             KB_LAUNCHED();
         }
     }

@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(KB_FD_NEWTON_THREADS, KB_FD_NEWTON_MINBLOCKS) 
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nd * w) return;
-    const size_t m = idx / nd + 1, d = idx % nd;
+    // the cost of a cell grows with log2(m): the blocks with the large multipliers go first, so that the launch does not
+    // end on them (each launch waits for its slowest block)
+    const size_t m = w - idx / nd, d = idx % nd;
     const size_t j = m + t - 2 - w;
     uint32_t* qm = (m & 1) ? q1 : q0;         // row m
     const uint32_t* qp = (m & 1) ? q0 : q1;   // row m - 1
@@ -113,11 +115,12 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_scale(size_t nd, size_t t, co
     if (live) kb_fd_store(KB_FD_AT(dout, k, d, nd), h);
 }
 
-// one evaluation point: evals[d][i] = Δ^0 (the value at x = i + 1), then dst[k] = src[k] + src[k+1]
-__global__ void __launch_bounds__(KB_THREADS) k_fd_step(size_t nd, size_t t, size_t n, size_t i, const uint32_t* src, uint32_t* dst, uint32_t* evals)
+// one evaluation point: evals[d][i] = Δ^0 (the value at x = i + 1), then dst[k] = src[k] + src[k+1] for the `live`
+// lowest orders (the host drops the orders that can no longer reach a value)
+__global__ void __launch_bounds__(KB_THREADS) k_fd_step(size_t nd, size_t t, size_t live, size_t n, size_t i, const uint32_t* src, uint32_t* dst, uint32_t* evals)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nd * t) return;
+    if (idx >= nd * live) return;
     const size_t k = idx / nd, d = idx % nd;
     ge_p3 p;
     kb_fd_load(p, KB_FD_AT(src, k, d, nd));
