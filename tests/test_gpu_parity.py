@@ -643,7 +643,8 @@ def test_pubpoly_sum_dkg_key(ctx, coracle, golden_records):
     assert (one == pts[:t]).all()
 
 
-def test_cfg4_shape_full_t_two_dealers(ctx, coracle):
+@pytest.mark.parametrize("path", ["horner", "forward-differences"])
+def test_cfg4_shape_full_t_two_dealers(ctx, ctx_fd, coracle, path):
     """BASELINE config 4 shape at full threshold and full verifier count (n = 1024, t = 683) for two dealers
     (the full round is 1024 dealers — CPU-days for the oracle): honest shares are computed independently with
     Python integers (PriPoly::eval, poly.rs:133), a few are corrupted, dealer 1 carries a torsion-contaminated
@@ -669,7 +670,9 @@ def test_cfg4_shape_full_t_two_dealers(ctx, coracle):
     torsion_ok = np.zeros(n, dtype=np.uint8)
     torsion_ok[7::8] = 1            # x = i + 1 divisible by 8
     want[1] &= torsion_ok
-    got = ctx.dkg_verify_round(n, t, commits, shares).reshape(nd, n)
+    # two dealers alone are below the cost threshold of the forward-difference round: ctx_fd forces it, so that its
+    # 682 wavefronts, the 683 factorials mod 8L and all 1024 difference steps are held to the same expected verdicts
+    got = (ctx if path == "horner" else ctx_fd).dkg_verify_round(n, t, commits, shares).reshape(nd, n)
     assert (got == want).all(), np.argwhere(got != want)[:10]
     for d, i in ((0, 0), (0, 1), (0, 1023), (1, 7), (1, 8), (1, 15)):
         cs = commits[d * t:(d + 1) * t]
