@@ -32,6 +32,13 @@
 extern "C" {
 #endif
 
+/* Environment switches read once by kb_ctx_create (tests, tuning and A/B measurements; none changes a result):
+ *   KB_VERIFY_FULL=1          signature verifiers: the full-length (253-doubling) kernels instead of the half-size-scalar ones
+ *   KB_VERIFY_MIN_WINDOWS=k   half-size-scalar verifier: lower bound on the block-uniform window count (tests)
+ *   KB_VERIFY_CHUNK_LOG2=k    host-buffer verify calls: 2^k signatures per pipelined chunk (default: n/4 within 2^15..2^18)
+ *   KB_DKG_FD=0|1             kb_dkg_verify_round: never / always by forward differences (default: by cost)
+ *   KB_FD_GROUPS=g            forward-difference round: g independent dealer groups on their own streams (default 2)
+ *   KB_MSM_C=c                Pippenger window bits (default floor(log2 n) - 3 within 4..16) */
 typedef struct kb_ctx kb_ctx;
 
 typedef enum kb_err {
