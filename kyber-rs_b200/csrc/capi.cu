@@ -25,6 +25,7 @@ struct kb_ctx {
     ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
+    int msm_c;               // KB_MSM_C: Pippenger window bits override (0 = by size)
     int fd_groups;           // KB_FD_GROUPS: independent dealer groups (streams) of the forward-difference round
     cudaStream_t fd_stream[4];
     cudaEvent_t fd_event[4];
@@ -109,10 +110,7 @@ static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uin
         kb_msm_plan pl;
         pl.n = (uint32_t)cn;
         pl.c = kb_msm_window_bits_host(cn);
-        if (const char* ce = getenv("KB_MSM_C")) {   // tuning override (tools/bench_msm.py sweeps)
-            const int cv = atoi(ce);
-            if (cv >= 4 && cv <= 16) pl.c = (uint32_t)cv;   // measured at 2^22: c = 15 / 16 / 17 -> 15.6 / 15.3 / 15.6 ms
-        }
+        if (ctx->msm_c) pl.c = (uint32_t)ctx->msm_c;   // KB_MSM_C tuning override; measured at 2^22: c = 15 / 16 / 17 -> 15.6 / 15.3 / 15.6 ms
         pl.windows = (257 + pl.c - 1) / pl.c;
         pl.half = 1u << (pl.c - 1);
         pl.nb = pl.windows * pl.half;
@@ -201,6 +199,9 @@ int kb_ctx_create(int device, kb_ctx** out)
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
         const char* fd = getenv("KB_DKG_FD");
         ctx->dkg_fd = fd ? atoi(fd) : -1;
+        const char* mc = getenv("KB_MSM_C");
+        const int mcv = mc ? atoi(mc) : 0;
+        ctx->msm_c = (mcv >= 4 && mcv <= 16) ? mcv : 0;
         const char* fg = getenv("KB_FD_GROUPS");
         ctx->fd_groups = fg ? atoi(fg) : 2;
         if (ctx->fd_groups < 1) ctx->fd_groups = 1;
