@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_scale(size_t nd, size_t t, co
 }
 
 // one evaluation point: evals[d][i] = Δ^0 (the value at x = i + 1), then dst[k] = src[k] + src[k+1] for the `live`
-// lowest orders (the host drops the orders that can no longer reach a value)
+// lowest orders (the host drops the orders that can no longer reach a value).  ncu: multiplier pipe 57 % busy,
+// long-scoreboard stall 2.5 per issue (a load, one addition, a store per thread).  Two or three elements per thread
+// with all loads issued first were SLOWER (251 / 256 ms per round against 239: 168 / 254 registers), and so were
+// launch bounds for 5 or 6 blocks per SM (245 ms).
 __global__ void __launch_bounds__(KB_THREADS) k_fd_step(size_t nd, size_t t, size_t live, size_t n, size_t i, const uint32_t* src, uint32_t* dst, uint32_t* evals)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
