@@ -381,75 +381,6 @@ static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_com
     }
     return KB_OK;
 }
-// fact[k] = k! mod 8L in signed form: 8 words of magnitude (<= 4L, inside the domain of the radix-16 recoding) + 1 word
-// of sign.  Host integers only (this is table construction, like the window counts of the MSM plan).
-static void kb_factorials_mod_8l(size_t t, uint32_t* out)
-{
-    const uint64_t N[4] = {0xc09318d2e7ae9f68ull, 0xa6f7cef517bce6b2ull, 0ull, 0x8000000000000000ull};
-    const uint64_t H[4] = {0x60498c6973d74fb4ull, 0x537be77a8bde7359ull, 0ull, 0x4000000000000000ull};   // N / 2 = 4L
-    uint64_t x[4] = {1, 0, 0, 0};
-    for (size_t k = 0; k < t; k++) {
-        if (k >= 2) {
-            uint64_t y[5];
-            unsigned __int128 c = 0;
-            for (int i = 0; i < 4; i++) {
-                c += (unsigned __int128)x[i] * (uint64_t)k;
-                y[i] = (uint64_t)c;
-                c >>= 64;
-            }
-            y[4] = (uint64_t)c;
-            // N = 2^255 + (a 128-bit number): floor(y / 2^255) is the quotient or one more
-            const uint64_t q = (y[4] << 1) | (y[3] >> 63);
-            unsigned __int128 mc = 0;
-            uint64_t qn[5];
-            for (int i = 0; i < 4; i++) {
-                mc += (unsigned __int128)N[i] * q;
-                qn[i] = (uint64_t)mc;
-                mc >>= 64;
-            }
-            qn[4] = (uint64_t)mc;
-            uint64_t borrow = 0;
-            for (int i = 0; i < 5; i++) {
-                const unsigned __int128 dd = (unsigned __int128)y[i] - qn[i] - borrow;
-                y[i] = (uint64_t)dd;
-                borrow = (uint64_t)(dd >> 64) & 1u;
-            }
-            if (borrow) {   // one N too many: add it back
-                unsigned __int128 a = 0;
-                for (int i = 0; i < 5; i++) {
-                    a += (unsigned __int128)y[i] + (i < 4 ? N[i] : 0);
-                    y[i] = (uint64_t)a;
-                    a >>= 64;
-                }
-            }
-            for (int i = 0; i < 4; i++) x[i] = y[i];
-        }
-        // signed representative
-        bool big = false;
-        for (int i = 3; i >= 0; i--) {
-            if (x[i] != H[i]) {
-                big = x[i] > H[i];
-                break;
-            }
-        }
-        uint64_t m[4];
-        if (big) {
-            uint64_t borrow = 0;
-            for (int i = 0; i < 4; i++) {
-                const unsigned __int128 dd = (unsigned __int128)N[i] - x[i] - borrow;
-                m[i] = (uint64_t)dd;
-                borrow = (uint64_t)(dd >> 64) & 1u;
-            }
-        } else {
-            for (int i = 0; i < 4; i++) m[i] = x[i];
-        }
-        for (int i = 0; i < 4; i++) {
-            out[9 * k + 2 * i] = (uint32_t)m[i];
-            out[9 * k + 2 * i + 1] = (uint32_t)(m[i] >> 32);
-        }
-        out[9 * k + 8] = big ? 1u : 0u;
-    }
-}
 // The whole round by forward differences (dkgfd.cuh): t - 1 wavefront launches, one scaling launch, n step launches,
 // one check launch — per GROUP of dealers.  Every launch waits for the previous one of its group, so its tail (the
 // last blocks running on a mostly idle GPU) is lost time; KB_FD_GROUPS independent groups on their own streams fill

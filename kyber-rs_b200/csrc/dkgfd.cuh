@@ -22,6 +22,110 @@
 // Arrays are laid out [k][dealer] (dealer fastest): a warp holds 32 dealers and ONE (m, j), so the NAF of the
 // multiplier is warp-uniform and its loads are contiguous.
 #pragma once
+#include "ops.cuh"
+#include "poly.cuh"
+
+// ---- per-cell bodies (KB_FN: also compiled by the host emulation of tests/emu) ------------------------------
+// A: one cell of the Newton conversion, v = m * v + prev
+KB_FN void kb_fd_newton_cell(ge_p3& v, const ge_p3& prev, uint64_t m)
+{
+    ge_cached c;
+    ge_to_cached(c, prev);
+    kb_naf xn;
+    kb_naf_from(xn, m);
+    kb_horner_step(v, xn, c);
+}
+// B: h = fact * a, fact = 8 words of magnitude (<= 4L) + 1 word of sign; `tbl` is the caller's 8-entry scratch table
+KB_FN void kb_fd_scale_cell(ge_p3& h, const ge_p3& a, const uint32_t* fact9, ge_cached* tbl)
+{
+    int8_t e[64];
+    sc_recode16(e, fact9);
+    ge_build_table8(tbl, a);
+    ge_scalarmult<false>(h, e, tbl);
+    if (fact9[8]) {
+        fe_neg(h.X, h.X);
+        fe_neg(h.T, h.T);
+    }
+}
+// C: p += q
+KB_FN void kb_fd_step_cell(ge_p3& p, const ge_p3& q)
+{
+    ge_cached c;
+    ge_to_cached(c, q);
+    ge_add<true>(p, p, c);
+}
+
+// fact[k] = k! mod 8L in signed form: 8 words of magnitude (<= 4L, inside the domain of the radix-16 recoding) + 1 word
+// of sign.  Host integers only (table construction, like the window counts of the MSM plan).
+static inline void kb_factorials_mod_8l(size_t t, uint32_t* out)
+{
+    const uint64_t N[4] = {0xc09318d2e7ae9f68ull, 0xa6f7cef517bce6b2ull, 0ull, 0x8000000000000000ull};
+    const uint64_t H[4] = {0x60498c6973d74fb4ull, 0x537be77a8bde7359ull, 0ull, 0x4000000000000000ull};   // N / 2 = 4L
+    uint64_t x[4] = {1, 0, 0, 0};
+    for (size_t k = 0; k < t; k++) {
+        if (k >= 2) {
+            uint64_t y[5];
+            unsigned __int128 c = 0;
+            for (int i = 0; i < 4; i++) {
+                c += (unsigned __int128)x[i] * (uint64_t)k;
+                y[i] = (uint64_t)c;
+                c >>= 64;
+            }
+            y[4] = (uint64_t)c;
+            // N = 2^255 + (a 128-bit number): floor(y / 2^255) is the quotient or one more
+            const uint64_t q = (y[4] << 1) | (y[3] >> 63);
+            unsigned __int128 mc = 0;
+            uint64_t qn[5];
+            for (int i = 0; i < 4; i++) {
+                mc += (unsigned __int128)N[i] * q;
+                qn[i] = (uint64_t)mc;
+                mc >>= 64;
+            }
+            qn[4] = (uint64_t)mc;
+            uint64_t borrow = 0;
+            for (int i = 0; i < 5; i++) {
+                const unsigned __int128 dd = (unsigned __int128)y[i] - qn[i] - borrow;
+                y[i] = (uint64_t)dd;
+                borrow = (uint64_t)(dd >> 64) & 1u;
+            }
+            if (borrow) {   // one N too many: add it back
+                unsigned __int128 a = 0;
+                for (int i = 0; i < 5; i++) {
+                    a += (unsigned __int128)y[i] + (i < 4 ? N[i] : 0);
+                    y[i] = (uint64_t)a;
+                    a >>= 64;
+                }
+            }
+            for (int i = 0; i < 4; i++) x[i] = y[i];
+        }
+        // signed representative
+        bool big = false;
+        for (int i = 3; i >= 0; i--) {
+            if (x[i] != H[i]) {
+                big = x[i] > H[i];
+                break;
+            }
+        }
+        uint64_t m[4];
+        if (big) {
+            uint64_t borrow = 0;
+            for (int i = 0; i < 4; i++) {
+                const unsigned __int128 dd = (unsigned __int128)N[i] - x[i] - borrow;
+                m[i] = (uint64_t)dd;
+                borrow = (uint64_t)(dd >> 64) & 1u;
+            }
+        } else {
+            for (int i = 0; i < 4; i++) m[i] = x[i];
+        }
+        for (int i = 0; i < 4; i++) {
+            out[9 * k + 2 * i] = (uint32_t)m[i];
+            out[9 * k + 2 * i + 1] = (uint32_t)(m[i] >> 32);
+        }
+        out[9 * k + 8] = big ? 1u : 0u;
+    }
+}
+
+#if !defined(KB_HOST_EMU)
 #include "kernels.cuh"
 
 #define KB_FD_AT(arr, k, d, nd) ((arr) + (((size_t)(k) * (nd) + (d)) * 32))
@@ -79,11 +183,7 @@ __global__ void __launch_bounds__(KB_FD_NEWTON_THREADS, KB_FD_NEWTON_MINBLOCKS) 
     ge_p3 v, prev;
     kb_fd_load(v, KB_FD_AT(qm, j + 1, d, nd));
     kb_fd_load(prev, KB_FD_AT(qp, j, d, nd));
-    ge_cached c;
-    ge_to_cached(c, prev);
-    kb_naf xn;
-    kb_naf_from(xn, (uint64_t)m);
-    kb_horner_step(v, xn, c);   // v = m * v + prev
+    kb_fd_newton_cell(v, prev, (uint64_t)m);   // v = m * v + prev
     kb_fd_store(KB_FD_AT(qm, j, d, nd), v);
 }
 
@@ -98,19 +198,11 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_scale(size_t nd, size_t t, co
     const uint32_t* src = ((k + 1) & 1) ? q1 : q0;
     ge_p3 a, h;
     kb_fd_load(a, KB_FD_AT(src, k, d, nd));
-    uint32_t s[8];
+    uint32_t f9[9];
 #pragma unroll
-    for (int q = 0; q < 8; q++) s[q] = fact[9 * k + q];
-    const uint32_t neg = fact[9 * k + 8];
-    int8_t e[64];
-    sc_recode16(e, s);
+    for (int q = 0; q < 9; q++) f9[q] = fact[9 * k + q];
     ge_cached tbl[8];
-    ge_build_table8(tbl, a);
-    ge_scalarmult<false>(h, e, tbl);
-    if (neg) {
-        fe_neg(h.X, h.X);
-        fe_neg(h.T, h.T);
-    }
+    kb_fd_scale_cell(h, a, f9, tbl);
     if (k < 2) h = a;   // 0! = 1! = 1
     if (live) kb_fd_store(KB_FD_AT(dout, k, d, nd), h);
 }
@@ -131,9 +223,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_step(size_t nd, size_t t, siz
     if (k + 1 < t) {
         ge_p3 q;
         kb_fd_load(q, KB_FD_AT(src, k + 1, d, nd));
-        ge_cached c;
-        ge_to_cached(c, q);
-        ge_add<true>(p, p, c);
+        kb_fd_step_cell(p, q);
     }
     kb_fd_store(KB_FD_AT(dst, k, d, nd), p);
 }
@@ -162,3 +252,4 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_check(size_t nd, size_t n, co
     same &= fe_is_zero(df);
     verdict[slot] = (uint8_t)(same & (dealer_bad[d] ? 0u : 1u));
 }
+#endif  // !KB_HOST_EMU

@@ -7,10 +7,12 @@
 // library has no host compute path.
 #define KB_HOST_EMU 1
 #include <string.h>
+#include <utility>
 #include <vector>
 #include "../../kyber-rs_b200/csrc/ops.cuh"
 #include "../../kyber-rs_b200/csrc/poly.cuh"
 #include "../../kyber-rs_b200/csrc/msm.cuh"
+#include "../../kyber-rs_b200/csrc/dkgfd.cuh"
 
 static void ld(uint32_t* w, const uint8_t* b, int nwords) { memcpy(w, b, 4 * nwords); }
 static void st(uint8_t* b, const uint32_t* w, int nwords) { memcpy(b, w, 4 * nwords); }
@@ -229,6 +231,53 @@ int emu_pubpoly_eval(uint8_t* out, const uint8_t* commits, int t, uint32_t idx)
     }
     ge_compress(o, v);
     st(out, o, 8);
+    return 1;
+}
+
+// The forward-difference DKG round of dkgfd.cuh for ONE dealer, with the kernels' per-cell bodies and the same
+// wavefront / two-row schedule: out[i] = encoding of P(i + 1), i = 0..n-1.  Returns 0 if a commitment does not decode.
+int emu_dkg_fd(uint8_t* out, const uint8_t* commits, int t, int n)
+{
+    std::vector<ge_p3> q0(t), q1(t), d0(t), d1(t);
+    for (int j = 0; j < t; j++) {
+        uint32_t w[8];
+        ld(w, commits + 32 * j, 8);
+        if (!ge_decompress(q0[j], w)) return 0;
+    }
+    q1[t - 1] = q0[t - 1];
+    for (int w = 1; w + 1 <= t; w++) {            // k_fd_newton, wavefront w
+        std::vector<std::pair<int, ge_p3>> wr;     // all reads of a wavefront happen before its writes
+        for (int m = 1; m <= w; m++) {
+            const int j = m + t - 2 - w;
+            std::vector<ge_p3>& qm = (m & 1) ? q1 : q0;
+            std::vector<ge_p3>& qp = (m & 1) ? q0 : q1;
+            ge_p3 v = qm[j + 1];
+            kb_fd_newton_cell(v, qp[j], (uint64_t)m);
+            wr.push_back({m, v});
+        }
+        for (auto& e : wr) ((e.first & 1) ? q1 : q0)[e.first + t - 2 - w] = e.second;
+    }
+    std::vector<uint32_t> fact(9 * (size_t)t);
+    kb_factorials_mod_8l((size_t)t, fact.data());
+    for (int k = 0; k < t; k++) {                  // k_fd_scale
+        const ge_p3& a = (((k + 1) & 1) ? q1 : q0)[k];
+        ge_cached tbl[8];
+        kb_fd_scale_cell(d0[k], a, fact.data() + 9 * k, tbl);
+        if (k < 2) d0[k] = a;
+    }
+    std::vector<ge_p3>*src = &d0, *dst = &d1;
+    for (int i = 0; i < n; i++) {                  // k_fd_step with the dead orders dropped
+        uint32_t o[8];
+        ge_compress(o, (*src)[0]);
+        st(out + 32 * i, o, 8);
+        const int live = (n - i < t) ? n - i : t;
+        for (int k = 0; k < live; k++) {
+            ge_p3 p = (*src)[k];
+            if (k + 1 < t) kb_fd_step_cell(p, (*src)[k + 1]);
+            (*dst)[k] = p;
+        }
+        std::swap(src, dst);
+    }
     return 1;
 }
 

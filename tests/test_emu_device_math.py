@@ -32,6 +32,7 @@ def emu():
     E.emu_eddsa_sign.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64]
     E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
+    E.emu_dkg_fd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     return E
 
 
@@ -214,6 +215,31 @@ def test_pubpoly_short_horner(emu, coracle, golden_records):
         for idx in (0, 1, 2, 6, 255, 1023, 65535, 2**32 - 1):
             assert emu.emu_pubpoly_eval(out, flat, len(cs), idx) == 1
             assert out.raw == coracle.pubpoly_eval(cs, idx)
+
+
+def test_dkg_forward_differences(emu, coracle, golden_records):
+    """csrc/dkgfd.cuh (Newton conversion by wavefronts, k! mod 8L scaling, difference steps with the dead orders
+    dropped) on one dealer: every P(i + 1) equals PubPoly::eval, also for a polynomial whose commitments carry
+    small-order components (only integer-linear identities are used), for n < t, n = t and n > t."""
+    commits = [r[1] for r in golden_records[100:140]]
+    t8 = O.point_decode(O.WEAK_KEYS[2])
+    tors = list(commits)
+    tors[1] = O.point_encode(O.point_add(O.point_decode(tors[1]), t8))
+    tors[5] = O.point_encode(O.point_add(O.point_decode(tors[5]), O.point_add(t8, t8)))
+    for cs, t, n in ((commits, 1, 4), (commits, 2, 5), (commits, 3, 3), (commits, 9, 4), (commits, 12, 30), (tors, 7, 20), (commits, 33, 40), (tors, 40, 44)):
+        flat = b"".join(cs[:t])
+        out = ctypes.create_string_buffer(32 * n)
+        assert emu.emu_dkg_fd(out, flat, t, n) == 1
+        for i in range(n):
+            assert out.raw[32 * i:32 * i + 32] == coracle.pubpoly_eval(cs[:t], i), (t, n, i)
+    assert emu.emu_dkg_fd(ctypes.create_string_buffer(32), coracle_bad_point(coracle), 1, 1) == 0
+
+
+def coracle_bad_point(coracle):
+    k = 0
+    while coracle.point_decode_ok(bytes([k]) + b"\x13" * 31):
+        k += 1
+    return bytes([k]) + b"\x13" * 31
 
 
 def test_pippenger_stages(emu, coracle, golden_records):
