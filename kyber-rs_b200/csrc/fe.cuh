@@ -63,6 +63,50 @@ KB_FN void kb_cmad4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32
 #endif
 }
 
+// Two variants for rows whose surroundings are known to be FRESH words, so that no accumulator register has to be
+// zeroed beforehand and no needless carry is captured (ptxas places both kinds of instruction on the multiplier pipe):
+// kb_cmad4_top: like kb_cmad4, but `top` is a fresh word — it RECEIVES the carry out of word 7 (0 or 1).
+KB_FN void kb_cmad4_top(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    top = 0;
+    kb_cmad4(acc, a0, a1, a2, a3, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#endif
+}
+// kb_cmad4_hi: like kb_cmad4, but word 7 is a fresh word (it receives the high half of the last product plus the
+// carry, which cannot overflow) and nothing is carried further.
+KB_FN void kb_cmad4_hi(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[7] = 0;
+    kb_cmad4(acc, a0, a1, a2, a3, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "=r"(acc[7])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#endif
+}
+
 // Same, for N = 1..3 products (used by the squaring's triangular rows).
 KB_FN void kb_cmad3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t& top)
 {
@@ -130,6 +174,116 @@ KB_FN void kb_cmad1(uint32_t* acc, uint32_t a0, uint32_t b, uint32_t& top)
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(top)
         : "r"(a0), "r"(b));
 #endif
+}
+
+// the same two fresh-word variants (see kb_cmad4_top / kb_cmad4_hi) for the squaring's triangular rows
+KB_FN void kb_cmad3_top(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    top = 0;
+    kb_cmad3(acc, a0, a1, a2, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(top)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#endif
+}
+KB_FN void kb_cmad3_hi(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[5] = 0;
+    kb_cmad3(acc, a0, a1, a2, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %9, %4;\n\t"
+        "madc.hi.u32 %5, %8, %9, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "=r"(acc[5])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#endif
+}
+KB_FN void kb_cmad2_top(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    top = 0;
+    kb_cmad2(acc, a0, a1, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(top)
+        : "r"(a0), "r"(a1), "r"(b));
+#endif
+}
+KB_FN void kb_cmad2_hi(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[3] = 0;
+    kb_cmad2(acc, a0, a1, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %6, %2;\n\t"
+        "madc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "=r"(acc[3])
+        : "r"(a0), "r"(a1), "r"(b));
+#endif
+}
+KB_FN void kb_cmad1_top(uint32_t* acc, uint32_t a0, uint32_t b, uint32_t& top)
+{
+#if defined(KB_HOST_EMU)
+    top = 0;
+    kb_cmad1(acc, a0, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "=r"(top)
+        : "r"(a0), "r"(b));
+#endif
+}
+KB_FN void kb_cmad1_hi(uint32_t* acc, uint32_t a0, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[1] = 0;
+    kb_cmad1(acc, a0, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;"
+        : "+r"(acc[0]), "=r"(acc[1])
+        : "r"(a0), "r"(b));
+#endif
+}
+
+// acc[0..2N) = {a0, ...} * b on FRESH word pairs: N independent IMAD.WIDE.U32 with no addend — no zeroed
+// accumulator registers to set up, no carry chain, no carry to capture (used for the first row of a product)
+KB_FN void kb_cmul4(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b)
+{
+    const uint64_t p0 = (uint64_t)a0 * b, p1 = (uint64_t)a1 * b, p2 = (uint64_t)a2 * b, p3 = (uint64_t)a3 * b;
+    acc[0] = (uint32_t)p0; acc[1] = (uint32_t)(p0 >> 32);
+    acc[2] = (uint32_t)p1; acc[3] = (uint32_t)(p1 >> 32);
+    acc[4] = (uint32_t)p2; acc[5] = (uint32_t)(p2 >> 32);
+    acc[6] = (uint32_t)p3; acc[7] = (uint32_t)(p3 >> 32);
+}
+KB_FN void kb_cmul3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b)
+{
+    const uint64_t p0 = (uint64_t)a0 * b, p1 = (uint64_t)a1 * b, p2 = (uint64_t)a2 * b;
+    acc[0] = (uint32_t)p0; acc[1] = (uint32_t)(p0 >> 32);
+    acc[2] = (uint32_t)p1; acc[3] = (uint32_t)(p1 >> 32);
+    acc[4] = (uint32_t)p2; acc[5] = (uint32_t)(p2 >> 32);
 }
 
 // acc[0..15) += x[0..15) (no carry out: callers guarantee it fits)
@@ -370,8 +524,8 @@ KB_FN void kb_sqr_acc8(uint32_t* t, const uint32_t* a)
 KB_FN void fe_reduce512(fe& r, uint32_t* t)
 {
     // even high words: (t0..t7) += 38 * {t8,t10,t12,t14}, carry into r8
-    uint32_t r8 = 0;
-    kb_cmad4(t, t[8], t[10], t[12], t[14], 38u, r8);
+    uint32_t r8;
+    kb_cmad4_top(t, t[8], t[10], t[12], t[14], 38u, r8);
     // odd high words: 38*t9, 38*t11, 38*t13, 38*t15 land on word pairs (1,2) (3,4) (5,6) (7,8)
     uint32_t o[8];
     KB_UNROLL
@@ -398,24 +552,31 @@ KB_FN void fe_reduce512(fe& r, uint32_t* t)
 KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g)
 {
     uint32_t ev[17], od[16];
-    KB_UNROLL
-    for (int i = 0; i < 17; i++) ev[i] = 0;
-    KB_UNROLL
-    for (int i = 0; i < 16; i++) od[i] = 0;
     const uint32_t* a = f.v;
     const uint32_t* b = g.v;
     // Operand scanning over b; products a[j]*b[i] with i+j even accumulate in ev (word i+j),
     // those with i+j odd in od (od[k] is word k+1), so every IMAD.WIDE is pair-aligned.
-    KB_UNROLL
-    for (int i = 0; i < 8; i++) {
-        if ((i & 1) == 0) {
-            kb_cmad4(&ev[i], a[0], a[2], a[4], a[6], b[i], ev[i + 8]);
-            kb_cmad4(&od[i], a[1], a[3], a[5], a[7], b[i], od[i + 8]);
-        } else {
-            kb_cmad4(&ev[i + 1], a[1], a[3], a[5], a[7], b[i], ev[i + 9]);
-            kb_cmad4(&od[i - 1], a[0], a[2], a[4], a[6], b[i], od[i + 7]);
-        }
-    }
+    // Row 0 lands on fresh words: plain products, nothing to zero and no carries.
+    kb_cmul4(&ev[0], a[0], a[2], a[4], a[6], b[0]);
+    kb_cmul4(&od[0], a[1], a[3], a[5], a[7], b[0]);
+    // Later rows: an even row ends on a fresh word that takes its carry (kb_cmad4_top); an odd row's last product
+    // lands on (a word holding at most that carry, a fresh word) and cannot carry out (kb_cmad4_hi).  ev[16] and
+    // od[15] are never touched.  Only ev[8] has to be zeroed.
+    ev[8] = 0;
+    kb_cmad4_hi(&ev[2], a[1], a[3], a[5], a[7], b[1]);              // words 2..9
+    kb_cmad4_top(&od[0], a[0], a[2], a[4], a[6], b[1], od[8]);      // words 1..8, carry -> 9
+    kb_cmad4_top(&ev[2], a[0], a[2], a[4], a[6], b[2], ev[10]);
+    kb_cmad4_hi(&od[2], a[1], a[3], a[5], a[7], b[2]);
+    kb_cmad4_hi(&ev[4], a[1], a[3], a[5], a[7], b[3]);
+    kb_cmad4_top(&od[2], a[0], a[2], a[4], a[6], b[3], od[10]);
+    kb_cmad4_top(&ev[4], a[0], a[2], a[4], a[6], b[4], ev[12]);
+    kb_cmad4_hi(&od[4], a[1], a[3], a[5], a[7], b[4]);
+    kb_cmad4_hi(&ev[6], a[1], a[3], a[5], a[7], b[5]);
+    kb_cmad4_top(&od[4], a[0], a[2], a[4], a[6], b[5], od[12]);
+    kb_cmad4_top(&ev[6], a[0], a[2], a[4], a[6], b[6], ev[14]);
+    kb_cmad4_hi(&od[6], a[1], a[3], a[5], a[7], b[6]);
+    kb_cmad4_hi(&ev[8], a[1], a[3], a[5], a[7], b[7]);
+    kb_cmad4_top(&od[6], a[0], a[2], a[4], a[6], b[7], od[14]);
     kb_acc15(&ev[1], &od[0]);
     fe_reduce512(h, ev);
 }
@@ -424,25 +585,25 @@ KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g)
 KB_FN void fe_sq_inl(fe& h, const fe& f)
 {
     uint32_t ev[17], od[16];
-    KB_UNROLL
-    for (int i = 0; i < 17; i++) ev[i] = 0;
-    KB_UNROLL
-    for (int i = 0; i < 16; i++) od[i] = 0;
     const uint32_t* a = f.v;
-    // row i: a[j]*a[i] for j > i, word i+j
-    kb_cmad4(&od[0], a[1], a[3], a[5], a[7], a[0], od[8]);   // words 1,3,5,7
-    kb_cmad3(&ev[2], a[2], a[4], a[6], a[0], ev[8]);         // words 2,4,6
-    kb_cmad3(&od[2], a[2], a[4], a[6], a[1], od[8]);         // words 3,5,7
-    kb_cmad3(&ev[4], a[3], a[5], a[7], a[1], ev[10]);        // words 4,6,8
-    kb_cmad3(&od[4], a[3], a[5], a[7], a[2], od[10]);        // words 5,7,9
-    kb_cmad2(&ev[6], a[4], a[6], a[2], ev[10]);              // words 6,8
-    kb_cmad2(&od[6], a[4], a[6], a[3], od[10]);              // words 7,9
-    kb_cmad2(&ev[8], a[5], a[7], a[3], ev[12]);              // words 8,10
-    kb_cmad2(&od[8], a[5], a[7], a[4], od[12]);              // words 9,11
-    kb_cmad1(&ev[10], a[6], a[4], ev[12]);                   // word 10
-    kb_cmad1(&od[10], a[6], a[5], od[12]);                   // word 11
-    kb_cmad1(&ev[12], a[7], a[5], ev[14]);                   // word 12
-    kb_cmad1(&od[12], a[7], a[6], od[14]);                   // word 13
+    // row i: a[j]*a[i] for j > i, word i+j; row 0 lands on fresh words (plain products, no zeroing, no carries)
+    kb_cmul4(&od[0], a[1], a[3], a[5], a[7], a[0]);          // words 1,3,5,7
+    kb_cmul3(&ev[2], a[2], a[4], a[6], a[0]);                // words 2,4,6
+    // later rows end either on a fresh word that takes the carry (_top) or on (at most a carry, a fresh word) and
+    // cannot carry out (_hi); only the six words no product reaches are zeroed
+    ev[0] = ev[1] = ev[8] = ev[14] = ev[15] = 0;
+    od[14] = 0;
+    kb_cmad3_top(&od[2], a[2], a[4], a[6], a[1], od[8]);     // words 3,5,7
+    kb_cmad3_hi(&ev[4], a[3], a[5], a[7], a[1]);             // words 4,6,8
+    kb_cmad3_hi(&od[4], a[3], a[5], a[7], a[2]);             // words 5,7,9
+    kb_cmad2_top(&ev[6], a[4], a[6], a[2], ev[10]);          // words 6,8
+    kb_cmad2_top(&od[6], a[4], a[6], a[3], od[10]);          // words 7,9
+    kb_cmad2_hi(&ev[8], a[5], a[7], a[3]);                   // words 8,10
+    kb_cmad2_hi(&od[8], a[5], a[7], a[4]);                   // words 9,11
+    kb_cmad1_top(&ev[10], a[6], a[4], ev[12]);               // word 10
+    kb_cmad1_top(&od[10], a[6], a[5], od[12]);               // word 11
+    kb_cmad1_hi(&ev[12], a[7], a[5]);                        // word 12
+    kb_cmad1_hi(&od[12], a[7], a[6]);                        // word 13
     kb_acc15(&ev[1], &od[0]);
     kb_dbl16(ev);        // double the cross terms (top bit is clear: sum < 2^511)
     kb_sqr_acc8(ev, a);  // add the squares a[i]^2 on word pairs (2i, 2i+1)
