@@ -43,7 +43,7 @@ EXEC_MAIN_PER_VERIFY = 110_000    # 128 doublings, 66 + 20 additions, two 8-entr
 IMAD_EQ_PER_MSM_POINT = 20_700
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
 # dram__bytes_read.sum + dram__bytes_write.sum at 2^20 signatures, ncu --set full (profiles/r1_ncu_k_verify_half.txt)
-VERIFY_DRAM_BYTES_2P20 = {"k_verify_half_prep": 197_185_000 + 305_416_000, "k_verify_half_main": 12_329_228_000 + 2_203_952_000}
+VERIFY_DRAM_BYTES_2P20 = {"k_verify_half_prep": 197_734_000 + 313_023_000, "k_verify_half_main": 15_152_038_000 + 2_182_434_000}
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
 NONCANON = bytes([0xEF]) + b"\xff" * 31
@@ -441,7 +441,7 @@ def main():
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": traffic,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one step at 2^20 signatures (ncu --set full, profiles/r1_ncu_k_verify_half.txt): "
                                      + json.dumps(VERIFY_DRAM_BYTES_2P20) + "; algorithmic bytes are 168 MB in + 1 MB out per step plus the 319 MB of records written by the first launch and read by the second; "
-                                     "the rest is the two per-thread 1 KiB tables (multiples of A and of R, local memory) that do not all fit the 126 MB L2 (DESIGN.md 6); DRAM runs at about 10 % of its peak, the step is bound by the multiplier pipe",
+                                     "the rest is the two per-thread 1 KiB tables (multiples of A and of R, local memory) that do not all fit the 126 MB L2 (DESIGN.md 6); DRAM runs at about 12 % of its peak, the step is bound by the multiplier pipe",
                      "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents CHARGED per signature (SURVEY 8d: decompress A + 253-doubling Straus + compress) / CUDA-event step time; "
                              "peak = best IMAD.WIDE.U32 stream measured live by kb_probe_imad (back-to-back field multiplications), ~93% of the architectural 32 lanes/clk/SM of the fmaheavy pipe. "
                              "The kernels EXECUTE fewer multiplies than charged (half-size scalars: 128 doublings, csrc/half.cuh): see `executed`",
