@@ -405,6 +405,24 @@ def main():
             dist.all_gather_object(encs, enc)
             assert len(set(encs)) == 1, "ranks disagree on the sharded MSM result"
         extras["cfg5_msm_result"] = enc.hex()
+        # BASELINE configs 3 and 4: one deal-verification round (all n^2 share checks), dealers sharded over the ranks,
+        # random commitments and shares (the kernels' work does not depend on the verdicts; tools/bench_dkg.py is the
+        # version that also checks honest / corrupted / torsion-contaminated dealers against expected verdicts)
+        for tag, (rn, rt) in (("cfg3_vss_n256_t171", (256, 171)), ("cfg4_dkg_n1024_t683", (1024, 683))):
+            if rn % world:
+                continue
+            nd = rn // world
+            coeff = xof(f"kyber-b200/bench/{tag}/rank{rank}", 32 * nd * rt).reshape(-1, 32).copy()
+            coeff[:, 31] &= 0x0F
+            d_coeff = torch.from_numpy(coeff).to(dev)
+            d_commits = torch.empty(nd * rt, 32, dtype=torch.uint8, device=dev)
+            ctx.dev_point_mul_base(nd * rt, d_coeff, d_commits, 1)
+            sh = xof(f"kyber-b200/bench/{tag}/shares{rank}", 32 * nd * rn).reshape(-1, 32).copy()
+            sh[:, 31] &= 0x0F
+            d_sh = torch.from_numpy(sh).to(dev)
+            d_v = torch.empty(nd * rn, dtype=torch.uint8, device=dev)
+            extras[tag + "_round_ms"] = timed(lambda: ctx.dev_dkg_verify_round(rn, rt, nd, d_commits, d_sh, d_v), reps=2) * 1e3
+            del d_coeff, d_commits, d_sh, d_v
 
     if rank != 0:
         if world > 1:
