@@ -477,6 +477,11 @@ static bool kb_dkg_use_fd(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
     if (ctx->dkg_fd == 1) return true;
     const double horner = (double)n * t * 6800.0;
     const double fd = 0.5 * t * t * 4600.0 + t * 138300.0 + (double)n * t * 660.0 + n * 11000.0;
+    // its arrays: three of nd*t extended points and the nd*n recorded values — fall back to the per-share kernel
+    // (a few MB of scratch) rather than fail when they would not fit next to what is already allocated
+    size_t free_b = 0, total_b = 0;
+    const double need = 3.0 * 128.0 * nd * t + 96.0 * nd * n;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > 0.8 * (double)free_b + (double)(ctx->slot_bytes[8] + ctx->slot_bytes[30] + ctx->slot_bytes[31] + ctx->slot_bytes[KB_SLOT_XYZ])) return false;
     // every wavefront / step is a launch of nd * (up to t) threads: it needs a GPU's worth of them to pay
     return nd * t >= 32768 && fd * 1.25 < horner;   // measured: n=256,t=171: 8.6 vs 10.0 ms; n=512,t=341: 35.6 vs 68.7 ms; n=1024,t=683: 262 vs 584 ms
 }
