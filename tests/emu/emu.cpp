@@ -281,6 +281,9 @@ int emu_dkg_fd(uint8_t* out, const uint8_t* commits, int t, int n)
     return 1;
 }
 
+// the host-side table of the forward-difference round: out = t x 9 words (|k! mod 8L| in signed form + sign)
+void emu_factorials_mod_8l(uint32_t* out, int t) { kb_factorials_mod_8l((size_t)t, out); }
+
 // Pippenger stage bodies of msm.cuh, run "thread by thread" on the host; the final
 // warp-shuffle tree (GPU only) is replaced by a plain sum of the same group partials.
 int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* points, int c_override, int k_override)

@@ -33,6 +33,7 @@ def emu():
     E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
     E.emu_dkg_fd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    E.emu_factorials_mod_8l.argtypes = [ctypes.c_void_p, ctypes.c_int]
     return E
 
 
@@ -233,6 +234,22 @@ def test_dkg_forward_differences(emu, coracle, golden_records):
         for i in range(n):
             assert out.raw[32 * i:32 * i + 32] == coracle.pubpoly_eval(cs[:t], i), (t, n, i)
     assert emu.emu_dkg_fd(ctypes.create_string_buffer(32), coracle_bad_point(coracle), 1, 1) == 0
+
+
+def test_factorials_mod_8l(emu):
+    """kb_factorials_mod_8l (host integers in csrc/dkgfd.cuh): k! mod 8L in signed form, magnitude <= 4L, for every k
+    up to well beyond BASELINE config 4's t = 683."""
+    import math
+
+    t = 1500
+    buf = (ctypes.c_uint32 * (9 * t))()
+    emu.emu_factorials_mod_8l(buf, t)
+    N = 8 * O.L
+    for k in range(t):
+        mag = sum(buf[9 * k + i] << (32 * i) for i in range(8))
+        neg = buf[9 * k + 8]
+        assert neg in (0, 1) and mag <= 4 * O.L
+        assert (-mag if neg else mag) % N == math.factorial(k) % N, k
 
 
 def coracle_bad_point(coracle):
