@@ -15,7 +15,10 @@
  *  - All buffers are caller-owned.  `kb_*` functions take HOST pointers, copy in, run the
  *    CUDA kernels, copy out and return after the device has finished.  `kb_dev_*` functions
  *    take DEVICE pointers plus a CUDA stream (cudaStream_t as void*, NULL = default stream)
- *    and only enqueue work; nothing is retained after return.
+ *    and only enqueue work; nothing is retained after return.  They use the context's scratch
+ *    buffers, which grow (cudaMalloc, a device synchronisation) the first time a larger batch is
+ *    seen and never in steady state; calls of one context on DIFFERENT streams are ordered one
+ *    after the other by the library (a shared event), so they are safe but do not overlap.
  *  - Return value: KB_OK or a negative kb_err.  Per-item outcomes go to status arrays.
  *  - There is no CPU fallback: with no usable CUDA device every call fails with
  *    KB_ERR_CUDA.
@@ -37,7 +40,7 @@ extern "C" {
  *   KB_VERIFY_MIN_WINDOWS=k   half-size-scalar verifier: lower bound on the block-uniform window count (tests)
  *   KB_VERIFY_CHUNK_LOG2=k    host-buffer verify calls: 2^k signatures per pipelined chunk (default: n/4 within 2^15..2^18)
  *   KB_DKG_FD=0|1             kb_dkg_verify_round: never / always by forward differences (default: by cost)
- *   KB_FD_GROUPS=g            forward-difference round: g independent dealer groups on their own streams (default 2)
+ *   KB_FD_PARTS=p             forward-difference round: cut each polynomial into p coefficient blocks, 1..4 (default: by cost)
  *   KB_MSM_C=c                Pippenger window bits (default floor(log2 n) - 3 within 4..16) */
 typedef struct kb_ctx kb_ctx;
 
@@ -155,6 +158,12 @@ int kb_vss_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t
  * to verifier i; verdict[d*n + i] as above.  Dealers [dealer_lo, dealer_hi) only — the unit a
  * rank owns when the round is sharded by dealer. */
 int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const uint8_t* commits, const uint8_t* shares, uint8_t* verdict);
+/* The same round with the commitments in the reference's in-memory / serde form — X, Y, Z, T as 10 signed 25.5-bit i32
+ * limbs each, 40 int32 per point (ge.rs:75-83; what a Rust caller holds in a PubPoly, so that it does not pay one field
+ * inversion per commitment for marshal_binary).  The reference never validates that form (Deal::decode,
+ * share/vss/pedersen/vss.rs:155-159); here a dealer with an element that is not a consistent representation of a curve
+ * point (Z = 0, T Z != X Y, or off the curve) gets verdict 0 throughout. */
+int kb_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const int32_t* commit_limbs, const uint8_t* shares, uint8_t* verdict);
 /* PubPoly::add (poly.rs:486-509): out[j] = a[j] + b[j] — kb_point_add_batch on t points.
  * dkg_key (share/dkg/pedersen/dkg.rs:905-954) folds PubPoly::add over all qualified dealers:
  * out[j] = sum_d commits[d*t + j], j < t; status[j] = 1 (and out[j] zero) if a commitment of column j is undecodable. */
@@ -175,6 +184,7 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
 int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status, uint32_t flags, void* stream);
 int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out32, void* d_partial128, void* d_bad_points, void* stream);
 int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream);
+int kb_dev_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commit_limbs, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream);
 
 /* ---- measurement ---------------------------------------------------------------------- */

@@ -37,8 +37,8 @@ EXPORTS = [
     "kb_ctx_create", "kb_ctx_destroy", "kb_ctx_wipe", "kb_last_error", "kb_device_sm_count", "kb_launch_count", "kb_host_alloc", "kb_host_free",
     "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch", "kb_point_decompress_batch", "kb_point_compress_batch", "kb_point_eq_batch",
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
-    "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
-    "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_point_sum",
+    "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_dkg_verify_round_limbs", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
+    "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_dkg_verify_round_limbs", "kb_dev_point_sum",
     "kb_probe_imad", "kb_verify_kernel_times",
 ]
 
@@ -84,6 +84,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_pubpoly_eval_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
     L.kb_vss_verify_deals_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp]
     L.kb_dkg_verify_round.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
+    L.kb_dkg_verify_round_limbs.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
     L.kb_pubpoly_sum.argtypes = [vp, sz, sz, vp, vp, vp]
     L.kb_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.kb_point_sum.argtypes = [vp, sz, vp, vp]
@@ -92,6 +93,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_dev_point_mul.argtypes = [vp, sz, vp, vp, vp, vp, u32, vp]
     L.kb_dev_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
     L.kb_dev_dkg_verify_round.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
+    L.kb_dev_dkg_verify_round_limbs.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_point_sum.argtypes = [vp, sz, vp, vp, vp]
     L.kb_probe_imad.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.kb_verify_kernel_times.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
@@ -219,6 +221,8 @@ class Context:
     def point_eq_batch(self, p, q):
         """Point::eq per pair: bit 0 = equal, bit 1 = an operand does not decode."""
         p, q = _u8(p, (-1, 32)), _u8(q, (-1, 32))
+        if p.shape != q.shape:
+            raise ValueError("point_eq_batch: operands must have the same number of points")
         out = np.empty(p.shape[0], dtype=np.uint8)
         self._check(self.L.kb_point_eq_batch(self.h, p.shape[0], _ptr(p), _ptr(q), _ptr(out)), "kb_point_eq_batch")
         return out
@@ -277,6 +281,8 @@ class Context:
         poly_id = np.ascontiguousarray(poly_id, dtype=np.uint32)
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
         m = idx.shape[0]
+        if poly_id.shape[0] != m:
+            raise ValueError("pubpoly_eval_batch: poly_id and idx must have one entry per item")
         out = np.empty((m, 32), dtype=np.uint8)
         st = np.empty(m, dtype=np.uint8)
         self._check(self.L.kb_pubpoly_eval_batch(self.h, npoly, t, _ptr(c), m, _ptr(poly_id), _ptr(idx), _ptr(out), _ptr(st)), "kb_pubpoly_eval_batch")
@@ -290,19 +296,29 @@ class Context:
         idx = np.ascontiguousarray(idx, dtype=np.uint32)
         sh = _u8(shares, (-1, 32))
         m = idx.shape[0]
+        if poly_id.shape[0] != m or sh.shape[0] != m:
+            raise ValueError("vss_verify_deals_batch: poly_id, idx and shares must have one row per item")
         verdict = np.empty(m, dtype=np.uint8)
         self._check(self.L.kb_vss_verify_deals_batch(self.h, npoly, t, _ptr(c), m, _ptr(poly_id), _ptr(idx), _ptr(sh), _ptr(verdict)), "kb_vss_verify_deals_batch")
         return verdict
 
-    def dkg_verify_round(self, n, t, commits, shares, dealer_lo=0, dealer_hi=None, verdict=None):
-        c = _u8(commits, (-1, 32))
+    def dkg_verify_round(self, n, t, commits, shares, dealer_lo=0, dealer_hi=None, verdict=None, limbs=False):
+        """commits: (ndealers*t, 32) uint8 encodings, or with limbs=True (ndealers*t, 40) int32 raw ref10 limbs."""
+        c = np.ascontiguousarray(commits, dtype=np.int32).reshape(-1, 40) if limbs else _u8(commits, (-1, 32))
         sh = _u8(shares, (-1, 32))
         ndealers = c.shape[0] // t
+        if ndealers * t != c.shape[0] or sh.shape[0] != ndealers * n:
+            raise ValueError("dkg_verify_round: commits must hold ndealers*t points and shares ndealers*n scalars")
         if dealer_hi is None:
             dealer_hi = ndealers
+        if not (0 <= dealer_lo <= dealer_hi <= ndealers):
+            raise ValueError("dkg_verify_round: dealer range outside the commitments")
         if verdict is None:
             verdict = np.zeros(ndealers * n, dtype=np.uint8)
-        self._check(self.L.kb_dkg_verify_round(self.h, n, t, dealer_lo, dealer_hi, _ptr(c), _ptr(sh), _ptr(verdict)), "kb_dkg_verify_round")
+        if verdict.shape[0] != ndealers * n:
+            raise ValueError("dkg_verify_round: verdict must hold ndealers*n bytes")
+        fn = self.L.kb_dkg_verify_round_limbs if limbs else self.L.kb_dkg_verify_round
+        self._check(fn(self.h, n, t, dealer_lo, dealer_hi, _ptr(c), _ptr(sh), _ptr(verdict)), "kb_dkg_verify_round")
         return verdict
 
     def pubpoly_sum(self, commits, t):
@@ -369,8 +385,9 @@ class Context:
     def dev_msm(self, n, scalars, points, out32, partial128, bad):
         self._check(self.L.kb_dev_msm(self.h, n, self._dp(scalars), self._dp(points), self._dp(out32), self._dp(partial128), self._dp(bad), self._stream()), "kb_dev_msm")
 
-    def dev_dkg_verify_round(self, n, t, ndealers, commits, shares, verdict):
-        self._check(self.L.kb_dev_dkg_verify_round(self.h, n, t, ndealers, self._dp(commits), self._dp(shares), self._dp(verdict), self._stream()), "kb_dev_dkg_verify_round")
+    def dev_dkg_verify_round(self, n, t, ndealers, commits, shares, verdict, limbs=False):
+        fn = self.L.kb_dev_dkg_verify_round_limbs if limbs else self.L.kb_dev_dkg_verify_round
+        self._check(fn(self.h, n, t, ndealers, self._dp(commits), self._dp(shares), self._dp(verdict), self._stream()), "kb_dev_dkg_verify_round")
 
     def dev_point_sum(self, k, partials, out32):
         self._check(self.L.kb_dev_point_sum(self.h, k, self._dp(partials), self._dp(out32), self._stream()), "kb_dev_point_sum")

@@ -1,69 +1,11 @@
-// capi.cu — the C ABI declared in include/kyber_b200.h.  Host code here only moves bytes
-// and launches kernels; there is deliberately no CPU implementation of any operation.
-#include <cuda_runtime.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "../../include/kyber_b200.h"
+// capi.cu — context, scratch and the per-item entry points of the C ABI declared in include/kyber_b200.h.
+// Host code here only moves bytes and launches kernels; there is deliberately no CPU implementation of any operation.
+#define KB_K_POINT
+#include "ctx.cuh"
 #include "kernels.cuh"
-#include "msm.cuh"
-#include "dkgfd.cuh"
-
-#define KB_NSLOTS 48
-#define KB_VERIFY_CHUNK (1u << 18)   // largest signatures-per-chunk of the pipelined host-buffer verify calls
-#define KB_SLOT_XYZ 28
-#define KB_SLOT_FLAGS 29
-
-struct kb_ctx {
-    int device;
-    int sm_count;
-    cudaStream_t stream;
-    cudaStream_t stream2;    // second copy/compute lane of the pipelined host entry points
-    ge_precomp* base_table;  // 64 x 8 entries: (j+1) * 16^w * B
-    ge_precomp* base128;     // 128 entries: (j+1) * B
-    ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
-    int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
-    size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
-    int msm_c;               // KB_MSM_C: Pippenger window bits override (0 = by size)
-    int fd_groups;           // KB_FD_GROUPS: independent dealer groups (streams) of the forward-difference round
-    cudaStream_t fd_stream[4];
-    cudaEvent_t fd_event[4];
-    int dkg_fd;              // KB_DKG_FD: 1 = always / 0 = never use the forward-difference DKG round (default: by cost)
-    int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
-    int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
-    int timing_valid;
-    cudaEvent_t tev[3];
-    void* slot[KB_NSLOTS];
-    size_t slot_bytes[KB_NSLOTS];
-    uint64_t launches;
-    char err[256];
-};
-
-static int kb_fail(kb_ctx* ctx, cudaError_t e, const char* what)
-{
-    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
-    return KB_ERR_CUDA;
-}
-#define KB_CUDA(call)                                              \
-    do {                                                           \
-        cudaError_t e_ = (call);                                   \
-        if (e_ != cudaSuccess) return kb_fail(ctx, e_, #call);     \
-    } while (0)
-#define KB_LAUNCHED()                                              \
-    do {                                                           \
-        ctx->launches++;                                           \
-        cudaError_t e_ = cudaGetLastError();                       \
-        if (e_ != cudaSuccess) return kb_fail(ctx, e_, "launch");  \
-    } while (0)
-
-static inline unsigned kb_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
-// Block size of the long per-item kernels: a batch that fills the GPU less than about twice (config 1 is
-// 2^16 items = 512 blocks of 128 on 148 SMs) is cut into 64-thread blocks so that the SMs end up evenly loaded.
-static inline unsigned kb_item_threads(const kb_ctx* ctx, size_t n) { return n < (size_t)ctx->sm_count * 1024 ? 64u : (unsigned)KB_THREADS; }
 
 // growable device scratch buffer
-static int kb_scratch(kb_ctx* ctx, int s, size_t bytes, void** out)
+int kb_scratch(kb_ctx* ctx, int s, size_t bytes, void** out)
 {
     if (bytes == 0) bytes = 16;
     if (ctx->slot_bytes[s] < bytes) {
@@ -80,96 +22,22 @@ static int kb_scratch(kb_ctx* ctx, int s, size_t bytes, void** out)
     *out = ctx->slot[s];
     return KB_OK;
 }
-#define KB_SCRATCH(s, bytes, ptr)                                          \
-    do {                                                                   \
-        void* p_;                                                          \
-        int rc_ = kb_scratch(ctx, (s), (bytes), &p_);                      \
-        if (rc_ != KB_OK) return rc_;                                      \
-        (ptr) = reinterpret_cast<decltype(ptr)>(p_);                       \
-    } while (0)
-
-// ------------------------------------------------------------------------------------
-// Pippenger driver (msm.cuh): chunks of <= KB_MSM_CHUNK points, partial sums chained on device
-// ------------------------------------------------------------------------------------
-static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st)
+// kb_dev_* calls of one context share its scratch: a call on another stream than the previous one waits for it
+int kb_dev_begin(kb_ctx* ctx, cudaStream_t st)
 {
-    uint32_t* acc128 = d_partial128;
-    if (!acc128) KB_SCRATCH(10, 128, acc128);
-    uint32_t* bad;
-    if (d_bad) bad = reinterpret_cast<uint32_t*>(d_bad);
-    else KB_SCRATCH(11, 8, bad);
-    KB_CUDA(cudaMemsetAsync(bad, 0, 8, st));
-    if (n == 0) {
-        kb_msm_plan pl = {0, 4, 0, 8, 0, 16};
-        k_msm_finish<<<1, 32, 0, st>>>(pl, nullptr, acc128, 1, d_out32);
-        KB_LAUNCHED();
-        return KB_OK;
-    }
-    for (size_t off = 0; off < n; off += KB_MSM_CHUNK) {
-        const size_t cn = (n - off < KB_MSM_CHUNK) ? (n - off) : KB_MSM_CHUNK;
-        kb_msm_plan pl;
-        pl.n = (uint32_t)cn;
-        pl.c = kb_msm_window_bits_host(cn);
-        if (ctx->msm_c) pl.c = (uint32_t)ctx->msm_c;   // KB_MSM_C tuning override; measured at 2^22: c = 15 / 16 / 17 -> 15.6 / 15.3 / 15.6 ms
-        pl.windows = (257 + pl.c - 1) / pl.c;
-        pl.half = 1u << (pl.c - 1);
-        pl.nb = pl.windows * pl.half;
-        pl.k = kb_msm_chunk_entries(cn, pl.half);
-        const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
-        const size_t nthreads = (cn * pl.windows + pl.k - 1) / pl.k;
-        uint32_t *pts, *mags, *counts, *offsets, *cursor, *sorted, *bucket_sum, *heads, *tails, *partial, *tile_sums, *long_list, *win_sum;
-        uint8_t *negs, *flags;
-        KB_SCRATCH(12, 96 * cn, pts);
-        KB_SCRATCH(13, 32 * cn, mags);
-        KB_SCRATCH(14, cn, negs);
-        KB_SCRATCH(15, 4 * (size_t)pl.nb, counts);
-        KB_SCRATCH(16, 4 * ((size_t)pl.nb + 1), offsets);
-        KB_SCRATCH(17, 4 * (size_t)pl.nb, cursor);
-        KB_SCRATCH(18, 4 * cn * pl.windows, sorted);
-        KB_SCRATCH(19, 128 * (size_t)pl.nb, bucket_sum);
-        KB_SCRATCH(20, 128 * nthreads, heads);
-        KB_SCRATCH(21, 128 * nthreads, tails);
-        KB_SCRATCH(22, nthreads, flags);
-        KB_SCRATCH(23, 2 * 128 * (size_t)pl.windows * groups, partial);
-        uint32_t* part_tot = partial + 32 * (size_t)pl.windows * groups;
-        KB_SCRATCH(24, 4 * 2048, tile_sums);
-        KB_SCRATCH(25, 16 + 12 * (size_t)pl.nb, long_list);  // at most one long run per bucket
-        KB_SCRATCH(26, 128 * (size_t)pl.windows, win_sum);
-        if (pl.nb > 2048u * KB_SCAN_TILE) return KB_ERR_ARG;
-        KB_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)pl.nb, st));
-        k_msm_prepare<<<kb_blocks(cn, KB_THREADS), KB_THREADS, 0, st>>>(cn, d_points + 32 * off, d_scalars + 32 * off, pts, mags, negs, bad);
-        KB_LAUNCHED();
-        k_msm_hist<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, counts);
-        KB_LAUNCHED();
-        const uint32_t ntiles = (pl.nb + KB_SCAN_TILE - 1) / KB_SCAN_TILE;
-        k_msm_scan_tiles<<<ntiles, 256, 0, st>>>(pl.nb, counts, offsets, tile_sums);
-        KB_LAUNCHED();
-        k_msm_scan_sums<<<1, 1024, 0, st>>>(ntiles, pl.nb, tile_sums, offsets);
-        KB_LAUNCHED();
-        k_msm_scan_add<<<kb_blocks(pl.nb, 256), 256, 0, st>>>(pl.nb, tile_sums, offsets, cursor);
-        KB_LAUNCHED();
-        k_msm_scatter<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, negs, offsets, cursor, sorted);
-        KB_LAUNCHED();
-        k_msm_accum<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, sorted, pts, bucket_sum, heads, tails, flags);
-        KB_LAUNCHED();
-        KB_CUDA(cudaMemsetAsync(long_list, 0, 4, st));  // word 0 of the block is the queue length
-        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, long_list, long_list + 4, bucket_sum, heads, tails, flags);
-        KB_LAUNCHED();
-        k_msm_merge_long<<<ctx->sm_count * 2, KB_THREADS, 0, st>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
-        KB_LAUNCHED();
-        k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial, part_tot);
-        KB_LAUNCHED();
-        k_msm_window_sums<<<pl.windows, 256, 0, st>>>(pl, groups, partial, part_tot, win_sum);
-        KB_LAUNCHED();
-        const bool last = off + cn >= n;
-        k_msm_finish<<<1, 32, 0, st>>>(pl, win_sum, acc128, off == 0 ? 1 : 0, last ? d_out32 : nullptr);
-        KB_LAUNCHED();
-    }
+    if (!ctx) return KB_ERR_ARG;
+    KB_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->order_valid) KB_CUDA(cudaStreamWaitEvent(st, ctx->order_ev, 0));
+    return KB_OK;
+}
+int kb_dev_end(kb_ctx* ctx, cudaStream_t st)
+{
+    KB_CUDA(cudaEventRecord(ctx->order_ev, st));
+    ctx->order_valid = 1;
     return KB_OK;
 }
 
 extern "C" {
-
 int kb_ctx_create(int device, kb_ctx** out)
 {
     if (!out) return KB_ERR_ARG;
@@ -180,17 +48,25 @@ int kb_ctx_create(int device, kb_ctx** out)
     kb_ctx* ctx = (kb_ctx*)calloc(1, sizeof(kb_ctx));
     if (!ctx) return KB_ERR_NOMEM;
     ctx->device = device;
+    const char* vf = getenv("KB_VERIFY_FULL");
+    ctx->verify_full = (vf && vf[0] == '1') ? 1 : 0;
     cudaDeviceProp prop;
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
     if (ok) ctx->sm_count = prop.multiProcessorCount;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->fd_pw_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
+    if (ctx->verify_full) ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->comb, sizeof(ge_precomp) * KB_COMB_POS * KB_COMB_HALF) == cudaSuccess;
     if (ok) {
         k_base_init<<<1, 64, 0, ctx->stream>>>(ctx->base_table);
-        k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
+        ctx->launches++;
+        if (ctx->verify_full) {   // the 128-entry radix-256 table is only read by the full-length verifiers
+            k_base128_init<<<1, 32, 0, ctx->stream>>>(ctx->base128);
+            ctx->launches++;
+        }
         k_comb_init<<<kb_blocks((size_t)KB_COMB_POS * KB_COMB_HALF, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(ctx->comb, ctx->base_table);
         ctx->launches++;
         for (int k = 0; k < 3; k++) ok = ok && cudaEventCreate(&ctx->tev[k]) == cudaSuccess;
@@ -199,24 +75,15 @@ int kb_ctx_create(int device, kb_ctx** out)
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
         const char* fd = getenv("KB_DKG_FD");
         ctx->dkg_fd = fd ? atoi(fd) : -1;
+        const char* fp = getenv("KB_FD_PARTS");
+        ctx->fd_parts = fp ? atoi(fp) : 0;
         const char* mc = getenv("KB_MSM_C");
         const int mcv = mc ? atoi(mc) : 0;
         ctx->msm_c = (mcv >= 4 && mcv <= 16) ? mcv : 0;
-        const char* fg = getenv("KB_FD_GROUPS");
-        ctx->fd_groups = fg ? atoi(fg) : 2;
-        if (ctx->fd_groups < 1) ctx->fd_groups = 1;
-        if (ctx->fd_groups > 4) ctx->fd_groups = 4;
         const char* vw = getenv("KB_VERIFY_MIN_WINDOWS");
         const int vwn = vw ? atoi(vw) : 0;
         ctx->verify_min_windows = (vwn > KB_HALF_MIN_WINDOWS && vwn <= 64) ? vwn : KB_HALF_MIN_WINDOWS;
-        const char* vf = getenv("KB_VERIFY_FULL");
-        ctx->verify_full = (vf && vf[0] == '1') ? 1 : 0;
-        ctx->launches += 2;
-        cudaFuncSetAttribute(k_mul_base<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-        cudaFuncSetAttribute(k_mul_base<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-        cudaFuncSetAttribute(k_poly_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-        cudaFuncSetAttribute(k_sign_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 96);
-        ok = cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
     }
     if (!ok) {
         kb_ctx_destroy(ctx);   // releases whatever was created
@@ -230,19 +97,17 @@ void kb_ctx_destroy(kb_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    cudaDeviceSynchronize();
     for (int s = 0; s < KB_NSLOTS; s++)
         if (ctx->slot[s]) cudaFree(ctx->slot[s]);
     if (ctx->base_table) cudaFree(ctx->base_table);
     if (ctx->base128) cudaFree(ctx->base128);
     if (ctx->comb) cudaFree(ctx->comb);
+    if (ctx->fd_pw_host) cudaFreeHost(ctx->fd_pw_host);
     for (int k = 0; k < 3; k++)
         if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
-    for (int k = 0; k < 4; k++) {
-        if (ctx->fd_stream[k]) cudaStreamDestroy(ctx->fd_stream[k]);
-        if (ctx->fd_event[k]) cudaEventDestroy(ctx->fd_event[k]);
-    }
+    if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
+    if (ctx->fd_pw_ev) cudaEventDestroy(ctx->fd_pw_ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);
@@ -260,7 +125,6 @@ void kb_host_free(void* p)
 {
     if (p) cudaFreeHost(p);
 }
-
 // ------------------------------------------------------------------------------------
 // device-pointer entry points
 // ------------------------------------------------------------------------------------
@@ -269,6 +133,7 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
     if (!ctx || (n && (!d_scalars || !d_out))) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
     uint32_t* xyz;
     KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
     const size_t smem = 64 * 8 * 96;
@@ -286,13 +151,14 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
     KB_LAUNCHED();
     k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, nullptr, (uint8_t*)d_out);
     KB_LAUNCHED();
-    return KB_OK;
+    KB_DEV_RETURN(st, KB_OK);
 }
 int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status, uint32_t flags, void* stream)
 {
     if (!ctx || (n && (!d_scalars || !d_points || !d_out))) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
     uint32_t* xyz;
     uint8_t* bad = (uint8_t*)d_status;
     KB_SCRATCH(KB_SLOT_XYZ, 96 * n, xyz);
@@ -306,204 +172,8 @@ int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d
     KB_LAUNCHED();
     k_compress_batch<<<kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(n, xyz, bad, (uint8_t*)d_out);
     KB_LAUNCHED();
-    return KB_OK;
+    KB_DEV_RETURN(st, KB_OK);
 }
-// per-signature scratch of the verifiers: 304-byte records (half-size-scalar path) / 96-byte points (full-length path)
-#define KB_VERIFY_SCRATCH_BYTES (4 * KB_HALF_REC_WORDS)
-static int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, uint64_t msg_base, const uint8_t* d_sig, uint8_t* d_status, int schnorr,
-                            uint32_t* xyz, uint8_t* fl, cudaStream_t st)
-{
-    const unsigned th = kb_item_threads(ctx, n);
-    const unsigned g1 = kb_blocks(n, th), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
-    const bool tm = ctx->timing != 0;
-    if (!ctx->verify_full) {
-        // the 96-byte-per-item xyz scratch of the full-length path is not needed; `xyz` carries the 304-byte records
-        const unsigned gp = kb_blocks(n, KB_THREADS);
-        if (tm) cudaEventRecord(ctx->tev[0], st);
-        if (schnorr) k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
-        else k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
-        KB_LAUNCHED();
-        if (tm) cudaEventRecord(ctx->tev[1], st);
-        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
-        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
-        KB_LAUNCHED();
-        if (tm) {
-            cudaEventRecord(ctx->tev[2], st);
-            ctx->timing_valid = 1;
-        }
-        return KB_OK;
-    }
-    if (tm) cudaEventRecord(ctx->tev[0], st);
-    if (schnorr) k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
-    else k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
-    KB_LAUNCHED();
-    if (tm) cudaEventRecord(ctx->tev[1], st);
-    if (schnorr) k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
-    else k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
-    KB_LAUNCHED();
-    if (tm) {
-        cudaEventRecord(ctx->tev[2], st);
-        ctx->timing_valid = 1;
-    }
-    return KB_OK;
-}
-int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream)
-{
-    if (!ctx || (n && (!d_pk || !d_msg_off || !d_sig || !d_status))) return KB_ERR_ARG;
-    if (n == 0) return KB_OK;
-    uint32_t* xyz;
-    uint8_t* fl;
-    KB_SCRATCH(KB_SLOT_XYZ, KB_VERIFY_SCRATCH_BYTES * n, xyz);
-    KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
-    return kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, 0, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, (cudaStream_t)stream);
-}
-// commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel
-static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* d_commits, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
-                       const uint8_t* d_shares, uint8_t* d_out, uint8_t* d_status, cudaStream_t st)
-{
-    uint32_t* cached;
-    uint8_t* bad;
-    const size_t nc = npoly * t;
-    KB_SCRATCH(8, nc * 128, cached);
-    KB_SCRATCH(9, nc, bad);
-    k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, st>>>(nc, d_commits, cached, bad);
-    KB_LAUNCHED();
-    if (d_shares) {
-        k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, d_shares, nullptr, nullptr, d_out, ctx->base_table);
-        KB_LAUNCHED();
-    } else {
-        uint32_t* xyz;
-        KB_SCRATCH(KB_SLOT_XYZ, 96 * m, xyz);
-        k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 0, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, nullptr, xyz, d_status, nullptr, ctx->base_table);
-        KB_LAUNCHED();
-        k_compress_batch<<<kb_blocks((m + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(m, xyz, d_status, d_out);
-        KB_LAUNCHED();
-    }
-    return KB_OK;
-}
-// The whole round by forward differences (dkgfd.cuh): t - 1 wavefront launches, one scaling launch, n step launches,
-// one check launch — per GROUP of dealers.  Every launch waits for the previous one of its group, so its tail (the
-// last blocks running on a mostly idle GPU) is lost time; KB_FD_GROUPS independent groups on their own streams fill
-// each other's tails.
-#define KB_FD_MAX_GROUPS 4
-static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, const uint8_t* d_commits, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
-{
-    uint32_t *q0, *q1, *q2, *evals, *dbad, *fact;
-    const size_t cells = nd * t;
-    KB_SCRATCH(8, 128 * cells, q0);
-    KB_SCRATCH(30, 128 * cells, q1);
-    KB_SCRATCH(31, 128 * cells, q2);
-    KB_SCRATCH(KB_SLOT_XYZ, 96 * nd * n, evals);
-    KB_SCRATCH(9, 4 * nd, dbad);
-    KB_SCRATCH(27, 36 * t, fact);
-    {
-        uint32_t* hf = (uint32_t*)malloc(36 * t);
-        if (!hf) return KB_ERR_NOMEM;
-        kb_factorials_mod_8l(t, hf);
-        cudaError_t e = cudaMemcpyAsync(fact, hf, 36 * t, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // hf is pageable: the copy is staged, but keep it simple
-        free(hf);
-        if (e != cudaSuccess) return kb_fail(ctx, e, "factorial table");
-    }
-    KB_CUDA(cudaMemsetAsync(dbad, 0, 4 * nd, st));
-    // groups of dealers (multiples of 32 so that warps stay uniform), each a contiguous slice of every array
-    int ng = ctx->fd_groups;
-    while (ng > 1 && nd / ng < 64) ng--;
-    size_t g0[KB_FD_MAX_GROUPS + 1];
-    for (int g = 0; g <= ng; g++) g0[g] = (g == ng) ? nd : (nd * g / ng) / 32 * 32;
-    cudaStream_t gs[KB_FD_MAX_GROUPS];
-    gs[0] = st;
-    for (int g = 1; g < ng; g++) {
-        if (!ctx->fd_stream[g]) {
-            KB_CUDA(cudaStreamCreateWithFlags(&ctx->fd_stream[g], cudaStreamNonBlocking));
-            KB_CUDA(cudaEventCreateWithFlags(&ctx->fd_event[g], cudaEventDisableTiming));
-        }
-        gs[g] = ctx->fd_stream[g];
-    }
-    if (ng > 1) {
-        if (!ctx->fd_event[0]) KB_CUDA(cudaEventCreateWithFlags(&ctx->fd_event[0], cudaEventDisableTiming));
-        KB_CUDA(cudaEventRecord(ctx->fd_event[0], st));
-        for (int g = 1; g < ng; g++) KB_CUDA(cudaStreamWaitEvent(gs[g], ctx->fd_event[0], 0));
-    }
-#define KB_FD_G(ptr, words_per_dealer) ((ptr) + (size_t)(words_per_dealer) * g0[g])
-    for (int g = 0; g < ng; g++) {
-        const size_t dn = g0[g + 1] - g0[g];
-        k_fd_init<<<kb_blocks(dn * t, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, d_commits + 32 * t * g0[g], KB_FD_G(q0, 32 * t), KB_FD_G(q1, 32 * t), dbad + g0[g]);
-        KB_LAUNCHED();
-    }
-    for (size_t w = 1; w + 1 <= t; w++) {
-        for (int g = 0; g < ng; g++) {
-            const size_t dn = g0[g + 1] - g0[g];
-            k_fd_newton<<<kb_blocks(dn * w, KB_FD_NEWTON_THREADS), KB_FD_NEWTON_THREADS, 0, gs[g]>>>(dn, t, w, KB_FD_G(q0, 32 * t), KB_FD_G(q1, 32 * t));
-            KB_LAUNCHED();
-        }
-    }
-    for (int g = 0; g < ng; g++) {
-        const size_t dn = g0[g + 1] - g0[g];
-        k_fd_scale<<<kb_blocks(dn * t, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, KB_FD_G(q0, 32 * t), KB_FD_G(q1, 32 * t), fact, KB_FD_G(q2, 32 * t));
-        KB_LAUNCHED();
-    }
-    // difference steps.  (Walking the dealers in sequential groups whose two arrays fit the L2 was measured SLOWER —
-    // the steps are bound by the additions and by the per-launch tail, not by memory.)
-    // A difference of order k only reaches the value k steps later: with R = n - i points still to produce, the orders
-    // >= R are dead and are not updated any more (the last live order reads its neighbour from the array that
-    // neighbour was last written to, which is this step's source).  Saves the final triangle, t^2/2 of the n*t additions.
-    for (size_t i = 0; i < n; i++) {
-        const size_t live = (n - i < t) ? n - i : t;
-        for (int g = 0; g < ng; g++) {
-            const size_t dn = g0[g + 1] - g0[g];
-            uint32_t* a = (i & 1) ? KB_FD_G(q0, 32 * t) : KB_FD_G(q2, 32 * t);
-            uint32_t* b2 = (i & 1) ? KB_FD_G(q2, 32 * t) : KB_FD_G(q0, 32 * t);
-            k_fd_step<<<kb_blocks(dn * live, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, t, live, n, i, a, b2, KB_FD_G(evals, 24 * n));
-            KB_LAUNCHED();
-        }
-    }
-    for (int g = 0; g < ng; g++) {
-        const size_t dn = g0[g + 1] - g0[g];
-        k_fd_check<<<kb_blocks(dn * n, KB_THREADS), KB_THREADS, 0, gs[g]>>>(dn, n, KB_FD_G(evals, 24 * n), d_shares + 32 * n * g0[g], dbad + g0[g], ctx->comb, d_verdict + n * g0[g]);
-        KB_LAUNCHED();
-    }
-#undef KB_FD_G
-    for (int g = 1; g < ng; g++) {
-        KB_CUDA(cudaEventRecord(ctx->fd_event[g], gs[g]));
-        KB_CUDA(cudaStreamWaitEvent(st, ctx->fd_event[g], 0));
-    }
-    return KB_OK;
-}
-// multiplies (IMAD-eq) per dealer: Horner per share check against Newton conversion + scaling + difference steps
-static bool kb_dkg_use_fd(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
-{
-    if (ctx->dkg_fd == 0) return false;
-    if (ctx->dkg_fd == 1) return true;
-    const double horner = (double)n * t * 6800.0;
-    const double fd = 0.5 * t * t * 4600.0 + t * 138300.0 + (double)n * t * 660.0 + n * 11000.0;
-    // its arrays: three of nd*t extended points and the nd*n recorded values — fall back to the per-share kernel
-    // (a few MB of scratch) rather than fail when they would not fit next to what is already allocated
-    size_t free_b = 0, total_b = 0;
-    const double need = 3.0 * 128.0 * nd * t + 96.0 * nd * n;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > 0.8 * (double)free_b + (double)(ctx->slot_bytes[8] + ctx->slot_bytes[30] + ctx->slot_bytes[31] + ctx->slot_bytes[KB_SLOT_XYZ])) return false;
-    // every wavefront / step is a launch of nd * (up to t) threads: it needs a GPU's worth of them to pay
-    return nd * t >= 32768 && fd * 1.25 < horner;   // measured: n=256,t=171: 8.6 vs 10.0 ms; n=512,t=341: 35.6 vs 68.7 ms; n=1024,t=683: 262 vs 584 ms
-}
-int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream)
-{
-    if (!ctx || !t || (n && ndealers && (!d_commits || !d_shares || !d_verdict))) return KB_ERR_ARG;
-    if (n == 0 || ndealers == 0) return KB_OK;
-    if (kb_dkg_use_fd(ctx, n, t, ndealers))
-        return kb_dkg_fd_run(ctx, n, t, ndealers, (const uint8_t*)d_commits, (const uint8_t*)d_shares, (uint8_t*)d_verdict, (cudaStream_t)stream);
-    return kb_poly_run(ctx, ndealers, t, (const uint8_t*)d_commits, n * ndealers, nullptr, nullptr, n, (const uint8_t*)d_shares, (uint8_t*)d_verdict, nullptr, (cudaStream_t)stream);
-}
-
-// ------------------------------------------------------------------------------------
-// host-pointer entry points: H2D, kernels, D2H, synchronise
-// ------------------------------------------------------------------------------------
-#define KB_H2D(dst, src, bytes) KB_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
-#define KB_D2H(dst, src, bytes) KB_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, ctx->stream))
-#define KB_SYNC() KB_CUDA(cudaStreamSynchronize(ctx->stream))
-#define KB_ENTER()                                  \
-    if (!ctx) return KB_ERR_ARG;                    \
-    KB_CUDA(cudaSetDevice(ctx->device))
-
 int kb_ctx_wipe(kb_ctx* ctx)
 {
     KB_ENTER();
@@ -523,6 +193,8 @@ int kb_point_mul_base_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, uint8
     KB_SCRATCH(1, 32 * n, d_o);
     KB_H2D(d_s, scalars, 32 * n);
     int rc = kb_dev_point_mul_base(ctx, n, d_s, d_o, flags, ctx->stream);
+    // scalars that are not declared public (KB_FLAG_VARTIME) do not outlive the call in device scratch
+    if (!(flags & KB_FLAG_VARTIME)) KB_CUDA(cudaMemsetAsync(d_s, 0, 32 * n, ctx->stream));
     if (rc != KB_OK) return rc;
     KB_D2H(out, d_o, 32 * n);
     KB_SYNC();
@@ -542,6 +214,7 @@ int kb_point_mul_batch(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint
     KB_H2D(d_s, scalars, 32 * n);
     KB_H2D(d_p, points, 32 * np);
     int rc = kb_dev_point_mul(ctx, n, d_s, d_p, d_o, d_st, flags, ctx->stream);
+    if (!(flags & KB_FLAG_VARTIME)) KB_CUDA(cudaMemsetAsync(d_s, 0, 32 * n, ctx->stream));
     if (rc != KB_OK) return rc;
     KB_D2H(out, d_o, 32 * n);
     if (status) KB_D2H(status, d_st, n);
@@ -705,6 +378,10 @@ int kb_sc_muladd_batch(kb_ctx* ctx, size_t n, const uint8_t* a, const uint8_t* b
     KB_H2D(d_c, c, 32 * n);
     k_sc_muladd<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_a, d_b, d_c, d_o);
     KB_LAUNCHED();
+    // the operands may be private keys / nonces (s = k + x h): they do not stay in device scratch
+    KB_CUDA(cudaMemsetAsync(d_a, 0, 32 * n, ctx->stream));
+    KB_CUDA(cudaMemsetAsync(d_b, 0, 32 * n, ctx->stream));
+    KB_CUDA(cudaMemsetAsync(d_c, 0, 32 * n, ctx->stream));
     KB_D2H(out, d_o, 32 * n);
     KB_SYNC();
     return KB_OK;
@@ -729,6 +406,7 @@ int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t*
     KB_ENTER();
     if (n && (!r32 || !a32 || !msg_off || !out32)) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
+    if (!kb_msg_off_ok(n, msg_off)) return KB_ERR_ARG;
     const size_t mbytes = (size_t)msg_off[n];
     if (mbytes && !msg) return KB_ERR_ARG;
     uint8_t *d_r, *d_a, *d_m, *d_o;
@@ -746,257 +424,6 @@ int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t*
     KB_LAUNCHED();
     KB_D2H(out32, d_o, 32 * n);
     KB_SYNC();
-    return KB_OK;
-}
-// Host-buffer verification, pipelined: the batch is cut into chunks of KB_VERIFY_CHUNK signatures that
-// alternate between two streams, so the H2D copy of chunk k+1 and the D2H of chunk k-1 overlap the
-// kernels of chunk k (each stream owns its own staging and scratch buffers).
-static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr)
-{
-    KB_ENTER();
-    if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
-    if (n == 0) return KB_OK;
-    if (msg_off[n] && !msg) return KB_ERR_ARG;
-    // measured on a 2^20 batch (tools/e2e_sweep.py): 2^18-signature chunks give the best overlap of copies and kernels
-    size_t chunk = ctx->verify_chunk;
-    if (chunk == 0) {
-        chunk = (size_t)1 << 15;
-        while (chunk < KB_VERIFY_CHUNK && chunk * 4 < n) chunk <<= 1;
-    }
-    size_t max_mbytes = 0;
-    for (size_t lo = 0; lo < n; lo += chunk) {
-        const size_t hi = (lo + chunk < n) ? lo + chunk : n;
-        if (msg_off[hi] < msg_off[lo]) return KB_ERR_ARG;
-        const size_t mb = (size_t)(msg_off[hi] - msg_off[lo]);
-        if (mb > max_mbytes) max_mbytes = mb;
-    }
-    const size_t cn_max = n < chunk ? n : chunk;
-    cudaStream_t lane[2] = {ctx->stream, ctx->stream2};
-    uint8_t *d_pk[2], *d_sig[2], *d_m[2], *d_st[2], *fl[2];
-    uint64_t* d_off[2];
-    uint32_t* xyz[2];
-    for (int l = 0; l < 2; l++) {
-        const int b = 32 + 7 * l;
-        KB_SCRATCH(b + 0, 32 * cn_max, d_pk[l]);
-        KB_SCRATCH(b + 1, 64 * cn_max, d_sig[l]);
-        KB_SCRATCH(b + 2, max_mbytes, d_m[l]);
-        KB_SCRATCH(b + 3, 8 * (cn_max + 1), d_off[l]);
-        KB_SCRATCH(b + 4, cn_max, d_st[l]);
-        KB_SCRATCH(b + 5, KB_VERIFY_SCRATCH_BYTES * cn_max, xyz[l]);
-        KB_SCRATCH(b + 6, cn_max, fl[l]);
-    }
-    int l = 0;
-    for (size_t lo = 0; lo < n; lo += chunk, l ^= 1) {
-        const size_t hi = (lo + chunk < n) ? lo + chunk : n, cn = hi - lo;
-        const size_t m0 = (size_t)msg_off[lo], mb = (size_t)msg_off[hi] - m0;
-        cudaStream_t st = lane[l];
-        KB_CUDA(cudaMemcpyAsync(d_pk[l], pk + 32 * lo, 32 * cn, cudaMemcpyHostToDevice, st));
-        KB_CUDA(cudaMemcpyAsync(d_sig[l], sig + 64 * lo, 64 * cn, cudaMemcpyHostToDevice, st));
-        if (mb) KB_CUDA(cudaMemcpyAsync(d_m[l], msg + m0, mb, cudaMemcpyHostToDevice, st));
-        KB_CUDA(cudaMemcpyAsync(d_off[l], msg_off + lo, 8 * (cn + 1), cudaMemcpyHostToDevice, st));
-        // offsets stay absolute; the kernel is told that d_m[l] starts at byte m0 of the caller's array
-        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l], d_off[l], (uint64_t)m0, d_sig[l], d_st[l], schnorr, xyz[l], fl[l], st);
-        if (rc != KB_OK) return rc;
-        KB_CUDA(cudaMemcpyAsync(status + lo, d_st[l], cn, cudaMemcpyDeviceToHost, st));
-    }
-    KB_CUDA(cudaStreamSynchronize(ctx->stream));
-    KB_CUDA(cudaStreamSynchronize(ctx->stream2));
-    return KB_OK;
-}
-int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)
-{
-    return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 0);
-}
-int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)
-{
-    return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 1);
-}
-
-int kb_eddsa_sign_batch(kb_ctx* ctx, size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint8_t* sig, uint8_t* pk)
-{
-    KB_ENTER();
-    if (n && (!seeds || !msg_off || !sig)) return KB_ERR_ARG;
-    if (n == 0) return KB_OK;
-    const size_t mbytes = (size_t)msg_off[n];
-    if (mbytes && !msg) return KB_ERR_ARG;
-    uint8_t *d_seed, *d_m, *d_a, *d_r, *d_ra, *d_sig, *d_pk;
-    uint64_t* d_off;
-    uint32_t* xyz;
-    KB_SCRATCH(0, 32 * n, d_seed);
-    KB_SCRATCH(4, mbytes, d_m);
-    KB_SCRATCH(5, 8 * (n + 1), d_off);
-    KB_SCRATCH(2, 64 * n, d_sig);
-    KB_SCRATCH(1, 32 * n, d_pk);
-    KB_SCRATCH(6, 32 * n, d_a);
-    KB_SCRATCH(7, 32 * n, d_r);
-    KB_SCRATCH(8, 64 * n, d_ra);
-    KB_SCRATCH(KB_SLOT_XYZ, 96 * 2 * n, xyz);
-    KB_H2D(d_seed, seeds, 32 * n);
-    if (mbytes) KB_H2D(d_m, msg, mbytes);
-    KB_H2D(d_off, msg_off, 8 * (n + 1));
-    k_sign_stage1<<<kb_blocks(n, KB_THREADS), KB_THREADS, 64 * 8 * 96, ctx->stream>>>(n, d_seed, d_m, d_off, xyz, d_a, d_r, ctx->base_table);
-    KB_LAUNCHED();
-    k_compress_batch<<<kb_blocks((2 * n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(2 * n, xyz, nullptr, d_ra);
-    KB_LAUNCHED();
-    k_sign_finish<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_ra, d_m, d_off, d_a, d_r, d_sig, d_pk);
-    KB_LAUNCHED();
-    KB_D2H(sig, d_sig, 64 * n);
-    if (pk) KB_D2H(pk, d_pk, 32 * n);
-    // the secret scalars do not outlive the call
-    KB_CUDA(cudaMemsetAsync(d_a, 0, 32 * n, ctx->stream));
-    KB_CUDA(cudaMemsetAsync(d_r, 0, 32 * n, ctx->stream));
-    KB_CUDA(cudaMemsetAsync(d_seed, 0, 32 * n, ctx->stream));
-    KB_SYNC();
-    return KB_OK;
-}
-static int kb_poly_host(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* out,
-                        uint8_t* status)
-{
-    KB_ENTER();
-    if (!npoly || !t || !commits || (m && (!poly_id || !idx || !out))) return KB_ERR_ARG;
-    if (m == 0) return KB_OK;
-    for (size_t k = 0; k < m; k++)
-        if (poly_id[k] >= npoly) return KB_ERR_ARG;
-    uint8_t *d_c, *d_sh = nullptr, *d_o, *d_st;
-    uint32_t *d_pid, *d_idx;
-    const size_t out_bytes = shares ? m : 32 * m;
-    KB_SCRATCH(0, 32 * npoly * t, d_c);
-    KB_SCRATCH(5, 4 * m, d_pid);
-    KB_SCRATCH(6, 4 * m, d_idx);
-    KB_SCRATCH(1, out_bytes, d_o);
-    KB_SCRATCH(3, m, d_st);
-    KB_H2D(d_c, commits, 32 * npoly * t);
-    KB_H2D(d_pid, poly_id, 4 * m);
-    KB_H2D(d_idx, idx, 4 * m);
-    if (shares) {
-        KB_SCRATCH(2, 32 * m, d_sh);
-        KB_H2D(d_sh, shares, 32 * m);
-    }
-    int rc = kb_poly_run(ctx, npoly, t, d_c, m, d_pid, d_idx, 0, d_sh, d_o, d_st, ctx->stream);
-    if (rc != KB_OK) return rc;
-    KB_D2H(out, d_o, out_bytes);
-    if (status && !shares) KB_D2H(status, d_st, m);
-    KB_SYNC();
-    return KB_OK;
-}
-int kb_pubpoly_eval_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, uint8_t* out, uint8_t* status)
-{
-    return kb_poly_host(ctx, npoly, t, commits, m, poly_id, idx, nullptr, out, status);
-}
-int kb_vss_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* verdict)
-{
-    if (m && !shares) return KB_ERR_ARG;
-    return kb_poly_host(ctx, npoly, t, commits, m, poly_id, idx, shares, verdict, nullptr);
-}
-int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const uint8_t* commits, const uint8_t* shares, uint8_t* verdict)
-{
-    KB_ENTER();
-    if (!t || dealer_hi < dealer_lo || !commits || !shares || !verdict) return KB_ERR_ARG;
-    const size_t nd = dealer_hi - dealer_lo;
-    if (nd == 0 || n == 0) return KB_OK;
-    uint8_t *d_c, *d_sh, *d_v;
-    KB_SCRATCH(0, 32 * nd * t, d_c);
-    KB_SCRATCH(2, 32 * nd * n, d_sh);
-    KB_SCRATCH(1, nd * n, d_v);
-    KB_H2D(d_c, commits + 32 * dealer_lo * t, 32 * nd * t);
-    KB_H2D(d_sh, shares + 32 * dealer_lo * n, 32 * nd * n);
-    int rc = kb_dev_dkg_verify_round(ctx, n, t, nd, d_c, d_sh, d_v, ctx->stream);
-    if (rc != KB_OK) return rc;
-    KB_D2H(verdict + dealer_lo * n, d_v, nd * n);
-    KB_SYNC();
-    return KB_OK;
-}
-
-int kb_pubpoly_sum(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, uint8_t* out, uint8_t* status)
-{
-    KB_ENTER();
-    if (!npoly || !t || !commits || !out) return KB_ERR_ARG;
-    const size_t nc = npoly * t;
-    uint8_t *d_c, *bad, *d_o, *d_st;
-    uint32_t *cached, *xyz;
-    KB_SCRATCH(0, 32 * nc, d_c);
-    KB_SCRATCH(8, 128 * nc, cached);
-    KB_SCRATCH(9, nc, bad);
-    KB_SCRATCH(KB_SLOT_XYZ, 96 * t, xyz);
-    KB_SCRATCH(3, t, d_st);
-    KB_SCRATCH(1, 32 * t, d_o);
-    KB_H2D(d_c, commits, 32 * nc);
-    k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(nc, d_c, cached, bad);
-    KB_LAUNCHED();
-    k_poly_colsum<<<kb_blocks(32 * t, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(npoly, t, cached, bad, xyz, d_st);
-    KB_LAUNCHED();
-    k_compress_batch<<<kb_blocks((t + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(t, xyz, d_st, d_o);
-    KB_LAUNCHED();
-    KB_D2H(out, d_o, 32 * t);
-    if (status) KB_D2H(status, d_st, t);
-    KB_SYNC();
-    return KB_OK;
-}
-
-// ------------------------------------------------------------------------------------
-// MSM
-// ------------------------------------------------------------------------------------
-int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out32, void* d_partial128, void* d_bad_points, void* stream)
-{
-    if (!ctx || (n && (!d_scalars || !d_points)) || (!d_out32 && !d_partial128)) return KB_ERR_ARG;
-    return kb_msm_run(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out32, (uint32_t*)d_partial128, (unsigned long long*)d_bad_points, (cudaStream_t)stream);
-}
-int kb_msm(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out32, uint8_t* partial128, uint64_t* bad_points)
-{
-    KB_ENTER();
-    if ((n && (!scalars || !points)) || (!out32 && !partial128)) return KB_ERR_ARG;
-    uint8_t *d_s, *d_p, *d_o;
-    KB_SCRATCH(0, 32 * n, d_s);
-    KB_SCRATCH(2, 32 * n, d_p);
-    KB_SCRATCH(1, 32 + 128 + 8, d_o);
-    if (n) {
-        KB_H2D(d_s, scalars, 32 * n);
-        KB_H2D(d_p, points, 32 * n);
-    }
-    int rc = kb_dev_msm(ctx, n, d_s, d_p, d_o, d_o + 32, d_o + 160, ctx->stream);
-    if (rc != KB_OK) return rc;
-    if (out32) KB_D2H(out32, d_o, 32);
-    if (partial128) KB_D2H(partial128, d_o + 32, 128);
-    if (bad_points) KB_D2H(bad_points, d_o + 160, 8);
-    KB_SYNC();
-    return KB_OK;
-}
-int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream)
-{
-    if (!ctx || !d_out32 || (k && !d_partials128)) return KB_ERR_ARG;
-    k_point_sum<<<1, 32, 0, (cudaStream_t)stream>>>(k, (const uint32_t*)d_partials128, (uint8_t*)d_out32);
-    KB_LAUNCHED();
-    return KB_OK;
-}
-int kb_point_sum(kb_ctx* ctx, size_t k, const uint8_t* partials128, uint8_t* out32)
-{
-    KB_ENTER();
-    if (!out32 || (k && !partials128)) return KB_ERR_ARG;
-    uint8_t *d_i, *d_o;
-    KB_SCRATCH(0, 128 * k, d_i);
-    KB_SCRATCH(1, 32, d_o);
-    if (k) KB_H2D(d_i, partials128, 128 * k);
-    int rc = kb_dev_point_sum(ctx, k, d_i, d_o, ctx->stream);
-    if (rc != KB_OK) return rc;
-    KB_D2H(out32, d_o, 32);
-    KB_SYNC();
-    return KB_OK;
-}
-
-// ------------------------------------------------------------------------------------
-// measurement
-// ------------------------------------------------------------------------------------
-int kb_verify_kernel_times(kb_ctx* ctx, int enable, float* ms_out)
-{
-    KB_ENTER();
-    if (ms_out) {
-        if (!ctx->timing || !ctx->timing_valid) return KB_ERR_ARG;
-        KB_CUDA(cudaEventSynchronize(ctx->tev[2]));
-        KB_CUDA(cudaEventElapsedTime(&ms_out[0], ctx->tev[0], ctx->tev[1]));
-        KB_CUDA(cudaEventElapsedTime(&ms_out[1], ctx->tev[1], ctx->tev[2]));
-    }
-    ctx->timing = enable ? 1 : 0;
-    if (!enable) ctx->timing_valid = 0;
     return KB_OK;
 }
 int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double* elapsed_ms)

@@ -1,0 +1,257 @@
+// capi_poly.cu — committed polynomials: PubPoly::eval / check, DKG deal-verification rounds, dkg_key
+#define KB_K_POLY
+#include "ctx.cuh"
+#include "kernels.cuh"
+#include "msm.cuh"
+#include "dkgfd.cuh"
+// commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel
+static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const void* d_commits, int limbs, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
+                       const uint8_t* d_shares, uint8_t* d_out, uint8_t* d_status, cudaStream_t st)
+{
+    uint32_t* cached;
+    uint8_t* bad;
+    const size_t nc = npoly * t;
+    KB_SCRATCH(8, nc * 128, cached);
+    KB_SCRATCH(9, nc, bad);
+    if (limbs) k_commit_prepare_limbs<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, st>>>(nc, (const int32_t*)d_commits, cached, bad);
+    else k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, st>>>(nc, (const uint8_t*)d_commits, cached, bad);
+    KB_LAUNCHED();
+    if (d_shares) {
+        k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, d_shares, nullptr, nullptr, d_out, ctx->base_table);
+        KB_LAUNCHED();
+    } else {
+        uint32_t* xyz;
+        KB_SCRATCH(KB_SLOT_XYZ, 96 * m, xyz);
+        k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 0, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, nullptr, xyz, d_status, nullptr, ctx->base_table);
+        KB_LAUNCHED();
+        k_compress_batch<<<kb_blocks((m + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(m, xyz, d_status, d_out);
+        KB_LAUNCHED();
+    }
+    return KB_OK;
+}
+// The whole round by forward differences (dkgfd.cuh): one decode launch, h - 1 conversion launches, ONE launch for all
+// n difference steps, one combine-and-check launch.
+static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t parts, const void* d_commits, int limbs, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
+{
+    const size_t h = (t + parts - 1) / parts;
+    parts = (t + h - 1) / h;                 // no empty block
+    if (parts > KB_FD_MAX_PARTS || h > KB_FD_MAX_H) return KB_ERR_ARG;
+    const size_t rows = parts * h;
+    uint32_t *dec, *ra, *rb, *evals, *dbad, *pw;
+    KB_SCRATCH(31, 128 * nd * t, dec);
+    KB_SCRATCH(8, 128 * nd * rows, ra);
+    KB_SCRATCH(30, 128 * nd * rows, rb);
+    KB_SCRATCH(KB_SLOT_XYZ, 128 * parts * n * nd, evals);
+    KB_SCRATCH(9, 4 * nd, dbad);
+    const size_t pw_words = 9 * n * (parts - 1);
+    KB_SCRATCH(27, 4 * pw_words, pw);
+    if (parts > 1 && (ctx->fd_pw_key[0] != n || ctx->fd_pw_key[1] != h || ctx->fd_pw_key[2] != parts)) {
+        // the public multipliers (i+1)^(q h) mod 8L: host integers, built when the shape of the round changes and kept
+        // (in pinned memory and on the device) for the calls that follow
+        KB_CUDA(cudaEventSynchronize(ctx->fd_pw_ev));   // an earlier upload may still be reading the pinned buffer
+        if (ctx->fd_pw_host_words < pw_words) {
+            if (ctx->fd_pw_host) cudaFreeHost(ctx->fd_pw_host);
+            ctx->fd_pw_host = nullptr;
+            ctx->fd_pw_host_words = 0;
+            KB_CUDA(cudaMallocHost(&ctx->fd_pw_host, 4 * pw_words));
+            ctx->fd_pw_host_words = pw_words;
+        }
+        kb_fd_power_table(n, h, parts, ctx->fd_pw_host);
+        KB_CUDA(cudaMemcpyAsync(pw, ctx->fd_pw_host, 4 * pw_words, cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaEventRecord(ctx->fd_pw_ev, st));
+        ctx->fd_pw_key[0] = n;
+        ctx->fd_pw_key[1] = h;
+        ctx->fd_pw_key[2] = parts;
+    }
+    KB_CUDA(cudaMemsetAsync(dbad, 0, 4 * nd, st));
+    if (limbs) k_fd_decode_limbs<<<kb_blocks(nd * t, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, (const int32_t*)d_commits, dec, dbad);
+    else k_fd_decode<<<kb_blocks(nd * t, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, (const uint8_t*)d_commits, dec, dbad);
+    KB_LAUNCHED();
+    const size_t hl = kb_fd_part_len(t, h, parts - 1);
+    for (size_t s = 1; s < h; s++) {
+        const size_t sl = s + hl >= h ? s + hl - h : 0;
+        const size_t cells = (parts - 1) * s + sl;
+        if (cells == 0) continue;
+        const uint32_t* src = (s & 1) ? rb : ra;
+        uint32_t* dst = (s & 1) ? ra : rb;
+        k_fd_conv<<<kb_blocks(nd * cells, KB_FD_CONV_THREADS), KB_FD_CONV_THREADS, 0, st>>>(nd, t, h, parts, s, dec, src, dst);
+        KB_LAUNCHED();
+    }
+    const uint32_t* diffs = ((h - 1) & 1) ? ra : rb;   // what the last iteration wrote
+    const unsigned step_threads = 32u * (unsigned)((h + 31) / 32);
+    k_fd_steps<<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
+    KB_LAUNCHED();
+    k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
+    KB_LAUNCHED();
+    return KB_OK;
+}
+// How to run a round: 0 = the per-share Horner kernel, p >= 1 = forward differences with p coefficient blocks.
+// Estimated from multiply counts (IMAD-eq) per dealer and the length of the chains of dependent launches / steps.
+static size_t kb_dkg_plan(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
+{
+    if (ctx->dkg_fd == 0) return 0;
+    const size_t pmin = (t + KB_FD_MAX_H - 1) / KB_FD_MAX_H;
+    if (pmin > KB_FD_MAX_PARTS) return 0;
+    const double rate = 7.0e12;   // sustained multiplies per second these kernels reach
+    double best_time = 0;
+    size_t best = 0;
+    for (size_t p = pmin ? pmin : 1; p <= KB_FD_MAX_PARTS && p <= t; p++) {
+        const size_t h = (t + p - 1) / p;
+        const size_t pe = (t + h - 1) / h;
+        if (pe != p) continue;
+        double lg = 0;
+        for (size_t x = h; x > 1; x >>= 1) lg += 1;
+        const double cell = 900.0 + 590.0 * (lg > 1.5 ? lg - 1.5 : 0.0);
+        const double conv = 0.5 * t * h * cell;
+        const double steps = ((double)n * t - 0.5 * t * h > 0 ? (double)n * t - 0.5 * t * h : 0) * 660.0;
+        const double comb = p > 1 ? (double)n * (101000.0 + (p - 1) * 42000.0) : 0.0;
+        const double work = (conv + steps + comb + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
+        const double chain = h * 22e-6 + n * 2.5e-6;   // one cell per conversion launch, one addition per step
+        const double time = work > chain ? work + 0.3 * chain : chain + 0.3 * work;
+        if (best == 0 || time < best_time) {
+            best = p;
+            best_time = time;
+        }
+    }
+    if (ctx->fd_parts >= 1 && ctx->fd_parts <= KB_FD_MAX_PARTS && (size_t)ctx->fd_parts >= pmin && (size_t)ctx->fd_parts <= t) {
+        const size_t h = (t + ctx->fd_parts - 1) / ctx->fd_parts;
+        best = (t + h - 1) / h;
+    }
+    if (best == 0) return 0;
+    // its arrays: decoded commitments, two difference arrays, the recorded values — fall back to the per-share kernel
+    // (a few MB of scratch) rather than fail when they would not fit next to what is already allocated
+    {
+        const size_t h = (t + best - 1) / best;
+        size_t free_b = 0, total_b = 0;
+        const double need = 128.0 * nd * ((double)t + 2.0 * best * h + (double)best * n);
+        const double have = (double)(ctx->slot_bytes[8] + ctx->slot_bytes[30] + ctx->slot_bytes[31] + ctx->slot_bytes[KB_SLOT_XYZ]);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > 0.8 * (double)free_b + have) return 0;
+    }
+    if (ctx->dkg_fd == 1) return best;
+    const double horner = ((double)n * t * 6800.0 + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
+    // a round too small to fill the GPU is cheaper in one launch of the per-share kernel
+    return (nd * t >= 8192 && best_time * 1.15 < horner) ? best : 0;
+}
+int kb_dkg_round_run(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, int limbs, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
+{
+    const size_t parts = kb_dkg_plan(ctx, n, t, ndealers);
+    if (parts) return kb_dkg_fd_run(ctx, n, t, ndealers, parts, d_commits, limbs, d_shares, d_verdict, st);
+    return kb_poly_run(ctx, ndealers, t, d_commits, limbs, n * ndealers, nullptr, nullptr, n, d_shares, d_verdict, nullptr, st);
+}
+
+extern "C" {
+int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream)
+{
+    if (!ctx || !t || (n && ndealers && (!d_commits || !d_shares || !d_verdict))) return KB_ERR_ARG;
+    if (n == 0 || ndealers == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    KB_DEV_RETURN(st, kb_dkg_round_run(ctx, n, t, ndealers, d_commits, 0, (const uint8_t*)d_shares, (uint8_t*)d_verdict, st));
+}
+int kb_dev_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commit_limbs, const void* d_shares, void* d_verdict, void* stream)
+{
+    if (!ctx || !t || (n && ndealers && (!d_commit_limbs || !d_shares || !d_verdict))) return KB_ERR_ARG;
+    if (n == 0 || ndealers == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    KB_DEV_RETURN(st, kb_dkg_round_run(ctx, n, t, ndealers, d_commit_limbs, 1, (const uint8_t*)d_shares, (uint8_t*)d_verdict, st));
+}
+static int kb_poly_host(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* out,
+                        uint8_t* status)
+{
+    KB_ENTER();
+    if (!npoly || !t || !commits || (m && (!poly_id || !idx || !out))) return KB_ERR_ARG;
+    if (m == 0) return KB_OK;
+    for (size_t k = 0; k < m; k++)
+        if (poly_id[k] >= npoly) return KB_ERR_ARG;
+    uint8_t *d_c, *d_sh = nullptr, *d_o, *d_st;
+    uint32_t *d_pid, *d_idx;
+    const size_t out_bytes = shares ? m : 32 * m;
+    KB_SCRATCH(0, 32 * npoly * t, d_c);
+    KB_SCRATCH(5, 4 * m, d_pid);
+    KB_SCRATCH(6, 4 * m, d_idx);
+    KB_SCRATCH(1, out_bytes, d_o);
+    KB_SCRATCH(3, m, d_st);
+    KB_H2D(d_c, commits, 32 * npoly * t);
+    KB_H2D(d_pid, poly_id, 4 * m);
+    KB_H2D(d_idx, idx, 4 * m);
+    if (shares) {
+        KB_SCRATCH(2, 32 * m, d_sh);
+        KB_H2D(d_sh, shares, 32 * m);
+    }
+    int rc = kb_poly_run(ctx, npoly, t, d_c, 0, m, d_pid, d_idx, 0, d_sh, d_o, d_st, ctx->stream);
+    if (rc != KB_OK) return rc;
+    KB_D2H(out, d_o, out_bytes);
+    if (status && !shares) KB_D2H(status, d_st, m);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_pubpoly_eval_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, uint8_t* out, uint8_t* status)
+{
+    return kb_poly_host(ctx, npoly, t, commits, m, poly_id, idx, nullptr, out, status);
+}
+int kb_vss_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, size_t m, const uint32_t* poly_id, const uint32_t* idx, const uint8_t* shares, uint8_t* verdict)
+{
+    if (m && !shares) return KB_ERR_ARG;
+    return kb_poly_host(ctx, npoly, t, commits, m, poly_id, idx, shares, verdict, nullptr);
+}
+static int kb_dkg_round_host(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const void* commits, int limbs, const uint8_t* shares, uint8_t* verdict)
+{
+    KB_ENTER();
+    if (!t || dealer_hi < dealer_lo || !commits || !shares || !verdict) return KB_ERR_ARG;
+    const size_t nd = dealer_hi - dealer_lo;
+    if (nd == 0 || n == 0) return KB_OK;
+    const size_t cbytes = limbs ? 160 : 32;   // per commitment
+    uint8_t *d_c, *d_sh, *d_v;
+    KB_SCRATCH(0, cbytes * nd * t, d_c);
+    KB_SCRATCH(2, 32 * nd * n, d_sh);
+    KB_SCRATCH(1, nd * n, d_v);
+    KB_H2D(d_c, (const uint8_t*)commits + cbytes * dealer_lo * t, cbytes * nd * t);
+    KB_H2D(d_sh, shares + 32 * dealer_lo * n, 32 * nd * n);
+    int rc = kb_dkg_round_run(ctx, n, t, nd, d_c, limbs, d_sh, d_v, ctx->stream);
+    // the shares are secrets of the verifiers: they do not stay in device scratch
+    cudaMemsetAsync(d_sh, 0, 32 * nd * n, ctx->stream);
+    if (rc != KB_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    KB_D2H(verdict + dealer_lo * n, d_v, nd * n);
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const uint8_t* commits, const uint8_t* shares, uint8_t* verdict)
+{
+    return kb_dkg_round_host(ctx, n, t, dealer_lo, dealer_hi, commits, 0, shares, verdict);
+}
+int kb_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const int32_t* commit_limbs, const uint8_t* shares, uint8_t* verdict)
+{
+    return kb_dkg_round_host(ctx, n, t, dealer_lo, dealer_hi, commit_limbs, 1, shares, verdict);
+}
+
+int kb_pubpoly_sum(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, uint8_t* out, uint8_t* status)
+{
+    KB_ENTER();
+    if (!npoly || !t || !commits || !out) return KB_ERR_ARG;
+    const size_t nc = npoly * t;
+    uint8_t *d_c, *bad, *d_o, *d_st;
+    uint32_t *cached, *xyz;
+    KB_SCRATCH(0, 32 * nc, d_c);
+    KB_SCRATCH(8, 128 * nc, cached);
+    KB_SCRATCH(9, nc, bad);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * t, xyz);
+    KB_SCRATCH(3, t, d_st);
+    KB_SCRATCH(1, 32 * t, d_o);
+    KB_H2D(d_c, commits, 32 * nc);
+    k_commit_prepare<<<kb_blocks(nc, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(nc, d_c, cached, bad);
+    KB_LAUNCHED();
+    k_poly_colsum<<<kb_blocks(32 * t, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(npoly, t, cached, bad, xyz, d_st);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((t + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(t, xyz, d_st, d_o);
+    KB_LAUNCHED();
+    KB_D2H(out, d_o, 32 * t);
+    if (status) KB_D2H(status, d_st, t);
+    KB_SYNC();
+    return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// capi_verify.cu — eddsa::verify_with_checks / schnorr::verify_with_checks and EdDSA::sign entry points
+#define KB_K_SIGN
+#include "ctx.cuh"
+#include "kernels.cuh"
+// per-signature scratch of the verifiers: 304-byte records (half-size-scalar path) / 96-byte points (full-length path)
+static_assert(KB_VERIFY_SCRATCH_BYTES == 4 * KB_HALF_REC_WORDS, "ctx.cuh: KB_VERIFY_SCRATCH_BYTES");
+int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, uint64_t msg_base, const uint8_t* d_sig, uint8_t* d_status, int schnorr,
+                            uint32_t* xyz, uint8_t* fl, cudaStream_t st)
+{
+    const unsigned th = kb_item_threads(ctx, n);
+    const unsigned g1 = kb_blocks(n, th), g2 = kb_blocks((n + KB_INV_K - 1) / KB_INV_K, KB_THREADS);
+    const bool tm = ctx->timing != 0;
+    if (!ctx->verify_full) {
+        // the 96-byte-per-item xyz scratch of the full-length path is not needed; `xyz` carries the 304-byte records
+        const unsigned gp = kb_blocks(n, KB_THREADS);
+        if (tm) cudaEventRecord(ctx->tev[0], st);
+        if (schnorr) k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+        else k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+        KB_LAUNCHED();
+        if (tm) cudaEventRecord(ctx->tev[1], st);
+        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
+        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
+        KB_LAUNCHED();
+        if (tm) {
+            cudaEventRecord(ctx->tev[2], st);
+            ctx->timing_valid = 1;
+        }
+        return KB_OK;
+    }
+    if (tm) cudaEventRecord(ctx->tev[0], st);
+    if (schnorr) k_verify_stage1<true><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
+    else k_verify_stage1<false><<<g1, th, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, fl, ctx->base128);
+    KB_LAUNCHED();
+    if (tm) cudaEventRecord(ctx->tev[1], st);
+    if (schnorr) k_verify_stage2<true><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
+    else k_verify_stage2<false><<<g2, KB_THREADS, 0, st>>>(n, xyz, fl, d_sig, d_status);
+    KB_LAUNCHED();
+    if (tm) {
+        cudaEventRecord(ctx->tev[2], st);
+        ctx->timing_valid = 1;
+    }
+    return KB_OK;
+}
+
+extern "C" {
+int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream)
+{
+    if (!ctx || (n && (!d_pk || !d_msg_off || !d_sig || !d_status))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    uint32_t* xyz;
+    uint8_t* fl;
+    KB_SCRATCH(KB_SLOT_XYZ, KB_VERIFY_SCRATCH_BYTES * n, xyz);
+    KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
+    KB_DEV_RETURN(st, kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, 0, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, st));
+}
+// Host-buffer verification, pipelined: the batch is cut into chunks of KB_VERIFY_CHUNK signatures that
+// alternate between two streams, so the H2D copy of chunk k+1 and the D2H of chunk k-1 overlap the
+// kernels of chunk k (each stream owns its own staging and scratch buffers).
+static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr)
+{
+    KB_ENTER();
+    if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    if (!kb_msg_off_ok(n, msg_off) || (msg_off[n] && !msg)) return KB_ERR_ARG;
+    // measured on a 2^20 batch (tools/e2e_sweep.py): 2^18-signature chunks give the best overlap of copies and kernels
+    size_t chunk = ctx->verify_chunk;
+    if (chunk == 0) {
+        chunk = (size_t)1 << 15;
+        while (chunk < KB_VERIFY_CHUNK && chunk * 4 < n) chunk <<= 1;
+    }
+    size_t max_mbytes = 0;
+    for (size_t lo = 0; lo < n; lo += chunk) {
+        const size_t hi = (lo + chunk < n) ? lo + chunk : n;
+        if (msg_off[hi] < msg_off[lo]) return KB_ERR_ARG;
+        const size_t mb = (size_t)(msg_off[hi] - msg_off[lo]);
+        if (mb > max_mbytes) max_mbytes = mb;
+    }
+    const size_t cn_max = n < chunk ? n : chunk;
+    cudaStream_t lane[2] = {ctx->stream, ctx->stream2};
+    uint8_t *d_pk[2], *d_sig[2], *d_m[2], *d_st[2], *fl[2];
+    uint64_t* d_off[2];
+    uint32_t* xyz[2];
+    for (int l = 0; l < 2; l++) {
+        const int b = 32 + 7 * l;
+        KB_SCRATCH(b + 0, 32 * cn_max, d_pk[l]);
+        KB_SCRATCH(b + 1, 64 * cn_max, d_sig[l]);
+        KB_SCRATCH(b + 2, max_mbytes, d_m[l]);
+        KB_SCRATCH(b + 3, 8 * (cn_max + 1), d_off[l]);
+        KB_SCRATCH(b + 4, cn_max, d_st[l]);
+        KB_SCRATCH(b + 5, KB_VERIFY_SCRATCH_BYTES * cn_max, xyz[l]);
+        KB_SCRATCH(b + 6, cn_max, fl[l]);
+    }
+    int l = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, l ^= 1) {
+        const size_t hi = (lo + chunk < n) ? lo + chunk : n, cn = hi - lo;
+        const size_t m0 = (size_t)msg_off[lo], mb = (size_t)msg_off[hi] - m0;
+        cudaStream_t st = lane[l];
+        KB_CUDA(cudaMemcpyAsync(d_pk[l], pk + 32 * lo, 32 * cn, cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaMemcpyAsync(d_sig[l], sig + 64 * lo, 64 * cn, cudaMemcpyHostToDevice, st));
+        if (mb) KB_CUDA(cudaMemcpyAsync(d_m[l], msg + m0, mb, cudaMemcpyHostToDevice, st));
+        KB_CUDA(cudaMemcpyAsync(d_off[l], msg_off + lo, 8 * (cn + 1), cudaMemcpyHostToDevice, st));
+        // offsets stay absolute; the kernel is told that d_m[l] starts at byte m0 of the caller's array
+        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l], d_off[l], (uint64_t)m0, d_sig[l], d_st[l], schnorr, xyz[l], fl[l], st);
+        if (rc != KB_OK) return rc;
+        KB_CUDA(cudaMemcpyAsync(status + lo, d_st[l], cn, cudaMemcpyDeviceToHost, st));
+    }
+    KB_CUDA(cudaStreamSynchronize(ctx->stream));
+    KB_CUDA(cudaStreamSynchronize(ctx->stream2));
+    return KB_OK;
+}
+int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)
+{
+    return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 0);
+}
+int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status)
+{
+    return kb_verify_host(ctx, n, pk, msg, msg_off, sig, status, 1);
+}
+
+// device part of kb_eddsa_sign_batch; the caller wipes the secret scratch whatever this returns
+static int kb_sign_run(kb_ctx* ctx, size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, size_t mbytes, uint8_t* sig, uint8_t* pk, uint8_t* d_seed, uint8_t* d_a, uint8_t* d_r)
+{
+    uint8_t *d_m, *d_ra, *d_sig, *d_pk;
+    uint64_t* d_off;
+    uint32_t* xyz;
+    KB_SCRATCH(4, mbytes, d_m);
+    KB_SCRATCH(5, 8 * (n + 1), d_off);
+    KB_SCRATCH(2, 64 * n, d_sig);
+    KB_SCRATCH(1, 32 * n, d_pk);
+    KB_SCRATCH(8, 64 * n, d_ra);
+    KB_SCRATCH(KB_SLOT_XYZ, 96 * 2 * n, xyz);
+    KB_H2D(d_seed, seeds, 32 * n);
+    if (mbytes) KB_H2D(d_m, msg, mbytes);
+    KB_H2D(d_off, msg_off, 8 * (n + 1));
+    k_sign_stage1<<<kb_blocks(n, KB_THREADS), KB_THREADS, 64 * 8 * 96, ctx->stream>>>(n, d_seed, d_m, d_off, xyz, d_a, d_r, ctx->base_table);
+    KB_LAUNCHED();
+    k_compress_batch<<<kb_blocks((2 * n + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(2 * n, xyz, nullptr, d_ra);
+    KB_LAUNCHED();
+    k_sign_finish<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, ctx->stream>>>(n, d_ra, d_m, d_off, d_a, d_r, d_sig, d_pk);
+    KB_LAUNCHED();
+    KB_D2H(sig, d_sig, 64 * n);
+    if (pk) KB_D2H(pk, d_pk, 32 * n);
+    return KB_OK;
+}
+int kb_eddsa_sign_batch(kb_ctx* ctx, size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint8_t* sig, uint8_t* pk)
+{
+    KB_ENTER();
+    if (n && (!seeds || !msg_off || !sig)) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    if (!kb_msg_off_ok(n, msg_off)) return KB_ERR_ARG;
+    const size_t mbytes = (size_t)msg_off[n];
+    if (mbytes && !msg) return KB_ERR_ARG;
+    uint8_t *d_seed, *d_a, *d_r;
+    KB_SCRATCH(0, 32 * n, d_seed);
+    KB_SCRATCH(6, 32 * n, d_a);
+    KB_SCRATCH(7, 32 * n, d_r);
+    const int rc = kb_sign_run(ctx, n, seeds, msg, msg_off, mbytes, sig, pk, d_seed, d_a, d_r);
+    // the secret scalars do not outlive the call, on the error paths either
+    cudaMemsetAsync(d_a, 0, 32 * n, ctx->stream);
+    cudaMemsetAsync(d_r, 0, 32 * n, ctx->stream);
+    cudaMemsetAsync(d_seed, 0, 32 * n, ctx->stream);
+    if (rc != KB_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    KB_SYNC();
+    return KB_OK;
+}
+int kb_verify_kernel_times(kb_ctx* ctx, int enable, float* ms_out)
+{
+    KB_ENTER();
+    if (ms_out) {
+        if (!ctx->timing || !ctx->timing_valid) return KB_ERR_ARG;
+        KB_CUDA(cudaEventSynchronize(ctx->tev[2]));
+        KB_CUDA(cudaEventElapsedTime(&ms_out[0], ctx->tev[0], ctx->tev[1]));
+        KB_CUDA(cudaEventElapsedTime(&ms_out[1], ctx->tev[1], ctx->tev[2]));
+    }
+    ctx->timing = enable ? 1 : 0;
+    if (!enable) ctx->timing_valid = 0;
+    return KB_OK;
+}
+
+}  // extern "C"

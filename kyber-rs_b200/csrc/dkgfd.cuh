@@ -2,50 +2,65 @@
 //
 // The reference checks every share with its own PubPoly::eval (share/poly.rs:457-469): for dealer d and verifier
 // i, a Horner run over the t commitments at x = i + 1, i.e. n * t small-scalar steps per dealer (k_poly_eval does
-// exactly that, at 96 % of the multiplier pipe).  But the n evaluation points of one dealer are CONSECUTIVE integers,
-// and for consecutive points a polynomial of degree t - 1 obeys  Δ^k P(x + 1) = Δ^k P(x) + Δ^(k+1) P(x):  once the t
-// forward differences at x = 1 are known, every further evaluation costs t - 1 point ADDITIONS instead of t
-// multiplications by x.  All identities used are integer-linear combinations of the commitments, so they hold in any
-// abelian group — in particular for commitments that carry a small-order component; the only
-// "division" is avoided by going through the Newton form:
+// exactly that).  But the n evaluation points of one dealer are CONSECUTIVE integers, and for consecutive points a
+// polynomial of degree h - 1 obeys  Δ^k E(x + 1) = Δ^k E(x) + Δ^(k+1) E(x):  once the h forward differences at one
+// point are known, every further evaluation costs h - 1 point ADDITIONS instead of h multiplications by x.
+// Everything below is an integer-linear combination of the commitments, so it holds in any abelian group — in
+// particular for commitments that carry a small-order component.
 //
-//   A  Newton coefficients a_k of P on the nodes 1, 2, ..., t  (P(x) = sum_k a_k (x-1)(x-2)...(x-k)) by repeated
-//      synthetic division:  step m = 1..t-1:  q[j] += m * q[j+1]  for j = t-2 down to m-1;  then a_k = q[k].
-//      t(t-1)/2 cells, each ONE kb_horner_step with a multiplier <= t; cell (m, j) depends on (m, j+1) and (m-1, j),
-//      so the cells with m + (t-2-j) = w form wavefront w, w = 1..t-1, and a wavefront is one launch over all dealers.
-//      Two arrays hold the rows of even / odd m (Q_m[j] = Q_(m-1)[j] + m * Q_m[j+1]).
-//   B  Δ^k P(1) = k! * a_k, with k! taken mod 8L (the group has exponent 8L) — one full scalar multiplication each.
-//   C  n steps: record P(x) = Δ^0, then Δ^k += Δ^(k+1) for all k (ping-pong between two arrays).
-//   D  verdict(d, i) = [P_d(i+1) == share * B], projectively (as k_poly_eval does), share * B through the comb.
+//   0  The t commitments of a dealer are cut into `parts` blocks of h consecutive coefficients,
+//          P(x) = sum_q x^(q h) E_q(x),   E_q(x) = sum_{j<h} C_(q h + j) x^j
+//      (the last block may be shorter).  Shorter blocks make stage A cheaper (it is quadratic in h) and its chain of
+//      dependent launches shorter; they are paid for in stage D.
+//   A  Forward differences r_k = Δ^k E_q(0) by Horner's rule in the BINOMIAL basis: E = sum_k r_k C(x, k), and because
+//      x C(x, k) = k C(x, k) + (k+1) C(x, k+1), multiplying by x and adding the next coefficient c is
+//          r'_k = k (r_k + r_(k-1))   (k >= 1),      r'_0 = c.
+//      One launch per coefficient (h - 1 launches for ALL blocks and dealers), every cell one point addition and one
+//      multiplication by the small integer k < h.  No division and no factorial ever appears.
+//   C  ONE launch runs all n difference steps: a thread block owns one (dealer, block), its lanes are the ORDERS k,
+//      the state lives in registers for the whole run, neighbours exchange the operand by warp shuffle (and through
+//      shared memory across a warp boundary); lane 0 records E_q(i + 1) after step i.
+//   D  verdict(d, i) = [ E_0 + sum_q (x^(q h) mod 8L) E_q == share * B ],  x = i + 1: Straus over the parts - 1 tables with
+//      shared doublings (the multipliers are public and the same for the 32 dealers of a warp), the share through the
+//      constant-time fixed-base comb (shares are secret), compared projectively as k_poly_eval does
+//      (vss/pedersen/vss.rs:899-912).
 //
-// For n = 1024, t = 683 this is 1.6 x 10^9 multiplies per dealer instead of 4.75 x 10^9.
-// Arrays are laid out [k][dealer] (dealer fastest): a warp holds 32 dealers and ONE (m, j), so the NAF of the
-// multiplier is warp-uniform and its loads are contiguous.
+// For n = 1024, t = 683, 4 blocks this is ~0.9 x 10^9 multiplies per dealer instead of 4.75 x 10^9 (Horner per share).
 #pragma once
 #include "ops.cuh"
 #include "poly.cuh"
 
+#define KB_FD_MAX_PARTS 4
+#define KB_FD_MAX_H 256     // orders of one block = threads of one k_fd_steps block
+
 // ---- per-cell bodies (KB_FN: also compiled by the host emulation of tests/emu) ------------------------------
-// A: one cell of the Newton conversion, v = m * v + prev
-KB_FN void kb_fd_newton_cell(ge_p3& v, const ge_p3& prev, uint64_t m)
+// v = k * v for a small public integer k >= 1 given by its NAF; T is valid on return
+KB_FN void kb_small_mul(ge_p3& v, const kb_naf& k)
 {
-    ge_cached c;
-    ge_to_cached(c, prev);
-    kb_naf xn;
-    kb_naf_from(xn, m);
-    kb_horner_step(v, xn, c);
-}
-// B: h = fact * a, fact = 8 words of magnitude (<= 4L) + 1 word of sign; `tbl` is the caller's 8-entry scratch table
-KB_FN void kb_fd_scale_cell(ge_p3& h, const ge_p3& a, const uint32_t* fact9, ge_cached* tbl)
-{
-    int8_t e[64];
-    sc_recode16(e, fact9);
-    ge_build_table8(tbl, a);
-    ge_scalarmult<false>(h, e, tbl);
-    if (fact9[8]) {
-        fe_neg(h.X, h.X);
-        fe_neg(h.T, h.T);
+    if (k.len <= 1) return;
+    ge_cached vc;
+    ge_to_cached(vc, v);
+    ge_p3 acc = v;
+    KB_NOUNROLL
+    for (int i = k.len - 2; i >= 0; i--) {
+        const int d = k.d[i];
+        ge_dbl_rt(acc, acc, d != 0 || i == 0);
+        if (d != 0) ge_addsub_rt(acc, acc, vc, d < 0, i == 0);
     }
+    v = acc;
+}
+// A: one cell of the conversion, v = k * (v + lower); with has_self == false (the order that appears in this
+// iteration) v = k * lower
+KB_FN void kb_fd_conv_cell(ge_p3& v, const ge_p3& lower, bool has_self, const kb_naf& k)
+{
+    if (has_self) {
+        ge_cached c;
+        ge_to_cached(c, lower);
+        ge_add<true>(v, v, c);
+    } else {
+        v = lower;
+    }
+    kb_small_mul(v, k);
 }
 // C: p += q
 KB_FN void kb_fd_step_cell(ge_p3& p, const ge_p3& q)
@@ -54,86 +69,145 @@ KB_FN void kb_fd_step_cell(ge_p3& p, const ge_p3& q)
     ge_to_cached(c, q);
     ge_add<true>(p, p, c);
 }
+// D: W = E_0 + sum_{q=1..nt} s_q * E_q.  load(q, P) fetches E_q; pw9 = nt x 9 words (|s_q| <= 4L as 8 words + sign);
+// tbl = 8 * nt entries and e = 64 * nt digits of caller-provided scratch.
+template <typename LD>
+KB_FN void kb_fd_combine(ge_p3& W, int nt, const uint32_t* pw9, ge_cached* tbl, int8_t* e, LD load)
+{
+    ge_p3 P;
+    KB_NOUNROLL
+    for (int q = 0; q < nt; q++) {
+        load(q + 1, P);
+        if (pw9[9 * q + 8]) {
+            fe_neg(P.X, P.X);
+            fe_neg(P.T, P.T);
+        }
+        sc_recode16(e + 64 * q, pw9 + 9 * q);
+        ge_build_table8(tbl + 8 * q, P);
+    }
+    ge_identity(W);
+    if (nt > 0) {
+        KB_NOUNROLL
+        for (int i = 63; i >= 0; i--) {
+            KB_LOCKSTEP();
+            if (i != 63) {
+                KB_NOUNROLL
+                for (int k = 0; k < 4; k++) ge_dbl_rt(W, W, k == 3);
+            }
+            KB_NOUNROLL
+            for (int q = 0; q < nt; q++) {
+                ge_cached c;
+                ge_select_cached<false>(c, tbl + 8 * q, e[64 * q + i]);
+                ge_add_rt(W, W, c, q + 1 < nt || i == 0);
+            }
+        }
+    }
+    load(0, P);
+    ge_cached c0;
+    ge_to_cached(c0, P);
+    ge_add<true>(W, W, c0);
+}
 
-// fact[k] = k! mod 8L in signed form: 8 words of magnitude (<= 4L, inside the domain of the radix-16 recoding) + 1 word
-// of sign.  Host integers only (table construction, like the window counts of the MSM plan).
-static inline void kb_factorials_mod_8l(size_t t, uint32_t* out)
+// ---- host integers: the table of stage D -----------------------------------------------------------------------
+// x <- x * k mod 8L for a small k (< 2^32); x = 4 x 64-bit words, < 8L
+static inline void kb_mul_small_mod_8l(uint64_t* x, uint64_t k)
+{
+    const uint64_t N[4] = {0xc09318d2e7ae9f68ull, 0xa6f7cef517bce6b2ull, 0ull, 0x8000000000000000ull};
+    uint64_t y[5];
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 4; i++) {
+        c += (unsigned __int128)x[i] * k;
+        y[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    y[4] = (uint64_t)c;
+    // N = 2^255 + (a 128-bit number): floor(y / 2^255) is the quotient or one more
+    const uint64_t q = (y[4] << 1) | (y[3] >> 63);
+    unsigned __int128 mc = 0;
+    uint64_t qn[5];
+    for (int i = 0; i < 4; i++) {
+        mc += (unsigned __int128)N[i] * q;
+        qn[i] = (uint64_t)mc;
+        mc >>= 64;
+    }
+    qn[4] = (uint64_t)mc;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 5; i++) {
+        const unsigned __int128 dd = (unsigned __int128)y[i] - qn[i] - borrow;
+        y[i] = (uint64_t)dd;
+        borrow = (uint64_t)(dd >> 64) & 1u;
+    }
+    if (borrow) {   // one N too many: add it back
+        unsigned __int128 a = 0;
+        for (int i = 0; i < 5; i++) {
+            a += (unsigned __int128)y[i] + (i < 4 ? N[i] : 0);
+            y[i] = (uint64_t)a;
+            a >>= 64;
+        }
+    }
+    for (int i = 0; i < 4; i++) x[i] = y[i];
+}
+// signed representative of x mod 8L: 8 words of magnitude (<= 4L, inside the domain of the radix-16 recoding) + 1 word of sign
+static inline void kb_signed_mod_8l(uint32_t* out9, const uint64_t* x)
 {
     const uint64_t N[4] = {0xc09318d2e7ae9f68ull, 0xa6f7cef517bce6b2ull, 0ull, 0x8000000000000000ull};
     const uint64_t H[4] = {0x60498c6973d74fb4ull, 0x537be77a8bde7359ull, 0ull, 0x4000000000000000ull};   // N / 2 = 4L
-    uint64_t x[4] = {1, 0, 0, 0};
-    for (size_t k = 0; k < t; k++) {
-        if (k >= 2) {
-            uint64_t y[5];
-            unsigned __int128 c = 0;
-            for (int i = 0; i < 4; i++) {
-                c += (unsigned __int128)x[i] * (uint64_t)k;
-                y[i] = (uint64_t)c;
-                c >>= 64;
-            }
-            y[4] = (uint64_t)c;
-            // N = 2^255 + (a 128-bit number): floor(y / 2^255) is the quotient or one more
-            const uint64_t q = (y[4] << 1) | (y[3] >> 63);
-            unsigned __int128 mc = 0;
-            uint64_t qn[5];
-            for (int i = 0; i < 4; i++) {
-                mc += (unsigned __int128)N[i] * q;
-                qn[i] = (uint64_t)mc;
-                mc >>= 64;
-            }
-            qn[4] = (uint64_t)mc;
-            uint64_t borrow = 0;
-            for (int i = 0; i < 5; i++) {
-                const unsigned __int128 dd = (unsigned __int128)y[i] - qn[i] - borrow;
-                y[i] = (uint64_t)dd;
-                borrow = (uint64_t)(dd >> 64) & 1u;
-            }
-            if (borrow) {   // one N too many: add it back
-                unsigned __int128 a = 0;
-                for (int i = 0; i < 5; i++) {
-                    a += (unsigned __int128)y[i] + (i < 4 ? N[i] : 0);
-                    y[i] = (uint64_t)a;
-                    a >>= 64;
-                }
-            }
-            for (int i = 0; i < 4; i++) x[i] = y[i];
+    bool big = false;
+    for (int i = 3; i >= 0; i--) {
+        if (x[i] != H[i]) {
+            big = x[i] > H[i];
+            break;
         }
-        // signed representative
-        bool big = false;
-        for (int i = 3; i >= 0; i--) {
-            if (x[i] != H[i]) {
-                big = x[i] > H[i];
-                break;
-            }
-        }
-        uint64_t m[4];
-        if (big) {
-            uint64_t borrow = 0;
-            for (int i = 0; i < 4; i++) {
-                const unsigned __int128 dd = (unsigned __int128)N[i] - x[i] - borrow;
-                m[i] = (uint64_t)dd;
-                borrow = (uint64_t)(dd >> 64) & 1u;
-            }
-        } else {
-            for (int i = 0; i < 4; i++) m[i] = x[i];
-        }
+    }
+    uint64_t m[4];
+    if (big) {
+        uint64_t borrow = 0;
         for (int i = 0; i < 4; i++) {
-            out[9 * k + 2 * i] = (uint32_t)m[i];
-            out[9 * k + 2 * i + 1] = (uint32_t)(m[i] >> 32);
+            const unsigned __int128 dd = (unsigned __int128)N[i] - x[i] - borrow;
+            m[i] = (uint64_t)dd;
+            borrow = (uint64_t)(dd >> 64) & 1u;
         }
-        out[9 * k + 8] = big ? 1u : 0u;
+    } else {
+        for (int i = 0; i < 4; i++) m[i] = x[i];
+    }
+    for (int i = 0; i < 4; i++) {
+        out9[2 * i] = (uint32_t)m[i];
+        out9[2 * i + 1] = (uint32_t)(m[i] >> 32);
+    }
+    out9[8] = big ? 1u : 0u;
+}
+// out[(i * (parts - 1) + (q - 1)) * 9 ..] = (i + 1)^(q h) mod 8L in signed form, i < n, 1 <= q < parts.
+// Host integers only (table construction, like the window counts of the MSM plan): (parts - 1) * h small
+// multiplications per evaluation point.
+static inline void kb_fd_power_table(size_t n, size_t h, size_t parts, uint32_t* out)
+{
+    if (parts < 2) return;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t x[4] = {1, 0, 0, 0};
+        for (size_t q = 1; q < parts; q++) {
+            for (size_t r = 0; r < h; r++) kb_mul_small_mod_8l(x, (uint64_t)i + 1);
+            kb_signed_mod_8l(out + (i * (parts - 1) + (q - 1)) * 9, x);
+        }
     }
 }
+// length of block q when t coefficients are cut into blocks of h
+#if defined(KB_HOST_EMU)
+#define KB_HD static inline
+#else
+#define KB_HD __host__ __device__ __forceinline__
+#endif
+KB_HD size_t kb_fd_part_len(size_t t, size_t h, size_t q) { return (q + 1) * h <= t ? h : t - q * h; }
 
 #if !defined(KB_HOST_EMU)
 #include "kernels.cuh"
 
-#define KB_FD_AT(arr, k, d, nd) ((arr) + (((size_t)(k) * (nd) + (d)) * 32))
-#ifndef KB_FD_NEWTON_THREADS
-#define KB_FD_NEWTON_THREADS 128
+// arrays of extended points, 32 words each: row-major [row][dealer] (a warp = 32 dealers of one row)
+#define KB_FD_AT(arr, row, d, nd) ((arr) + (((size_t)(row) * (nd) + (d)) * 32))
+#ifndef KB_FD_CONV_THREADS
+#define KB_FD_CONV_THREADS 128
 #endif
-#ifndef KB_FD_NEWTON_MINBLOCKS
-#define KB_FD_NEWTON_MINBLOCKS 3
+#ifndef KB_FD_CONV_MINBLOCKS
+#define KB_FD_CONV_MINBLOCKS 3
 #endif
 
 __device__ __forceinline__ void kb_fd_load(ge_p3& p, const uint32_t* o)
@@ -151,9 +225,8 @@ __device__ __forceinline__ void kb_fd_store(uint32_t* o, const ge_p3& p)
     kb_store_fe(o + 24, p.T);
 }
 
-// Q0[j][d] = commitment j of dealer d (decoded); the top coefficient also into Q1 (it is never updated, and both
-// parities read it); dealer_bad[d] |= 1 if any commitment does not decode
-__global__ void __launch_bounds__(KB_THREADS) k_fd_init(size_t nd, size_t t, const uint8_t* commits, uint32_t* q0, uint32_t* q1, uint32_t* dealer_bad)
+// dec[j][d] = commitment j of dealer d, decoded; dealer_bad[d] |= 1 if any commitment does not decode
+static __global__ void __launch_bounds__(KB_THREADS) k_fd_decode(size_t nd, size_t t, const uint8_t* commits, uint32_t* dec, uint32_t* dealer_bad)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nd * t) return;
@@ -165,91 +238,161 @@ __global__ void __launch_bounds__(KB_THREADS) k_fd_init(size_t nd, size_t t, con
         ge_identity(p);
         atomicOr(dealer_bad + d, 1u);
     }
-    kb_fd_store(KB_FD_AT(q0, j, d, nd), p);
-    if (j == t - 1) kb_fd_store(KB_FD_AT(q1, j, d, nd), p);
+    kb_fd_store(KB_FD_AT(dec, j, d, nd), p);
 }
-
-// wavefront w of the Newton conversion: cells m = 1..w, j = m + t - 2 - w
-__global__ void __launch_bounds__(KB_FD_NEWTON_THREADS, KB_FD_NEWTON_MINBLOCKS) k_fd_newton(size_t nd, size_t t, size_t w, uint32_t* q0, uint32_t* q1)
+// The same from the reference's in-memory / serde form of a Point: X, Y, Z, T as 10 signed 25.5-bit limbs each
+// (ge.rs:75-83).  That form is not validated by the reference; here an element that is not a
+// consistent representation of a curve point (T Z != X Y, Z = 0 or off the curve) marks its dealer bad.
+static __global__ void __launch_bounds__(KB_THREADS) k_fd_decode_limbs(size_t nd, size_t t, const int32_t* limbs, uint32_t* dec, uint32_t* dealer_bad)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nd * w) return;
-    // the cost of a cell grows with log2(m): the blocks with the large multipliers go first, so that the launch does not
-    // end on them (each launch waits for its slowest block)
-    const size_t m = w - idx / nd, d = idx % nd;
-    const size_t j = m + t - 2 - w;
-    uint32_t* qm = (m & 1) ? q1 : q0;         // row m
-    const uint32_t* qp = (m & 1) ? q0 : q1;   // row m - 1
-    ge_p3 v, prev;
-    kb_fd_load(v, KB_FD_AT(qm, j + 1, d, nd));
-    kb_fd_load(prev, KB_FD_AT(qp, j, d, nd));
-    kb_fd_newton_cell(v, prev, (uint64_t)m);   // v = m * v + prev
-    kb_fd_store(KB_FD_AT(qm, j, d, nd), v);
-}
-
-// D[k][d] = (k! mod 8L) * a_k,  a_k = row (k+1) entry k (k <= t-2), a_(t-1) = the top coefficient.
-// fact[k] = 8 words magnitude (<= 4L) + 1 word sign.
-__global__ void __launch_bounds__(KB_THREADS) k_fd_scale(size_t nd, size_t t, const uint32_t* q0, const uint32_t* q1, const uint32_t* fact, uint32_t* dout)
-{
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = idx < nd * t;   // ge_scalarmult holds block barriers: tail threads redo the last item
-    if (!live) idx = nd * t - 1;
-    const size_t k = idx / nd, d = idx % nd;
-    const uint32_t* src = ((k + 1) & 1) ? q1 : q0;
-    ge_p3 a, h;
-    kb_fd_load(a, KB_FD_AT(src, k, d, nd));
-    uint32_t f9[9];
-#pragma unroll
-    for (int q = 0; q < 9; q++) f9[q] = fact[9 * k + q];
-    ge_cached tbl[8];
-    kb_fd_scale_cell(h, a, f9, tbl);
-    if (k < 2) h = a;   // 0! = 1! = 1
-    if (live) kb_fd_store(KB_FD_AT(dout, k, d, nd), h);
-}
-
-// one evaluation point: evals[d][i] = Δ^0 (the value at x = i + 1), then dst[k] = src[k] + src[k+1] for the `live`
-// lowest orders (the host drops the orders that can no longer reach a value).  ncu: multiplier pipe 57 % busy,
-// long-scoreboard stall 2.5 per issue (a load, one addition, a store per thread).  Two or three elements per thread
-// with all loads issued first were SLOWER (251 / 256 ms per round against 239: 168 / 254 registers), and so were
-// launch bounds for 5 or 6 blocks per SM (245 ms).
-__global__ void __launch_bounds__(KB_THREADS) k_fd_step(size_t nd, size_t t, size_t live, size_t n, size_t i, const uint32_t* src, uint32_t* dst, uint32_t* evals)
-{
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nd * live) return;
-    const size_t k = idx / nd, d = idx % nd;
+    if (idx >= nd * t) return;
+    const size_t j = idx / nd, d = idx % nd;
     ge_p3 p;
-    kb_fd_load(p, KB_FD_AT(src, k, d, nd));
-    if (k == 0) kb_store_xyz(evals, d * n + i, p);
-    if (k + 1 < t) {
-        ge_p3 q;
-        kb_fd_load(q, KB_FD_AT(src, k + 1, d, nd));
-        kb_fd_step_cell(p, q);
+    if (!kb_point_from_limbs_checked(p, limbs + 40 * (d * t + j))) {
+        ge_identity(p);
+        atomicOr(dealer_bad + d, 1u);
     }
-    kb_fd_store(KB_FD_AT(dst, k, d, nd), p);
+    kb_fd_store(KB_FD_AT(dec, j, d, nd), p);
 }
 
-// verdict[d * n + i] = [evals[d][i] == share(d, i) * B] and no undecodable commitment (vss/pedersen/vss.rs:899-912)
-__global__ void __launch_bounds__(KB_THREADS) k_fd_check(size_t nd, size_t n, const uint32_t* evals, const uint8_t* shares, const uint32_t* dealer_bad, const ge_precomp* comb, uint8_t* verdict)
+// Stage A, iteration s = 1 .. h-1.  Block q of a dealer has length hq; it is right-aligned in the iteration count
+// (sq = s - (h - hq) is its own iteration number), so that all blocks finish together.  Its iteration sq brings in
+// coefficient hq-1-sq and touches the orders k = 1 .. sq:  dst[k] = k * (src[k] + src[k-1]), where src[0] is the
+// coefficient brought in by the previous iteration (read from `dec`) and src[sq] is still zero.
+// Rows of src / dst: q * h + k.
+static __global__ void __launch_bounds__(KB_FD_CONV_THREADS, KB_FD_CONV_MINBLOCKS) k_fd_conv(size_t nd, size_t t, size_t h, size_t parts, size_t s, const uint32_t* dec, const uint32_t* src, uint32_t* dst)
 {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= nd * n) return;
-    const size_t d = slot / n;
-    ge_p3 v, h;
-    kb_load_fe(v.X, evals + 24 * slot);
-    kb_load_fe(v.Y, evals + 24 * slot + 8);
-    kb_load_fe(v.Z, evals + 24 * slot + 16);
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t hl = kb_fd_part_len(t, h, parts - 1);          // length of the last block
+    const size_t sl = s + hl >= h ? s + hl - h : 0;            // its iteration number (0: not started)
+    const size_t cells = (parts - 1) * s + sl;                  // per dealer
+    if (idx >= nd * cells) return;
+    // the cost of a cell grows with log2(k): the cells with the large multipliers go first, so that the launch does
+    // not end on them
+    const size_t c = idx / nd, d = idx % nd;
+    size_t q, k, sq, hq;
+    if (c < (parts - 1) * s) {
+        q = c % (parts - 1);
+        k = s - c / (parts - 1);
+        sq = s;
+        hq = h;
+    } else {
+        q = parts - 1;
+        k = sl - (c - (parts - 1) * s);
+        sq = sl;
+        hq = hl;
+    }
+    ge_p3 v, lower;
+    if (k == 1) kb_fd_load(lower, KB_FD_AT(dec, q * h + (hq - sq), d, nd));
+    else kb_fd_load(lower, KB_FD_AT(src, q * h + k - 1, d, nd));
+    const bool has_self = k < sq;
+    if (has_self) kb_fd_load(v, KB_FD_AT(src, q * h + k, d, nd));
+    kb_naf kn;
+    kb_naf_from(kn, (uint64_t)k);
+    kb_fd_conv_cell(v, lower, has_self, kn);
+    kb_fd_store(KB_FD_AT(dst, q * h + k, d, nd), v);
+}
+
+// Stage C.  Block = one (dealer, block q); thread = order k.  All n steps in one launch: per step every lane turns its
+// value into the operand form (1 M), hands it to the lane below (shuffle; the lowest lane of a warp through shared
+// memory, double-buffered so that one barrier per step is enough), adds what it received (8 M), and lane 0 records the
+// value E_q(i + 1) into evals[(q * n + i) * nd + d].  An order k can only reach the value k steps later, so the orders
+// above n - step are dead and their warps idle (they still meet the barrier).
+static __global__ void __launch_bounds__(KB_FD_MAX_H) k_fd_steps(size_t nd, size_t t, size_t h, size_t parts, size_t n, const uint32_t* dec, const uint32_t* diffs, uint32_t* evals)
+{
+    __shared__ uint4 xch_raw[2 * (KB_FD_MAX_H / 32) * 8];   // 2 buffers x warps x 32 words
+    uint32_t* xch = reinterpret_cast<uint32_t*>(xch_raw);
+    const size_t d = blockIdx.x / parts, q = blockIdx.x % parts;
+    const size_t hq = kb_fd_part_len(t, h, q);
+    const unsigned k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarps = blockDim.x >> 5;
+    ge_p3 p;
+    ge_identity(p);
+    if (k == 0) kb_fd_load(p, KB_FD_AT(dec, q * h, d, nd));
+    else if (k < hq) kb_fd_load(p, KB_FD_AT(diffs, q * h + k, d, nd));
+    const bool top = k + 1 >= hq;   // nothing above: the operand is the identity
+    for (size_t i = 0; i < n; i++) {
+        const size_t reach = n - i;   // the orders <= reach can still matter
+        const bool warp_live = 32u * warp < hq && 32u * warp <= reach;
+        uint32_t* buf = xch + (i & 1) * (KB_FD_MAX_H / 32) * 32;
+        ge_cached c;
+        if (warp_live) {
+            ge_to_cached(c, p);
+            if (lane == 0 && warp > 0) {
+                uint32_t* o = buf + 32 * warp;
+                kb_store_fe(o, c.YpX);
+                kb_store_fe(o + 8, c.YmX);
+                kb_store_fe(o + 16, c.T2d);
+                kb_store_fe(o + 24, c.Z);
+            }
+        }
+        __syncthreads();
+        if (warp_live) {
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                c.YpX.v[w] = __shfl_down_sync(0xffffffffu, c.YpX.v[w], 1);
+                c.YmX.v[w] = __shfl_down_sync(0xffffffffu, c.YmX.v[w], 1);
+                c.T2d.v[w] = __shfl_down_sync(0xffffffffu, c.T2d.v[w], 1);
+                c.Z.v[w] = __shfl_down_sync(0xffffffffu, c.Z.v[w], 1);
+            }
+            if (lane == 31) {
+                // the warp above may be dead (its orders can no longer matter, so nor can this lane's result) or
+                // absent: the operand then only has to be a valid point
+                const bool above_live = warp + 1 < nwarps && 32u * (warp + 1) < hq && 32u * (warp + 1) <= reach;
+                if (above_live) {
+                    const uint32_t* o = buf + 32 * (warp + 1);
+                    kb_load_fe(c.YpX, o);
+                    kb_load_fe(c.YmX, o + 8);
+                    kb_load_fe(c.T2d, o + 16);
+                    kb_load_fe(c.Z, o + 24);
+                } else {
+                    ge_cached_identity(c);
+                }
+            }
+            if (top) ge_cached_identity(c);
+            ge_add<true>(p, p, c);
+            if (k == 0) kb_fd_store(evals + ((q * n + i) * nd + d) * 32, p);
+        }
+    }
+}
+
+// Stage D: verdict[d * n + i] = [ P_d(i + 1) == share(d, i) * B ] and no undecodable commitment (vss/pedersen/vss.rs:899-912).
+// Item idx = i * nd + d: the 32 lanes of a warp hold 32 dealers and ONE evaluation point, so the public multipliers
+// x^(q h) mod 8L (pw) and with them every table index of the Straus loop are warp-uniform.  The share is secret: it only
+// meets the constant-time select of the fixed-base comb staged in shared memory (ge_scalarmult_base<true>).
+static __global__ void __launch_bounds__(KB_THREADS) k_fd_check(size_t nd, size_t n, size_t parts, const uint32_t* evals, const uint32_t* pw, const uint8_t* shares, const uint32_t* dealer_bad,
+                                                                  const ge_precomp* table, uint8_t* verdict)
+{
+    extern __shared__ uint4 smem4[];
+    ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
+    kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx < nd * n;   // the Straus loop holds block barriers: tail threads redo the last item
+    if (!live) idx = nd * n - 1;
+    const size_t i = idx / nd, d = idx % nd;
+    const size_t slot = d * n + i;
+    const int nt = (int)parts - 1;
+    ge_cached tbl[8 * (KB_FD_MAX_PARTS - 1)];
+    int8_t e[64 * (KB_FD_MAX_PARTS - 1)];
+    uint32_t pw9[9 * (KB_FD_MAX_PARTS - 1)];
+    for (int w = 0; w < 9 * nt; w++) pw9[w] = pw[i * 9 * nt + w];
+    ge_p3 v;
+    kb_fd_combine(v, nt, pw9, tbl, e, [&](int q, ge_p3& P) { kb_fd_load(P, evals + (((size_t)q * n + i) * nd + d) * 32); });
     uint32_t s[8];
+    int8_t es[64];
     kb_load32(s, shares, slot);
-    ge_scalarmult_base_comb(h, s, comb);
+    sc_recode16(es, s);
+    ge_p3 hb;
+    ge_scalarmult_base<true>(hb, es, base);
     fe l, r, df;
-    fe_mul(l, v.X, h.Z);
-    fe_mul(r, h.X, v.Z);
+    fe_mul(l, v.X, hb.Z);
+    fe_mul(r, hb.X, v.Z);
     fe_sub(df, l, r);
     uint32_t same = fe_is_zero(df);
-    fe_mul(l, v.Y, h.Z);
-    fe_mul(r, h.Y, v.Z);
+    fe_mul(l, v.Y, hb.Z);
+    fe_mul(r, hb.Y, v.Z);
     fe_sub(df, l, r);
     same &= fe_is_zero(df);
-    verdict[slot] = (uint8_t)(same & (dealer_bad[d] ? 0u : 1u));
+    if (live) verdict[slot] = (uint8_t)(same & (dealer_bad[d] ? 0u : 1u));
 }
 #endif  // !KB_HOST_EMU

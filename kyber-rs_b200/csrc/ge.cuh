@@ -324,6 +324,34 @@ KB_FN void fe_from_ref10(fe& h, const int32_t* l)
     fe_sub(h, a, b);
 }
 
+// A whole ExtendedGroupElement from its 40 limbs (X, Y, Z, T), for entry points that keep computing with it.  The
+// reference never validates this form (Deal::decode, share/vss/pedersen/vss.rs:155-159) and its results on
+// inconsistent limbs depend on its exact operation sequence; here an element is accepted only if it is a consistent
+// representation of a curve point:  Z != 0,  T Z = X Y  and  -X^2 + Y^2 = Z^2 + d T^2.  Returns 1 if so.
+KB_FN uint32_t kb_point_from_limbs_checked(ge_p3& p, const int32_t* l)
+{
+    fe_from_ref10(p.X, l);
+    fe_from_ref10(p.Y, l + 10);
+    fe_from_ref10(p.Z, l + 20);
+    fe_from_ref10(p.T, l + 30);
+    const fe d = KB_FE_D;
+    fe a, b, xx, yy, df;
+    fe_mul(a, p.T, p.Z);
+    fe_mul(b, p.X, p.Y);
+    fe_sub(df, a, b);
+    uint32_t ok = fe_is_zero(df) & (fe_is_zero(p.Z) ^ 1u);
+    fe_sq(xx, p.X);
+    fe_sq(yy, p.Y);
+    fe_sub(a, yy, xx);      // -X^2 + Y^2
+    fe_sq(b, p.T);
+    fe_mul(b, b, d);
+    fe_sq(xx, p.Z);
+    fe_add(b, b, xx);       // Z^2 + d T^2
+    fe_sub(df, a, b);
+    ok &= fe_is_zero(df);
+    return ok;
+}
+
 // ---------------------------------------------------------------------------------------
 // scalar recoding — the reference's signed radix-16 digits (ge.rs:443-458 / :521-535)
 // ---------------------------------------------------------------------------------------

@@ -59,8 +59,11 @@ __device__ __forceinline__ void kb_stage(uint32_t* dst, const uint32_t* src, int
     __syncthreads();
 }
 
+// Kernel groups: a translation unit defines KB_K_POINT / KB_K_SIGN / KB_K_POLY / KB_K_MSM for the non-template kernels it
+// launches (nvcc compiles every __global__ function it sees, used or not).
+#if defined(KB_K_POINT)
 // ---- base-point table: table[w*8 + j] = (j+1) * 16^w * B, w = 0..63 (replaces constants.rs:89 BASE)
-__global__ void k_base_init(ge_precomp* table)
+static __global__ void k_base_init(ge_precomp* table)
 {
     const int w = threadIdx.x;
     if (w >= 64) return;
@@ -73,7 +76,7 @@ __global__ void k_base_init(ge_precomp* table)
 }
 
 // base128[j] = (j+1) * B, j = 0..127: the radix-256 fixed-base table of the full-length verifiers
-__global__ void k_base128_init(ge_precomp* table)
+static __global__ void k_base128_init(ge_precomp* table)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ge_p3 pos;
@@ -83,7 +86,7 @@ __global__ void k_base128_init(ge_precomp* table)
     kb_base_window(table, pos, 128);
 }
 // comb[p][j] = (j+1) * 2^(13 p) * B: the fixed-base comb of the half-size-scalar verifiers (ops.cuh)
-__global__ void __launch_bounds__(KB_THREADS) k_comb_init(ge_precomp* comb, const ge_precomp* base_table)
+static __global__ void __launch_bounds__(KB_THREADS) k_comb_init(ge_precomp* comb, const ge_precomp* base_table)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= KB_COMB_POS * KB_COMB_HALF) return;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_comb_init(ge_precomp* comb, cons
     comb[k] = e;
 }
 
+#endif  // KB_K_POINT
 // ---- shared tail of every point-producing kernel: Montgomery's trick over KB_INV_K results -----
 // Stage-1 kernels leave (X, Y, Z) in `xyz` (24 words per item).  One thread then owns KB_INV_K
 // consecutive items, multiplies their Z's together, inverts ONCE (fe_invert, 254S + 11M) and
@@ -143,7 +147,7 @@ __device__ __forceinline__ void kb_batch_compress(size_t n, const uint32_t* xyz,
     }
 }
 // out[i] = encoding of item i; zeroed where bad[i] != 0
-__global__ void __launch_bounds__(KB_THREADS) k_compress_batch(size_t n, const uint32_t* xyz, const uint8_t* bad, uint8_t* out)
+static __global__ void __launch_bounds__(KB_THREADS) k_compress_batch(size_t n, const uint32_t* xyz, const uint8_t* bad, uint8_t* out)
 {
     kb_batch_compress(n, xyz, [&](size_t i, uint32_t* enc) {
         if (bad && bad[i]) {
@@ -154,11 +158,12 @@ __global__ void __launch_bounds__(KB_THREADS) k_compress_batch(size_t n, const u
     });
 }
 
+#if defined(KB_K_POINT)
 // ---- serde wire format of the reference: raw ExtendedGroupElement limbs -> (X, Y, Z) for the batch
 // compressor.  Z = 0 (e.g. Point::default(), all-zero limbs) encodes as 32 zero bytes in the reference
 // (fe_invert(0) = 0, ge.rs:112-122): flagged in zero_out and replaced by Z = 1 so that the shared inversion
 // of its group stays valid.
-__global__ void __launch_bounds__(KB_THREADS) k_points_from_limbs(size_t n, const int32_t* limbs, uint32_t* xyz, uint8_t* zero_out)
+static __global__ void __launch_bounds__(KB_THREADS) k_points_from_limbs(size_t n, const int32_t* limbs, uint32_t* xyz, uint8_t* zero_out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -199,7 +204,7 @@ __device__ __forceinline__ void kb_shfl_xor_point(ge_p3& q, const ge_p3& p, int 
     }
 }
 template <bool CT>
-__global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* table, int split)
+static __global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* table, int split)
 {
     extern __shared__ uint4 smem4[];
     ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const uint8_t
 }
 
 // public scalars (KB_FLAG_VARTIME): the shared comb, 20 mixed additions per scalar, nothing staged in shared memory
-__global__ void __launch_bounds__(KB_THREADS) k_mul_base_comb(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* comb)
+static __global__ void __launch_bounds__(KB_THREADS) k_mul_base_comb(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* comb)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul_base_comb(size_t n, const ui
 
 // ---- Point::mul(s, Some(p)): out[i] = compress(s_i * P_i)   (point.rs:207, ge.rs:508)
 template <bool CT>
-__global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint32_t* xyz, uint8_t* status)
+static __global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* scalars, const uint8_t* points, int shared_point, uint32_t* xyz, uint8_t* status)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;   // ge_scalarmult holds block barriers: tail threads redo the last item
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_mul(size_t n, const uint8_t* sca
 }
 
 // ---- Point::unmarshal_binary + marshal_binary   (ge.rs:124, :112)
-__global__ void __launch_bounds__(KB_THREADS) k_recode(size_t n, const uint8_t* in, uint8_t* out, uint8_t* status)
+static __global__ void __launch_bounds__(KB_THREADS) k_recode(size_t n, const uint8_t* in, uint8_t* out, uint8_t* status)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_recode(size_t n, const uint8_t* 
 }
 
 // ---- Point::add / Point::sub   (point.rs:179, :190)
-__global__ void __launch_bounds__(KB_THREADS) k_point_add(size_t n, const uint8_t* pa, const uint8_t* pb, uint8_t* out, uint8_t* status, int subtract)
+static __global__ void __launch_bounds__(KB_THREADS) k_point_add(size_t n, const uint8_t* pa, const uint8_t* pb, uint8_t* out, uint8_t* status, int subtract)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_point_add(size_t n, const uint8_
 
 // ---- the uncompressed, device-friendly form for chaining: X, Y, Z, T as 4 x 8 little-endian words (128 bytes per
 // point, the form kb_msm's partial sums use).  ExtendedGroupElement::set_bytes / write_bytes (ge.rs:124, :112).
-__global__ void __launch_bounds__(KB_THREADS) k_point_decompress(size_t n, const uint8_t* in, uint32_t* out128, uint8_t* status)
+static __global__ void __launch_bounds__(KB_THREADS) k_point_decompress(size_t n, const uint8_t* in, uint32_t* out128, uint8_t* status)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_point_decompress(size_t n, const
     if (status) status[i] = (uint8_t)(ok ^ 1u);
 }
 // 128-byte form -> (X, Y, Z) for the batch compressor; Z = 0 encodes as 32 zero bytes (fe_invert(0) = 0, ge.rs:112-122)
-__global__ void __launch_bounds__(KB_THREADS) k_points_from_raw(size_t n, const uint32_t* in128, uint32_t* xyz, uint8_t* zero_out)
+static __global__ void __launch_bounds__(KB_THREADS) k_points_from_raw(size_t n, const uint32_t* in128, uint32_t* xyz, uint8_t* zero_out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_points_from_raw(size_t n, const 
 }
 // ---- Point::eq (point.rs:227-241): equality of the canonical encodings of two decoded points; bit 1 of the
 // result flags an operand that does not decode (the reference cannot even construct such a Point)
-__global__ void __launch_bounds__(KB_THREADS) k_point_eq(size_t n, const uint8_t* pa, const uint8_t* pb, uint8_t* out)
+static __global__ void __launch_bounds__(KB_THREADS) k_point_eq(size_t n, const uint8_t* pa, const uint8_t* pb, uint8_t* out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_point_eq(size_t n, const uint8_t
 }
 
 // ---- Point::is_canonical / has_small_order / decodes   (point.rs:322, :286; ge.rs:124)
-__global__ void __launch_bounds__(KB_THREADS) k_point_check(size_t n, const uint8_t* in, uint8_t* flags)
+static __global__ void __launch_bounds__(KB_THREADS) k_point_check(size_t n, const uint8_t* in, uint8_t* flags)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_point_check(size_t n, const uint
 }
 
 // ---- scalars   (scalar.rs:175, :279)
-__global__ void __launch_bounds__(KB_THREADS) k_sc_reduce64(size_t n, const uint8_t* in, uint8_t* out)
+static __global__ void __launch_bounds__(KB_THREADS) k_sc_reduce64(size_t n, const uint8_t* in, uint8_t* out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_sc_reduce64(size_t n, const uint
     sc_reduce512(r, x);
     kb_store32(out, i, r);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_sc_muladd(size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out)
+static __global__ void __launch_bounds__(KB_THREADS) k_sc_muladd(size_t n, const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_sc_muladd(size_t n, const uint8_
     kb_store32(out, i, r);
 }
 // Scalar::inv (scalar.rs:192)
-__global__ void __launch_bounds__(KB_THREADS) k_sc_invert(size_t n, const uint8_t* a, uint8_t* out)
+static __global__ void __launch_bounds__(KB_THREADS) k_sc_invert(size_t n, const uint8_t* a, uint8_t* out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_sc_invert(size_t n, const uint8_
     kb_store32(out, i, r);
 }
 // h_i = SHA-512(R_i || A_i || M_i) mod L   (eddsa_sig.rs:195-200)
-__global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out)
+static __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_t* r32, const uint8_t* a32, const uint8_t* msg, const uint64_t* msg_off, uint8_t* out)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -419,13 +424,15 @@ __global__ void __launch_bounds__(KB_THREADS) k_challenge(size_t n, const uint8_
     kb_store32(out, i, h);
 }
 
+#endif  // KB_K_POINT
+#if defined(KB_K_SIGN)
 // ---- EdDSA::sign (sign/eddsa/eddsa_sig.rs:120-152) with the key derivation of
 // Curve::new_key_and_seed_with_input (group/edwards25519/curve.rs:74-87), three launches:
 //   k_sign_stage1   (a, prefix) = clamp(SHA-512(seed)); r = SHA-512(prefix || M) mod L; r*B and a*B (constant-time comb)
 //   k_compress_batch on the 2n points  ->  R and A encodings
 //   k_sign_finish   h = SHA-512(R || A || M) mod L; s = (r + h*a) mod L; sig = R || s
 // The secret scalars a and r only ever meet the constant-time select (no secret-dependent address or branch).
-__global__ void __launch_bounds__(KB_THREADS) k_sign_stage1(size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint32_t* xyz, uint8_t* a_out, uint8_t* r_out,
+static __global__ void __launch_bounds__(KB_THREADS) k_sign_stage1(size_t n, const uint8_t* seeds, const uint8_t* msg, const uint64_t* msg_off, uint32_t* xyz, uint8_t* a_out, uint8_t* r_out,
                                                             const ge_precomp* table)
 {
     extern __shared__ uint4 smem4[];
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_sign_stage1(size_t n, const uint
     kb_store32(a_out, i, a);
     kb_store32(r_out, i, r);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_sign_finish(size_t n, const uint8_t* ra, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* a_in, const uint8_t* r_in, uint8_t* sig, uint8_t* pk)
+static __global__ void __launch_bounds__(KB_THREADS) k_sign_finish(size_t n, const uint8_t* ra, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* a_in, const uint8_t* r_in, uint8_t* sig, uint8_t* pk)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -473,12 +480,13 @@ __global__ void __launch_bounds__(KB_THREADS) k_sign_finish(size_t n, const uint
     if (pk) kb_store32(pk, i, aw);
 }
 
+#endif  // KB_K_SIGN
 // ---- eddsa::verify_with_checks / schnorr::verify_with_checks, two launches (ops.cuh: sig_stage1 / sig_finish)
 #ifndef KB_VERIFY_MINBLOCKS
 #define KB_VERIFY_MINBLOCKS 3
 #endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
+static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stage1(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* xyz, uint8_t* flags,
                                                               const ge_precomp* table128)
 {
     __shared__ uint4 base_raw[128 * 24 / 4];
@@ -502,7 +510,7 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_MINBLOCKS) k_verify_stag
     }
 }
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const uint32_t* xyz, const uint8_t* flags, const uint8_t* sig, uint8_t* status)
+static __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const uint32_t* xyz, const uint8_t* flags, const uint8_t* sig, uint8_t* status)
 {
     kb_batch_compress(n, xyz, [&](size_t i, uint32_t* enc) {
         uint32_t rw[8];
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, const ui
 #define KB_VERIFY_PREP_MINBLOCKS 5
 #endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify_half_prep(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs)
+static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify_half_prep(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify
 #define KB_VERIFY_HALF_MINBLOCKS 3
 #endif
 template <bool SCHNORR>
-__global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb, int min_windows)
+static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb, int min_windows)
 {
     __shared__ int s_nwin;
     if (threadIdx.x == 0) s_nwin = min_windows;   // KB_HALF_MIN_WINDOWS, or more when a test forces long loops
@@ -597,9 +605,10 @@ __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify
     if (live) status[i] = (uint8_t)sig_half_finish<SCHNORR>(rec.f, W);
 }
 
+#if defined(KB_K_POLY)
 // ---- committed polynomials
 // commitments -> cached operand form, 32 words per commitment; bad[c] = 1 if undecodable
-__global__ void __launch_bounds__(KB_THREADS) k_commit_prepare(size_t ncommit, const uint8_t* commits, uint32_t* cached, uint8_t* bad)
+static __global__ void __launch_bounds__(KB_THREADS) k_commit_prepare(size_t ncommit, const uint8_t* commits, uint32_t* cached, uint8_t* bad)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncommit) return;
@@ -616,12 +625,29 @@ __global__ void __launch_bounds__(KB_THREADS) k_commit_prepare(size_t ncommit, c
     kb_store_fe(o + 24, c.Z);
     bad[i] = (uint8_t)(ok ^ 1u);
 }
+// the same from the reference's in-memory / serde form (40 limbs per point, ge.cuh kb_point_from_limbs_checked)
+static __global__ void __launch_bounds__(KB_THREADS) k_commit_prepare_limbs(size_t ncommit, const int32_t* limbs, uint32_t* cached, uint8_t* bad)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncommit) return;
+    ge_p3 p;
+    const uint32_t ok = kb_point_from_limbs_checked(p, limbs + 40 * i);
+    if (!ok) ge_identity(p);
+    ge_cached c;
+    ge_to_cached(c, p);
+    uint32_t* o = cached + 32 * i;
+    kb_store_fe(o, c.YpX);
+    kb_store_fe(o + 8, c.YmX);
+    kb_store_fe(o + 16, c.T2d);
+    kb_store_fe(o + 24, c.Z);
+    bad[i] = (uint8_t)(ok ^ 1u);
+}
 // PubPoly::eval (poly.rs:457-469) and, with shares != nullptr, the verify_deal comparison
 // (vss/pedersen/vss.rs:899-912).  Item k is (poly_id[k], idx[k]); with poly_id == nullptr the
 // items enumerate a DKG round: k = i * npoly + d (verifier-major), so the 32 lanes of a warp
 // hold 32 different dealers and the SAME evaluation point x = i + 1 — the double-and-add over
 // the bits of x is then branch-uniform across the warp.
-__global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, const uint32_t* poly_id,
+static __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, const uint32_t* poly_id,
                                                           const uint32_t* idx, size_t n_verifiers, const uint8_t* shares, uint32_t* xyz, uint8_t* status, uint8_t* verdict, const ge_precomp* table)
 {
     extern __shared__ uint4 smem4[];
@@ -684,9 +710,10 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_eval(size_t m, size_t npoly
     if (live) verdict[slot] = (uint8_t)(same & (anybad ^ 1u));
 }
 
+#endif  // KB_K_POLY
 // ---- integer-multiply roofline probe
 template <int KIND>
-__global__ void __launch_bounds__(256) k_probe(int iters, uint32_t seed, uint32_t* sink)
+static __global__ void __launch_bounds__(256) k_probe(int iters, uint32_t seed, uint32_t* sink)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (KIND == 0) {

@@ -336,7 +336,8 @@ KB_FN void kb_msm_window_chunk(ge_p3& t1, ge_p3& t2, uint32_t c0, uint32_t c1, c
 // ======================================================================================
 // kernels
 // ======================================================================================
-__global__ void __launch_bounds__(KB_THREADS) k_msm_prepare(size_t n, const uint8_t* points, const uint8_t* scalars, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad)
+#if defined(KB_K_MSM)
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_prepare(size_t n, const uint8_t* points, const uint8_t* scalars, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_msm_prepare(size_t n, const uint
     kb_load32(sw, scalars, i);
     kb_msm_prepare_body(i, pw, sw, pts, mags, negs, bad);
 }
-__global__ void __launch_bounds__(256) k_msm_hist(kb_msm_plan pl, const uint32_t* mags, uint32_t* counts)
+static __global__ void __launch_bounds__(256) k_msm_hist(kb_msm_plan pl, const uint32_t* mags, uint32_t* counts)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.n) return;
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(256) k_msm_hist(kb_msm_plan pl, const uint32_t
 //   sums  : one block scans the tile totals (<= 2048 tiles) and writes offsets[nb]
 //   add   : adds each tile's base; clears cursor
 #define KB_SCAN_TILE 2048
-__global__ void __launch_bounds__(256) k_msm_scan_tiles(uint32_t nb, const uint32_t* counts, uint32_t* offsets, uint32_t* tile_sums)
+static __global__ void __launch_bounds__(256) k_msm_scan_tiles(uint32_t nb, const uint32_t* counts, uint32_t* offsets, uint32_t* tile_sums)
 {
     __shared__ uint32_t buf[KB_SCAN_TILE];
     __shared__ uint32_t wsum[8];
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(256) k_msm_scan_tiles(uint32_t nb, const uint3
     }
     if (tid == 255) tile_sums[blockIdx.x] = excl + sum;
 }
-__global__ void __launch_bounds__(1024) k_msm_scan_sums(uint32_t ntiles, uint32_t nb, uint32_t* tile_sums, uint32_t* offsets)
+static __global__ void __launch_bounds__(1024) k_msm_scan_sums(uint32_t ntiles, uint32_t nb, uint32_t* tile_sums, uint32_t* offsets)
 {
     __shared__ uint32_t part[1024];
     const uint32_t tid = threadIdx.x;
@@ -416,40 +417,41 @@ __global__ void __launch_bounds__(1024) k_msm_scan_sums(uint32_t ntiles, uint32_
     if (2 * tid + 1 < ntiles) tile_sums[2 * tid + 1] = excl + a;
     if (tid == 1023) offsets[nb] = part[1023];
 }
-__global__ void __launch_bounds__(256) k_msm_scan_add(uint32_t nb, const uint32_t* tile_sums, uint32_t* offsets, uint32_t* cursor)
+static __global__ void __launch_bounds__(256) k_msm_scan_add(uint32_t nb, const uint32_t* tile_sums, uint32_t* offsets, uint32_t* cursor)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb) return;
     offsets[i] += tile_sums[i / KB_SCAN_TILE];
     cursor[i] = 0;
 }
-__global__ void __launch_bounds__(256) k_msm_scatter(kb_msm_plan pl, const uint32_t* mags, const uint8_t* negs, const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted)
+static __global__ void __launch_bounds__(256) k_msm_scatter(kb_msm_plan pl, const uint32_t* mags, const uint8_t* negs, const uint32_t* offsets, uint32_t* cursor, uint32_t* sorted)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pl.n) return;
     kb_msm_scatter_body(pl, i, mags, negs, offsets, cursor, sorted);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_msm_accum(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, const uint32_t* sorted, const uint32_t* pts, uint32_t* bucket_sum, uint32_t* heads,
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_accum(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, const uint32_t* sorted, const uint32_t* pts, uint32_t* bucket_sum, uint32_t* heads,
                                                           uint32_t* tails, uint8_t* flags)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
     kb_msm_accum_body(pl, t, offsets, sorted, pts, bucket_sum, heads, tails, flags);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, uint32_t* long_count, uint32_t* long_list, uint32_t* bucket_sum,
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, uint32_t* long_count, uint32_t* long_list, uint32_t* bucket_sum,
                                                           const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
     kb_msm_merge_body(pl, t, nthreads, offsets, 32u, long_count, long_list, bucket_sum, heads, tails, flags);
 }
-__global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* part_run, uint32_t* part_tot)
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* part_run, uint32_t* part_tot)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)pl.windows * groups) return;
     kb_msm_reduce_body(pl, tid, groups, offsets, bucket_sum, part_run, part_tot);
 }
 
+#endif  // KB_K_MSM (first part)
 // butterfly sum of one point per lane: after the call every lane holds the warp total
 __device__ __forceinline__ void kb_warp_sum_point(ge_p3& p)
 {
@@ -468,9 +470,10 @@ __device__ __forceinline__ void kb_warp_sum_point(ge_p3& p)
         ge_add<true>(p, p, qc);
     }
 }
+#if defined(KB_K_MSM)
 // long runs: one warp per queued (t, u_end, bucket): lanes stride over the head partials of chunks
 // t+1 .. u_end-1, butterfly-sum them with shuffles, lane 0 adds tail[t] and owns the bucket.
-__global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nthreads, const uint32_t* long_count, const uint32_t* long_list, uint32_t* bucket_sum, const uint32_t* heads,
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nthreads, const uint32_t* long_count, const uint32_t* long_list, uint32_t* bucket_sum, const uint32_t* heads,
                                                                const uint32_t* tails, const uint8_t* flags)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nthreads, 
 // window sums: block w folds the group partials of window w:  S_w = sum_g tot_g + gs * sum_g g * run_g.
 // Each of the 256 threads owns a contiguous run of groups (kb_msm_window_chunk), the two partial points are summed
 // with a warp-shuffle butterfly and then across the 8 warps through shared memory.
-__global__ void __launch_bounds__(256) k_msm_window_sums(kb_msm_plan pl, uint32_t groups, const uint32_t* part_run, const uint32_t* part_tot, uint32_t* win_sum)
+static __global__ void __launch_bounds__(256) k_msm_window_sums(kb_msm_plan pl, uint32_t groups, const uint32_t* part_run, const uint32_t* part_tot, uint32_t* win_sum)
 {
     __shared__ uint32_t wtot[2 * 8 * 32];
     const uint32_t w = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -585,7 +588,7 @@ __device__ __forceinline__ void kb_dbl_quad(ge_p3& p)
 }
 // finish: Horner over the windows (c quad-doublings per window), add to the running total `acc128`
 // (X,Y,Z,T words) and, if out32 != nullptr, write its encoding.  One warp; all quads compute the same thing.
-__global__ void k_msm_finish(kb_msm_plan pl, const uint32_t* win_sum, uint32_t* acc128, int first_chunk, uint8_t* out32)
+static __global__ void k_msm_finish(kb_msm_plan pl, const uint32_t* win_sum, uint32_t* acc128, int first_chunk, uint8_t* out32)
 {
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     ge_p3 tot;
@@ -614,8 +617,9 @@ __global__ void k_msm_finish(kb_msm_plan pl, const uint32_t* win_sum, uint32_t* 
         kb_store32(out32, 0, o);
     }
 }
+#endif  // KB_K_MSM (second part)
 // out = compress(sum of k uncompressed partials): the fold after the cross-GPU gather
-__global__ void k_point_sum(size_t k, const uint32_t* partials, uint8_t* out32)
+static __global__ void k_point_sum(size_t k, const uint32_t* partials, uint8_t* out32)
 {
     const uint32_t lane = threadIdx.x & 31;
     ge_p3 s;
@@ -638,7 +642,7 @@ __global__ void k_point_sum(size_t k, const uint32_t* partials, uint8_t* out32)
 // Column sums of npoly committed polynomials: out[j] = sum_d commits[d][j] — the repeated PubPoly::add of
 // dkg_key (share/dkg/pedersen/dkg.rs:905-954, share/poly.rs:486-509).  One warp per coefficient: lanes
 // stride over the dealers (cached operand form from k_commit_prepare), shuffle butterfly, lane 0 stores.
-__global__ void __launch_bounds__(KB_THREADS) k_poly_colsum(size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, uint32_t* xyz, uint8_t* status)
+static __global__ void __launch_bounds__(KB_THREADS) k_poly_colsum(size_t npoly, size_t t, const uint32_t* cached, const uint8_t* bad, uint32_t* xyz, uint8_t* status)
 {
     const uint32_t lane = threadIdx.x & 31;
     const size_t j = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -665,6 +669,4 @@ __global__ void __launch_bounds__(KB_THREADS) k_poly_colsum(size_t npoly, size_t
     }
 }
 
-struct kb_ctx;
-static int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st);
 #endif  // !KB_HOST_EMU

@@ -9,7 +9,7 @@
 #if defined(KB_HOST_EMU)
 #define KB_CONST static const
 #else
-#define KB_CONST __device__ __constant__
+#define KB_CONST static __device__ __constant__
 #endif
 
 KB_CONST uint64_t KB_K512[80] = {

@@ -677,6 +677,14 @@ void oracle_mul_base_limbs(int32_t out[40], const uint8_t a[32])
     ge_p3 h; oracle_init(); ge_scalarmult_base(&h, a);
     memcpy(out, h.X, 40); memcpy(out + 10, h.Y, 40); memcpy(out + 20, h.Z, 40); memcpy(out + 30, h.T, 40);
 }
+/* the limbs ExtendedGroupElement::set_bytes (ge.rs:124-179) leaves for an encoding (Z = 1); returns 0 if it does not decode */
+int oracle_point_limbs(int32_t out[40], const uint8_t s[32])
+{
+    ge_p3 h; oracle_init();
+    if (!ge_frombytes(&h, s)) return 0;
+    memcpy(out, h.X, 40); memcpy(out + 10, h.Y, 40); memcpy(out + 20, h.Z, 40); memcpy(out + 30, h.T, 40);
+    return 1;
+}
 /* write_bytes (ge.rs:112-122) of an element given by raw limbs */
 void oracle_limbs_tobytes(uint8_t out[32], const int32_t in[40])
 {

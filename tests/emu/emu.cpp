@@ -235,54 +235,86 @@ int emu_pubpoly_eval(uint8_t* out, const uint8_t* commits, int t, uint32_t idx)
 }
 
 // The forward-difference DKG round of dkgfd.cuh for ONE dealer, with the kernels' per-cell bodies and the same
-// wavefront / two-row schedule: out[i] = encoding of P(i + 1), i = 0..n-1.  Returns 0 if a commitment does not decode.
-int emu_dkg_fd(uint8_t* out, const uint8_t* commits, int t, int n)
+// schedule (blocks of h coefficients right-aligned in the iteration count, ping-pong arrays, n difference steps with
+// the dead orders dropped, Straus combination with the host-built power table): out[i] = encoding of P(i + 1),
+// i = 0..n-1.  Returns 0 if a commitment does not decode.
+int emu_dkg_fd(uint8_t* out, const uint8_t* commits, int t, int n, int parts_req)
 {
-    std::vector<ge_p3> q0(t), q1(t), d0(t), d1(t);
+    size_t parts = parts_req < 1 ? 1 : (size_t)parts_req;
+    if (parts > (size_t)t) parts = t;
+    const size_t h = ((size_t)t + parts - 1) / parts;
+    parts = ((size_t)t + h - 1) / h;
+    if (parts > KB_FD_MAX_PARTS) return -1;
+    std::vector<ge_p3> dec(t);
     for (int j = 0; j < t; j++) {
         uint32_t w[8];
         ld(w, commits + 32 * j, 8);
-        if (!ge_decompress(q0[j], w)) return 0;
+        if (!ge_decompress(dec[j], w)) return 0;
     }
-    q1[t - 1] = q0[t - 1];
-    for (int w = 1; w + 1 <= t; w++) {            // k_fd_newton, wavefront w
-        std::vector<std::pair<int, ge_p3>> wr;     // all reads of a wavefront happen before its writes
-        for (int m = 1; m <= w; m++) {
-            const int j = m + t - 2 - w;
-            std::vector<ge_p3>& qm = (m & 1) ? q1 : q0;
-            std::vector<ge_p3>& qp = (m & 1) ? q0 : q1;
-            ge_p3 v = qm[j + 1];
-            kb_fd_newton_cell(v, qp[j], (uint64_t)m);
-            wr.push_back({m, v});
+    const size_t rows = parts * h;
+    std::vector<ge_p3> ra(rows), rb(rows);
+    const size_t hl = kb_fd_part_len(t, h, parts - 1);
+    for (size_t s = 1; s < h; s++) {                // k_fd_conv, iteration s: reads src, writes dst
+        std::vector<ge_p3>& src = (s & 1) ? rb : ra;
+        std::vector<ge_p3>& dst = (s & 1) ? ra : rb;
+        for (size_t q = 0; q < parts; q++) {
+            const size_t hq = kb_fd_part_len(t, h, q);
+            const size_t sq = (q + 1 < parts) ? s : (s + hl >= h ? s + hl - h : 0);
+            for (size_t k = 1; k <= sq; k++) {
+                ge_p3 v, lower = (k == 1) ? dec[q * h + (hq - sq)] : src[q * h + k - 1];
+                const bool has_self = k < sq;
+                if (has_self) v = src[q * h + k];
+                kb_naf kn;
+                kb_naf_from(kn, (uint64_t)k);
+                kb_fd_conv_cell(v, lower, has_self, kn);
+                dst[q * h + k] = v;
+            }
         }
-        for (auto& e : wr) ((e.first & 1) ? q1 : q0)[e.first + t - 2 - w] = e.second;
     }
-    std::vector<uint32_t> fact(9 * (size_t)t);
-    kb_factorials_mod_8l((size_t)t, fact.data());
-    for (int k = 0; k < t; k++) {                  // k_fd_scale
-        const ge_p3& a = (((k + 1) & 1) ? q1 : q0)[k];
-        ge_cached tbl[8];
-        kb_fd_scale_cell(d0[k], a, fact.data() + 9 * k, tbl);
-        if (k < 2) d0[k] = a;
+    std::vector<ge_p3>& diffs = ((h - 1) & 1) ? ra : rb;
+    std::vector<ge_p3> evals(parts * (size_t)n);
+    for (size_t q = 0; q < parts; q++) {            // k_fd_steps, one block
+        const size_t hq = kb_fd_part_len(t, h, q);
+        std::vector<ge_p3> p(hq);
+        p[0] = dec[q * h];
+        for (size_t k = 1; k < hq; k++) p[k] = diffs[q * h + k];
+        for (int i = 0; i < n; i++) {
+            const size_t reach = (size_t)(n - i);
+            for (size_t k = 0; k < hq; k++) {       // ascending: p[k + 1] is still the old value
+                const size_t warp = k >> 5;
+                if (32 * warp > reach) break;        // dead warp
+                if (k + 1 < hq && 32 * ((k + 1) >> 5) <= reach) kb_fd_step_cell(p[k], p[k + 1]);
+            }
+            evals[q * n + i] = p[0];
+        }
     }
-    std::vector<ge_p3>*src = &d0, *dst = &d1;
-    for (int i = 0; i < n; i++) {                  // k_fd_step with the dead orders dropped
+    std::vector<uint32_t> pw(9 * (size_t)n * (parts > 1 ? parts - 1 : 1));
+    kb_fd_power_table(n, h, parts, pw.data());
+    const int nt = (int)parts - 1;
+    for (int i = 0; i < n; i++) {                    // the combination of k_fd_check
+        ge_cached tbl[8 * (KB_FD_MAX_PARTS - 1)];
+        int8_t e[64 * (KB_FD_MAX_PARTS - 1)];
+        ge_p3 W;
+        kb_fd_combine(W, nt, pw.data() + (size_t)i * 9 * nt, tbl, e, [&](int q, ge_p3& P) { P = evals[(size_t)q * n + i]; });
         uint32_t o[8];
-        ge_compress(o, (*src)[0]);
+        ge_compress(o, W);
         st(out + 32 * i, o, 8);
-        const int live = (n - i < t) ? n - i : t;
-        for (int k = 0; k < live; k++) {
-            ge_p3 p = (*src)[k];
-            if (k + 1 < t) kb_fd_step_cell(p, (*src)[k + 1]);
-            (*dst)[k] = p;
-        }
-        std::swap(src, dst);
     }
     return 1;
 }
 
-// the host-side table of the forward-difference round: out = t x 9 words (|k! mod 8L| in signed form + sign)
-void emu_factorials_mod_8l(uint32_t* out, int t) { kb_factorials_mod_8l((size_t)t, out); }
+// the host-side table of the forward-difference round: out = n x (parts - 1) x 9 words ((i+1)^(q h) mod 8L, signed form)
+void emu_fd_power_table(uint32_t* out, int n, int h, int parts) { kb_fd_power_table((size_t)n, (size_t)h, (size_t)parts, out); }
+// a point given as the reference's 40 limbs: 1 and its encoding if it is a consistent curve point, else 0
+int emu_point_from_limbs_checked(uint8_t* out, const int32_t* limbs)
+{
+    ge_p3 p;
+    if (!kb_point_from_limbs_checked(p, limbs)) return 0;
+    uint32_t o[8];
+    ge_compress(o, p);
+    st(out, o, 8);
+    return 1;
+}
 
 // Pippenger stage bodies of msm.cuh, run "thread by thread" on the host; the final
 // warp-shuffle tree (GPU only) is replaced by a plain sum of the same group partials.

@@ -57,6 +57,7 @@ class COracle:
         L.oracle_msm.argtypes = [u8p, ctypes.c_size_t, vp, vp]
         L.oracle_mul_base_limbs.argtypes = [vp, u8p]
         L.oracle_limbs_tobytes.argtypes = [u8p, vp]
+        L.oracle_point_limbs.argtypes = [vp, u8p]
         L.oracle_init()
 
     # ---- single-item wrappers
@@ -107,6 +108,12 @@ class COracle:
     def mul_base_limbs(self, a):
         out = np.empty(40, dtype=np.int32)
         self.L.oracle_mul_base_limbs(self._p(out), a)
+        return out
+
+    def point_limbs(self, enc):
+        """40 int32 limbs (X, Y, Z, T) of a decodable encoding, as the reference holds it in memory."""
+        out = np.empty(40, dtype=np.int32)
+        assert self.L.oracle_point_limbs(self._p(out), bytes(enc)) == 1
         return out
 
     def limbs_tobytes(self, limbs):

@@ -32,8 +32,8 @@ def emu():
     E.emu_eddsa_sign.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64]
     E.emu_msm.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     E.emu_pubpoly_eval.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32]
-    E.emu_dkg_fd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
-    E.emu_factorials_mod_8l.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    E.emu_dkg_fd.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    E.emu_fd_power_table.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return E
 
 
@@ -219,37 +219,40 @@ def test_pubpoly_short_horner(emu, coracle, golden_records):
 
 
 def test_dkg_forward_differences(emu, coracle, golden_records):
-    """csrc/dkgfd.cuh (Newton conversion by wavefronts, k! mod 8L scaling, difference steps with the dead orders
-    dropped) on one dealer: every P(i + 1) equals PubPoly::eval, also for a polynomial whose commitments carry
-    small-order components (only integer-linear identities are used), for n < t, n = t and n > t."""
-    commits = [r[1] for r in golden_records[100:140]]
+    """csrc/dkgfd.cuh (coefficient blocks, binomial-basis Horner conversion, difference steps with the dead orders
+    dropped, Straus combination with the x^(q h) mod 8L table) on one dealer: every P(i + 1) equals PubPoly::eval, also
+    for a polynomial whose commitments carry small-order components (only integer-linear identities are used), for
+    n < t, n = t and n > t, for 1..4 blocks of equal and unequal length."""
+    commits = [r[1] for r in golden_records[100:170]]
     t8 = O.point_decode(O.WEAK_KEYS[2])
     tors = list(commits)
     tors[1] = O.point_encode(O.point_add(O.point_decode(tors[1]), t8))
     tors[5] = O.point_encode(O.point_add(O.point_decode(tors[5]), O.point_add(t8, t8)))
-    for cs, t, n in ((commits, 1, 4), (commits, 2, 5), (commits, 3, 3), (commits, 9, 4), (commits, 12, 30), (tors, 7, 20), (commits, 33, 40), (tors, 40, 44)):
+    cases = ((commits, 1, 4, 1), (commits, 2, 5, 1), (commits, 2, 5, 2), (commits, 3, 3, 2), (commits, 9, 4, 1), (commits, 9, 12, 4), (commits, 12, 30, 3), (tors, 7, 20, 1), (tors, 7, 20, 3),
+             (commits, 33, 40, 1), (commits, 33, 70, 2), (tors, 40, 44, 4), (tors, 41, 36, 3), (commits, 70, 75, 2), (commits, 67, 34, 4))
+    for cs, t, n, parts in cases:
         flat = b"".join(cs[:t])
         out = ctypes.create_string_buffer(32 * n)
-        assert emu.emu_dkg_fd(out, flat, t, n) == 1
+        assert emu.emu_dkg_fd(out, flat, t, n, parts) == 1
         for i in range(n):
-            assert out.raw[32 * i:32 * i + 32] == coracle.pubpoly_eval(cs[:t], i), (t, n, i)
-    assert emu.emu_dkg_fd(ctypes.create_string_buffer(32), coracle_bad_point(coracle), 1, 1) == 0
+            assert out.raw[32 * i:32 * i + 32] == coracle.pubpoly_eval(cs[:t], i), (t, n, parts, i)
+    assert emu.emu_dkg_fd(ctypes.create_string_buffer(32), coracle_bad_point(coracle), 1, 1, 1) == 0
 
 
-def test_factorials_mod_8l(emu):
-    """kb_factorials_mod_8l (host integers in csrc/dkgfd.cuh): k! mod 8L in signed form, magnitude <= 4L, for every k
-    up to well beyond BASELINE config 4's t = 683."""
-    import math
-
-    t = 1500
-    buf = (ctypes.c_uint32 * (9 * t))()
-    emu.emu_factorials_mod_8l(buf, t)
+def test_fd_power_table(emu):
+    """kb_fd_power_table (host integers in csrc/dkgfd.cuh): (i+1)^(q h) mod 8L in signed form, magnitude <= 4L, at
+    BASELINE config 4's shape (n = 1024, t = 683 in 4 blocks of 171) and a few others."""
     N = 8 * O.L
-    for k in range(t):
-        mag = sum(buf[9 * k + i] << (32 * i) for i in range(8))
-        neg = buf[9 * k + 8]
-        assert neg in (0, 1) and mag <= 4 * O.L
-        assert (-mag if neg else mag) % N == math.factorial(k) % N, k
+    for n, h, parts in ((1024, 171, 4), (300, 228, 3), (64, 1, 2), (17, 256, 2)):
+        buf = (ctypes.c_uint32 * (9 * n * (parts - 1)))()
+        emu.emu_fd_power_table(buf, n, h, parts)
+        for i in range(n):
+            for q in range(1, parts):
+                o = 9 * (i * (parts - 1) + (q - 1))
+                mag = sum(buf[o + k] << (32 * k) for k in range(8))
+                neg = buf[o + 8]
+                assert neg in (0, 1) and mag <= 4 * O.L
+                assert (-mag if neg else mag) % N == pow(i + 1, q * h, N), (n, h, parts, i, q)
 
 
 def coracle_bad_point(coracle):

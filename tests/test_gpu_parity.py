@@ -439,8 +439,26 @@ def test_dkg_round_small(ctx, coracle):
 
 @pytest.fixture(scope="module")
 def ctx_fd(kb):
-    """A context that always runs DKG rounds by forward differences (csrc/dkgfd.cuh); the default picks by cost."""
-    os.environ["KB_DKG_FD"] = "1"
+    """Contexts that always run DKG rounds by forward differences (csrc/dkgfd.cuh), one per number of coefficient
+    blocks 1..4 (index 0: blocks chosen by cost); the default context picks FD or Horner by cost."""
+    cs = []
+    for parts in (0, 1, 2, 3, 4):
+        os.environ["KB_DKG_FD"] = "1"
+        if parts:
+            os.environ["KB_FD_PARTS"] = str(parts)
+        try:
+            cs.append(kb.Context(0))
+        finally:
+            del os.environ["KB_DKG_FD"]
+            os.environ.pop("KB_FD_PARTS", None)
+    yield cs
+    for c in cs:
+        c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_horner(kb):
+    os.environ["KB_DKG_FD"] = "0"
     try:
         c = kb.Context(0)
     finally:
@@ -449,13 +467,15 @@ def ctx_fd(kb):
     c.close()
 
 
-@pytest.mark.parametrize("n,t,nd", [(24, 16, 24), (5, 1, 3), (7, 2, 4), (9, 3, 33), (40, 40, 5), (12, 30, 7), (130, 67, 40), (20, 9, 200)])
-def test_dkg_round_forward_differences(ctx, ctx_fd, coracle, n, t, nd):
-    """The forward-difference round (Newton conversion, k! scaling, difference steps) gives the verdicts of the
-    per-share Horner kernel and of the oracle: honest and corrupted shares, a dealer whose commitment carries a
-    small-order component (integer identities only: exact there too), a dealer with an undecodable commitment."""
+@pytest.mark.parametrize("n,t,nd", [(24, 16, 24), (5, 1, 3), (7, 2, 4), (9, 3, 33), (40, 40, 5), (12, 30, 7), (130, 67, 40), (20, 9, 200), (70, 130, 9), (300, 256, 3)])
+def test_dkg_round_forward_differences(ctx_horner, ctx_fd, coracle, n, t, nd):
+    """The forward-difference round (coefficient blocks, binomial-basis conversion, one-launch difference steps,
+    Straus combination) gives the verdicts of the per-share Horner kernel and of the oracle for every number of
+    blocks: honest and corrupted shares, a dealer whose commitment carries a small-order component (integer identities
+    only: exact there too), a dealer with an undecodable commitment; the commitments as 32-byte encodings and as the
+    reference's raw limbs."""
     polys = [_poly(b"fd%d" % d, t) for d in range(nd)]
-    commits = ctx.point_mul_base_batch(np.frombuffer(b"".join(b"".join(p) for p in polys), dtype=np.uint8).reshape(-1, 32)).copy()
+    commits = ctx_horner.point_mul_base_batch(np.frombuffer(b"".join(b"".join(p) for p in polys), dtype=np.uint8).reshape(-1, 32)).copy()
     shares = np.frombuffer(b"".join(O.pripoly_eval(polys[d], i) for d in range(nd) for i in range(n)), dtype=np.uint8).reshape(-1, 32).copy()
     rng = np.random.default_rng(n * 1000 + t)
     for _ in range(max(2, nd * n // 10)):
@@ -464,19 +484,31 @@ def test_dkg_round_forward_differences(ctx, ctx_fd, coracle, n, t, nd):
         j = min(1, t - 1)
         c = O.point_add(O.point_decode(commits[1 * t + j].tobytes()), O.point_decode(O.WEAK_KEYS[2]))
         commits[1 * t + j] = np.frombuffer(O.point_encode(c), dtype=np.uint8)
+    limbs = np.stack([coracle.point_limbs(c.tobytes()) for c in commits])
+    if nd > 2:
         k = 0
         while coracle.point_decode_ok(bytes([k]) + b"\x13" * 31):
             k += 1
         commits[2 * t + (t - 1)] = np.frombuffer(bytes([k]) + b"\x13" * 31, dtype=np.uint8)
-    a = ctx.dkg_verify_round(n, t, commits, shares, dealer_lo=0, dealer_hi=nd).reshape(-1)[:nd * n]
-    b = ctx_fd.dkg_verify_round(n, t, commits, shares, dealer_lo=0, dealer_hi=nd).reshape(-1)[:nd * n]
-    assert (a == b).all(), np.nonzero(a != b)[0][:10]
+        limbs[2 * t + (t - 1), 30] += 1    # T no longer equals X Y / Z
+    a = ctx_horner.dkg_verify_round(n, t, commits, shares, dealer_lo=0, dealer_hi=nd).reshape(-1)[:nd * n]
+    for parts, c in enumerate(ctx_fd):
+        b = c.dkg_verify_round(n, t, commits, shares, dealer_lo=0, dealer_hi=nd).reshape(-1)[:nd * n]
+        assert (a == b).all(), (parts, np.nonzero(a != b)[0][:10])
+    bl = ctx_fd[0].dkg_verify_round(n, t, limbs, shares, limbs=True).reshape(-1)
+    assert (a == bl).all(), np.nonzero(a != bl)[0][:10]
+    hl = ctx_horner.dkg_verify_round(n, t, limbs, shares, limbs=True).reshape(-1)
+    assert (a == hl).all(), np.nonzero(a != hl)[0][:10]
     for d in range(min(nd, 4)):
         if nd > 2 and d == 2:
-            assert not b[d * n:(d + 1) * n].any()
+            assert not a[d * n:(d + 1) * n].any()
             continue
         row = coracle.vss_verify_batch(commits[d * t:(d + 1) * t], np.arange(n, dtype=np.uint32), shares[d * n:(d + 1) * n], nthreads=4)
-        assert (row == b[d * n:(d + 1) * n]).all()
+        assert (row == a[d * n:(d + 1) * n]).all()
+    # a sub-range of the dealers (what a rank owns when the round is sharded)
+    if nd >= 4:
+        part = ctx_fd[0].dkg_verify_round(n, t, commits, shares, dealer_lo=1, dealer_hi=nd - 1)
+        assert (part[n:(nd - 1) * n] == a[n:(nd - 1) * n]).all()
 
 
 # ---- MSM -------------------------------------------------------------------------------------------
@@ -643,8 +675,8 @@ def test_pubpoly_sum_dkg_key(ctx, coracle, golden_records):
     assert (one == pts[:t]).all()
 
 
-@pytest.mark.parametrize("path", ["horner", "forward-differences"])
-def test_cfg4_shape_full_t_two_dealers(ctx, ctx_fd, coracle, path):
+@pytest.mark.parametrize("path", ["horner", "fd-3-blocks", "fd-4-blocks"])
+def test_cfg4_shape_full_t_two_dealers(ctx, ctx_horner, ctx_fd, coracle, path):
     """BASELINE config 4 shape at full threshold and full verifier count (n = 1024, t = 683) for two dealers
     (the full round is 1024 dealers — CPU-days for the oracle): honest shares are computed independently with
     Python integers (PriPoly::eval, poly.rs:133), a few are corrupted, dealer 1 carries a torsion-contaminated
@@ -671,8 +703,9 @@ def test_cfg4_shape_full_t_two_dealers(ctx, ctx_fd, coracle, path):
     torsion_ok[7::8] = 1            # x = i + 1 divisible by 8
     want[1] &= torsion_ok
     # two dealers alone are below the cost threshold of the forward-difference round: ctx_fd forces it, so that its
-    # 682 wavefronts, the 683 factorials mod 8L and all 1024 difference steps are held to the same expected verdicts
-    got = (ctx if path == "horner" else ctx_fd).dkg_verify_round(n, t, commits, shares).reshape(nd, n)
+    # conversion launches, the x^(q h) mod 8L table and all 1024 difference steps are held to the same expected verdicts
+    c = {"horner": ctx_horner, "fd-3-blocks": ctx_fd[3], "fd-4-blocks": ctx_fd[4]}[path]
+    got = c.dkg_verify_round(n, t, commits, shares).reshape(nd, n)
     assert (got == want).all(), np.argwhere(got != want)[:10]
     for d, i in ((0, 0), (0, 1), (0, 1023), (1, 7), (1, 8), (1, 15)):
         cs = commits[d * t:(d + 1) * t]
