@@ -31,10 +31,9 @@ static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const void* d_commit
 }
 // The whole round by forward differences (dkgfd.cuh): one decode launch, h - 1 conversion launches, ONE launch for all
 // n difference steps, one combine-and-check launch.
-static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t parts, const void* d_commits, int limbs, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
+static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, const void* d_commits, int limbs, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
 {
-    const size_t h = (t + parts - 1) / parts;
-    parts = (t + h - 1) / h;                 // no empty block
+    const size_t parts = (t + h - 1) / h;
     if (parts > KB_FD_MAX_PARTS || h > KB_FD_MAX_H) return KB_ERR_ARG;
     const size_t rows = parts * h;
     uint32_t *dec, *ra, *rb, *evals, *dbad, *pw;
@@ -79,14 +78,18 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t part
     }
     const uint32_t* diffs = ((h - 1) & 1) ? ra : rb;   // what the last iteration wrote
     const unsigned step_threads = 32u * (unsigned)((h + 31) / 32);
-    k_fd_steps<<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
+    // up to 192 orders per block: 3 blocks (18 warps) per SM at 112 registers; up to 256: 2 blocks
+    static const int wide = getenv("KB_FD_STEPS_WIDE") ? atoi(getenv("KB_FD_STEPS_WIDE")) : 0;   // A/B switch (tuning)
+    if (step_threads <= 192 && !wide) k_fd_steps<192, 3><<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
+    else k_fd_steps<KB_FD_MAX_H, 2><<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
     KB_LAUNCHED();
     k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
     KB_LAUNCHED();
     return KB_OK;
 }
-// How to run a round: 0 = the per-share Horner kernel, p >= 1 = forward differences with p coefficient blocks.
-// Estimated from multiply counts (IMAD-eq) per dealer and the length of the chains of dependent launches / steps.
+// How to run a round: h = 0 means the per-share Horner kernel, otherwise forward differences with coefficient blocks of
+// h.  Estimated from multiply counts (IMAD-eq) per dealer and the length of the chains of dependent launches / steps.
+// The orders of a block are the lanes of k_fd_steps, so h is rounded up to whole warps where that keeps the block count.
 static size_t kb_dkg_plan(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
 {
     if (ctx->dkg_fd == 0) return 0;
@@ -94,48 +97,51 @@ static size_t kb_dkg_plan(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
     if (pmin > KB_FD_MAX_PARTS) return 0;
     const double rate = 7.0e12;   // sustained multiplies per second these kernels reach
     double best_time = 0;
-    size_t best = 0;
+    size_t best_h = 0, best_p = 0;
     for (size_t p = pmin ? pmin : 1; p <= KB_FD_MAX_PARTS && p <= t; p++) {
-        const size_t h = (t + p - 1) / p;
+        if (ctx->fd_parts >= 1 && (size_t)ctx->fd_parts >= pmin && (size_t)ctx->fd_parts <= t && (size_t)ctx->fd_parts <= KB_FD_MAX_PARTS && p != (size_t)ctx->fd_parts) continue;
+        size_t h = (t + p - 1) / p;
+        const size_t h32 = (h + 31) / 32 * 32;
+        if (h32 <= KB_FD_MAX_H && h32 < t && (t + h32 - 1) / h32 == (t + h - 1) / h) h = h32;
         const size_t pe = (t + h - 1) / h;
-        if (pe != p) continue;
         double lg = 0;
         for (size_t x = h; x > 1; x >>= 1) lg += 1;
         const double cell = 900.0 + 590.0 * (lg > 1.5 ? lg - 1.5 : 0.0);
-        const double conv = 0.5 * t * h * cell;
-        const double steps = ((double)n * t - 0.5 * t * h > 0 ? (double)n * t - 0.5 * t * h : 0) * 660.0;
-        const double comb = p > 1 ? (double)n * (101000.0 + (p - 1) * 42000.0) : 0.0;
+        double conv = 0, lanes = 0;
+        for (size_t q = 0; q < pe; q++) {
+            const double hq = (double)kb_fd_part_len(t, h, q);
+            conv += 0.5 * hq * hq * cell;
+            lanes += 32.0 * (double)((kb_fd_part_len(t, h, q) + 31) / 32);
+        }
+        const double steps = (double)n * lanes * 660.0 * 0.93;   // the dead orders of the last h steps are skipped
+        const double comb = pe > 1 ? (double)n * (101000.0 + (pe - 1) * 42000.0) : 0.0;
         const double work = (conv + steps + comb + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
         const double chain = h * 22e-6 + n * 2.5e-6;   // one cell per conversion launch, one addition per step
         const double time = work > chain ? work + 0.3 * chain : chain + 0.3 * work;
-        if (best == 0 || time < best_time) {
-            best = p;
+        if (best_h == 0 || time < best_time) {
+            best_h = h;
+            best_p = pe;
             best_time = time;
         }
     }
-    if (ctx->fd_parts >= 1 && ctx->fd_parts <= KB_FD_MAX_PARTS && (size_t)ctx->fd_parts >= pmin && (size_t)ctx->fd_parts <= t) {
-        const size_t h = (t + ctx->fd_parts - 1) / ctx->fd_parts;
-        best = (t + h - 1) / h;
-    }
-    if (best == 0) return 0;
+    if (best_h == 0) return 0;
     // its arrays: decoded commitments, two difference arrays, the recorded values — fall back to the per-share kernel
     // (a few MB of scratch) rather than fail when they would not fit next to what is already allocated
     {
-        const size_t h = (t + best - 1) / best;
         size_t free_b = 0, total_b = 0;
-        const double need = 128.0 * nd * ((double)t + 2.0 * best * h + (double)best * n);
+        const double need = 128.0 * nd * ((double)t + 2.0 * best_p * best_h + (double)best_p * n);
         const double have = (double)(ctx->slot_bytes[8] + ctx->slot_bytes[30] + ctx->slot_bytes[31] + ctx->slot_bytes[KB_SLOT_XYZ]);
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > 0.8 * (double)free_b + have) return 0;
     }
-    if (ctx->dkg_fd == 1) return best;
+    if (ctx->dkg_fd == 1) return best_h;
     const double horner = ((double)n * t * 6800.0 + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
     // a round too small to fill the GPU is cheaper in one launch of the per-share kernel
-    return (nd * t >= 8192 && best_time * 1.15 < horner) ? best : 0;
+    return (nd * t >= 8192 && best_time * 1.15 < horner) ? best_h : 0;
 }
 int kb_dkg_round_run(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, int limbs, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
 {
-    const size_t parts = kb_dkg_plan(ctx, n, t, ndealers);
-    if (parts) return kb_dkg_fd_run(ctx, n, t, ndealers, parts, d_commits, limbs, d_shares, d_verdict, st);
+    const size_t h = kb_dkg_plan(ctx, n, t, ndealers);
+    if (h) return kb_dkg_fd_run(ctx, n, t, ndealers, h, d_commits, limbs, d_shares, d_verdict, st);
     return kb_poly_run(ctx, ndealers, t, d_commits, limbs, n * ndealers, nullptr, nullptr, n, d_shares, d_verdict, nullptr, st);
 }
 

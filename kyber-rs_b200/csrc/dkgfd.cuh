@@ -299,9 +299,10 @@ static __global__ void __launch_bounds__(KB_FD_CONV_THREADS, KB_FD_CONV_MINBLOCK
 // memory, double-buffered so that one barrier per step is enough), adds what it received (8 M), and lane 0 records the
 // value E_q(i + 1) into evals[(q * n + i) * nd + d].  An order k can only reach the value k steps later, so the orders
 // above n - step are dead and their warps idle (they still meet the barrier).
-static __global__ void __launch_bounds__(KB_FD_MAX_H) k_fd_steps(size_t nd, size_t t, size_t h, size_t parts, size_t n, const uint32_t* dec, const uint32_t* diffs, uint32_t* evals)
+template <int MAXH, int MINB>
+static __global__ void __launch_bounds__(MAXH, MINB) k_fd_steps(size_t nd, size_t t, size_t h, size_t parts, size_t n, const uint32_t* dec, const uint32_t* diffs, uint32_t* evals)
 {
-    __shared__ uint4 xch_raw[2 * (KB_FD_MAX_H / 32) * 8];   // 2 buffers x warps x 32 words
+    __shared__ uint4 xch_raw[2 * (MAXH / 32) * 8];   // 2 buffers x warps x 32 words
     uint32_t* xch = reinterpret_cast<uint32_t*>(xch_raw);
     const size_t d = blockIdx.x / parts, q = blockIdx.x % parts;
     const size_t hq = kb_fd_part_len(t, h, q);
@@ -314,7 +315,7 @@ static __global__ void __launch_bounds__(KB_FD_MAX_H) k_fd_steps(size_t nd, size
     for (size_t i = 0; i < n; i++) {
         const size_t reach = n - i;   // the orders <= reach can still matter
         const bool warp_live = 32u * warp < hq && 32u * warp <= reach;
-        uint32_t* buf = xch + (i & 1) * (KB_FD_MAX_H / 32) * 32;
+        uint32_t* buf = xch + (i & 1) * (MAXH / 32) * 32;
         ge_cached c;
         if (warp_live) {
             ge_to_cached(c, p);
