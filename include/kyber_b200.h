@@ -169,6 +169,58 @@ int kb_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo,
  * out[j] = sum_d commits[d*t + j], j < t; status[j] = 1 (and out[j] zero) if a commitment of column j is undecodable. */
 int kb_pubpoly_sum(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, uint8_t* out, uint8_t* status);
 
+/* ---- protocol-level operations: the group math of the VSS / DKG / DSS verifiers as whole calls --------------------- */
+/* How a caller hands over points that it holds as the reference's Point values. */
+typedef enum kb_point_fmt {
+    KB_POINT_ENC32 = 0,   /* 32-byte encodings (Point::marshal_binary, point.rs:35-41) */
+    KB_POINT_LIMBS40 = 1  /* the in-memory / serde form: X, Y, Z, T as 10 signed 25.5-bit i32 limbs each (ge.rs:75-83) */
+} kb_point_fmt;
+
+/* session_id (share/vss/pedersen/vss.rs:1069-1090) for ndealers deals over the same verifier list:
+ *   out32[d] = SHA-256( dealers[d] || verifiers[0..n) || commits[d*t .. (d+1)*t) || t as u32 LE )
+ * over the points' canonical encodings (marshal_to), which are produced on the device (one shared inversion per 8 points —
+ * the reference pays 1 + n + t inversions per call).  status[d] = 1 if a point that enters sid_d does not decode. */
+int kb_vss_session_ids(kb_ctx* ctx, size_t ndealers, size_t n, size_t t, int fmt, const void* dealers, const void* verifiers, const void* commits, uint8_t* out32, uint8_t* status);
+/* find_pub (share/dkg/pedersen/dkg.rs:1109-1116; the scan of new_verifier, share/vss/pedersen/vss.rs:541-550) for m queries
+ * against one list: index_out[k] = smallest i with list[i] == queries[k] under Point::eq (canonical encodings), -1 if there
+ * is none, -2 if the query does not decode.  The reference compresses both operands of every comparison. */
+int kb_find_pub_batch(kb_ctx* ctx, size_t nlist, const void* list, size_t m, const void* queries, int fmt, int32_t* index_out);
+/* One Pedersen-DKG deal-verification round for the dealers [dealer_lo, dealer_hi) as every verifier sees it
+ * (share/dkg/pedersen/dkg.rs:513-597 process_deal, share/vss/pedersen/vss.rs:931-946 verify_response):
+ *   verdict[d*n + i]      the share check of kb_dkg_verify_round (commits in `fmt`, whole arrays indexed by dealer)
+ *   deal_status[k]        schnorr::verify of the dealer's signature on deal k        (dkg.rs:531)
+ *   resp_status[k]        schnorr::verify of verifier i's signature on its response  (vss.rs:943)
+ * where k = (d - dealer_lo)*n + i and the signature arrays (pk 32 B, sig 64 B, messages as flat bytes + n+1 offsets, the
+ * layout of kb_schnorr_verify_batch) hold exactly the items of the dealer range.  A batch whose sig pointer is NULL is skipped. */
+int kb_dkg_process_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, int fmt, const void* commits, const uint8_t* shares, uint8_t* verdict,
+                         const uint8_t* deal_pk, const uint8_t* deal_msg, const uint64_t* deal_msg_off, const uint8_t* deal_sig, uint8_t* deal_status,
+                         const uint8_t* resp_pk, const uint8_t* resp_msg, const uint64_t* resp_msg_off, const uint8_t* resp_sig, uint8_t* resp_status);
+/* vss::rabin verify_deal group math (share/vss/rabin/vss.rs:889-900): verdict[k] = 1 iff
+ * f_shares[k]*G + g_shares[k]*H == poly[poly_id[k]].eval(idx[k]); H = derive_h(verifiers) supplied by the caller.
+ * Both shares only meet constant-time table selects. */
+int kb_vss_rabin_verify_deals_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, const uint8_t* h_point, size_t m, const uint32_t* poly_id, const uint32_t* idx,
+                                    const uint8_t* f_shares, const uint8_t* g_shares, uint8_t* verdict);
+/* DSS::process_partial_sig group math (sign/dss/dss_sig.rs:263-273) for m partial signatures of one signing session:
+ *   hash = Scalar::set_bytes(SHA-512(random_commits[0] || long_commits[0] || msg))      (hash_sig, :312-326)
+ *   verdict[k] = 1 iff partials[k]*B == random_poly.eval(idx[k]) + hash * long_poly.eval(idx[k])
+ * in one chain of launches with the intermediate points kept uncompressed on the device.  hash_out32 (may be NULL) receives
+ * hash.  The Schnorr check of the partial signature's own signature (:252) is kb_schnorr_verify_batch on the same batch. */
+int kb_dss_verify_partials(kb_ctx* ctx, size_t t, const uint8_t* random_commits, const uint8_t* long_commits, const uint8_t* msg, size_t msg_len, size_t m, const uint32_t* idx, const uint8_t* partials,
+                           uint8_t* verdict, uint8_t* hash_out32);
+/* recover_commit (share/poly.rs:566-603) for ncols independent columns over the same k share indices idx (distinct):
+ *   out[c] = sum_i lambda_i * points[c*k + i],   lambda_i = prod_{j!=i} x_j / prod_{j!=i} (x_j - x_i) mod L,  x = idx + 1
+ * (the caller passes the first t shares in index order, xy_commit :535-562).  status[c] = 1 if a point of column c does
+ * not decode. */
+int kb_recover_commit_batch(kb_ctx* ctx, size_t ncols, size_t k, const uint32_t* idx, const uint8_t* points, uint8_t* out, uint8_t* status);
+/* recover_pub_poly (share/poly.rs:607-635): the k commitments of the polynomial through the k public shares
+ * (idx[j], points[j]):  out[c] = sum_j basis_j[c] * points[j] with the Lagrange basis polynomials of :640-671.  k <= 1023.
+ * (The reference indexes its maps by position and therefore only works for idx = 0..k-1; any distinct indices are accepted here.) */
+int kb_recover_pub_poly(kb_ctx* ctx, size_t k, const uint32_t* idx, const uint8_t* points, uint8_t* out, uint8_t* status);
+/* resharing_key group math (share/dkg/pedersen/dkg.rs:996-1031): coeffs[i*new_t + c] = commitment c of the deal of the i-th
+ * qualified old node (index idx[i]); out_commits[c] = recover_commit over column c; *check_out = pub_poly.check(share)
+ * for the new share (share_idx, share32) — skipped when share32 or check_out is NULL. */
+int kb_dkg_resharing_key(kb_ctx* ctx, size_t new_t, size_t k, const uint32_t* idx, const uint8_t* coeffs, uint32_t share_idx, const uint8_t* share32, uint8_t* out_commits, uint8_t* status, uint8_t* check_out);
+
 /* ---- multi-scalar multiplication ------------------------------------------------------ */
 /* out = compress(sum_i scalars[i] * P_i), the fold of Point::mul + Point::add (point.rs:179,207)
  * computed with Pippenger's bucket method.  *bad_points = number of undecodable inputs (the
@@ -186,6 +238,10 @@ int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_point
 int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commit_limbs, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream);
+/* kb_dkg_process_round on device buffers for ndealers dealers (arrays start at the first of them) */
+int kb_dev_dkg_process_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, int fmt, const void* d_commits, const void* d_shares, void* d_verdict,
+                             const void* d_deal_pk, const void* d_deal_msg, const void* d_deal_msg_off, const void* d_deal_sig, void* d_deal_status,
+                             const void* d_resp_pk, const void* d_resp_msg, const void* d_resp_msg_off, const void* d_resp_sig, void* d_resp_status, void* stream);
 
 /* ---- measurement ---------------------------------------------------------------------- */
 /* Integer-multiply roofline probe: runs `iters` dependent-chain-free IMAD.WIDE.U32 per thread

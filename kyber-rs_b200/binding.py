@@ -38,6 +38,8 @@ EXPORTS = [
     "kb_point_mul_base_batch", "kb_point_mul_batch", "kb_point_recode_batch", "kb_point_from_limbs_batch", "kb_point_add_batch", "kb_point_check_batch", "kb_point_decompress_batch", "kb_point_compress_batch", "kb_point_eq_batch",
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_dkg_verify_round_limbs", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
+    "kb_vss_session_ids", "kb_find_pub_batch", "kb_dkg_process_round", "kb_vss_rabin_verify_deals_batch", "kb_dss_verify_partials", "kb_recover_commit_batch", "kb_recover_pub_poly", "kb_dkg_resharing_key",
+    "kb_dev_dkg_process_round",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_dkg_verify_round_limbs", "kb_dev_point_sum",
     "kb_probe_imad", "kb_verify_kernel_times",
 ]
@@ -87,6 +89,15 @@ def load_library(path: str = LIB_PATH):
     L.kb_dkg_verify_round_limbs.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
     L.kb_pubpoly_sum.argtypes = [vp, sz, sz, vp, vp, vp]
     L.kb_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.kb_vss_session_ids.argtypes = [vp, sz, sz, sz, i32, vp, vp, vp, vp, vp]
+    L.kb_find_pub_batch.argtypes = [vp, sz, vp, sz, vp, i32, vp]
+    L.kb_dkg_process_round.argtypes = [vp, sz, sz, sz, sz, i32, vp, vp, vp] + [vp] * 10
+    L.kb_dev_dkg_process_round.argtypes = [vp, sz, sz, sz, i32, vp, vp, vp] + [vp] * 10 + [vp]
+    L.kb_vss_rabin_verify_deals_batch.argtypes = [vp, sz, sz, vp, vp, sz, vp, vp, vp, vp, vp]
+    L.kb_dss_verify_partials.argtypes = [vp, sz, vp, vp, vp, sz, sz, vp, vp, vp, vp]
+    L.kb_recover_commit_batch.argtypes = [vp, sz, sz, vp, vp, vp, vp]
+    L.kb_recover_pub_poly.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.kb_dkg_resharing_key.argtypes = [vp, sz, sz, vp, vp, u32, vp, vp, vp, vp]
     L.kb_point_sum.argtypes = [vp, sz, vp, vp]
     L.kb_dev_eddsa_verify.argtypes = [vp, sz, vp, vp, vp, vp, vp, i32, vp]
     L.kb_dev_point_mul_base.argtypes = [vp, sz, vp, vp, u32, vp]
@@ -330,6 +341,124 @@ class Context:
         self._check(self.L.kb_pubpoly_sum(self.h, npoly, t, _ptr(c), _ptr(out), _ptr(st)), "kb_pubpoly_sum")
         return out, st
 
+    # ---- protocol-level operations ----------------------------------------------------------
+    @staticmethod
+    def _points(a, limbs):
+        return np.ascontiguousarray(a, dtype=np.int32).reshape(-1, 40) if limbs else _u8(a, (-1, 32))
+
+    def vss_session_ids(self, dealers, verifiers, commits, t, limbs=False):
+        """session_id per dealer (vss/pedersen/vss.rs:1069): (ndealers,32) digests, (ndealers,) status."""
+        d, v, c = self._points(dealers, limbs), self._points(verifiers, limbs), self._points(commits, limbs)
+        nd = d.shape[0]
+        if c.shape[0] != nd * t:
+            raise ValueError("vss_session_ids: commits must hold ndealers*t points")
+        out = np.empty((nd, 32), dtype=np.uint8)
+        st = np.empty(nd, dtype=np.uint8)
+        self._check(self.L.kb_vss_session_ids(self.h, nd, v.shape[0], t, int(limbs), _ptr(d), _ptr(v), _ptr(c), _ptr(out), _ptr(st)), "kb_vss_session_ids")
+        return out, st
+
+    def find_pub_batch(self, plist, queries, limbs=False):
+        l, q = self._points(plist, limbs), self._points(queries, limbs)
+        out = np.empty(q.shape[0], dtype=np.int32)
+        self._check(self.L.kb_find_pub_batch(self.h, l.shape[0], _ptr(l), q.shape[0], _ptr(q), int(limbs), _ptr(out)), "kb_find_pub_batch")
+        return out
+
+    def dkg_process_round(self, n, t, commits, shares, deal=None, resp=None, dealer_lo=0, dealer_hi=None, limbs=False):
+        """One deal-verification round: share checks + Schnorr verification of the deal and response signatures.
+        deal / resp = (pk[m,32], msg flat, msg_off[m+1], sig[m,64]) for the m = (dealer_hi-dealer_lo)*n items, or None.
+        Returns (verdict[ndealers*n], deal_status[m] | None, resp_status[m] | None)."""
+        c = self._points(commits, limbs)
+        sh = _u8(shares, (-1, 32))
+        ndealers = c.shape[0] // t
+        if dealer_hi is None:
+            dealer_hi = ndealers
+        if ndealers * t != c.shape[0] or sh.shape[0] != ndealers * n or not (0 <= dealer_lo <= dealer_hi <= ndealers):
+            raise ValueError("dkg_process_round: inconsistent shapes")
+        m = (dealer_hi - dealer_lo) * n
+        verdict = np.zeros(ndealers * n, dtype=np.uint8)
+        args, outs, keep = [], [], []
+        for batch in (deal, resp):
+            if batch is None:
+                args += [None] * 5
+                outs.append(None)
+                continue
+            pk, msg, off, sig = _u8(batch[0], (-1, 32)), _u8(batch[1]), np.ascontiguousarray(batch[2], dtype=np.uint64), _u8(batch[3], (-1, 64))
+            if pk.shape[0] != m or sig.shape[0] != m or off.shape[0] != m + 1:
+                raise ValueError("dkg_process_round: a signature batch must hold one item per (dealer, verifier) of the range")
+            st = np.empty(m, dtype=np.uint8)
+            keep += [pk, msg, off, sig]
+            args += [_ptr(pk), _ptr(msg), _ptr(off), _ptr(sig), _ptr(st)]
+            outs.append(st)
+        self._check(self.L.kb_dkg_process_round(self.h, n, t, dealer_lo, dealer_hi, int(limbs), _ptr(c), _ptr(sh), _ptr(verdict), *args), "kb_dkg_process_round")
+        return verdict, outs[0], outs[1]
+
+    def vss_rabin_verify_deals_batch(self, commits, t, h_point, poly_id, idx, f_shares, g_shares):
+        c = _u8(commits, (-1, 32))
+        npoly = c.shape[0] // t
+        hp = _u8(h_point, (32,))
+        poly_id = np.ascontiguousarray(poly_id, dtype=np.uint32)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        f, g = _u8(f_shares, (-1, 32)), _u8(g_shares, (-1, 32))
+        m = idx.shape[0]
+        if npoly * t != c.shape[0] or poly_id.shape[0] != m or f.shape[0] != m or g.shape[0] != m:
+            raise ValueError("vss_rabin_verify_deals_batch: inconsistent shapes")
+        verdict = np.empty(m, dtype=np.uint8)
+        self._check(self.L.kb_vss_rabin_verify_deals_batch(self.h, npoly, t, _ptr(c), _ptr(hp), m, _ptr(poly_id), _ptr(idx), _ptr(f), _ptr(g), _ptr(verdict)), "kb_vss_rabin_verify_deals_batch")
+        return verdict
+
+    def dss_verify_partials(self, random_commits, long_commits, msg, idx, partials):
+        """(verdict[m], hash scalar bytes) of DSS::process_partial_sig's group math for one signing session."""
+        r, l = _u8(random_commits, (-1, 32)), _u8(long_commits, (-1, 32))
+        if r.shape != l.shape:
+            raise ValueError("dss_verify_partials: the two polynomials must have the same threshold")
+        mb = _u8(np.frombuffer(bytes(msg), dtype=np.uint8)) if len(msg) else np.zeros(0, dtype=np.uint8)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        p = _u8(partials, (-1, 32))
+        m = idx.shape[0]
+        if p.shape[0] != m:
+            raise ValueError("dss_verify_partials: one partial per index")
+        verdict = np.empty(m, dtype=np.uint8)
+        hs = np.empty(32, dtype=np.uint8)
+        self._check(self.L.kb_dss_verify_partials(self.h, r.shape[0], _ptr(r), _ptr(l), _ptr(mb) if mb.size else None, mb.size, m, _ptr(idx), _ptr(p), _ptr(verdict), _ptr(hs)), "kb_dss_verify_partials")
+        return verdict, hs.tobytes()
+
+    def recover_commit_batch(self, idx, points, ncols=1):
+        """points: (ncols*k, 32) as [column][share]; returns (out[ncols,32], status[ncols])."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        p = _u8(points, (-1, 32))
+        k = idx.shape[0]
+        if p.shape[0] != ncols * k:
+            raise ValueError("recover_commit_batch: points must hold ncols*k encodings")
+        out = np.empty((ncols, 32), dtype=np.uint8)
+        st = np.empty(ncols, dtype=np.uint8)
+        self._check(self.L.kb_recover_commit_batch(self.h, ncols, k, _ptr(idx), _ptr(p), _ptr(out), _ptr(st)), "kb_recover_commit_batch")
+        return out, st
+
+    def recover_pub_poly(self, idx, points):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        p = _u8(points, (-1, 32))
+        k = idx.shape[0]
+        if p.shape[0] != k:
+            raise ValueError("recover_pub_poly: one point per index")
+        out = np.empty((k, 32), dtype=np.uint8)
+        st = np.empty(k, dtype=np.uint8)
+        self._check(self.L.kb_recover_pub_poly(self.h, k, _ptr(idx), _ptr(p), _ptr(out), _ptr(st)), "kb_recover_pub_poly")
+        return out, st
+
+    def dkg_resharing_key(self, new_t, idx, coeffs, share_idx=0, share=None):
+        """coeffs: (k*new_t, 32) as [qualified node][coefficient]; returns (commits[new_t,32], status[new_t], check | None)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        c = _u8(coeffs, (-1, 32))
+        k = idx.shape[0]
+        if c.shape[0] != k * new_t:
+            raise ValueError("dkg_resharing_key: coeffs must hold k*new_t encodings")
+        out = np.empty((new_t, 32), dtype=np.uint8)
+        st = np.empty(new_t, dtype=np.uint8)
+        chk = np.zeros(1, dtype=np.uint8)
+        sh = _u8(share, (32,)) if share is not None else None
+        self._check(self.L.kb_dkg_resharing_key(self.h, new_t, k, _ptr(idx), _ptr(c), int(share_idx), _ptr(sh), _ptr(out), _ptr(st), _ptr(chk) if sh is not None else None), "kb_dkg_resharing_key")
+        return out, st, (bool(chk[0]) if sh is not None else None)
+
     def msm(self, scalars, points, want_partial=False):
         s, p = _u8(scalars, (-1, 32)), _u8(points, (-1, 32))
         assert s.shape == p.shape
@@ -388,6 +517,13 @@ class Context:
     def dev_dkg_verify_round(self, n, t, ndealers, commits, shares, verdict, limbs=False):
         fn = self.L.kb_dev_dkg_verify_round_limbs if limbs else self.L.kb_dev_dkg_verify_round
         self._check(fn(self.h, n, t, ndealers, self._dp(commits), self._dp(shares), self._dp(verdict), self._stream()), "kb_dev_dkg_verify_round")
+
+    def dev_dkg_process_round(self, n, t, ndealers, commits, shares, verdict, deal=None, resp=None, limbs=False):
+        """deal / resp = (pk, msg, msg_off, sig, status) CUDA tensors or None."""
+        a = []
+        for batch in (deal, resp):
+            a += [self._dp(x) for x in batch] if batch is not None else [None] * 5
+        self._check(self.L.kb_dev_dkg_process_round(self.h, n, t, ndealers, int(limbs), self._dp(commits), self._dp(shares), self._dp(verdict), *a, self._stream()), "kb_dev_dkg_process_round")
 
     def dev_point_sum(self, k, partials, out32):
         self._check(self.L.kb_dev_point_sum(self.h, k, self._dp(partials), self._dp(out32), self._stream()), "kb_dev_point_sum")

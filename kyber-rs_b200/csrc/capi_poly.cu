@@ -4,8 +4,11 @@
 #include "kernels.cuh"
 #include "msm.cuh"
 #include "dkgfd.cuh"
-// commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel
-static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const void* d_commits, int limbs, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
+// commitments -> cached form into scratch slots 8 (cached) / 9 (bad flags); then the eval kernel.
+//   d_shares != 0           verdicts of the share checks into d_out (one byte per item)
+//   d_shares == 0, d_out    encodings of the evaluations into d_out, per-item status into d_status
+//   d_shares == 0, !d_out   the evaluations stay as (X, Y, Z) in scratch slot KB_SLOT_XYZ, status into d_status
+int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const void* d_commits, int limbs, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,
                        const uint8_t* d_shares, uint8_t* d_out, uint8_t* d_status, cudaStream_t st)
 {
     uint32_t* cached;
@@ -24,6 +27,7 @@ static int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const void* d_commit
         KB_SCRATCH(KB_SLOT_XYZ, 96 * m, xyz);
         k_poly_eval<<<kb_blocks(m, KB_THREADS), KB_THREADS, 0, st>>>(m, npoly, t, cached, bad, d_poly_id, d_idx, n_verifiers, nullptr, xyz, d_status, nullptr, ctx->base_table);
         KB_LAUNCHED();
+        if (!d_out) return KB_OK;   // the caller goes on with the uncompressed values in KB_SLOT_XYZ
         k_compress_batch<<<kb_blocks((m + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(m, xyz, d_status, d_out);
         KB_LAUNCHED();
     }

@@ -158,7 +158,6 @@ static __global__ void __launch_bounds__(KB_THREADS) k_compress_batch(size_t n, 
     });
 }
 
-#if defined(KB_K_POINT)
 // ---- serde wire format of the reference: raw ExtendedGroupElement limbs -> (X, Y, Z) for the batch
 // compressor.  Z = 0 (e.g. Point::default(), all-zero limbs) encodes as 32 zero bytes in the reference
 // (fe_invert(0) = 0, ge.rs:112-122): flagged in zero_out and replaced by Z = 1 so that the shared inversion
@@ -189,6 +188,7 @@ static __global__ void __launch_bounds__(KB_THREADS) k_points_from_limbs(size_t 
     zero_out[i] = (uint8_t)z0;
 }
 
+#if defined(KB_K_POINT)
 // ---- Point::mul(s, None): out[i] = compress(s_i * B)   (point.rs:207, ge.rs:442)
 // `split` (1, 2 or 4) adjacent lanes share one scalar: each walks 64/split of the comb windows and the partial
 // points are added with a shuffle butterfly.  The comb has no doublings, so the windows are independent; small

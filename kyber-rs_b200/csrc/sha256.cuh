@@ -68,6 +68,22 @@ KB_FN void sha256_words(kb_sha256& s, const uint32_t* le, int nw)
     }
     s.words += (uint64_t)nw;
 }
+// absorb one 32-byte record (8 little-endian words); only valid while everything absorbed so far was whole records
+// (the buffer is then empty or half full, and every index below is a compile-time constant)
+KB_FN void sha256_rec32(kb_sha256& s, const uint32_t* le)
+{
+    if (s.fill == 0) {
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) s.w[i] = kb_bswap32(le[i]);
+        s.fill = 8;
+    } else {
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) s.w[8 + i] = kb_bswap32(le[i]);
+        sha256_compress(s.h, s.w);
+        s.fill = 0;
+    }
+    s.words += 8;
+}
 // out = digest as 8 little-endian words (digest bytes in memory order)
 KB_FN void sha256_final(kb_sha256& s, uint32_t* out)
 {

@@ -322,38 +322,41 @@ def msm(scalars, points, ctx: Context | None = None) -> Point:
 
 def vss_rabin_verify_deals_batch(commits, idx, f_shares, g_shares, h_point: Point, ctx: Context | None = None):
     """vss::rabin verify_deal group math (share/vss/rabin/vss.rs:889-900): fi*G + gi*H == eval(fi.i) on
-    canonical encodings, for m (index, f share, g share) triples against one polynomial.
-    Composed from the batch primitives (eval, fixed-base mul, shared-point mul, add)."""
+    canonical encodings, for m (index, f share, g share) triples against one polynomial — one C-ABI call
+    (kb_vss_rabin_verify_deals_batch): evaluation, both constant-time multiplications and the comparison stay on the device."""
     ctx = ctx or default_context()
     poly = PubPoly(commits)
     idx = np.asarray(idx, dtype=np.uint32)
-    ev, st = ctx.pubpoly_eval_batch(poly._flat(), poly.threshold(), np.zeros_like(idx), idx)
     f = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in f_shares), np.uint8).reshape(-1, 32)
     g = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in g_shares), np.uint8).reshape(-1, 32)
-    fg = ctx.point_mul_base_batch(f)
-    gh, st2 = ctx.point_mul_batch(g, np.frombuffer(h_point.b, np.uint8).reshape(1, 32))
-    ci, st3 = ctx.point_add_batch(fg, gh)
-    return ((ci == ev).all(axis=1) & (st == 0) & (st2 == 0) & (st3 == 0)).astype(np.uint8)
+    return ctx.vss_rabin_verify_deals_batch(poly._flat(), poly.threshold(), np.frombuffer(h_point.b, np.uint8), np.zeros_like(idx), idx, f, g)
 
 
-def dss_verify_partials_batch(random_commits, long_commits, idx, partials, hash_scalar: Scalar, ctx: Context | None = None):
-    """Group math of DSS::process_partial_sig (sign/dss/dss_sig.rs:263-273) for m partial signatures:
-    partial_i * B == random_poly.eval(i) + hash * long_poly.eval(i)."""
+def dss_verify_partials_batch(random_commits, long_commits, idx, partials, msg: bytes, ctx: Context | None = None):
+    """Group math of DSS::process_partial_sig (sign/dss/dss_sig.rs:263-273) for m partial signatures of one session:
+    partial_i * B == random_poly.eval(i) + hash_sig() * long_poly.eval(i), hash_sig = H(R || A || msg) (:312-326).
+    One C-ABI call (kb_dss_verify_partials).  Returns (verdict[m], hash Scalar)."""
     ctx = ctx or default_context()
-    idx = np.asarray(idx, dtype=np.uint32)
     rp, lp = PubPoly(random_commits), PubPoly(long_commits)
-    both = np.concatenate([rp._flat().reshape(-1, 32), lp._flat().reshape(-1, 32)])
-    assert rp.threshold() == lp.threshold()
-    pid = np.concatenate([np.zeros_like(idx), np.ones_like(idx)])
-    ev, st = ctx.pubpoly_eval_batch(both, rp.threshold(), pid, np.concatenate([idx, idx]))
-    m = idx.shape[0]
-    rand_share, long_share = ev[:m], ev[m:]
-    hs = np.tile(np.frombuffer(hash_scalar.v, np.uint8), (m, 1))
-    hl, st2 = ctx.point_mul_batch(hs, long_share, 1)   # public data: vartime
-    right, st3 = ctx.point_add_batch(rand_share, hl)
     p = np.frombuffer(b"".join(s.v if isinstance(s, Scalar) else bytes(s) for s in partials), np.uint8).reshape(-1, 32)
-    left = ctx.point_mul_base_batch(p)
-    return ((left == right).all(axis=1) & (st[:m] == 0) & (st[m:] == 0) & (st2 == 0) & (st3 == 0)).astype(np.uint8)
+    verdict, h = ctx.dss_verify_partials(rp._flat(), lp._flat(), msg, np.asarray(idx, dtype=np.uint32), p)
+    return verdict, Scalar(h)
+
+
+def session_id(dealer: Point, verifiers, commitments, t: int, ctx: Context | None = None) -> bytes:
+    """session_id (share/vss/pedersen/vss.rs:1069-1090)."""
+    ctx = ctx or default_context()
+    flat = lambda pts: np.frombuffer(b"".join(p.b for p in pts), np.uint8)
+    out, st = ctx.vss_session_ids(np.frombuffer(dealer.b, np.uint8), flat(verifiers), flat(commitments), t)
+    if st[0]:
+        raise MarshallingError("invalid Ed25519 curve point")
+    return out[0].tobytes()
+
+
+def find_pub(points, to_find: Point, ctx: Context | None = None):
+    """find_pub (share/dkg/pedersen/dkg.rs:1109-1116): (index, found)."""
+    i = int((ctx or default_context()).find_pub_batch(np.frombuffer(b"".join(p.b for p in points), np.uint8), np.frombuffer(to_find.b, np.uint8))[0])
+    return (i, True) if i >= 0 else (0, False)
 
 
 def schnorr_sign_batch(privates, msgs, nonces, ctx: Context | None = None):
@@ -371,35 +374,43 @@ def schnorr_sign_batch(privates, msgs, nonces, ctx: Context | None = None):
     return np.concatenate([r, s], axis=1), pub
 
 
-def recover_commit(shares, t: int, n: int, ctx: Context | None = None) -> Point:
-    """share::poly::recover_commit (share/poly.rs:566-603): Lagrange interpolation in the exponent of the
-    secret commitment p(0) from public shares [(index, Point), ...] — the first t of them in index order
-    (xy_commit, poly.rs:535-562).  The Lagrange coefficients num/den are built with the batched scalar
-    kernels, the weighted sum is ONE Pippenger MSM (kb_msm) instead of t scalar mults and t additions."""
-    ctx = ctx or default_context()
+def _xy_commit(shares, t: int):
+    """xy_commit (share/poly.rs:535-562): the first t present shares in index order."""
     good = sorted(((i, p) for i, p in shares if p is not None), key=lambda s: s[0])[:t]
     if len(good) < t:
         raise ValueError("not enough good public shares to reconstruct secret commitment")   # PolyError::NotEnoughtGoodPublics
-    k = len(good)
-    xs = np.zeros((k, 32), dtype=np.uint8)
-    for r, (i, _) in enumerate(good):
-        xs[r] = np.frombuffer((i + 1).to_bytes(32, "little"), dtype=np.uint8)      # set_int64(idx + 1)
-    one = np.zeros((k, 32), dtype=np.uint8)
-    one[:, 0] = 1
-    zero = np.zeros((k, 32), dtype=np.uint8)
-    lm1 = np.tile(np.frombuffer(_L_MINUS_1, dtype=np.uint8), (k, 1))
-    num, den = one.copy(), one.copy()
-    for j in range(k):
-        xj = np.tile(xs[j], (k, 1))
-        diff = ctx.sc_muladd_batch(xs, lm1, xj)          # x_j - x_i  (Scalar::sub, scalar.rs:162)
-        fnum, fden = xj.copy(), diff
-        fnum[j] = one[0]                                  # skip i == j
-        fden[j] = one[0]
-        num = ctx.sc_muladd_batch(num, fnum, zero)
-        den = ctx.sc_muladd_batch(den, fden, zero)
-    lam = ctx.sc_muladd_batch(num, ctx.sc_invert_batch(den), zero)                  # num.div(num, den)
-    pts = np.frombuffer(b"".join(p.b for _, p in good), dtype=np.uint8).reshape(-1, 32)
-    enc, bad = ctx.msm(lam, pts)
-    if bad:
+    return good
+
+
+def recover_commit(shares, t: int, n: int, ctx: Context | None = None) -> Point:
+    """share::poly::recover_commit (share/poly.rs:566-603): Lagrange interpolation in the exponent of the
+    secret commitment p(0) from public shares [(index, Point), ...].  One C-ABI call (kb_recover_commit_batch):
+    the Lagrange coefficients, the t scalar multiplications and their sum are computed on the device."""
+    good = _xy_commit(shares, t)
+    out, st = (ctx or default_context()).recover_commit_batch([i for i, _ in good], np.frombuffer(b"".join(p.b for _, p in good), np.uint8))
+    if st[0]:
         raise MarshallingError("invalid Ed25519 curve point")
-    return Point(enc)
+    return Point(out[0].tobytes())
+
+
+def recover_pub_poly(shares, t: int, n: int, ctx: Context | None = None) -> PubPoly:
+    """share::poly::recover_pub_poly (share/poly.rs:607-635)."""
+    good = _xy_commit(shares, t)
+    out, st = (ctx or default_context()).recover_pub_poly([i for i, _ in good], np.frombuffer(b"".join(p.b for _, p in good), np.uint8))
+    if st.any():
+        raise MarshallingError("invalid Ed25519 curve point")
+    return PubPoly([Point(o.tobytes()) for o in out])
+
+
+def resharing_key_commits(deal_commits, old_t: int, new_t: int, share_index: int, share: Scalar, ctx: Context | None = None):
+    """The group math of resharing_key (share/dkg/pedersen/dkg.rs:996-1031): deal_commits = {old node index: [new_t
+    Points]} of the qualified deals; returns the new_t commitments of the new public polynomial and whether it checks
+    against the new private share (DKGError::ShareDoesNotMatchPublicPoly otherwise)."""
+    good = sorted(deal_commits.items())[:old_t]
+    if len(good) < old_t:
+        raise ValueError("not enough good public shares to reconstruct secret commitment")
+    flat = np.frombuffer(b"".join(p.b for _, row in good for p in row[:new_t]), np.uint8)
+    out, st, chk = (ctx or default_context()).dkg_resharing_key(new_t, [i for i, _ in good], flat, share_index, np.frombuffer(share.v, np.uint8))
+    if st.any():
+        raise MarshallingError("invalid Ed25519 curve point")
+    return [Point(o.tobytes()) for o in out], chk

@@ -57,6 +57,21 @@ extern "C" {
     pub fn kb_msm(ctx: *mut kb_ctx, n: usize, scalars: *const u8, points: *const u8, out32: *mut u8, partial128: *mut u8, bad_points: *mut u64) -> c_int;
     pub fn kb_point_sum(ctx: *mut kb_ctx, k: usize, partials128: *const u8, out32: *mut u8) -> c_int;
 
+    // protocol-level operations (fmt: 0 = 32-byte encodings, 1 = 40 x i32 limbs per point)
+    pub fn kb_vss_session_ids(ctx: *mut kb_ctx, ndealers: usize, n: usize, t: usize, fmt: c_int, dealers: *const c_void, verifiers: *const c_void, commits: *const c_void, out32: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_find_pub_batch(ctx: *mut kb_ctx, nlist: usize, list: *const c_void, m: usize, queries: *const c_void, fmt: c_int, index_out: *mut i32) -> c_int;
+    pub fn kb_dkg_process_round(ctx: *mut kb_ctx, n: usize, t: usize, dealer_lo: usize, dealer_hi: usize, fmt: c_int, commits: *const c_void, shares: *const u8, verdict: *mut u8,
+        deal_pk: *const u8, deal_msg: *const u8, deal_msg_off: *const u64, deal_sig: *const u8, deal_status: *mut u8,
+        resp_pk: *const u8, resp_msg: *const u8, resp_msg_off: *const u64, resp_sig: *const u8, resp_status: *mut u8) -> c_int;
+    pub fn kb_vss_rabin_verify_deals_batch(ctx: *mut kb_ctx, npoly: usize, t: usize, commits: *const u8, h_point: *const u8, m: usize, poly_id: *const u32, idx: *const u32, f_shares: *const u8, g_shares: *const u8, verdict: *mut u8) -> c_int;
+    pub fn kb_dss_verify_partials(ctx: *mut kb_ctx, t: usize, random_commits: *const u8, long_commits: *const u8, msg: *const u8, msg_len: usize, m: usize, idx: *const u32, partials: *const u8, verdict: *mut u8, hash_out32: *mut u8) -> c_int;
+    pub fn kb_recover_commit_batch(ctx: *mut kb_ctx, ncols: usize, k: usize, idx: *const u32, points: *const u8, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_recover_pub_poly(ctx: *mut kb_ctx, k: usize, idx: *const u32, points: *const u8, out: *mut u8, status: *mut u8) -> c_int;
+    pub fn kb_dkg_resharing_key(ctx: *mut kb_ctx, new_t: usize, k: usize, idx: *const u32, coeffs: *const u8, share_idx: u32, share32: *const u8, out_commits: *mut u8, status: *mut u8, check_out: *mut u8) -> c_int;
+    pub fn kb_dev_dkg_process_round(ctx: *mut kb_ctx, n: usize, t: usize, ndealers: usize, fmt: c_int, d_commits: *const c_void, d_shares: *const c_void, d_verdict: *mut c_void,
+        d_deal_pk: *const c_void, d_deal_msg: *const c_void, d_deal_msg_off: *const c_void, d_deal_sig: *const c_void, d_deal_status: *mut c_void,
+        d_resp_pk: *const c_void, d_resp_msg: *const c_void, d_resp_msg_off: *const c_void, d_resp_sig: *const c_void, d_resp_status: *mut c_void, stream: *mut c_void) -> c_int;
+
     pub fn kb_dev_eddsa_verify(ctx: *mut kb_ctx, n: usize, d_pk: *const c_void, d_msg: *const c_void, d_msg_off: *const c_void, d_sig: *const c_void, d_status: *mut c_void, schnorr: c_int, stream: *mut c_void) -> c_int;
     pub fn kb_dev_point_mul_base(ctx: *mut kb_ctx, n: usize, d_scalars: *const c_void, d_out: *mut c_void, flags: u32, stream: *mut c_void) -> c_int;
     pub fn kb_dev_point_mul(ctx: *mut kb_ctx, n: usize, d_scalars: *const c_void, d_points: *const c_void, d_out: *mut c_void, d_status: *mut c_void, flags: u32, stream: *mut c_void) -> c_int;

@@ -481,3 +481,74 @@ def msm(scalars, points):
     for s, pt in zip(scalars, points):
         acc = _ext_add(acc, _to_ext(_mul_int(scalar_effective(s), pt)))
     return _from_ext(acc)
+
+
+# --------------------------------------------------------------------------- interpolation in the exponent, session ids
+def recover_commit(shares):
+    """recover_commit (share/poly.rs:566-603) on the shares [(index, point)] already selected by xy_commit
+    (:535-562: the first t in index order): sum_i (prod_{j!=i} x_j / (x_j - x_i)) * y_i with x = index + 1."""
+    acc = IDENTITY
+    xs = {i: scalar_set_int64(i + 1) for i, _ in shares}
+    for i, yi in shares:
+        num, den = scalar_set_int64(1), scalar_set_int64(1)
+        for j, _ in shares:
+            if i == j:
+                continue
+            num = sc_mul(num, xs[j])
+            den = sc_mul(den, sc_sub(xs[j], xs[i]))
+        lam = sc_mul(num, sc_inv(den))          # num.div(num, den)
+        acc = point_add(acc, point_mul(lam, yi))
+    return acc
+
+
+def lagrange_basis(i, xs):
+    """lagrange_basis (share/poly.rs:640-671): coefficients (low order first) of prod_{m!=i} (x - x_m) / (x_i - x_m)."""
+    basis = [scalar_set_int64(1)]
+    acc = scalar_set_int64(1)
+    for m, xm in xs.items():
+        if m == i:
+            continue
+        neg = sc_neg(xm)
+        nxt = [bytes(32)] * (len(basis) + 1)
+        for d, c in enumerate(basis):          # basis.mul(minus_const(xm))
+            nxt[d] = sc_add(nxt[d], sc_mul(c, neg))
+            nxt[d + 1] = sc_add(nxt[d + 1], c)
+        basis = nxt
+        acc = sc_mul(acc, sc_inv(sc_sub(xs[i], xm)))
+    return [sc_mul(c, acc) for c in basis]
+
+
+def recover_pub_poly(shares):
+    """recover_pub_poly (share/poly.rs:607-635): sum_j L_j(x) * y_j in point space -> the commitments."""
+    xs = {i: scalar_set_int64(i + 1) for i, _ in shares}
+    acc = None
+    for j, yj in shares:
+        tmp = [point_mul(c, yj) for c in lagrange_basis(j, xs)]
+        acc = tmp if acc is None else pubpoly_add(acc, tmp)
+    return acc
+
+
+def session_id(dealer, verifiers, commitments, t: int) -> bytes:
+    """session_id (share/vss/pedersen/vss.rs:1069-1090): SHA-256 over the marshalled points and t as u32 LE
+    (SuiteEd25519::hash is SHA-256, group/edwards25519/suite.rs:93-96)."""
+    h = hashlib.sha256()
+    h.update(point_encode(dealer))
+    for v in verifiers:
+        h.update(point_encode(v))
+    for c in commitments:
+        h.update(point_encode(c))
+    h.update(int(t).to_bytes(4, "little"))
+    return h.digest()
+
+
+def find_pub(points, to_find):
+    """find_pub (share/dkg/pedersen/dkg.rs:1109-1116): (index, found) of the first list entry equal to to_find."""
+    for i, p in enumerate(points):
+        if point_eq(p, to_find):
+            return i, True
+    return 0, False
+
+
+def dss_hash_sig(random_commit0, long_commit0, msg: bytes) -> bytes:
+    """hash_sig (sign/dss/dss_sig.rs:312-326): H(R || A || msg) as a scalar."""
+    return challenge(point_encode(random_commit0), point_encode(long_commit0), msg)

@@ -781,10 +781,131 @@ int oracle_vss_verify_deal(const uint8_t *commits32, int t, uint32_t idx, const 
     return pt_eq(&fig, &v);
 }
 
+/* ------------------------------------------------------------------ scalars used by the interpolation code */
+static const uint8_t SC_LM1[32] = {0xec, 0xd3, 0xf5, 0x5c, 0x1a, 0x63, 0x12, 0x58, 0xd6, 0x9c, 0xf7, 0xa2, 0xde, 0xf9, 0xde, 0x14, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10};   /* L - 1 */
+static const uint8_t SC_ZERO[32] = {0};
+static void sc_mul(uint8_t out[32], const uint8_t a[32], const uint8_t b[32]) { oracle_sc_muladd(out, a, b, SC_ZERO); }      /* scalar.rs:132 */
+static void sc_sub(uint8_t out[32], const uint8_t a[32], const uint8_t b[32]) { oracle_sc_muladd(out, SC_LM1, b, a); }        /* scalar.rs:162: a - b */
+/* Scalar::inv (scalar.rs:192-214): a^(L-2) by square-and-multiply */
+void oracle_sc_invert(uint8_t out[32], const uint8_t a[32])
+{
+    uint8_t e[32], r[32] = {1};
+    memcpy(e, SC_LM1, 32); e[0] -= 1;   /* L - 2 */
+    for (int i = 252; i >= 0; i--) {
+        sc_mul(r, r, r);
+        if ((e[i >> 3] >> (i & 7)) & 1) sc_mul(r, r, a);
+    }
+    memcpy(out, r, 32);
+}
+
+/* ------------------------------------------------------------------ rabin VSS, DSS, interpolation in the exponent */
+/* share/vss/rabin/vss.rs:889-900: f*G + g*H == eval(idx).  1 = verifies, 0 = does not, -1 = a point does not decode */
+int oracle_rabin_verify_deal(const uint8_t *commits32, int t, uint32_t idx, const uint8_t f[32], const uint8_t g[32], const uint8_t h32[32])
+{
+    oracle_init();
+    ge_p3 *c = (ge_p3 *)malloc(sizeof(ge_p3) * (size_t)t), v, fig, gih, H, ci;
+    for (int j = 0; j < t; j++) if (!ge_frombytes(&c[j], commits32 + 32 * j)) { free(c); return -1; }
+    if (!ge_frombytes(&H, h32)) { free(c); return -1; }
+    ge_scalarmult_base(&fig, f);
+    ge_scalarmult(&gih, g, &H);
+    pt_add(&ci, &fig, &gih);
+    pubpoly_eval_p3(&v, c, t, idx);
+    free(c);
+    return pt_eq(&ci, &v);
+}
+/* sign/dss/dss_sig.rs:263-273 with hash_sig :312-326: partial*B == random.eval(idx) + H(R || A || msg) * long.eval(idx) */
+int oracle_dss_partial_check(const uint8_t *rand32, const uint8_t *long32, int t, uint32_t idx, const uint8_t *msg, size_t mlen, const uint8_t partial[32], uint8_t hash_out[32])
+{
+    oracle_init();
+    ge_p3 *r = (ge_p3 *)malloc(sizeof(ge_p3) * (size_t)t), *l = (ge_p3 *)malloc(sizeof(ge_p3) * (size_t)t), rs, ls, right, left;
+    int ok = 1;
+    for (int j = 0; j < t; j++) if (!ge_frombytes(&r[j], rand32 + 32 * j) || !ge_frombytes(&l[j], long32 + 32 * j)) ok = 0;
+    if (!ok) { free(r); free(l); return -1; }
+    uint8_t rb[32], ab[32], h[32];
+    ge_p3_tobytes(rb, &r[0]); ge_p3_tobytes(ab, &l[0]);   /* marshal_to of the two free coefficients */
+    challenge(h, rb, ab, msg, mlen);
+    if (hash_out) memcpy(hash_out, h, 32);
+    pubpoly_eval_p3(&rs, r, t, idx);
+    pubpoly_eval_p3(&ls, l, t, idx);
+    ge_scalarmult(&right, h, &ls);
+    pt_add(&right, &rs, &right);
+    ge_scalarmult_base(&left, partial);
+    free(r); free(l);
+    return pt_eq(&left, &right);
+}
+/* recover_commit (share/poly.rs:566-603) on the k shares (idx[i], points[i]) already selected by xy_commit; 0 = a point does not decode */
+int oracle_recover_commit(uint8_t out[32], int k, const uint32_t *idx, const uint8_t *points32)
+{
+    oracle_init();
+    ge_p3 acc, P, tmp;
+    ge_p3_0(&acc);
+    for (int i = 0; i < k; i++) {
+        uint8_t num[32] = {1}, den[32] = {1}, xi[32], xj[32], d[32], inv[32];
+        sc_from_u64(xi, 1 + (uint64_t)idx[i]);
+        for (int j = 0; j < k; j++) {
+            if (j == i) continue;
+            sc_from_u64(xj, 1 + (uint64_t)idx[j]);
+            sc_mul(num, num, xj);
+            sc_sub(d, xj, xi);
+            sc_mul(den, den, d);
+        }
+        oracle_sc_invert(inv, den);
+        sc_mul(num, num, inv);                      /* num.div(num, den) */
+        if (!ge_frombytes(&P, points32 + 32 * i)) return 0;
+        ge_scalarmult(&tmp, num, &P);
+        pt_add(&acc, &acc, &tmp);
+    }
+    ge_p3_tobytes(out, &acc);
+    return 1;
+}
+/* recover_pub_poly (share/poly.rs:607-635) with lagrange_basis (:640-671): out = k encodings; 0 = a point does not decode */
+int oracle_recover_pub_poly(uint8_t *out, int k, const uint32_t *idx, const uint8_t *points32)
+{
+    oracle_init();
+    ge_p3 *acc = (ge_p3 *)malloc(sizeof(ge_p3) * (size_t)k), Y, tmp;
+    uint8_t *basis = (uint8_t *)malloc(32 * (size_t)(k + 1)), *next = (uint8_t *)malloc(32 * (size_t)(k + 1));
+    int ok = 1;
+    for (int j = 0; j < k && ok; j++) {
+        /* basis = prod_{m != j} (x - x_m), acc_s = prod 1 / (x_j - x_m) */
+        uint8_t xj[32], xm[32], d[32], accs[32] = {1};
+        int deg = 0;
+        memset(basis, 0, 32 * (size_t)(k + 1)); basis[0] = 1;
+        sc_from_u64(xj, 1 + (uint64_t)idx[j]);
+        for (int m = 0; m < k; m++) {
+            if (m == j) continue;
+            sc_from_u64(xm, 1 + (uint64_t)idx[m]);
+            uint8_t neg[32];
+            sc_sub(neg, SC_ZERO, xm);               /* minus_const: [-x_m, 1] */
+            memset(next, 0, 32 * (size_t)(k + 1));
+            for (int i = 0; i <= deg; i++) {
+                uint8_t p[32];
+                sc_mul(p, basis + 32 * i, neg);
+                oracle_sc_muladd(next + 32 * i, p, (const uint8_t[32]){1}, next + 32 * i);
+                oracle_sc_muladd(next + 32 * (i + 1), basis + 32 * i, (const uint8_t[32]){1}, next + 32 * (i + 1));
+            }
+            deg++;
+            memcpy(basis, next, 32 * (size_t)(k + 1));
+            sc_sub(d, xj, xm);
+            oracle_sc_invert(d, d);
+            sc_mul(accs, accs, d);
+        }
+        if (!ge_frombytes(&Y, points32 + 32 * j)) { ok = 0; break; }
+        for (int i = 0; i < k; i++) {
+            uint8_t c[32];
+            sc_mul(c, basis + 32 * i, accs);
+            ge_scalarmult(&tmp, c, &Y);              /* basis.commit(Some(y_j)) */
+            if (j == 0) acc[i] = tmp; else pt_add(&acc[i], &acc[i], &tmp);
+        }
+    }
+    if (ok) for (int i = 0; i < k; i++) ge_p3_tobytes(out + 32 * i, &acc[i]);
+    free(acc); free(basis); free(next);
+    return ok;
+}
+
 /* ------------------------------------------------------------------ threaded batch drivers (CPU baseline: one thread per core over disjoint index ranges) */
 typedef struct {
     int kind; size_t lo, hi;
-    const uint8_t *a, *b, *c; const uint64_t *off; const uint32_t *idx; uint8_t *out; int t;
+    const uint8_t *a, *b, *c, *h; const uint64_t *off; const uint32_t *idx; uint8_t *out; int t; size_t mlen;
 } job_t;
 
 static void *job_run(void *arg)
@@ -797,6 +918,8 @@ static void *job_run(void *arg)
         case 2: j->out[i] = (uint8_t)oracle_eddsa_verify(j->a + 32 * i, j->b + j->off[i], (size_t)(j->off[i + 1] - j->off[i]), j->c + 64 * i, 64); break;
         case 3: j->out[i] = (uint8_t)oracle_schnorr_verify(j->a + 32 * i, j->b + j->off[i], (size_t)(j->off[i + 1] - j->off[i]), j->c + 64 * i, 64); break;
         case 4: j->out[i] = (uint8_t)(oracle_vss_verify_deal(j->a, j->t, j->idx[i], j->b + 32 * i) == 1); break;
+        case 5: j->out[i] = (uint8_t)(oracle_rabin_verify_deal(j->a, j->t, j->idx[i], j->b + 32 * i, j->c + 32 * i, j->h) == 1); break;
+        case 6: j->out[i] = (uint8_t)(oracle_dss_partial_check(j->a, j->h, j->t, j->idx[i], j->c, j->mlen, j->b + 32 * i, NULL) == 1); break;
         }
     }
     return NULL;
@@ -826,6 +949,13 @@ void oracle_schnorr_verify_batch(size_t n, const uint8_t *pk, const uint8_t *msg
 /* one polynomial, m (idx, share) pairs */
 void oracle_vss_verify_batch(const uint8_t *commits32, int t, size_t m, const uint32_t *idx, const uint8_t *shares, uint8_t *verdict, int nthreads)
 { job_t p = {0}; p.kind = 4; p.a = commits32; p.t = t; p.idx = idx; p.b = shares; p.out = verdict; run_jobs(p, m, nthreads); }
+
+/* one rabin polynomial, m (idx, f share, g share) triples */
+void oracle_rabin_verify_batch(const uint8_t *commits32, int t, const uint8_t h32[32], size_t m, const uint32_t *idx, const uint8_t *f, const uint8_t *g, uint8_t *verdict, int nthreads)
+{ job_t p = {0}; p.kind = 5; p.a = commits32; p.t = t; p.idx = idx; p.b = f; p.c = g; p.h = h32; p.out = verdict; run_jobs(p, m, nthreads); }
+/* one DSS session, m (idx, partial) pairs */
+void oracle_dss_partial_batch(const uint8_t *rand32, const uint8_t *long32, int t, const uint8_t *msg, size_t mlen, size_t m, const uint32_t *idx, const uint8_t *partials, uint8_t *verdict, int nthreads)
+{ job_t p = {0}; p.kind = 6; p.a = rand32; p.h = long32; p.t = t; p.idx = idx; p.b = partials; p.c = msg; p.mlen = mlen; p.out = verdict; run_jobs(p, m, nthreads); }
 
 /* Sum_i Point::mul(s_i, P_i) folded with Point::add; returns 0 if a point fails to decode */
 int oracle_msm(uint8_t out[32], size_t n, const uint8_t *scalars, const uint8_t *points)

@@ -58,6 +58,12 @@ class COracle:
         L.oracle_mul_base_limbs.argtypes = [vp, u8p]
         L.oracle_limbs_tobytes.argtypes = [u8p, vp]
         L.oracle_point_limbs.argtypes = [vp, u8p]
+        L.oracle_sc_invert.argtypes = [u8p, u8p]
+        L.oracle_rabin_verify_batch.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
+        L.oracle_dss_partial_batch.argtypes = [vp, vp, ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
+        L.oracle_dss_partial_check.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_uint32, u8p, ctypes.c_size_t, u8p, u8p]
+        L.oracle_recover_commit.argtypes = [u8p, ctypes.c_int, vp, vp]
+        L.oracle_recover_pub_poly.argtypes = [vp, ctypes.c_int, vp, vp]
         L.oracle_init()
 
     # ---- single-item wrappers
@@ -172,6 +178,45 @@ class COracle:
         out = np.empty(idx.shape[0], dtype=np.uint8)
         self.L.oracle_vss_verify_batch(self._p(commits), commits.shape[0], idx.shape[0], self._p(idx), self._p(shares), self._p(out), nthreads)
         return out
+
+    def sc_invert(self, a):
+        out = ctypes.create_string_buffer(32)
+        self.L.oracle_sc_invert(out, a)
+        return out.raw
+
+    def rabin_verify_batch(self, commits, h_point, idx, f, g, nthreads=1):
+        commits = np.ascontiguousarray(commits, dtype=np.uint8)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        f, g = np.ascontiguousarray(f, dtype=np.uint8), np.ascontiguousarray(g, dtype=np.uint8)
+        out = np.empty(idx.shape[0], dtype=np.uint8)
+        self.L.oracle_rabin_verify_batch(self._p(commits), commits.shape[0], bytes(h_point), idx.shape[0], self._p(idx), self._p(f), self._p(g), self._p(out), nthreads)
+        return out
+
+    def dss_partial_batch(self, rand_commits, long_commits, msg, idx, partials, nthreads=1):
+        r, l = np.ascontiguousarray(rand_commits, dtype=np.uint8), np.ascontiguousarray(long_commits, dtype=np.uint8)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        p = np.ascontiguousarray(partials, dtype=np.uint8)
+        out = np.empty(idx.shape[0], dtype=np.uint8)
+        self.L.oracle_dss_partial_batch(self._p(r), self._p(l), r.shape[0], bytes(msg), len(msg), idx.shape[0], self._p(idx), self._p(p), self._p(out), nthreads)
+        return out
+
+    def dss_hash_sig(self, rand_commits, long_commits, msg):
+        r, l = np.ascontiguousarray(rand_commits, dtype=np.uint8), np.ascontiguousarray(long_commits, dtype=np.uint8)
+        h = ctypes.create_string_buffer(32)
+        self.L.oracle_dss_partial_check(r.tobytes(), l.tobytes(), r.shape[0], 0, bytes(msg), len(msg), bytes(32), h)
+        return h.raw
+
+    def recover_commit(self, idx, points):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        p = np.ascontiguousarray(points, dtype=np.uint8)
+        out = ctypes.create_string_buffer(32)
+        return out.raw if self.L.oracle_recover_commit(out, idx.shape[0], self._p(idx), self._p(p)) else None
+
+    def recover_pub_poly(self, idx, points):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        p = np.ascontiguousarray(points, dtype=np.uint8)
+        out = np.empty((idx.shape[0], 32), dtype=np.uint8)
+        return out if self.L.oracle_recover_pub_poly(self._p(out), idx.shape[0], self._p(idx), self._p(p)) else None
 
     def msm(self, scalars, points):
         scalars = np.ascontiguousarray(scalars, dtype=np.uint8)

@@ -588,12 +588,12 @@ def test_rabin_dss_and_signing_compositions(kb, ctx, coracle):
     # DSS: partial_i = r_i + hash * l_i verifies; a corrupted one does not (dss_test.rs)
     rp, lp = _poly(b"dss-r", t), _poly(b"dss-l", t)
     rc, lc = O.pripoly_commit(rp), O.pripoly_commit(lp)
-    hs = O.scalar_set_bytes(hashlib.sha512(b"msg").digest())
+    hs = O.dss_hash_sig(rc[0], lc[0], b"msg")                     # hash_sig (dss_sig.rs:312-326)
     parts = [O.sc_add(O.pripoly_eval(rp, i), O.sc_mul(hs, O.pripoly_eval(lp, i))) for i in range(n)]
     parts[7] = O.sc_add(parts[7], O.scalar_set_int64(2))
-    got = H.dss_verify_partials_batch([O.point_encode(c) for c in rc], [O.point_encode(c) for c in lc], range(n), parts, H.Scalar(hs))
+    got, hgot = H.dss_verify_partials_batch([O.point_encode(c) for c in rc], [O.point_encode(c) for c in lc], range(n), parts, b"msg")
     want = [O.dss_verify_partial(rc, lc, i, parts[i], hs) for i in range(n)]
-    assert got.astype(bool).tolist() == want and want.count(False) == 1
+    assert hgot.v == hs and got.astype(bool).tolist() == want and want.count(False) == 1
     # batched Schnorr signing: equals the oracle's signatures and verifies under BOTH verifiers
     priv = [O.scalar_set_bytes(hashlib.sha512(b"x%d" % i).digest()) for i in range(16)]
     nonce = [O.scalar_set_bytes(hashlib.sha512(b"k%d" % i).digest()) for i in range(16)]
@@ -754,7 +754,7 @@ def test_eddsa_sign_golden_file(kb, ctx, golden_records):
 
 def test_recover_commit_lagrange_msm(kb, ctx):
     """share/poly_test.rs recover tests (n = 10, t = 6 there; also a larger one): the secret commitment p(0) is
-    recovered from t public shares by Lagrange interpolation in the exponent — here ONE Pippenger MSM —
+    recovered from t public shares by Lagrange interpolation in the exponent — here one kb_recover_commit_batch call —
     and equals commit[0]; with fewer than t shares the reference's error is raised."""
     H = kb.host
     for n, t, seed in ((10, 6, b"rc1"), (40, 27, b"rc2")):

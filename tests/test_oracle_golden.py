@@ -4,6 +4,7 @@ CPU only."""
 import hashlib
 import os
 
+import numpy as np
 import pytest
 
 from oracle import ed25519_bigint as O
@@ -173,3 +174,73 @@ def test_pubpoly_eval_and_deal(golden_records, coracle):
     benc = [O.point_encode(c) for c in bad]
     for i in (1, 2, 6):
         assert coracle.pubpoly_eval(benc, i) == O.point_encode(O.pubpoly_eval(bad, i))
+
+
+def _share_setup(t, n, tag):
+    import hashlib
+
+    coeffs = [O.scalar_set_bytes(hashlib.sha512(b"%s/%d" % (tag, j)).digest()) for j in range(t)]
+    commits = O.pripoly_commit(coeffs)
+    shares = [O.pripoly_eval(coeffs, i) for i in range(n)]
+    return coeffs, commits, shares
+
+
+def test_interpolation_oracles(coracle):
+    """recover_commit / recover_pub_poly (share/poly.rs:566-635) have no known answers in the reference; the two
+    restatements (C: the reference's operation sequence on ref10 limbs; Python: big integers) must agree with each
+    other AND with what interpolation has to return: the commitment of the secret, resp. the commitments themselves."""
+    t, n = 5, 9
+    coeffs, commits, shares = _share_setup(t, n, b"interp")
+    for pick in ([0, 1, 2, 3, 4], [8, 2, 5, 3, 0], [4, 5, 6, 7, 8]):
+        pub = [(i, O.point_mul(shares[i])) for i in pick]
+        enc = np.frombuffer(b"".join(O.point_encode(p) for _, p in pub), dtype=np.uint8).reshape(-1, 32)
+        want = O.point_encode(commits[0])
+        assert O.point_encode(O.recover_commit(pub)) == want
+        assert coracle.recover_commit(pick, enc) == want
+        got = coracle.recover_pub_poly(pick, enc)
+        assert [g.tobytes() for g in got] == [O.point_encode(c) for c in commits]
+        assert [O.point_encode(c) for c in O.recover_pub_poly(pub)] == [O.point_encode(c) for c in commits]
+    a = bytes(range(1, 33))
+    assert O.sc_mul(coracle.sc_invert(a), O.scalar_set_bytes(a)) == (1).to_bytes(32, "little")
+
+
+def test_rabin_and_dss_oracles(coracle):
+    """vss::rabin verify_deal (rabin/vss.rs:889-900) and DSS::process_partial_sig (dss_sig.rs:263-273): C and Python
+    restatements agree, honest inputs verify, corrupted ones do not."""
+    t, n = 4, 6
+    fc, fcom, fsh = _share_setup(t, n, b"rabin-f")
+    gc, gcom, gsh = _share_setup(t, n, b"rabin-g")
+    H = O.point_mul(bytes(range(7, 39)))
+    commits = [O.point_add(a, O.point_mul(g, H)) for a, g in zip(fcom, gc)]     # f_j*G + g_j*H
+    enc = np.frombuffer(b"".join(O.point_encode(c) for c in commits), dtype=np.uint8).reshape(-1, 32)
+    f = np.frombuffer(b"".join(fsh), dtype=np.uint8).reshape(-1, 32).copy()
+    g = np.frombuffer(b"".join(gsh), dtype=np.uint8).reshape(-1, 32).copy()
+    g[3, 0] ^= 1
+    got = coracle.rabin_verify_batch(enc, O.point_encode(H), np.arange(n), f, g, nthreads=2)
+    want = [O.vss_rabin_verify_deal(commits, i, f[i].tobytes(), g[i].tobytes(), H) for i in range(n)]
+    assert got.tolist() == [int(w) for w in want] == [1, 1, 1, 0, 1, 1]
+    # DSS: partial_i = r_i + hash * l_i
+    rc, rcom, rsh = _share_setup(t, n, b"dss-r")
+    lc, lcom, lsh = _share_setup(t, n, b"dss-l")
+    msg = b"dss message"
+    renc = np.frombuffer(b"".join(O.point_encode(c) for c in rcom), dtype=np.uint8).reshape(-1, 32)
+    lenc = np.frombuffer(b"".join(O.point_encode(c) for c in lcom), dtype=np.uint8).reshape(-1, 32)
+    h = O.dss_hash_sig(rcom[0], lcom[0], msg)
+    assert coracle.dss_hash_sig(renc, lenc, msg) == h
+    partials = np.frombuffer(b"".join(O.sc_add(rsh[i], O.sc_mul(h, lsh[i])) for i in range(n)), dtype=np.uint8).reshape(-1, 32).copy()
+    partials[1, 5] ^= 8
+    got = coracle.dss_partial_batch(renc, lenc, msg, np.arange(n), partials, nthreads=2)
+    want = [O.dss_verify_partial(rcom, lcom, i, partials[i].tobytes(), h) for i in range(n)]
+    assert got.tolist() == [int(w) for w in want] == [1, 0, 1, 1, 1, 1]
+
+
+def test_session_id_and_find_pub_oracle():
+    """session_id (vss/pedersen/vss.rs:1069-1090) is SHA-256 over canonical encodings; a non-canonical input encoding
+    (y >= p) of the same point gives the same id because marshal_to re-encodes."""
+    import hashlib
+
+    pts = [O.point_mul(bytes([k + 1]) + bytes(31)) for k in range(6)]
+    sid = O.session_id(pts[0], pts[1:4], pts[4:6], 2)
+    want = hashlib.sha256(b"".join(O.point_encode(p) for p in pts) + (2).to_bytes(4, "little")).digest()
+    assert sid == want
+    assert O.find_pub(pts, pts[3]) == (3, True) and O.find_pub(pts[:3], pts[4]) == (0, False)
