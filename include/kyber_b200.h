@@ -49,6 +49,7 @@ typedef enum kb_err {
     KB_ERR_ARG = -1,   /* null pointer / bad size / bad flag */
     KB_ERR_CUDA = -2,  /* CUDA runtime error; kb_last_error() has the text */
     KB_ERR_NOMEM = -3,
+    KB_ERR_NCCL = -4   /* NCCL could not be loaded or failed (multi-device context only) */
 } kb_err;
 
 /* Per-signature outcome; mirrors SignatureError (sign/error.rs:6-25) in the order the
@@ -242,6 +243,37 @@ int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_o
 int kb_dev_dkg_process_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, int fmt, const void* d_commits, const void* d_shares, void* d_verdict,
                              const void* d_deal_pk, const void* d_deal_msg, const void* d_deal_msg_off, const void* d_deal_sig, void* d_deal_status,
                              const void* d_resp_pk, const void* d_resp_msg, const void* d_resp_msg_off, const void* d_resp_sig, void* d_resp_status, void* stream);
+
+/* ---- multi-device context: ONE host batch sharded over the GPUs of a box, from one process ---------------------------
+ * (SURVEY §8b/§8e).  kb_mctx_create builds one kb_ctx per listed device and, for more than one device, an NCCL communicator
+ * over them (libnccl.so.2 is bound at run time; KB_NCCL_LIB overrides the name).  Every call takes ordinary HOST buffers
+ * holding the WHOLE batch and returns the WHOLE result:
+ *   signatures, scalar multiplications   split by index      — no exchange between devices
+ *   DKG rounds                           split by dealer     — no exchange between devices
+ *   MSM                                  split by points     — each device reduces its points to one 128-byte partial,
+ *                                        ncclAllGather of the partials over NVLink, every device folds them (the only
+ *                                        data-path collective there is)
+ * One host thread per device drives it, so the shards' copies run concurrently.  A kb_mctx is not thread-safe. */
+#define KB_MAX_DEVICES 16
+typedef struct kb_mctx kb_mctx;
+int kb_mctx_create(const int* devices, int ndev, kb_mctx** out);
+void kb_mctx_destroy(kb_mctx* m);
+int kb_mctx_device_count(const kb_mctx* m);
+kb_ctx* kb_mctx_ctx(kb_mctx* m, int i);   /* the single-device context of the i-th device (owned by m) */
+const char* kb_mctx_last_error(const kb_mctx* m);
+uint64_t kb_mctx_launch_count(const kb_mctx* m);
+/* kb_eddsa_verify_batch / kb_schnorr_verify_batch (schnorr != 0) over all devices */
+int kb_mctx_verify_batch(kb_mctx* m, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr);
+int kb_mctx_point_mul_base_batch(kb_mctx* m, size_t n, const uint8_t* scalars, uint8_t* out, uint32_t flags);
+int kb_mctx_point_mul_batch(kb_mctx* m, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out, uint8_t* status, uint32_t flags);
+/* kb_dkg_verify_round / kb_dkg_process_round for ndealers dealers (all arrays whole: commitments and shares by dealer,
+ * the signature arrays with one item per (dealer, verifier), k = d*n + i) */
+int kb_mctx_dkg_verify_round(kb_mctx* m, size_t n, size_t t, size_t ndealers, int fmt, const void* commits, const uint8_t* shares, uint8_t* verdict);
+int kb_mctx_dkg_process_round(kb_mctx* m, size_t n, size_t t, size_t ndealers, int fmt, const void* commits, const uint8_t* shares, uint8_t* verdict,
+                              const uint8_t* deal_pk, const uint8_t* deal_msg, const uint64_t* deal_msg_off, const uint8_t* deal_sig, uint8_t* deal_status,
+                              const uint8_t* resp_pk, const uint8_t* resp_msg, const uint64_t* resp_msg_off, const uint8_t* resp_sig, uint8_t* resp_status);
+/* kb_msm over all devices */
+int kb_mctx_msm(kb_mctx* m, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out32, uint64_t* bad_points);
 
 /* ---- measurement ---------------------------------------------------------------------- */
 /* Integer-multiply roofline probe: runs `iters` dependent-chain-free IMAD.WIDE.U32 per thread

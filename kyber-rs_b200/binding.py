@@ -40,6 +40,8 @@ EXPORTS = [
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_dkg_verify_round_limbs", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
     "kb_vss_session_ids", "kb_find_pub_batch", "kb_dkg_process_round", "kb_vss_rabin_verify_deals_batch", "kb_dss_verify_partials", "kb_recover_commit_batch", "kb_recover_pub_poly", "kb_dkg_resharing_key",
     "kb_dev_dkg_process_round",
+    "kb_mctx_create", "kb_mctx_destroy", "kb_mctx_device_count", "kb_mctx_ctx", "kb_mctx_last_error", "kb_mctx_launch_count", "kb_mctx_verify_batch", "kb_mctx_point_mul_base_batch", "kb_mctx_point_mul_batch",
+    "kb_mctx_dkg_verify_round", "kb_mctx_dkg_process_round", "kb_mctx_msm",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_dkg_verify_round_limbs", "kb_dev_point_sum",
     "kb_probe_imad", "kb_verify_kernel_times",
 ]
@@ -106,6 +108,22 @@ def load_library(path: str = LIB_PATH):
     L.kb_dev_dkg_verify_round.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_dkg_verify_round_limbs.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_point_sum.argtypes = [vp, sz, vp, vp, vp]
+    L.kb_mctx_create.argtypes = [ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+    L.kb_mctx_destroy.argtypes = [vp]
+    L.kb_mctx_destroy.restype = None
+    L.kb_mctx_device_count.argtypes = [vp]
+    L.kb_mctx_ctx.argtypes = [vp, i32]
+    L.kb_mctx_ctx.restype = vp
+    L.kb_mctx_last_error.argtypes = [vp]
+    L.kb_mctx_last_error.restype = ctypes.c_char_p
+    L.kb_mctx_launch_count.argtypes = [vp]
+    L.kb_mctx_launch_count.restype = ctypes.c_uint64
+    L.kb_mctx_verify_batch.argtypes = [vp, sz, vp, vp, vp, vp, vp, i32]
+    L.kb_mctx_point_mul_base_batch.argtypes = [vp, sz, vp, vp, u32]
+    L.kb_mctx_point_mul_batch.argtypes = [vp, sz, vp, vp, vp, vp, u32]
+    L.kb_mctx_dkg_verify_round.argtypes = [vp, sz, sz, sz, i32, vp, vp, vp]
+    L.kb_mctx_dkg_process_round.argtypes = [vp, sz, sz, sz, i32, vp, vp, vp] + [vp] * 10
+    L.kb_mctx_msm.argtypes = [vp, sz, vp, vp, vp, vp]
     L.kb_probe_imad.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.kb_verify_kernel_times.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
     _LIB = L
@@ -527,3 +545,97 @@ class Context:
 
     def dev_point_sum(self, k, partials, out32):
         self._check(self.L.kb_dev_point_sum(self.h, k, self._dp(partials), self._dp(out32), self._stream()), "kb_dev_point_sum")
+
+
+class MultiContext:
+    """One kb_mctx: the GPUs `devices` of this box driven from one process; every call takes the whole host batch."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        devs = (ctypes.c_int * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        rc = self.L.kb_mctx_create(devs, len(devices), ctypes.byref(h))
+        if rc != 0:
+            raise KBError(f"kb_mctx_create({list(devices)}) failed with {rc} (-2: no usable CUDA device, -4: NCCL); there is no CPU fallback")
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kb_mctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise KBError(f"{what} failed with {rc}: {self.L.kb_mctx_last_error(self.h).decode(errors='replace')}")
+
+    @property
+    def launches(self):
+        return int(self.L.kb_mctx_launch_count(self.h))
+
+    def verify_batch(self, pk, msg, msg_off, sig, schnorr=False, out=None):
+        pk, sig = _u8(pk, (-1, 32)), _u8(sig, (-1, 64))
+        msg = _u8(msg)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        n = pk.shape[0]
+        assert sig.shape[0] == n and msg_off.shape[0] == n + 1
+        st = out if out is not None else np.empty(n, dtype=np.uint8)
+        self._check(self.L.kb_mctx_verify_batch(self.h, n, _ptr(pk), _ptr(msg), _ptr(msg_off), _ptr(sig), _ptr(st), int(schnorr)), "kb_mctx_verify_batch")
+        return st
+
+    def point_mul_base_batch(self, scalars, flags=0):
+        s = _u8(scalars, (-1, 32))
+        out = np.empty_like(s)
+        self._check(self.L.kb_mctx_point_mul_base_batch(self.h, s.shape[0], _ptr(s), _ptr(out), flags), "kb_mctx_point_mul_base_batch")
+        return out
+
+    def point_mul_batch(self, scalars, points, flags=0):
+        s, p = _u8(scalars, (-1, 32)), _u8(points, (-1, 32))
+        if p.shape[0] == 1 and s.shape[0] != 1:
+            flags |= FLAG_SHARED_POINT
+        out = np.empty_like(s)
+        st = np.empty(s.shape[0], dtype=np.uint8)
+        self._check(self.L.kb_mctx_point_mul_batch(self.h, s.shape[0], _ptr(s), _ptr(p), _ptr(out), _ptr(st), flags), "kb_mctx_point_mul_batch")
+        return out, st
+
+    def dkg_process_round(self, n, t, commits, shares, deal=None, resp=None, limbs=False, verdict=None):
+        c = Context._points(commits, limbs)
+        sh = _u8(shares, (-1, 32))
+        ndealers = c.shape[0] // t
+        if ndealers * t != c.shape[0] or sh.shape[0] != ndealers * n:
+            raise ValueError("dkg_process_round: inconsistent shapes")
+        m = ndealers * n
+        if verdict is None:
+            verdict = np.zeros(m, dtype=np.uint8)
+        args, outs, keep = [], [], []
+        for batch in (deal, resp):
+            if batch is None:
+                args += [None] * 5
+                outs.append(None)
+                continue
+            pk, msg, off, sig = _u8(batch[0], (-1, 32)), _u8(batch[1]), np.ascontiguousarray(batch[2], dtype=np.uint64), _u8(batch[3], (-1, 64))
+            if pk.shape[0] != m or sig.shape[0] != m or off.shape[0] != m + 1:
+                raise ValueError("dkg_process_round: a signature batch must hold one item per (dealer, verifier)")
+            st = np.empty(m, dtype=np.uint8)
+            keep += [pk, msg, off, sig]
+            args += [_ptr(pk), _ptr(msg), _ptr(off), _ptr(sig), _ptr(st)]
+            outs.append(st)
+        self._check(self.L.kb_mctx_dkg_process_round(self.h, n, t, ndealers, int(limbs), _ptr(c), _ptr(sh), _ptr(verdict), *args), "kb_mctx_dkg_process_round")
+        return verdict, outs[0], outs[1]
+
+    def dkg_verify_round(self, n, t, commits, shares, limbs=False, verdict=None):
+        return self.dkg_process_round(n, t, commits, shares, limbs=limbs, verdict=verdict)[0]
+
+    def msm(self, scalars, points):
+        s, p = _u8(scalars, (-1, 32)), _u8(points, (-1, 32))
+        assert s.shape == p.shape
+        out = np.empty(32, dtype=np.uint8)
+        bad = np.zeros(1, dtype=np.uint64)
+        self._check(self.L.kb_mctx_msm(self.h, s.shape[0], _ptr(s), _ptr(p), _ptr(out), _ptr(bad)), "kb_mctx_msm")
+        return out.tobytes(), int(bad[0])

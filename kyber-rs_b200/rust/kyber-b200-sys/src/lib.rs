@@ -9,7 +9,13 @@ pub struct kb_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+pub struct kb_mctx {
+    _private: [u8; 0],
+}
+
 pub const KB_OK: c_int = 0;
+pub const KB_ERR_NCCL: c_int = -4;
 pub const KB_ERR_ARG: c_int = -1;
 pub const KB_ERR_CUDA: c_int = -2;
 pub const KB_ERR_NOMEM: c_int = -3;
@@ -79,6 +85,22 @@ extern "C" {
     pub fn kb_dev_dkg_verify_round(ctx: *mut kb_ctx, n: usize, t: usize, ndealers: usize, d_commits: *const c_void, d_shares: *const c_void, d_verdict: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn kb_dev_dkg_verify_round_limbs(ctx: *mut kb_ctx, n: usize, t: usize, ndealers: usize, d_commit_limbs: *const c_void, d_shares: *const c_void, d_verdict: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn kb_dev_point_sum(ctx: *mut kb_ctx, k: usize, d_partials128: *const c_void, d_out32: *mut c_void, stream: *mut c_void) -> c_int;
+
+    // multi-device context
+    pub fn kb_mctx_create(devices: *const c_int, ndev: c_int, out: *mut *mut kb_mctx) -> c_int;
+    pub fn kb_mctx_destroy(m: *mut kb_mctx);
+    pub fn kb_mctx_device_count(m: *const kb_mctx) -> c_int;
+    pub fn kb_mctx_ctx(m: *mut kb_mctx, i: c_int) -> *mut kb_ctx;
+    pub fn kb_mctx_last_error(m: *const kb_mctx) -> *const c_char;
+    pub fn kb_mctx_launch_count(m: *const kb_mctx) -> u64;
+    pub fn kb_mctx_verify_batch(m: *mut kb_mctx, n: usize, pk: *const u8, msg: *const u8, msg_off: *const u64, sig: *const u8, status: *mut u8, schnorr: c_int) -> c_int;
+    pub fn kb_mctx_point_mul_base_batch(m: *mut kb_mctx, n: usize, scalars: *const u8, out: *mut u8, flags: u32) -> c_int;
+    pub fn kb_mctx_point_mul_batch(m: *mut kb_mctx, n: usize, scalars: *const u8, points: *const u8, out: *mut u8, status: *mut u8, flags: u32) -> c_int;
+    pub fn kb_mctx_dkg_verify_round(m: *mut kb_mctx, n: usize, t: usize, ndealers: usize, fmt: c_int, commits: *const c_void, shares: *const u8, verdict: *mut u8) -> c_int;
+    pub fn kb_mctx_dkg_process_round(m: *mut kb_mctx, n: usize, t: usize, ndealers: usize, fmt: c_int, commits: *const c_void, shares: *const u8, verdict: *mut u8,
+        deal_pk: *const u8, deal_msg: *const u8, deal_msg_off: *const u64, deal_sig: *const u8, deal_status: *mut u8,
+        resp_pk: *const u8, resp_msg: *const u8, resp_msg_off: *const u64, resp_sig: *const u8, resp_status: *mut u8) -> c_int;
+    pub fn kb_mctx_msm(m: *mut kb_mctx, n: usize, scalars: *const u8, points: *const u8, out32: *mut u8, bad_points: *mut u64) -> c_int;
 
     pub fn kb_probe_imad(ctx: *mut kb_ctx, kind: c_int, iters: c_int, macs_per_sec: *mut c_double, elapsed_ms: *mut c_double) -> c_int;
     pub fn kb_verify_kernel_times(ctx: *mut kb_ctx, enable: c_int, ms_out: *mut f32) -> c_int;
