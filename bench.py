@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the edwards25519 hot path (BASELINE.json metric).
+"""bench.py — benchmark of the edwards25519 hot path (BASELINE.json metric), with parity checks in the code path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 20]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 20] [--no-extras]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[1] — batched EdDSA verification
-(eddsa::verify_with_checks, sign/eddsa/eddsa_sig.rs:159-212) of 2^20 random keys / 64-byte
-messages / signatures per GPU, including the per-signature SHA-512 challenge; 1/64 of the items
-are deliberately invalid.  A "step" is one pass over that batch.  Weak scaling: every rank owns
-its own 2^20 signatures (independent shards, no data-path collective).
+Headline (config.workload): BASELINE.json configs[1] — batched EdDSA verification
+(eddsa::verify_with_checks, sign/eddsa/eddsa_sig.rs:159-212) of 2^20 random keys / 64-byte messages / signatures
+per GPU, including the per-signature SHA-512 challenge; 1/64 of the items are deliberately invalid (nine classes).
+A "step" is one pass over that batch.  One process per GPU; every rank owns its own 2^20 signatures (weak scaling,
+independent shards, no data-path collective).
 
-  value     verified signatures / s, inputs resident in HBM (CUDA events on the launch stream)
-  e2e       same metric through the host-buffer C-ABI call (pinned host buffers; H2D + D2H inside)
-  roofline  integer-multiply roofline of the verify step (k_verify_half_prep + k_verify_half_main):
-            154 k IMAD-eq CHARGED per signature / measured time, against the IMAD.WIDE peak
-            measured live by kb_probe_imad; the two kernels are also timed one by one (CUDA events on the
-            launch stream, recorded inside the library around each launch)
-  cpu_baseline  the oracle's ref10-style C port (oracle/ref10_port.c) on the host cores
+  value         verified signatures / s, inputs resident in HBM (CUDA events on the launch stream), all ranks
+  e2e           the same metric from HOST buffers through the C ABI's multi-device context (kb_mctx_verify_batch):
+                rank 0 hands ONE batch of N x 2^20 signatures to all N GPUs (H2D + D2H inside the timed region)
+  roofline      integer-multiply roofline of the verify step, 154 k IMAD-eq CHARGED per signature, against
+                the ARCHITECTURAL IMAD.WIDE rate 32 lanes x SMs x clock (kb_probe_imad's streams are reported next to it)
+  cpu_baseline  the oracle's ref10-style C port (oracle/ref10_port.c) on the host cores, on a prefix of the same batch
+  configs       BASELINE configs 1, 3, 4, 5 as first-class entries: value, roofline, e2e, cpu_baseline (N = 1), with the
+                STRONG-scaling shapes (cfg4: the fixed n = 1024 round split by dealer; cfg5: 2^16..2^26 TOTAL points)
+  stages        the pure decompress and hash stages: achieved HBM GB/s
+  parity_checked what was compared with the oracle / with expected verdicts inside this very run (any mismatch exits non-zero)
 
---impl reference times that same CPU port on all host cores (the reference is Rust; no Rust
-toolchain exists in this image).
+--impl reference times the CPU port on all host cores on a prefix of the SAME batch (the reference is Rust; there is no
+Rust toolchain in this image).
 """
 import argparse
 import importlib
@@ -36,17 +40,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-IMAD_EQ_PER_VERIFY = 154_000      # A decompress + Straus s*B - h*A + compress, M=72 S=44 (the CHARGED figure)
-# what the half-size-scalar kernels execute per signature (IMAD.WIDE, M=73 S=44):
-EXEC_PREP_PER_VERIFY = 25_600     # two decompressions (2 x (251+4 S + 22 M))
-EXEC_MAIN_PER_VERIFY = 110_000    # 128 doublings, 66 + 20 additions, two 8-entry tables
+# ---- algorithmic work per unit, SURVEY §8(d): M = 72, S = 44 IMAD-eq -------------------------------------------------
+IMAD_EQ_PER_VERIFY = 154_000      # A decompress + Straus s*B - h*A + compress (the CHARGED figure)
+IMAD_EQ_PER_BASE_MUL = 32_500
+IMAD_EQ_PER_VAR_MUL = 138_300
+IMAD_EQ_PER_EVAL_COEFF = 6_800    # PubPoly::eval per coefficient (x <= 1024)
 IMAD_EQ_PER_MSM_POINT = 20_700
+IMAD_EQ_PER_DECOMPRESS = 20 * 72 + 255 * 44
+# what the half-size-scalar kernels execute per signature (IMAD.WIDE, M = 73, S = 44):
+EXEC_PREP_PER_VERIFY = 25_600
+EXEC_MAIN_PER_VERIFY = 110_000
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
-# dram__bytes_read.sum + dram__bytes_write.sum at 2^20 signatures, ncu --set full (profiles/r1_ncu_k_verify_half.txt)
-VERIFY_DRAM_BYTES_2P20 = {"k_verify_half_prep": 197_734_000 + 313_023_000, "k_verify_half_main": 15_152_038_000 + 2_182_434_000}
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
 NONCANON = bytes([0xEF]) + b"\xff" * 31
+T8 = bytes.fromhex("26e8958fc2b227b045c3f489f2ef98f0d5dfac05d3c63339b13802886d53fc05")   # a point of order 8
+OFF_CURVE = bytes.fromhex("02" + "00" * 31)     # y = 2: (y^2 - 1) / (d y^2 + 1) is not a square (checked against the oracle below)
+INVALID_CLASSES = 9
+
+
+def a1_range(i: int) -> bytes:
+    """A canonical y that Point::is_canonical reports non-canonical (SURVEY §A1): low byte in [0x14, 0xEC]."""
+    return bytes([0x14 + (i % 0xD9)]) + b"\xff" * 30 + b"\x7f"
 
 
 def xof(seed: str, n: int) -> np.ndarray:
@@ -62,10 +77,9 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def make_batch(ctx, n: int, rank: int):
-    """Synthetic signatures, generated WITH the library's own batched primitives (fixed-base mul,
-    challenge hash, sc_mul_add — the signing equations of schnorr_sig.rs:25-47) and then spot-checked
-    against the oracle by the caller.  Returns numpy arrays + the statuses expected by construction."""
+# ---- the cfg2 batch: identical items for both arms --------------------------------------------------------------------
+def batch_secrets(n: int, rank: int):
+    """Keys, nonces and messages of batch `rank` (BLAKE3-XOF of an ASCII seed, the reference's suite.xof construction)."""
     tag = f"kyber-b200/cfg2/rank{rank}"
     a = xof(tag + "/keys", 32 * n).reshape(n, 32).copy()
     a[:, 0] &= 0xF8
@@ -74,29 +88,64 @@ def make_batch(ctx, n: int, rank: int):
     r = xof(tag + "/nonces", 32 * n).reshape(n, 32).copy()
     r[:, 31] &= 0x0F                        # < 2^252 < L
     msg = xof(tag + "/msgs", 64 * n).copy()
+    return a, r, msg
+
+
+def spoil(pk, msg, sig, lo: int, hi: int):
+    """Every 64th item of [lo, hi) is made invalid, cycling through nine classes; returns the statuses expected by
+    construction (the reference's check order, eddsa_sig.rs:159-212)."""
+    expect = np.zeros(hi - lo, dtype=np.uint8)
+    for i in range(lo + ((63 - lo) % 64), hi, 64):
+        k, j = (i // 64) % INVALID_CLASSES, i - lo
+        if k == 0:
+            msg[64 * j] ^= 1; expect[j] = 8                                  # flipped message bit -> InvalidSignature
+        elif k == 1:
+            v = (int.from_bytes(sig[j, 32:].tobytes(), "little") + L_ORDER) % (1 << 256)
+            sig[j, 32:] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8); expect[j] = 2   # s + L
+        elif k == 2:
+            sig[j, :32] = np.frombuffer(NONCANON, dtype=np.uint8); expect[j] = 3
+        elif k == 3:
+            sig[j, :32] = np.frombuffer(WEAK_R, dtype=np.uint8); expect[j] = 4
+        elif k == 4:
+            pk[j] = np.frombuffer(WEAK_R, dtype=np.uint8); expect[j] = 6
+        elif k == 5:
+            pk[j] = np.frombuffer(NONCANON, dtype=np.uint8); expect[j] = 5
+        elif k == 6:
+            sig[j, :32] = np.frombuffer(OFF_CURVE, dtype=np.uint8); expect[j] = 7      # R is not a curve point -> MarshallingError
+        elif k == 7:
+            sig[j, :32] = np.frombuffer(a1_range(i), dtype=np.uint8); expect[j] = 3    # §A1 quirk range in R
+        else:
+            pk[j] = np.frombuffer(a1_range(i), dtype=np.uint8); expect[j] = 5          # §A1 quirk range in the key
+    return expect
+
+
+def make_batch(ctx, n: int, rank: int):
+    """Synthetic signatures, signed WITH the library's own batched primitives (fixed-base mul, challenge hash,
+    sc_mul_add — the signing equations of schnorr_sig.rs:25-47); spot-checked against the oracle by the caller."""
+    a, r, msg = batch_secrets(n, rank)
     off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(64))
     pk = ctx.point_mul_base_batch(a)
     R = ctx.point_mul_base_batch(r)
     h = ctx.challenge_batch(R, pk, msg, off)
     s = ctx.sc_muladd_batch(h, a, r)
     sig = np.concatenate([R, s], axis=1)
-    expect = np.zeros(n, dtype=np.uint8)
-    bad = np.arange(63, n, 64)
-    for j, i in enumerate(bad):
-        k = j % 6
-        if k == 0:
-            msg[64 * i] ^= 1; expect[i] = 8
-        elif k == 1:
-            v = (int.from_bytes(sig[i, 32:].tobytes(), "little") + L_ORDER) % (1 << 256)
-            sig[i, 32:] = np.frombuffer(v.to_bytes(32, "little"), dtype=np.uint8); expect[i] = 2
-        elif k == 2:
-            sig[i, :32] = np.frombuffer(NONCANON, dtype=np.uint8); expect[i] = 3
-        elif k == 3:
-            sig[i, :32] = np.frombuffer(WEAK_R, dtype=np.uint8); expect[i] = 4
-        elif k == 4:
-            pk[i] = np.frombuffer(WEAK_R, dtype=np.uint8); expect[i] = 6
-        else:
-            pk[i] = np.frombuffer(NONCANON, dtype=np.uint8); expect[i] = 5
+    expect = spoil(pk, msg, sig, 0, n)
+    return pk, msg, off, sig, expect
+
+
+def make_batch_cpu(C, m: int, rank: int, n_full: int, threads: int):
+    """The first m items of the SAME batch, signed with the oracle (no GPU involved): what the reference arm verifies."""
+    a, r, msg = batch_secrets(n_full, rank)
+    a, r, msg = a[:m], r[:m], msg[:64 * m].copy()
+    off = (np.arange(m + 1, dtype=np.uint64) * np.uint64(64))
+    pk = C.mul_base_batch(a, nthreads=threads)
+    R = C.mul_base_batch(r, nthreads=threads)
+    sig = np.empty((m, 64), dtype=np.uint8)
+    sig[:, :32] = R
+    for i in range(m):
+        h = C.sc_reduce64(C.sha512(R[i].tobytes() + pk[i].tobytes() + msg[64 * i:64 * i + 64].tobytes()))
+        sig[i, 32:] = np.frombuffer(C.sc_muladd(h, a[i].tobytes(), r[i].tobytes()), dtype=np.uint8)
+    expect = spoil(pk, msg, sig, 0, m)
     return pk, msg, off, sig, expect
 
 
@@ -143,21 +192,26 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(C, pk, msg, off, sig, gpu_status, budget_s: float, threads: int):
-    """Times the oracle's C port on a bounded sample (adaptive: ~budget_s of CPU work) and checks the
-    GPU statuses of that sample against it."""
+def die(msg: str):
+    sys.stderr.write("bench: PARITY FAILURE: " + msg + "\n")
+    sys.stderr.flush()
+    os._exit(3)     # non-zero for the driver; os._exit so that no other rank's barrier can hang the exit
+
+
+def cpu_verify_baseline(C, pk, msg, off, sig, gpu_status, budget_s: float, threads: int):
+    """Times the oracle's C port on a bounded prefix (adaptive: ~budget_s of CPU work) and checks the GPU statuses of
+    that prefix against it."""
     probe = 256
     t0 = time.perf_counter()
-    st = C.verify_batch(pk[:probe], msg[: 64 * probe], off[: probe + 1], sig[:probe], nthreads=threads)
-    dt = time.perf_counter() - t0
-    rate = probe / dt
+    C.verify_batch(pk[:probe], msg[: 64 * probe], off[: probe + 1], sig[:probe], nthreads=threads)
+    rate = probe / (time.perf_counter() - t0)
     m = int(min(pk.shape[0], max(probe, rate * budget_s)))
     m -= m % 64
     t0 = time.perf_counter()
     st = C.verify_batch(pk[:m], msg[: 64 * m], off[: m + 1], sig[:m], nthreads=threads)
     dt = time.perf_counter() - t0
     if gpu_status is not None and not (st == gpu_status[:m]).all():
-        raise SystemExit("bench: GPU statuses differ from the oracle on the CPU-baseline sample")
+        die("GPU statuses differ from the oracle on the CPU-baseline prefix")
     sodium = None
     try:  # independent sanity anchor (SURVEY 8d): libsodium's own verifier, one core, same signatures
         import nacl.bindings as nb
@@ -173,57 +227,45 @@ def cpu_baseline(C, pk, msg, off, sig, gpu_status, budget_s: float, threads: int
     except Exception:  # pragma: no cover - optional
         pass
     return {"value": m / dt, "unit": "sigs/s", "cores": threads, "kind": "port", "libsodium_single_core_sigs_per_s": sodium,
-            "sample": f"first {m} of the 2^20 signatures of the same batch, oracle/ref10_port.c (ref10-style C restatement of the Rust path; no Rust toolchain in this image), {dt:.1f} s"}
+            "libsodium_all_cores_equivalent_sigs_per_s": sodium * threads if sodium else None,
+            "sample": f"first {m} of the 2^20 signatures of the same batch, oracle/ref10_port.c (ref10-style C restatement of the Rust path; no Rust toolchain in this image), {dt:.1f} s",
+            "checked_items": m}
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU port of the reference's algorithm on all host cores, on a prefix of the SAME batch
+    the GPU arm verifies (same seeds, same invalid mix), each step a bounded sample."""
     if rank != 0:
         return
     from helpers import load_c_oracle
 
     C = load_c_oracle()
     threads = host_cores()
-    # the reference arm needs signatures but must not depend on the GPU: sign with the oracle-independent
-    # libsodium if present, else reuse the golden file
-    from helpers import load_sign_input, make_sig_batch, pack_batch
-
-    NREF = 16384   # signatures available to the reference arm; a step verifies a bounded slice of them
-    pks, msgs, sigs = [], [], []
-    try:  # random keys / 64-byte messages signed by libsodium (independent of both the GPU path and the oracle)
-        import nacl.signing
-
-        seeds = xof("kyber-b200/cfg2/reference-arm/seeds", 32 * NREF).reshape(-1, 32)
-        body = xof("kyber-b200/cfg2/reference-arm/msgs", 64 * NREF).reshape(-1, 64)
-        for i in range(NREF):
-            sk = nacl.signing.SigningKey(seeds[i].tobytes())
-            m = body[i].tobytes()
-            pks.append(bytes(sk.verify_key)); msgs.append(m); sigs.append(sk.sign(m).signature)
-        what = "random keys / 64-byte messages signed by libsodium"
-    except ImportError:  # pragma: no cover
-        recs = [r for r in load_sign_input() if len(r[3]) >= 64]
-        for i in range(NREF):
-            _, pk, sig, msg = recs[i % len(recs)]
-            pks.append(pk); msgs.append(msg); sigs.append(sig)
-        what = "golden-file signatures (messages 64..1023 bytes)"
-    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
-    n = pk.shape[0]
+    n_full = 1 << args.log2n
+    NREF = min(n_full, 16384)
+    pk, msg, off, sg, expect = make_batch_cpu(C, NREF, 0, n_full, threads)
     t0 = time.perf_counter()
-    C.verify_batch(pk[:256], flat[: int(off[256])], off[:257], sg[:256], nthreads=threads)
+    C.verify_batch(pk[:256], msg[: 64 * 256], off[:257], sg[:256], nthreads=threads)
     rate = 256 / (time.perf_counter() - t0)
-    per_step = int(min(n, max(256, rate * 4.0)))
+    per_step = int(min(NREF, max(256, rate * 4.0)))
+    per_step -= per_step % 64
     for _ in range(args.warmup):
-        C.verify_batch(pk[:per_step], flat[: int(off[per_step])], off[: per_step + 1], sg[:per_step], nthreads=threads)
+        C.verify_batch(pk[:per_step], msg[: 64 * per_step], off[: per_step + 1], sg[:per_step], nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st = C.verify_batch(pk[:per_step], flat[: int(off[per_step])], off[: per_step + 1], sg[:per_step], nthreads=threads)
+        st = C.verify_batch(pk[:per_step], msg[: 64 * per_step], off[: per_step + 1], sg[:per_step], nthreads=threads)
     dt = time.perf_counter() - t0
-    assert not st.any()
+    if not (st == expect[:per_step]).all():
+        raise SystemExit("bench (reference arm): the oracle's statuses differ from the ones expected by construction")
     value = per_step * args.steps / dt
-    sample = f"{per_step} signatures per step ({what}), oracle/ref10_port.c on {threads} host threads"
+    sample = f"the first {per_step} signatures of the GPU arm's rank-0 batch (same seeds, same 1/64 invalid mix) per step, oracle/ref10_port.c on {threads} host threads"
     print(json.dumps({
         "impl": "reference", "metric": "verified Ed25519 sigs/sec", "value": value, "unit": "sigs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "batched EdDSA verify_with_checks, CPU port of the reference's path (no Rust toolchain in this image)", "sigs_per_step": per_step},
+        "config": {"workload": f"cfg2: batched EdDSA verify_with_checks of 2^{args.log2n} random keys / 64-byte messages / signatures per GPU incl. SHA-512 challenge, 1/64 invalid",
+                   "sigs_per_step": per_step, "same_batch_as_gpu_arm": True,
+                   "note": "CPU port of the reference's path (kyber-rs is Rust; no Rust toolchain in this image); it restates the reference's algorithm (4 inversions + constant-time variable-base mult per verify), "
+                           "which is ~3.4x slower per core than libsodium"},
         "cpu_baseline": {"value": value, "unit": "sigs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "sigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -236,7 +278,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=20)
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (configs 1, 3, 4, 5 and the stage measurements are skipped)")
+    ap.add_argument("--msm-max-log2", type=int, default=26)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -256,32 +299,73 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")      # host-side waits that must not occupy the other ranks' GPUs
     kb = importlib.import_module("kyber-rs_b200")
+    from helpers import load_c_oracle
+
     ctx = kb.Context(local_rank)
     dev = torch.device("cuda", local_rank)
     n = 1 << args.log2n
+    C = load_c_oracle() if rank == 0 else None
+    parity = []      # what this run compared, and against what
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- integer-multiply roofline denominator, measured on this GPU right now
-    # The path's multiplier is IMAD.WIDE.U32 (32x32+64 -> 64).  ncu shows it issuing on the "fmaheavy"
-    # pipe at 4 cycles per warp instruction, i.e. 32 lanes/clk/SM — half the IMAD (lo32) rate.  The peak
-    # we divide by is the best IMAD.WIDE stream we can MEASURE on this GPU now: back-to-back field
-    # multiplications (73 IMAD.WIDE each), which reach ~93 % of that architectural rate.
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(ok: bool, what: str):
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if not int(t.item()):
+            die(what)
+
+    def timed(fn, reps=3):
+        """seconds per call: CUDA events on the launch stream, barrier + synchronize on both sides, MAX over ranks"""
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); barrier()
+        return max_over_ranks(a.elapsed_time(b) / reps) * 1e-3
+
+    # ---- integer-multiply roofline denominator ---------------------------------------------------------------------
+    # The path's multiplier is IMAD.WIDE.U32 (32x32+64 -> 64); it issues on the "fmaheavy" pipe at 4 cycles per warp
+    # instruction, i.e. 32 lanes/clk/SM.  The denominator is that ARCHITECTURAL rate at the GPU's maximum SM clock; the
+    # measured streams of kb_probe_imad are reported next to it.
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    imad_peak = 32.0 * ctx.sm_count * sm_max_mhz * 1e6
     probe_wide_plain, _ = ctx.probe_imad(0, 1 << 14)
     probe_wide_chain, _ = ctx.probe_imad(2, 1 << 13)
     imad_peak_lo, _ = ctx.probe_imad(1, 1 << 14)
     fe_mul_rate, _ = ctx.probe_imad(3, 1 << 10)
-    imad_peak = max(probe_wide_plain, probe_wide_chain, fe_mul_rate * 73.0 / 72.0)
 
-    # ---- inputs
+    # ---- cfg2 inputs ---------------------------------------------------------------------------------------------------
     pk, msg, off, sig, expect = make_batch(ctx, n, rank)
+    if rank == 0 and C.point_decode_ok(OFF_CURVE):
+        die("the off-curve constant decodes")
     d_pk = torch.from_numpy(pk).to(dev)
     d_msg = torch.from_numpy(msg).to(dev)
     d_off = torch.from_numpy(off.view(np.int64)).to(dev)
@@ -295,11 +379,12 @@ def main():
         step_dev()
     torch.cuda.synchronize()
     got = d_st.cpu().numpy()
-    if not (got == expect).all():
-        bad = np.nonzero(got != expect)[0]
-        raise SystemExit(f"bench: {bad.size} statuses differ from the expected ones, first at {bad[:5]}: got {got[bad[:5]]} want {expect[bad[:5]]}")
+    bad = np.nonzero(got != expect)[0]
+    all_ok(bad.size == 0, f"rank {rank}: {bad.size} verify statuses differ from the expected ones, first at {bad[:5]}: got {got[bad[:5]]} want {expect[bad[:5]]}")
+    parity.append({"what": "cfg2 verify statuses vs the statuses expected by construction (valid + nine invalid classes incl. off-curve R = status 7 and the §A1 quirk range)",
+                   "items": n * world, "ranks": world, "statuses_seen": sorted(set(int(x) for x in np.unique(got)))})
 
-    # ---- timed region: device-resident value
+    # ---- timed region: device-resident value -----------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launches
@@ -324,144 +409,100 @@ def main():
         k_prep_ms.append(a_ms)
         k_main_ms.append(b_ms)
     ctx.verify_kernel_timing(False)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(total_ms)
     value = world * n * args.steps / (total_ms_max * 1e-3)
 
-    # ---- e2e: host buffers (pinned) through the C-ABI call a user makes; H2D and D2H inside
-    hp = [torch.from_numpy(x).pin_memory() for x in (pk, msg, off.view(np.int64), sig)]
-    h_pk, h_msg, h_off, h_sig = [x.numpy() for x in hp]
-    h_off = h_off.view(np.uint64)
-    h_out_t = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_out = h_out_t.numpy()
-    for _ in range(2):
-        ctx.verify_batch(h_pk, h_msg, h_off, h_sig, out=h_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.verify_batch(h_pk, h_msg, h_off, h_sig, out=h_out)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert (h_out == expect).all()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(t.item())
-    h2d = int(pk.nbytes + msg.nbytes + off.nbytes + sig.nbytes)
+    # ---- e2e: ONE host batch of world * n signatures through the multi-device context, on rank 0 -------------------
+    # (the other ranks wait on the host; their GPUs are idle and are driven by rank 0's kb_mctx)
+    e2e_value, h2d, e2e_launches = None, None, None
+    mctx = None
+    if rank == 0:
+        mctx = kb.MultiContext(list(range(world)))
+        batches = [(pk, msg, off, sig, expect)] + [make_batch(ctx, n, r) for r in range(1, world)]
+        big_pk = np.concatenate([b[0] for b in batches])
+        big_msg = np.concatenate([b[1] for b in batches])
+        big_off = (np.arange(world * n + 1, dtype=np.uint64) * np.uint64(64))
+        big_sig = np.concatenate([b[3] for b in batches])
+        big_expect = np.concatenate([b[4] for b in batches])
+        del batches
+        hp = [torch.from_numpy(x).pin_memory() for x in (big_pk, big_msg, big_off.view(np.int64), big_sig)]
+        h_pk, h_msg, h_off, h_sig = [x.numpy() for x in hp]
+        h_off = h_off.view(np.uint64)
+        h_out_t = torch.empty(world * n, dtype=torch.uint8).pin_memory()
+        h_out = h_out_t.numpy()
+    host_barrier()
+    if rank == 0:
+        for _ in range(2):
+            mctx.verify_batch(h_pk, h_msg, h_off, h_sig, out=h_out)
+        ml0 = mctx.launches
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mctx.verify_batch(h_pk, h_msg, h_off, h_sig, out=h_out)
+        e2e_s = time.perf_counter() - t0
+        e2e_launches = mctx.launches - ml0
+        if not (h_out == big_expect).all():
+            die("e2e statuses (multi-device context) differ from the expected ones")
+        e2e_value = world * n * args.steps / e2e_s
+        h2d = int(big_pk.nbytes + big_msg.nbytes + big_off.nbytes + big_sig.nbytes)
+        parity.append({"what": "e2e: kb_mctx_verify_batch statuses of ONE host batch sharded over all GPUs vs expected", "items": n * world, "devices": world})
+        del hp, h_out_t, big_pk, big_msg, big_sig
+    host_barrier()
 
-    # ---- extras: the other half of the metric (MSM points/s) and config-1 scalar mults
-    extras = {}
+    # ---- CPU baseline on rank 0 (N = 1 only): the oracle's C port on the host cores, bounded prefix; at N > 1 a short
+    # prefix is still checked against the oracle on rank 0
+    cpu = None
+    if rank == 0:
+        if world == 1:
+            cpu = cpu_verify_baseline(C, pk, msg, off, sig, got, budget_s=12.0, threads=host_cores())
+            parity.append({"what": "cfg2 verify statuses vs oracle/ref10_port.c", "items": cpu["checked_items"]})
+        else:
+            m = 16384
+            st = C.verify_batch(pk[:m], msg[:64 * m], off[:m + 1], sig[:m], nthreads=host_cores())
+            if not (st == got[:m]).all():
+                die("GPU statuses differ from the oracle on rank 0's prefix")
+            parity.append({"what": "cfg2 verify statuses vs oracle/ref10_port.c (rank 0 prefix)", "items": m})
+    host_barrier()
+
+    extras, configs, stages = {}, {}, {}
     if not args.no_extras:
-        def timed(fn, reps=3):
-            fn(); torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier(); a.record()
-            for _ in range(reps):
-                fn()
-            b.record(); barrier()
-            tt = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return float(tt.item()) * 1e-3
+        import bench_configs
 
-        m = 1 << 16
-        d_sc = d_sig[:m, 32:].contiguous()
-        d_o = torch.empty(m, 32, dtype=torch.uint8, device=dev)
-        d_s8 = torch.empty(m, dtype=torch.uint8, device=dev)
-        d_pts = d_pk[:m].clone()
-        d_pts[63::64] = d_pk[0]            # the invalid-key slots: use a valid point for the mult benches
-        extras["cfg1_mul_base_ct_per_s"] = world * m / timed(lambda: ctx.dev_point_mul_base(m, d_sc, d_o, 0))
-        extras["cfg1_mul_base_vartime_per_s"] = world * m / timed(lambda: ctx.dev_point_mul_base(m, d_sc, d_o, 1))
-        extras["cfg1_mul_var_ct_per_s"] = world * m / timed(lambda: ctx.dev_point_mul(m, d_sc, d_pts, d_o, d_s8, 0))
-        extras["cfg1_mul_var_vartime_per_s"] = world * m / timed(lambda: ctx.dev_point_mul(m, d_sc, d_pts, d_o, d_s8, 1))
-        # MSM: each rank reduces its own 2^20 points to one partial; the partials are all-gathered (NCCL,
-        # 128 B per rank) and folded on every rank — the only data-path collective
-        mm = n
-        d_mpts = d_pk.clone()
-        d_mpts[63::64] = d_pk[0]
-        d_msc = d_sig[:, 32:].contiguous()
-        d_part = torch.empty(128, dtype=torch.uint8, device=dev)
-        d_all = torch.empty(world * 128, dtype=torch.uint8, device=dev)
-        d_enc = torch.empty(32, dtype=torch.uint8, device=dev)
-        d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
+        env = dict(kb=kb, ctx=ctx, mctx=mctx, C=C, dev=dev, rank=rank, world=world, dist=dist, torch=torch, timed=timed, barrier=barrier, host_barrier=host_barrier,
+                   max_over_ranks=max_over_ranks, all_ok=all_ok, die=die, parity=parity, imad_peak=imad_peak, hbm_peak=hbm_peak, d_pk=d_pk, d_sig=d_sig, d_msg=d_msg, d_off=d_off,
+                   n=n, args=args, host_cores=host_cores(), xof=xof)
+        configs, stages = bench_configs.run_all(env)
 
-        def msm_step():
-            ctx.dev_msm(mm, d_msc, d_mpts, None, d_part, d_bad)
-            if world > 1:
-                dist.all_gather_into_tensor(d_all, d_part)
-                ctx.dev_point_sum(world, d_all, d_enc)
-            else:
-                ctx.dev_point_sum(1, d_part, d_enc)
-
-        tm = timed(msm_step, reps=2)
-        extras["cfg5_msm_points_per_s"] = world * mm / tm
-        extras["cfg5_msm_log2n_per_gpu"] = args.log2n
-        extras["cfg5_msm_roofline_frac"] = (world * mm / tm) * IMAD_EQ_PER_MSM_POINT / (imad_peak * world)
-        enc = bytes(d_enc.cpu().numpy().tobytes())
-        if world > 1:
-            encs = [None] * world
-            dist.all_gather_object(encs, enc)
-            assert len(set(encs)) == 1, "ranks disagree on the sharded MSM result"
-        extras["cfg5_msm_result"] = enc.hex()
-        # BASELINE configs 3 and 4: one deal-verification round (all n^2 share checks), dealers sharded over the ranks,
-        # random commitments and shares (the kernels' work does not depend on the verdicts; tools/bench_dkg.py is the
-        # version that also checks honest / corrupted / torsion-contaminated dealers against expected verdicts)
-        for tag, (rn, rt) in (("cfg3_vss_n256_t171", (256, 171)), ("cfg4_dkg_n1024_t683", (1024, 683))):
-            if rn % world:
-                continue
-            nd = rn // world
-            coeff = xof(f"kyber-b200/bench/{tag}/rank{rank}", 32 * nd * rt).reshape(-1, 32).copy()
-            coeff[:, 31] &= 0x0F
-            d_coeff = torch.from_numpy(coeff).to(dev)
-            d_commits = torch.empty(nd * rt, 32, dtype=torch.uint8, device=dev)
-            ctx.dev_point_mul_base(nd * rt, d_coeff, d_commits, 1)
-            sh = xof(f"kyber-b200/bench/{tag}/shares{rank}", 32 * nd * rn).reshape(-1, 32).copy()
-            sh[:, 31] &= 0x0F
-            d_sh = torch.from_numpy(sh).to(dev)
-            d_v = torch.empty(nd * rn, dtype=torch.uint8, device=dev)
-            extras[tag + "_round_ms"] = timed(lambda: ctx.dev_dkg_verify_round(rn, rt, nd, d_commits, d_sh, d_v), reps=2) * 1e3
-            del d_coeff, d_commits, d_sh, d_v
-
+    if mctx is not None:
+        mctx.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline on rank 0 (N=1 only): the oracle's C port on the host cores, bounded sample
-    cpu = None
-    if world == 1:
-        from helpers import load_c_oracle
-
-        cpu = cpu_baseline(load_c_oracle(), pk, msg, off, sig, got, budget_s=12.0, threads=host_cores())
-
     kernel_s = statistics.mean(kernel_ms) * 1e-3
     achieved = n * IMAD_EQ_PER_VERIFY / kernel_s
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     prep_s, main_s = statistics.mean(k_prep_ms) * 1e-3, statistics.mean(k_main_ms) * 1e-3
-    traffic = None
-    if args.log2n == 20 and all(VERIFY_DRAM_BYTES_2P20.values()):
-        traffic = sum(VERIFY_DRAM_BYTES_2P20.values())
+    traffic, traffic_src = None, None
+    try:   # dram__bytes of the two launches, measured by ncu on THIS build and stored by tools/ncu_traffic.py
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_verify_traffic.json")))
+        if tr.get("log2n") == args.log2n:
+            traffic, traffic_src = int(tr["dram_bytes_per_step"]), tr.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
     out = {
         "metric": "verified Ed25519 sigs/sec", "value": value, "unit": "sigs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"cfg2: batched EdDSA verify_with_checks of 2^{args.log2n} random keys / 64-byte messages / signatures per GPU incl. SHA-512 challenge, 1/64 invalid",
-                   "sigs_per_gpu": n, "l2_policy": "inputs (168 MiB per step) exceed the 126 MB L2; no explicit flush", "parallelism": f"index-sharded x{world}, no data-path collective"},
-        "e2e": {"value": e2e_value, "unit": "sigs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n)},
+                   "sigs_per_gpu": n, "l2_policy": "inputs (168 MiB per step) exceed the 126 MB L2; no explicit flush", "parallelism": f"index-sharded x{world}, no data-path collective",
+                   "same_batch_as_reference_arm": True},
+        "e2e": {"value": e2e_value, "unit": "sigs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(n * world),
+                "how": f"rank 0: kb_mctx_verify_batch on ONE pinned host batch of {world} x 2^{args.log2n} signatures, sharded by index over {world} GPU(s) inside the library (one host thread per device, "
+                       "two-stream chunked copy/compute overlap per device); wall clock around the calls", "gpu_launches": e2e_launches},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": traffic,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one step at 2^20 signatures (ncu --set full, profiles/r1_ncu_k_verify_half.txt): "
-                                     + json.dumps(VERIFY_DRAM_BYTES_2P20) + "; algorithmic bytes are 168 MB in + 1 MB out per step plus the 319 MB of records written by the first launch and read by the second; "
-                                     "the rest is the two per-thread 1 KiB tables (multiples of A and of R, local memory) that do not all fit the 126 MB L2 (DESIGN.md 6); DRAM runs at about 12 % of its peak, the step is bound by the multiplier pipe",
+        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD-eq/s", "frac": achieved / imad_peak, "traffic": traffic, "traffic_source": traffic_src,
                      "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents CHARGED per signature (SURVEY 8d: decompress A + 253-doubling Straus + compress) / CUDA-event step time; "
-                             "peak = best IMAD.WIDE.U32 stream measured live by kb_probe_imad (back-to-back field multiplications), ~93% of the architectural 32 lanes/clk/SM of the fmaheavy pipe. "
+                             f"peak = ARCHITECTURAL IMAD.WIDE.U32 rate, 32 lanes/clk/SM x {ctx.sm_count} SMs x {sm_max_mhz:.0f} MHz (the fmaheavy pipe issues one warp instruction per 4 cycles). "
                              "The kernels EXECUTE fewer multiplies than charged (half-size scalars: 128 doublings, csrc/half.cuh): see `executed`",
                      "kernel": "one step = k_verify_half_prep (checks, decompress A and R, SHA-512, lattice step) + k_verify_half_main (tables, 33-window loop, comb, verdict)",
                      "kernels_ms": {"k_verify_half_prep": prep_s * 1e3, "k_verify_half_main": main_s * 1e3, "timed_steps": len(k_main_ms),
@@ -470,11 +511,13 @@ def main():
                                   "frac_step": n * (EXEC_PREP_PER_VERIFY + EXEC_MAIN_PER_VERIFY) / kernel_s / imad_peak,
                                   "frac_k_verify_half_main": n * EXEC_MAIN_PER_VERIFY / main_s / imad_peak,
                                   "frac_k_verify_half_prep": n * EXEC_PREP_PER_VERIFY / prep_s / imad_peak},
-                     "probes_T_per_s": {"imad_lo32": imad_peak_lo / 1e12, "imad_wide_plain": probe_wide_plain / 1e12, "imad_wide_carry_chain": probe_wide_chain / 1e12, "fe_mul_as_imad_wide": fe_mul_rate * 73.0 / 72.0 / 1e12},
-                     "architectural_imad_wide_T_per_s": 32 * ctx.sm_count * 1.965e9 / 1e12},
+                     "probes_T_per_s": {"imad_lo32": imad_peak_lo / 1e12, "imad_wide_plain": probe_wide_plain / 1e12, "imad_wide_carry_chain": probe_wide_chain / 1e12, "fe_mul_as_imad_wide": fe_mul_rate * 73.0 / 72.0 / 1e12}},
         "roofline_hbm": {"bound": "hbm", "achieved": n * ALG_BYTES_PER_SIG / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": n * ALG_BYTES_PER_SIG / kernel_s / 1e9 / hbm_peak,
-                         "note": "161 algorithmic bytes per signature; the path is integer-pipe bound, not HBM bound (peak of measured MEASURED_PEAKS.json)" if peaks else "of fallback"},
+                         "note": "161 algorithmic bytes per signature; the path is integer-pipe bound, not HBM bound (peak: MEASURED_PEAKS.json)" if peaks else "peak: B200_PROFILING.md fallback"},
         "cpu_baseline": cpu,
+        "parity_checked": parity,
+        "configs": configs,
+        "stages": stages,
         "extras": extras,
     }
     os.write(real_stdout, (json.dumps(out) + "\n").encode())

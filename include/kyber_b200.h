@@ -165,6 +165,9 @@ int kb_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_
  * share/vss/pedersen/vss.rs:155-159); here a dealer with an element that is not a consistent representation of a curve
  * point (Z = 0, T Z != X Y, or off the curve) gets verdict 0 throughout. */
 int kb_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo, size_t dealer_hi, const int32_t* commit_limbs, const uint8_t* shares, uint8_t* verdict);
+/* PriPoly::eval (poly.rs:133-141) for npoly private polynomials of t coefficients at the indices 0..n-1:
+ * out[d*n + i] = poly[d].eval(i) — the shares a dealer hands out (new_dealer, share/vss/pedersen/vss.rs:313). */
+int kb_pripoly_eval_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* coeffs, size_t n, uint8_t* out);
 /* PubPoly::add (poly.rs:486-509): out[j] = a[j] + b[j] — kb_point_add_batch on t points.
  * dkg_key (share/dkg/pedersen/dkg.rs:905-954) folds PubPoly::add over all qualified dealers:
  * out[j] = sum_d commits[d*t + j], j < t; status[j] = 1 (and out[j] zero) if a commitment of column j is undecodable. */
@@ -239,6 +242,10 @@ int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_point
 int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commit_limbs, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream);
+/* the pure decompress (ExtendedGroupElement::set_bytes -> X, Y, Z, T words) and hash (SHA-512(R || A || M) mod L) stages */
+int kb_dev_point_decompress(kb_ctx* ctx, size_t n, const void* d_in, void* d_out128, void* d_status, void* stream);
+int kb_dev_challenge(kb_ctx* ctx, size_t n, const void* d_r32, const void* d_a32, const void* d_msg, const void* d_msg_off, void* d_out32, void* stream);
+int kb_dev_pripoly_eval(kb_ctx* ctx, size_t npoly, size_t t, const void* d_coeffs, size_t n, void* d_out, void* stream);
 /* kb_dkg_process_round on device buffers for ndealers dealers (arrays start at the first of them) */
 int kb_dev_dkg_process_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, int fmt, const void* d_commits, const void* d_shares, void* d_verdict,
                              const void* d_deal_pk, const void* d_deal_msg, const void* d_deal_msg_off, const void* d_deal_sig, void* d_deal_status,
@@ -278,7 +285,7 @@ int kb_mctx_msm(kb_mctx* m, size_t n, const uint8_t* scalars, const uint8_t* poi
 /* ---- measurement ---------------------------------------------------------------------- */
 /* Integer-multiply roofline probe: runs `iters` dependent-chain-free IMAD.WIDE.U32 per thread
  * on every SM and returns the achieved 32x32->64 multiply-accumulates per second.
- * kind: 0 = IMAD.WIDE.U32 (64-bit accumulate), 1 = IMAD (32-bit lo), 2 = IMAD.WIDE.U32.X carry chains,
+ * kind: 0 = IMAD.WIDE.U32 (64-bit accumulate, nothing else in the loop), 1 = IMAD (32-bit lo), 2 = IMAD.WIDE.U32.X carry chains,
  * 3 = the library's own fe_mul (reported in IMAD-eq at 72 per multiplication). */
 int kb_probe_imad(kb_ctx* ctx, int kind, int iters, double* macs_per_sec, double* elapsed_ms);
 /* Per-kernel timing of the verifiers.  enable = 1/0 switches CUDA-event recording (on the launch stream, around

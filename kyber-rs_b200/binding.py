@@ -39,7 +39,7 @@ EXPORTS = [
     "kb_sc_reduce64_batch", "kb_sc_muladd_batch", "kb_sc_invert_batch", "kb_challenge_batch", "kb_eddsa_verify_batch", "kb_schnorr_verify_batch", "kb_eddsa_sign_batch",
     "kb_pubpoly_eval_batch", "kb_vss_verify_deals_batch", "kb_dkg_verify_round", "kb_dkg_verify_round_limbs", "kb_pubpoly_sum", "kb_msm", "kb_point_sum",
     "kb_vss_session_ids", "kb_find_pub_batch", "kb_dkg_process_round", "kb_vss_rabin_verify_deals_batch", "kb_dss_verify_partials", "kb_recover_commit_batch", "kb_recover_pub_poly", "kb_dkg_resharing_key",
-    "kb_dev_dkg_process_round",
+    "kb_dev_dkg_process_round", "kb_dev_point_decompress", "kb_dev_challenge", "kb_pripoly_eval_batch", "kb_dev_pripoly_eval",
     "kb_mctx_create", "kb_mctx_destroy", "kb_mctx_device_count", "kb_mctx_ctx", "kb_mctx_last_error", "kb_mctx_launch_count", "kb_mctx_verify_batch", "kb_mctx_point_mul_base_batch", "kb_mctx_point_mul_batch",
     "kb_mctx_dkg_verify_round", "kb_mctx_dkg_process_round", "kb_mctx_msm",
     "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_dkg_verify_round_limbs", "kb_dev_point_sum",
@@ -108,6 +108,10 @@ def load_library(path: str = LIB_PATH):
     L.kb_dev_dkg_verify_round.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_dkg_verify_round_limbs.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_point_sum.argtypes = [vp, sz, vp, vp, vp]
+    L.kb_pripoly_eval_batch.argtypes = [vp, sz, sz, vp, sz, vp]
+    L.kb_dev_pripoly_eval.argtypes = [vp, sz, sz, vp, sz, vp, vp]
+    L.kb_dev_point_decompress.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.kb_dev_challenge.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
     L.kb_mctx_create.argtypes = [ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
     L.kb_mctx_destroy.argtypes = [vp]
     L.kb_mctx_destroy.restype = None
@@ -350,6 +354,16 @@ class Context:
         self._check(fn(self.h, n, t, dealer_lo, dealer_hi, _ptr(c), _ptr(sh), _ptr(verdict)), "kb_dkg_verify_round")
         return verdict
 
+    def pripoly_eval_batch(self, coeffs, t, n):
+        """PriPoly::eval for every polynomial at indices 0..n-1: (npoly*n, 32) shares, polynomial-major."""
+        c = _u8(coeffs, (-1, 32))
+        npoly = c.shape[0] // t
+        if npoly * t != c.shape[0]:
+            raise ValueError("pripoly_eval_batch: coeffs must hold npoly*t scalars")
+        out = np.empty((npoly * n, 32), dtype=np.uint8)
+        self._check(self.L.kb_pripoly_eval_batch(self.h, npoly, t, _ptr(c), n, _ptr(out)), "kb_pripoly_eval_batch")
+        return out
+
     def pubpoly_sum(self, commits, t):
         c = _u8(commits, (-1, 32))
         npoly = c.shape[0] // t
@@ -542,6 +556,15 @@ class Context:
         for batch in (deal, resp):
             a += [self._dp(x) for x in batch] if batch is not None else [None] * 5
         self._check(self.L.kb_dev_dkg_process_round(self.h, n, t, ndealers, int(limbs), self._dp(commits), self._dp(shares), self._dp(verdict), *a, self._stream()), "kb_dev_dkg_process_round")
+
+    def dev_pripoly_eval(self, npoly, t, coeffs, n, out):
+        self._check(self.L.kb_dev_pripoly_eval(self.h, npoly, t, self._dp(coeffs), n, self._dp(out), self._stream()), "kb_dev_pripoly_eval")
+
+    def dev_point_decompress(self, n, enc, out128, status):
+        self._check(self.L.kb_dev_point_decompress(self.h, n, self._dp(enc), self._dp(out128), self._dp(status), self._stream()), "kb_dev_point_decompress")
+
+    def dev_challenge(self, n, r32, a32, msg, msg_off, out32):
+        self._check(self.L.kb_dev_challenge(self.h, n, self._dp(r32), self._dp(a32), self._dp(msg), self._dp(msg_off), self._dp(out32), self._stream()), "kb_dev_challenge")
 
     def dev_point_sum(self, k, partials, out32):
         self._check(self.L.kb_dev_point_sum(self.h, k, self._dp(partials), self._dp(out32), self._stream()), "kb_dev_point_sum")

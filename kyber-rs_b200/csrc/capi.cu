@@ -278,6 +278,27 @@ int kb_point_add_batch(kb_ctx* ctx, size_t n, const uint8_t* p, const uint8_t* q
     KB_SYNC();
     return KB_OK;
 }
+// the pure decompress and hash stages on device buffers (what bench.py times for their HBM GB/s)
+int kb_dev_point_decompress(kb_ctx* ctx, size_t n, const void* d_in, void* d_out128, void* d_status, void* stream)
+{
+    if (!ctx || (n && (!d_in || !d_out128))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    k_point_decompress<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_in, (uint32_t*)d_out128, (uint8_t*)d_status);
+    KB_LAUNCHED();
+    KB_DEV_RETURN(st, KB_OK);
+}
+int kb_dev_challenge(kb_ctx* ctx, size_t n, const void* d_r32, const void* d_a32, const void* d_msg, const void* d_msg_off, void* d_out32, void* stream)
+{
+    if (!ctx || (n && (!d_r32 || !d_a32 || !d_msg_off || !d_out32))) return KB_ERR_ARG;
+    if (n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    k_challenge<<<kb_blocks(n, KB_THREADS), KB_THREADS, 0, st>>>(n, (const uint8_t*)d_r32, (const uint8_t*)d_a32, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, (uint8_t*)d_out32);
+    KB_LAUNCHED();
+    KB_DEV_RETURN(st, KB_OK);
+}
 int kb_point_decompress_batch(kb_ctx* ctx, size_t n, const uint8_t* in, uint8_t* out128, uint8_t* status)
 {
     KB_ENTER();

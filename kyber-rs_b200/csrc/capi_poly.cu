@@ -238,6 +238,37 @@ int kb_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t dealer_lo,
     return kb_dkg_round_host(ctx, n, t, dealer_lo, dealer_hi, commit_limbs, 1, shares, verdict);
 }
 
+int kb_dev_pripoly_eval(kb_ctx* ctx, size_t npoly, size_t t, const void* d_coeffs, size_t n, void* d_out, void* stream)
+{
+    if (!ctx || !t || (npoly && n && (!d_coeffs || !d_out))) return KB_ERR_ARG;
+    if (npoly == 0 || n == 0) return KB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    k_pripoly_eval<<<kb_blocks(npoly * n, KB_THREADS), KB_THREADS, 0, st>>>(npoly, t, (const uint8_t*)d_coeffs, n, (uint8_t*)d_out);
+    KB_LAUNCHED();
+    KB_DEV_RETURN(st, KB_OK);
+}
+int kb_pripoly_eval_batch(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* coeffs, size_t n, uint8_t* out)
+{
+    KB_ENTER();
+    if (!t || (npoly && n && (!coeffs || !out))) return KB_ERR_ARG;
+    if (npoly == 0 || n == 0) return KB_OK;
+    uint8_t *d_c, *d_o;
+    KB_SCRATCH(0, 32 * npoly * t, d_c);
+    KB_SCRATCH(1, 32 * npoly * n, d_o);
+    KB_H2D(d_c, coeffs, 32 * npoly * t);
+    int rc = kb_dev_pripoly_eval(ctx, npoly, t, d_c, n, d_o, ctx->stream);
+    cudaMemsetAsync(d_c, 0, 32 * npoly * t, ctx->stream);   // the private coefficients do not stay in device scratch
+    if (rc != KB_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    KB_D2H(out, d_o, 32 * npoly * n);
+    KB_CUDA(cudaMemsetAsync(d_o, 0, 32 * npoly * n, ctx->stream));
+    KB_SYNC();
+    return KB_OK;
+}
+
 int kb_pubpoly_sum(kb_ctx* ctx, size_t npoly, size_t t, const uint8_t* commits, uint8_t* out, uint8_t* status)
 {
     KB_ENTER();

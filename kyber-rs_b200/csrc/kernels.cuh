@@ -642,6 +642,24 @@ static __global__ void __launch_bounds__(KB_THREADS) k_commit_prepare_limbs(size
     kb_store_fe(o + 24, c.Z);
     bad[i] = (uint8_t)(ok ^ 1u);
 }
+// PriPoly::eval (share/poly.rs:133-141) for every (polynomial d, index i): out[d * n + i] = sum_j coeffs[d][j] (i+1)^j mod L
+// by Horner's rule with sc_mul_add — the dealer's side of a round (new_dealer, share/vss/pedersen/vss.rs:313: f.eval(i) for
+// all i).  The coefficients are secret: sc_muladd is branch-free and the evaluation point is public.
+static __global__ void __launch_bounds__(KB_THREADS) k_pripoly_eval(size_t npoly, size_t t, const uint8_t* coeffs, size_t n, uint8_t* out)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npoly * n) return;
+    const size_t d = k / n, i = k % n;
+    uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, v[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c[8];
+    const uint64_t xv = (uint64_t)i + 1;
+    x[0] = (uint32_t)xv;
+    x[1] = (uint32_t)(xv >> 32);
+    for (size_t j = t; j-- > 0;) {
+        kb_load32(c, coeffs, d * t + j);
+        sc_muladd(v, v, x, c);
+    }
+    kb_store32(out, k, v);
+}
 // PubPoly::eval (poly.rs:457-469) and, with shares != nullptr, the verify_deal comparison
 // (vss/pedersen/vss.rs:899-912).  Item k is (poly_id[k], idx[k]); with poly_id == nullptr the
 // items enumerate a DKG round: k = i * npoly + d (verifier-major), so the 32 lanes of a warp
@@ -717,14 +735,16 @@ static __global__ void __launch_bounds__(256) k_probe(int iters, uint32_t seed, 
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (KIND == 0) {
-        // 8 independent 64-bit accumulators: acc += a * b  (IMAD.WIDE.U32)
+        // 8 independent 64-bit accumulators: acc += lo32(acc) * b — one IMAD.WIDE.U32 per step and nothing else
+        // (the multiplicand is the accumulator's own low word, so the compiler can neither hoist the product nor
+        // has to spend an ALU instruction on making it vary)
         uint64_t acc[8];
-        uint32_t a = seed ^ tid, b = seed * 2654435761u + tid;
+        uint32_t b = (seed * 2654435761u + tid) | 1u;
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc[k] = tid + k;
+        for (int k = 0; k < 8; k++) acc[k] = ((uint64_t)(seed ^ tid) << 32) | (tid + 977u * k + 1u);
         for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = (uint64_t)((uint32_t)acc[k] ^ a) * b + acc[k];
+            for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(uint32_t)acc[k] * b + acc[k];
         }
         uint64_t x = 0;
 #pragma unroll

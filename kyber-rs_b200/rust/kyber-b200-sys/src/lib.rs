@@ -86,6 +86,10 @@ extern "C" {
     pub fn kb_dev_dkg_verify_round_limbs(ctx: *mut kb_ctx, n: usize, t: usize, ndealers: usize, d_commit_limbs: *const c_void, d_shares: *const c_void, d_verdict: *mut c_void, stream: *mut c_void) -> c_int;
     pub fn kb_dev_point_sum(ctx: *mut kb_ctx, k: usize, d_partials128: *const c_void, d_out32: *mut c_void, stream: *mut c_void) -> c_int;
 
+    pub fn kb_pripoly_eval_batch(ctx: *mut kb_ctx, npoly: usize, t: usize, coeffs: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn kb_dev_pripoly_eval(ctx: *mut kb_ctx, npoly: usize, t: usize, d_coeffs: *const c_void, n: usize, d_out: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_point_decompress(ctx: *mut kb_ctx, n: usize, d_in: *const c_void, d_out128: *mut c_void, d_status: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn kb_dev_challenge(ctx: *mut kb_ctx, n: usize, d_r32: *const c_void, d_a32: *const c_void, d_msg: *const c_void, d_msg_off: *const c_void, d_out32: *mut c_void, stream: *mut c_void) -> c_int;
     // multi-device context
     pub fn kb_mctx_create(devices: *const c_int, ndev: c_int, out: *mut *mut kb_mctx) -> c_int;
     pub fn kb_mctx_destroy(m: *mut kb_mctx);

@@ -247,3 +247,15 @@ def test_dkg_process_round_device_resident(kb, ctx, coracle, golden_records):
     ctx.dev_dkg_process_round(n, t, nd, up(commits), up(shares), d_v, deal=(up(pk), up(flat), up(off.view(np.int64)), up(sg), d_st))
     torch.cuda.synchronize()
     assert (d_v.cpu().numpy() == hv).all() and (d_st.cpu().numpy() == hd).all()
+
+
+def test_pripoly_eval_batch(ctx):
+    """PriPoly::eval (share/poly.rs:133-141) for whole polynomials at once: the shares a dealer hands out, against
+    Python integers; coefficients that are not reduced (a raw 32-byte scalar) are taken mod L like sc_mul_add does."""
+    for npoly, t, n in ((1, 1, 1), (3, 2, 5), (5, 171, 40), (2, 683, 9)):
+        coeffs = _scalars(b"pripoly%d" % t, npoly * t)
+        if t > 1:
+            coeffs[1] = 0xFF          # 2^256 - 1: an unreduced scalar
+        got = ctx.pripoly_eval_batch(coeffs, t, n)
+        for d in range(npoly):
+            assert (got[d * n:(d + 1) * n] == _shares(coeffs[d * t:(d + 1) * t], n)).all(), (npoly, t, n, d)
