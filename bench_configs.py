@@ -303,6 +303,35 @@ def cfg5(env):
         best = max(best, tot / s)
     out["value"] = best
     out["roofline"] = _roof(best, IMAD_EQ_PER_MSM_POINT, env)
+    # the same sweep over points that are ALREADY DECODED (kb_dev_msm_ext: what chained device-side use hands over)
+    lg_raw = min(max_log2, 24)
+    raw_cnt = _shard(1 << lg_raw, rank, world)
+    raw_cnt = raw_cnt[1] - raw_cnt[0]
+    d_raw = torch.empty(raw_cnt, 128, dtype=torch.uint8, device=dev)
+    d_s8 = torch.empty(raw_cnt, dtype=torch.uint8, device=dev)
+    ctx.dev_point_decompress(raw_cnt, d_pts, d_raw, d_s8)
+
+    def msm_raw(cnt):
+        ctx.dev_msm_ext(cnt, d_sc, d_raw, None, d_part, d_bad)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_part)
+            ctx.dev_point_sum(world, d_all, d_enc)
+        else:
+            ctx.dev_point_sum(1, d_part, d_enc)
+
+    out["sweep_decoded_points"] = {}
+    for lg in range(16, lg_raw + 1, 2):
+        tot = 1 << lg
+        plo, phi = _shard(tot, rank, world)
+        cnt = phi - plo
+        msm(cnt)
+        want = result()
+        msm_raw(cnt)
+        env["all_ok"](result() == want, f"cfg5: MSM over decoded points differs from the MSM over their encodings at 2^{lg}")
+        s = env["timed"](lambda: msm_raw(cnt), reps=3 if lg <= 22 else 2)
+        out["sweep_decoded_points"][f"2^{lg}"] = {"value": tot / s, "ms": s * 1e3}
+    env["parity"].append({"what": "cfg5: kb_dev_msm_ext (decoded points) vs kb_dev_msm (encodings), every size of the sweep", "items": (1 << lg_raw), "ranks": world})
+    del d_raw
     env["host_barrier"]()
     if rank == 0:
         mctx = env["mctx"]

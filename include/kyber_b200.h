@@ -239,6 +239,10 @@ int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_m
 int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_out, uint32_t flags, void* stream);
 int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status, uint32_t flags, void* stream);
 int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out32, void* d_partial128, void* d_bad_points, void* stream);
+/* kb_dev_msm for points that are ALREADY DECODED: 128 bytes each, X, Y, Z, T as 4 x 8 little-endian words with any Z != 0
+ * (the form of kb_point_decompress_batch, of partial128 and of every device-side producer): no decompression, the points
+ * are made affine with one shared inversion per 8.  A point with Z = 0 or off the curve counts in *d_bad_points. */
+int kb_dev_msm_ext(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points128, void* d_out32, void* d_partial128, void* d_bad_points, void* stream);
 int kb_dev_dkg_verify_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_dkg_verify_round_limbs(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commit_limbs, const void* d_shares, void* d_verdict, void* stream);
 int kb_dev_point_sum(kb_ctx* ctx, size_t k, const void* d_partials128, void* d_out32, void* stream);

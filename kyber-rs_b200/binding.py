@@ -42,7 +42,7 @@ EXPORTS = [
     "kb_dev_dkg_process_round", "kb_dev_point_decompress", "kb_dev_challenge", "kb_pripoly_eval_batch", "kb_dev_pripoly_eval",
     "kb_mctx_create", "kb_mctx_destroy", "kb_mctx_device_count", "kb_mctx_ctx", "kb_mctx_last_error", "kb_mctx_launch_count", "kb_mctx_verify_batch", "kb_mctx_point_mul_base_batch", "kb_mctx_point_mul_batch",
     "kb_mctx_dkg_verify_round", "kb_mctx_dkg_process_round", "kb_mctx_msm",
-    "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_dkg_verify_round", "kb_dev_dkg_verify_round_limbs", "kb_dev_point_sum",
+    "kb_dev_eddsa_verify", "kb_dev_point_mul_base", "kb_dev_point_mul", "kb_dev_msm", "kb_dev_msm_ext", "kb_dev_dkg_verify_round", "kb_dev_dkg_verify_round_limbs", "kb_dev_point_sum",
     "kb_probe_imad", "kb_verify_kernel_times",
 ]
 
@@ -105,6 +105,7 @@ def load_library(path: str = LIB_PATH):
     L.kb_dev_point_mul_base.argtypes = [vp, sz, vp, vp, u32, vp]
     L.kb_dev_point_mul.argtypes = [vp, sz, vp, vp, vp, vp, u32, vp]
     L.kb_dev_msm.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
+    L.kb_dev_msm_ext.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp]
     L.kb_dev_dkg_verify_round.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_dkg_verify_round_limbs.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp]
     L.kb_dev_point_sum.argtypes = [vp, sz, vp, vp, vp]
@@ -545,6 +546,10 @@ class Context:
 
     def dev_msm(self, n, scalars, points, out32, partial128, bad):
         self._check(self.L.kb_dev_msm(self.h, n, self._dp(scalars), self._dp(points), self._dp(out32), self._dp(partial128), self._dp(bad), self._stream()), "kb_dev_msm")
+
+    def dev_msm_ext(self, n, scalars, points128, out32, partial128, bad):
+        """MSM over points that are already decoded (128 bytes each: X, Y, Z, T words)."""
+        self._check(self.L.kb_dev_msm_ext(self.h, n, self._dp(scalars), self._dp(points128), self._dp(out32), self._dp(partial128), self._dp(bad), self._stream()), "kb_dev_msm_ext")
 
     def dev_dkg_verify_round(self, n, t, ndealers, commits, shares, verdict, limbs=False):
         fn = self.L.kb_dev_dkg_verify_round_limbs if limbs else self.L.kb_dev_dkg_verify_round

@@ -6,7 +6,7 @@
 // ------------------------------------------------------------------------------------
 // Pippenger driver (msm.cuh): chunks of <= KB_MSM_CHUNK points, partial sums chained on device
 // ------------------------------------------------------------------------------------
-int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st)
+int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const void* d_points, int ext, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st)
 {
     uint32_t* acc128 = d_partial128;
     if (!acc128) KB_SCRATCH(10, 128, acc128);
@@ -52,9 +52,9 @@ int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d
         KB_SCRATCH(26, 128 * (size_t)pl.windows, win_sum);
         if (pl.nb > 2048u * KB_SCAN_TILE) return KB_ERR_ARG;
         KB_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)pl.nb, st));
-        k_msm_prepare<<<kb_blocks(cn, KB_THREADS), KB_THREADS, 0, st>>>(cn, d_points + 32 * off, d_scalars + 32 * off, pts, mags, negs, bad);
-        KB_LAUNCHED();
-        k_msm_hist<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, counts);
+        // decode (or, for points that are already decoded, make affine with shared inversions) + digit histogram
+        if (ext) k_msm_prepare_ext<<<kb_blocks((cn + KB_INV_K - 1) / KB_INV_K, KB_THREADS), KB_THREADS, 0, st>>>(pl, (const uint32_t*)d_points + 32 * off, d_scalars + 32 * off, pts, mags, negs, bad, counts);
+        else k_msm_prepare<<<kb_blocks(cn, KB_THREADS), KB_THREADS, 0, st>>>(pl, (const uint8_t*)d_points + 32 * off, d_scalars + 32 * off, pts, mags, negs, bad, counts);
         KB_LAUNCHED();
         const uint32_t ntiles = (pl.nb + KB_SCAN_TILE - 1) / KB_SCAN_TILE;
         k_msm_scan_tiles<<<ntiles, 256, 0, st>>>(pl.nb, counts, offsets, tile_sums);
@@ -70,7 +70,7 @@ int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d
         KB_CUDA(cudaMemsetAsync(long_list, 0, 4, st));  // word 0 of the block is the queue length
         k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, long_list, long_list + 4, bucket_sum, heads, tails, flags);
         KB_LAUNCHED();
-        k_msm_merge_long<<<ctx->sm_count * 2, KB_THREADS, 0, st>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
+        k_msm_merge_long<<<ctx->sm_count * 2, KB_MSM_LONG_THREADS, 0, st>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
         KB_LAUNCHED();
         k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial, part_tot);
         KB_LAUNCHED();
@@ -92,7 +92,14 @@ int kb_dev_msm(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_point
     if (!ctx || (n && (!d_scalars || !d_points)) || (!d_out32 && !d_partial128)) return KB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     KB_DEV_ENTER(st);
-    KB_DEV_RETURN(st, kb_msm_run(ctx, n, (const uint8_t*)d_scalars, (const uint8_t*)d_points, (uint8_t*)d_out32, (uint32_t*)d_partial128, (unsigned long long*)d_bad_points, st));
+    KB_DEV_RETURN(st, kb_msm_run(ctx, n, (const uint8_t*)d_scalars, d_points, 0, (uint8_t*)d_out32, (uint32_t*)d_partial128, (unsigned long long*)d_bad_points, st));
+}
+int kb_dev_msm_ext(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points128, void* d_out32, void* d_partial128, void* d_bad_points, void* stream)
+{
+    if (!ctx || (n && (!d_scalars || !d_points128)) || (!d_out32 && !d_partial128)) return KB_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    KB_DEV_ENTER(st);
+    KB_DEV_RETURN(st, kb_msm_run(ctx, n, (const uint8_t*)d_scalars, d_points128, 1, (uint8_t*)d_out32, (uint32_t*)d_partial128, (unsigned long long*)d_bad_points, st));
 }
 int kb_msm(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t* out32, uint8_t* partial128, uint64_t* bad_points)
 {

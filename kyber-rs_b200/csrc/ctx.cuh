@@ -127,7 +127,8 @@ int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* 
                      uint32_t* xyz, uint8_t* fl, cudaStream_t st);
 #define KB_VERIFY_SCRATCH_BYTES 304   // per signature in `xyz` (4 * KB_HALF_REC_WORDS)
 // capi_msm.cu: Pippenger on device buffers
-int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const uint8_t* d_points, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st);
+// (ext != 0: the points are already decoded, 128 bytes each as X, Y, Z, T words)
+int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const void* d_points, int ext, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st);
 // capi_poly.cu: a deal-verification round on device buffers (commitments as 32-byte encodings, or as the reference's
 // 40-limb in-memory form when limbs != 0)
 int kb_poly_run(kb_ctx* ctx, size_t npoly, size_t t, const void* d_commits, int limbs, size_t m, const uint32_t* d_poly_id, const uint32_t* d_idx, size_t n_verifiers,

@@ -337,20 +337,89 @@ KB_FN void kb_msm_window_chunk(ge_p3& t1, ge_p3& t2, uint32_t c0, uint32_t c1, c
 // kernels
 // ======================================================================================
 #if defined(KB_K_MSM)
-static __global__ void __launch_bounds__(KB_THREADS) k_msm_prepare(size_t n, const uint8_t* points, const uint8_t* scalars, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad)
+// prepare + histogram in one pass: the digits are counted while the scalar is still at hand (counts zeroed by the caller)
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_prepare(kb_msm_plan pl, const uint8_t* points, const uint8_t* scalars, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad, uint32_t* counts)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= pl.n) return;
     uint32_t pw[8], sw[8];
     kb_load32(pw, points, i);   // coalesced 128-bit loads of the 32-byte encodings
     kb_load32(sw, scalars, i);
     kb_msm_prepare_body(i, pw, sw, pts, mags, negs, bad);
-}
-static __global__ void __launch_bounds__(256) k_msm_hist(kb_msm_plan pl, const uint32_t* mags, uint32_t* counts)
-{
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pl.n) return;
     kb_msm_hist_body(pl, i, mags, counts);
+}
+// The same for points that are already decoded: X, Y, Z, T as 4 x 8 words (any Z != 0) — what kb_point_decompress_batch,
+// the MSM partials and every device-side producer of this library emit.  No 252-squaring decompression: one thread
+// makes KB_INV_K points affine with ONE shared inversion (Montgomery's trick).  A point with Z = 0 or off the curve
+// counts as bad and is replaced by the identity.
+static __global__ void __launch_bounds__(KB_THREADS) k_msm_prepare_ext(kb_msm_plan pl, const uint32_t* points128, const uint8_t* scalars, uint32_t* pts, uint32_t* mags, uint8_t* negs, uint32_t* bad, uint32_t* counts)
+{
+    const size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * KB_INV_K;
+    if (base >= pl.n) return;
+    const int cnt = (pl.n - base < KB_INV_K) ? (int)(pl.n - base) : KB_INV_K;
+    fe pref[KB_INV_K];
+    fe acc, z, one;
+    uint32_t zbad = 0;
+    fe_set(one, 1);
+    fe_set(acc, 1);
+#pragma unroll 1
+    for (int k = 0; k < cnt; k++) {
+        kb_load_fe(z, points128 + 32 * (base + k) + 16);
+        const uint32_t z0 = fe_is_zero(z);
+        zbad |= z0 << k;
+        fe_cmov(z, one, z0);
+        fe_mul(acc, acc, z);
+        pref[k] = acc;
+    }
+    fe inv;
+    fe_invert(inv, acc);
+    const fe d = KB_FE_D, d2 = KB_FE_D2;
+#pragma unroll 1
+    for (int k = cnt - 1; k >= 0; k--) {
+        const size_t i = base + k;
+        fe zinv;
+        kb_load_fe(z, points128 + 32 * i + 16);
+        fe_cmov(z, one, (zbad >> k) & 1u);
+        if (k > 0) {
+            fe_mul(zinv, inv, pref[k - 1]);
+            fe_mul(inv, inv, z);
+        } else {
+            zinv = inv;
+        }
+        fe x, y, xx, yy, l, r;
+        kb_load_fe(x, points128 + 32 * i);
+        kb_load_fe(y, points128 + 32 * i + 8);
+        fe_mul(x, x, zinv);
+        fe_mul(y, y, zinv);
+        // on the curve:  -x^2 + y^2 = 1 + d x^2 y^2
+        fe_sq(xx, x);
+        fe_sq(yy, y);
+        fe_sub(l, yy, xx);
+        fe_mul(r, xx, yy);
+        fe_mul(r, r, d);
+        fe_add(r, r, one);
+        fe_sub(l, l, r);
+        const uint32_t ok = fe_is_zero(l) & (((zbad >> k) & 1u) ^ 1u);
+        ge_precomp q;
+        fe_add(q.ypx, y, x);
+        fe_sub(q.ymx, y, x);
+        fe_mul(q.xy2d, x, y);
+        fe_mul(q.xy2d, q.xy2d, d2);
+        if (!ok) {
+            ge_precomp_identity(q);
+            atomicAdd(bad, 1u);
+        }
+        uint32_t* o = pts + 24 * i;
+        kb_store_fe(o, q.ypx);
+        kb_store_fe(o + 8, q.ymx);
+        kb_store_fe(o + 16, q.xy2d);
+        uint32_t sw[8], mag[8], neg;
+        kb_load32(sw, scalars, i);
+        sc_effective(mag, neg, sw);
+        kb_store32(reinterpret_cast<uint8_t*>(mags), i, mag);
+        negs[i] = (uint8_t)neg;
+        kb_msm_hist_body(pl, i, mags, counts);
+    }
 }
 // exclusive scan of counts[0..nb) into offsets[0..nb], three launches:
 //   tiles : each block scans a 2048-element tile (coalesced through shared memory), emits its total
@@ -442,7 +511,7 @@ static __global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl,
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    kb_msm_merge_body(pl, t, nthreads, offsets, 32u, long_count, long_list, bucket_sum, heads, tails, flags);
+    kb_msm_merge_body(pl, t, nthreads, offsets, 8u, long_count, long_list, bucket_sum, heads, tails, flags);
 }
 static __global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* part_run, uint32_t* part_tot)
 {
@@ -471,22 +540,24 @@ __device__ __forceinline__ void kb_warp_sum_point(ge_p3& p)
     }
 }
 #if defined(KB_K_MSM)
-// long runs: one warp per queued (t, u_end, bucket): lanes stride over the head partials of chunks
-// t+1 .. u_end-1, butterfly-sum them with shuffles, lane 0 adds tail[t] and owns the bucket.
-static __global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nthreads, const uint32_t* long_count, const uint32_t* long_list, uint32_t* bucket_sum, const uint32_t* heads,
-                                                               const uint32_t* tails, const uint8_t* flags)
+// long runs: one BLOCK per queued (t, u_end, bucket): its threads stride over the head partials of chunks t+1 .. u_end-1,
+// sum them by warp butterflies and across the warps through shared memory; thread 0 adds tail[t] and owns the bucket.
+// (A run of thousands of chunks — the top window of reduced scalars holds a single bucket — used to be one warp's work.)
+#define KB_MSM_LONG_THREADS 256
+static __global__ void __launch_bounds__(KB_MSM_LONG_THREADS) k_msm_merge_long(size_t nthreads, const uint32_t* long_count, const uint32_t* long_list, uint32_t* bucket_sum, const uint32_t* heads,
+                                                                                 const uint32_t* tails, const uint8_t* flags)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ uint32_t wsum[(KB_MSM_LONG_THREADS / 32) * 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t count = *long_count;
-    for (uint32_t e = warp; e < count; e += nwarps) {
+    for (uint32_t e = blockIdx.x; e < count; e += gridDim.x) {
         const size_t t = long_list[3 * e];
         size_t u_end = long_list[3 * e + 1];
         if (u_end > nthreads) u_end = nthreads;
         const uint32_t b = long_list[3 * e + 2];
         ge_p3 s;
         ge_identity(s);
-        for (size_t u = t + 1 + lane; u < u_end; u += 32) {
+        for (size_t u = t + 1 + threadIdx.x; u < u_end; u += KB_MSM_LONG_THREADS) {
             if (flags[u] & 1u) {
                 ge_p3 h;
                 kb_load_p3(h, heads + 32 * u);
@@ -496,13 +567,21 @@ static __global__ void __launch_bounds__(KB_THREADS) k_msm_merge_long(size_t nth
             }
         }
         kb_warp_sum_point(s);
-        if (lane == 0) {
-            ge_p3 tl;
-            kb_load_p3(tl, tails + 32 * t);
-            ge_cached tc;
-            ge_to_cached(tc, tl);
-            ge_add<true>(s, s, tc);
-            kb_store_p3(bucket_sum + 32 * (size_t)b, s);
+        __syncthreads();   // the previous entry's readers are done with wsum
+        if (lane == 0) kb_store_p3(wsum + 32 * warp, s);
+        __syncthreads();
+        if (warp == 0) {
+            ge_identity(s);
+            if (lane < KB_MSM_LONG_THREADS / 32) kb_load_p3(s, wsum + 32 * lane);
+            kb_warp_sum_point(s);
+            if (lane == 0) {
+                ge_p3 tl;
+                kb_load_p3(tl, tails + 32 * t);
+                ge_cached tc;
+                ge_to_cached(tc, tl);
+                ge_add<true>(s, s, tc);
+                kb_store_p3(bucket_sum + 32 * (size_t)b, s);
+            }
         }
     }
 }

@@ -16,6 +16,9 @@ pub enum GpuError {
     Arg,
     Cuda(String),
     NoMem,
+    /// an input point does not decode (what `Point::unmarshal_binary` reports as MarshallingError::InvalidInput);
+    /// the index of the first such item
+    InvalidPoint(usize),
 }
 
 /// One CUDA device, one host thread — kyber-rs itself is single-threaded.
@@ -53,6 +56,12 @@ fn pack_scalars(s: &[EdScalar]) -> Vec<u8> {
 fn pack_points(p: &[EdPoint]) -> Vec<u8> {
     p.iter().flat_map(|x| x.marshal_binary().expect("32 bytes")).collect()
 }
+/// The in-memory form of a `Point` (ge.rs:75-83: X, Y, Z, T as 10 i32 limbs each) — what the `_limbs` / `KB_POINT_LIMBS40`
+/// entry points take, so that a caller holding thousands of commitments does not pay one field inversion each for
+/// `marshal_binary`.
+fn pack_point_limbs(p: &[EdPoint]) -> Vec<i32> {
+    p.iter().flat_map(|x| x.ge_mut_ref_limbs()).collect() // accessor to be added next to Point::ge (point.rs:24)
+}
 fn unpack_points(b: &[u8]) -> Vec<EdPoint> {
     b.chunks(32)
         .map(|c| {
@@ -80,6 +89,10 @@ impl BatchPoint for EdPoint {
                 let p = pack_points(ps);
                 let mut st = vec![0u8; n];
                 gpu.check(unsafe { sys::kb_point_mul_batch(gpu.ctx, n, s.as_ptr(), p.as_ptr(), out.as_mut_ptr(), st.as_mut_ptr(), 0) })?;
+                // an undecodable input leaves 32 zero bytes, which would decode as a valid order-4 point: report it instead
+                if let Some(i) = st.iter().position(|&x| x != 0) {
+                    return Err(GpuError::InvalidPoint(i));
+                }
             }
         }
         Ok(unpack_points(&out))
@@ -109,6 +122,12 @@ pub fn verify_batch(gpu: &Gpu, items: &[(&[u8], &[u8], &[u8])], schnorr: bool) -
     for (i, (p, m, s)) in items.iter().enumerate() {
         if s.len() != 64 {
             res[i] = Some(status_to_result(1)); // eddsa_sig.rs:161 / schnorr_sig.rs:68
+            continue;
+        }
+        if p.len() != 32 {
+            // the reference cannot even build such a key: unmarshal_binary fails; one wrong-length key must not
+            // misalign every later item of the packed batch
+            res[i] = Some(status_to_result(5));
             continue;
         }
         pk.extend_from_slice(p);
@@ -141,6 +160,9 @@ impl<G: kyber_rs::Group<POINT = EdPoint>> PubPolyBatch for PubPoly<G> {
         let mut out = vec![0u8; 32 * idx.len()];
         let mut st = vec![0u8; idx.len()];
         gpu.check(unsafe { sys::kb_pubpoly_eval_batch(gpu.ctx, 1, commits.len(), c.as_ptr(), idx.len(), pid.as_ptr(), idx.as_ptr(), out.as_mut_ptr(), st.as_mut_ptr()) })?;
+        if let Some(i) = st.iter().position(|&x| x != 0) {
+            return Err(GpuError::InvalidPoint(i));
+        }
         Ok(unpack_points(&out))
     }
     fn check_batch(&self, gpu: &Gpu, shares: &[PriShare<EdScalar>]) -> Result<Vec<bool>, GpuError> {
@@ -162,5 +184,22 @@ pub fn msm(gpu: &Gpu, scalars: &[EdScalar], points: &[EdPoint]) -> Result<EdPoin
     let mut out = [0u8; 32];
     let mut bad = 0u64;
     gpu.check(unsafe { sys::kb_msm(gpu.ctx, scalars.len(), s.as_ptr(), p.as_ptr(), out.as_mut_ptr(), std::ptr::null_mut(), &mut bad) })?;
+    if bad != 0 {
+        return Err(GpuError::InvalidPoint(0)); // the sum is undefined when an input does not decode
+    }
     Ok(unpack_points(&out).remove(0))
+}
+
+
+/// One DKG deal-verification round for this node's view of `dealers` (share/dkg/pedersen/dkg.rs:513-597): every dealer's
+/// committed polynomial against the share it sent to every verifier, the commitments handed over in their in-memory form
+/// (no per-commitment `marshal_binary`).  `verdict[d * n + i]` is what `Aggregator::verify_deal` (vss.rs:899-912) decides.
+pub fn dkg_verify_round(gpu: &Gpu, n: usize, polys: &[Vec<EdPoint>], shares: &[EdScalar]) -> Result<Vec<bool>, GpuError> {
+    let t = polys.first().map(|p| p.len()).unwrap_or(0);
+    assert!(polys.iter().all(|p| p.len() == t) && shares.len() == polys.len() * n);
+    let limbs: Vec<i32> = polys.iter().flat_map(|p| pack_point_limbs(p)).collect();
+    let sh = pack_scalars(shares);
+    let mut verdict = vec![0u8; polys.len() * n];
+    gpu.check(unsafe { sys::kb_dkg_verify_round_limbs(gpu.ctx, n, t, 0, polys.len(), limbs.as_ptr(), sh.as_ptr(), verdict.as_mut_ptr()) })?;
+    Ok(verdict.into_iter().map(|v| v == 1).collect())
 }

@@ -524,6 +524,45 @@ def test_msm_matches_oracle(ctx, coracle, golden_records, n):
     assert enc == want
 
 
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 1000, 70000])
+def test_msm_decoded_points(ctx, coracle, golden_records, n):
+    """kb_dev_msm_ext: the MSM over points that are already decoded (X, Y, Z, T words, any Z) equals the MSM over their
+    encodings; a point with Z = 0 or off the curve is counted as bad."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    pts = _golden_pks(golden_records, min(n, 1024))
+    pts = np.tile(pts, ((n + pts.shape[0] - 1) // pts.shape[0], 1))[:n]
+    s = random_scalars("msm-ext%d" % n, min(n, 2048))
+    s = np.tile(s, ((n + s.shape[0] - 1) // s.shape[0], 1))[:n]
+    want, bad = ctx.msm(s, pts)
+    assert bad == 0
+    raw, st = ctx.point_decompress_batch(pts)
+    assert not st.any()
+    # a projective representative with Z != 1: scale through an addition with the identity-free path — (X,Y,Z,T) of 2P - P
+    d_raw = torch.from_numpy(raw.view(np.uint8).reshape(n, 128)).to(dev)
+    d_s = torch.from_numpy(s).to(dev)
+    d_out = torch.zeros(32, dtype=torch.uint8, device=dev)
+    d_part = torch.zeros(128, dtype=torch.uint8, device=dev)
+    d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.dev_msm_ext(n, d_s, d_raw, d_out, d_part, d_bad)
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tobytes() == want and int(d_bad.item()) == 0
+    # the partial of an MSM has Z != 1: feed it back as a one-point MSM with scalar 1
+    one = torch.zeros(1, 32, dtype=torch.uint8, device=dev)
+    one[0, 0] = 1
+    ctx.dev_msm_ext(1, one, d_part.reshape(1, 128), d_out, None, d_bad)
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tobytes() == want
+    if n >= 9:
+        raw2 = raw.copy()
+        raw2[3, 16:24] = 0                 # Z = 0
+        raw2[8, 0] ^= 1                    # X off the curve
+        ctx.dev_msm_ext(n, d_s, torch.from_numpy(raw2.view(np.uint8).reshape(n, 128)).to(dev), d_out, None, d_bad)
+        torch.cuda.synchronize()
+        assert int(d_bad.item()) == 2
+
+
 def test_msm_skew_and_linearity(ctx, coracle, golden_records):
     """Size-independent properties at a size the oracle cannot reach quickly (2^16): linearity in the
     scalars, equal scalars (one giant bucket per window), partial + point_sum == whole."""
