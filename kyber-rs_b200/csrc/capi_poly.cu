@@ -84,6 +84,7 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     const unsigned step_threads = 32u * (unsigned)((h + 31) / 32);
     // up to 192 orders per block: 3 blocks (18 warps) per SM at 112 registers; up to 256: 2 blocks
     static const int wide = getenv("KB_FD_STEPS_WIDE") ? atoi(getenv("KB_FD_STEPS_WIDE")) : 0;   // A/B switch (tuning)
+    // (measured: 2, 3 or 4 resident blocks per SM give the same round time — the kernel is bound by the multiplier pipe)
     if (step_threads <= 192 && !wide) k_fd_steps<192, 3><<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
     else k_fd_steps<KB_FD_MAX_H, 2><<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
     KB_LAUNCHED();

@@ -304,7 +304,9 @@ static __global__ void __launch_bounds__(MAXH, MINB) k_fd_steps(size_t nd, size_
 {
     __shared__ uint4 xch_raw[2 * (MAXH / 32) * 8];   // 2 buffers x warps x 32 words
     uint32_t* xch = reinterpret_cast<uint32_t*>(xch_raw);
-    const size_t d = blockIdx.x / parts, q = blockIdx.x % parts;
+    // blocks of the same coefficient block are neighbours in the grid: the shorter last block (fewer live warps) comes
+    // last and fills the tail of the launch
+    const size_t q = blockIdx.x / nd, d = blockIdx.x % nd;
     const size_t hq = kb_fd_part_len(t, h, q);
     const unsigned k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarps = blockDim.x >> 5;
     ge_p3 p;
