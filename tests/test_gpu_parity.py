@@ -359,6 +359,21 @@ def test_verify_host_mirror_errors(kb, ctx, golden_records):
         H.Point.unmarshal_binary(hashlib.sha256(b"bad0").digest() if not ctx.point_check_batch(np.frombuffer(hashlib.sha256(b"bad0").digest(), np.uint8))[0] & 4 else b"\x02" + bytes(31))
 
 
+def test_bad_message_offsets_are_refused(kb, ctx, golden_records):
+    """A non-monotone offset array is an argument error (KB_ERR_ARG), not an out-of-bounds read on the device — also
+    when the bad entry sits in the middle of a pipelined chunk."""
+    pks, msgs, sigs = make_sig_batch(golden_records[:64], 5000, bad_every=0)
+    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+    assert not ctx.verify_batch(pk, flat, off, sg).any()
+    bad = off.copy()
+    bad[3333] = bad[3334] + 7
+    for fn in (lambda: ctx.verify_batch(pk, flat, bad, sg), lambda: ctx.verify_batch(pk, flat, bad, sg, schnorr=True), lambda: ctx.challenge_batch(sg[:, :32], pk, flat, bad),
+               lambda: ctx.eddsa_sign_batch(pk, flat, bad)):
+        with pytest.raises(kb.KBError):
+            fn()
+    assert not ctx.verify_batch(pk, flat, off, sg).any()      # the context is still usable
+
+
 def test_group_laws_host_mirror(kb, ctx):
     """util/test/group_test.rs:210-555 in miniature: 2G, -1*G + G = 0, DH commutativity, homomorphisms."""
     H = kb.host
