@@ -121,7 +121,7 @@ static size_t kb_dkg_plan(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
         const double steps = (double)n * lanes * 660.0 * 0.93;   // the dead orders of the last h steps are skipped
         const double comb = pe > 1 ? (double)n * (101000.0 + (pe - 1) * 42000.0) : 0.0;
         const double work = (conv + steps + comb + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
-        const double chain = h * 22e-6 + n * 2.5e-6;   // one cell per conversion launch, one addition per step
+        const double chain = h * 14e-6 + n * 2.5e-6 + (pe > 1 ? 0.3e-3 : 0.0);   // one cell per conversion launch, one addition per step, one Straus run
         const double time = work > chain ? work + 0.3 * chain : chain + 0.3 * work;
         if (best_h == 0 || time < best_time) {
             best_h = h;
@@ -139,9 +139,12 @@ static size_t kb_dkg_plan(const kb_ctx* ctx, size_t n, size_t t, size_t nd)
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need > 0.8 * (double)free_b + have) return 0;
     }
     if (ctx->dkg_fd == 1) return best_h;
-    const double horner = ((double)n * t * 6800.0 + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
-    // a round too small to fill the GPU is cheaper in one launch of the per-share kernel
-    return (nd * t >= 8192 && best_time * 1.15 < horner) ? best_h : 0;
+    // the per-share kernel: one launch, but a thread walks all t coefficients (about 14 us each) on its own
+    const double horner_work = ((double)n * t * 6800.0 + (double)n * 36000.0 + (double)t * 12700.0) * nd / rate;
+    const double horner_chain = t * 14e-6 + 0.2e-3;
+    const double horner = horner_work > horner_chain ? horner_work + 0.3 * horner_chain : horner_chain + 0.3 * horner_work;
+    // measured, n = 256, t = 171: 32 / 64 / 128 / 256 dealers -> Horner 4.2 ms at 32 dealers, forward differences 2.5 / 3.5 / 5.8 ms
+    return (nd * t >= 1024 && best_time * 1.15 < horner) ? best_h : 0;
 }
 int kb_dkg_round_run(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, const void* d_commits, int limbs, const uint8_t* d_shares, uint8_t* d_verdict, cudaStream_t st)
 {

@@ -296,66 +296,89 @@ static __global__ void __launch_bounds__(KB_FD_CONV_THREADS, KB_FD_CONV_MINBLOCK
 
 // Stage C.  Block = one (dealer, block q); thread = order k.  All n steps in one launch: per step every lane turns its
 // value into the operand form (1 M), hands it to the lane below (shuffle; the lowest lane of a warp through shared
-// memory, double-buffered so that one barrier per step is enough), adds what it received (8 M), and lane 0 records the
-// value E_q(i + 1) into evals[(q * n + i) * nd + d].  An order k can only reach the value k steps later, so the orders
-// above n - step are dead and their warps idle (they still meet the barrier).
+// memory), adds what it received (8 M), and lane 0 records the value E_q(i + 1) into evals[(q * n + i) * nd + d].  An order
+// k can only reach the value k steps later, so the orders above n - step are dead and their warps leave the loop.
+// Neighbouring warps hand the operand over through a one-slot mailbox guarded by two NAMED barriers per pair (FULL: the
+// upper warp arrives after writing, the lower warp waits; EMPTY: the lower warp arrives after reading, the upper warp
+// waits before the next write), so a warp only ever waits for its neighbour and the six warps of a block run as a
+// pipeline, up to one step apart per pair.  (A block-wide barrier per step was the largest stall of the first version of
+// this kernel: ncu `barrier` 3.2 per issue.)
+__device__ __forceinline__ void kb_bar_sync(unsigned id)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void kb_bar_arrive(unsigned id)
+{
+    __threadfence_block();
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
 template <int MAXH, int MINB>
 static __global__ void __launch_bounds__(MAXH, MINB) k_fd_steps(size_t nd, size_t t, size_t h, size_t parts, size_t n, const uint32_t* dec, const uint32_t* diffs, uint32_t* evals)
 {
-    __shared__ uint4 xch_raw[2 * (MAXH / 32) * 8];   // 2 buffers x warps x 32 words
+    __shared__ uint4 xch_raw[(MAXH / 32) * 8];   // one mailbox of 32 words per warp: the operand of its lowest order
     uint32_t* xch = reinterpret_cast<uint32_t*>(xch_raw);
     // blocks of the same coefficient block are neighbours in the grid: the shorter last block (fewer live warps) comes
     // last and fills the tail of the launch
     const size_t q = blockIdx.x / nd, d = blockIdx.x % nd;
     const size_t hq = kb_fd_part_len(t, h, q);
-    const unsigned k = threadIdx.x, lane = k & 31, warp = k >> 5, nwarps = blockDim.x >> 5;
+    const unsigned k = threadIdx.x, lane = k & 31, warp = k >> 5;
+    if (32u * warp >= hq) return;   // a warp without orders (the last coefficient block is shorter)
+    const unsigned nlive = (unsigned)((hq + 31) / 32);
     ge_p3 p;
     ge_identity(p);
     if (k == 0) kb_fd_load(p, KB_FD_AT(dec, q * h, d, nd));
     else if (k < hq) kb_fd_load(p, KB_FD_AT(diffs, q * h + k, d, nd));
     const bool top = k + 1 >= hq;   // nothing above: the operand is the identity
+    // barrier ids: pair (w, w + 1) uses FULL = 1 + 2 w and EMPTY = 2 + 2 w  (<= 14 for 8 warps; 0 is __syncthreads)
+    const unsigned full_up = 1 + 2 * warp, empty_up = 2 + 2 * warp;            // as the consumer of the warp above
+    const unsigned full_dn = 1 + 2 * (warp - 1), empty_dn = 2 + 2 * (warp - 1);  // as the producer for the warp below
+    // the warp above produces for step i while it is live at step i
+    if (warp + 1 < nlive && 32u * (warp + 1) <= n) kb_bar_arrive(empty_up);    // the mailbox starts empty
     for (size_t i = 0; i < n; i++) {
         const size_t reach = n - i;   // the orders <= reach can still matter
-        const bool warp_live = 32u * warp < hq && 32u * warp <= reach;
-        uint32_t* buf = xch + (i & 1) * (MAXH / 32) * 32;
+        if (32u * warp > reach) break;   // dead from here on (warp-uniform)
         ge_cached c;
-        if (warp_live) {
-            ge_to_cached(c, p);
-            if (lane == 0 && warp > 0) {
-                uint32_t* o = buf + 32 * warp;
+        ge_to_cached(c, p);
+        if (warp > 0) {
+            kb_bar_sync(empty_dn);   // the warp below has read the previous operand
+            if (lane == 0) {
+                uint32_t* o = xch + 32 * warp;
                 kb_store_fe(o, c.YpX);
                 kb_store_fe(o + 8, c.YmX);
                 kb_store_fe(o + 16, c.T2d);
                 kb_store_fe(o + 24, c.Z);
             }
+            __syncwarp();
+            kb_bar_arrive(full_dn);
         }
-        __syncthreads();
-        if (warp_live) {
 #pragma unroll
-            for (int w = 0; w < 8; w++) {
-                c.YpX.v[w] = __shfl_down_sync(0xffffffffu, c.YpX.v[w], 1);
-                c.YmX.v[w] = __shfl_down_sync(0xffffffffu, c.YmX.v[w], 1);
-                c.T2d.v[w] = __shfl_down_sync(0xffffffffu, c.T2d.v[w], 1);
-                c.Z.v[w] = __shfl_down_sync(0xffffffffu, c.Z.v[w], 1);
-            }
-            if (lane == 31) {
-                // the warp above may be dead (its orders can no longer matter, so nor can this lane's result) or
-                // absent: the operand then only has to be a valid point
-                const bool above_live = warp + 1 < nwarps && 32u * (warp + 1) < hq && 32u * (warp + 1) <= reach;
-                if (above_live) {
-                    const uint32_t* o = buf + 32 * (warp + 1);
-                    kb_load_fe(c.YpX, o);
-                    kb_load_fe(c.YmX, o + 8);
-                    kb_load_fe(c.T2d, o + 16);
-                    kb_load_fe(c.Z, o + 24);
-                } else {
-                    ge_cached_identity(c);
-                }
-            }
-            if (top) ge_cached_identity(c);
-            ge_add<true>(p, p, c);
-            if (k == 0) kb_fd_store(evals + ((q * n + i) * nd + d) * 32, p);
+        for (int w = 0; w < 8; w++) {
+            c.YpX.v[w] = __shfl_down_sync(0xffffffffu, c.YpX.v[w], 1);
+            c.YmX.v[w] = __shfl_down_sync(0xffffffffu, c.YmX.v[w], 1);
+            c.T2d.v[w] = __shfl_down_sync(0xffffffffu, c.T2d.v[w], 1);
+            c.Z.v[w] = __shfl_down_sync(0xffffffffu, c.Z.v[w], 1);
         }
+        // the warp above may be dead (its orders can no longer matter, so nor can this warp's top lane) or absent: the
+        // operand then only has to be a valid point
+        const bool above_live = warp + 1 < nlive && 32u * (warp + 1) <= reach;
+        if (above_live) {
+            kb_bar_sync(full_up);
+            if (lane == 31) {
+                const uint32_t* o = xch + 32 * (warp + 1);
+                kb_load_fe(c.YpX, o);
+                kb_load_fe(c.YmX, o + 8);
+                kb_load_fe(c.T2d, o + 16);
+                kb_load_fe(c.Z, o + 24);
+            }
+            __syncwarp();
+            // the warp above only waits for this if it will produce again: at its next step it is live iff 32 (w+1) <= reach - 1
+            if (32u * (warp + 1) + 1 <= reach) kb_bar_arrive(empty_up);
+        } else if (lane == 31) {
+            ge_cached_identity(c);
+        }
+        if (top) ge_cached_identity(c);
+        ge_add<true>(p, p, c);
+        if (k == 0) kb_fd_store(evals + ((q * n + i) * nd + d) * 32, p);
     }
 }
 
