@@ -1,12 +1,13 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q -k "msm" 2>&1 | tail -2
-python - <<'PY'
-import importlib, sys, torch, numpy as np
+timeout 300 python -m pytest tests -m gpu -x -q -k "msm" 2>&1 | tail -2
+cat > /tmp/msm_t.py <<'PY'
+import importlib, sys, torch, numpy as np, os
 sys.path.insert(0, '.')
 kb = importlib.import_module("kyber-rs_b200")
 ctx = kb.Context(0); dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(1)
-for lg in (20, 22):
+out = []
+for lg in (17, 20, 22):
     n = 1 << lg
     sc = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g); sc[:, 31] &= 0x0F
     ps = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g); ps[:, 31] &= 0x0F
@@ -20,5 +21,8 @@ for lg in (20, 22):
         for _ in range(5): fn()
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 5
-        print(lg, name, round(ms, 3), "ms", round(n / ms / 1e3, 1), "M pts/s")
+        out.append(f"2^{lg} {name} {ms:.3f} ms {n / ms / 1e3:.1f} M/s")
+print(os.environ.get("KB_MSM_ACCUM_MINB"), os.environ.get("KB_MSM_WS_THREADS"), " | ".join(out))
 PY
+for mb in 4 5 6; do KB_MSM_ACCUM_MINB=$mb python /tmp/msm_t.py 2>/dev/null | tail -1; done
+KB_MSM_WS_THREADS=512 python /tmp/msm_t.py 2>/dev/null | tail -1
