@@ -610,6 +610,182 @@ KB_FN void fe_sq_inl(fe& h, const fe& f)
     fe_reduce512(h, ev);
 }
 
+// ---------------------------------------------------------------------------------------
+// One level of (subtractive) Karatsuba for h = f * g: three 4 x 4-limb products (48 IMAD.WIDE) instead of 64.
+//   a = a0 + 2^128 a1, b = b0 + 2^128 b1:   a b = z0 + 2^128 (z0 + z2 - (a0 - a1)(b0 - b1)) + 2^256 z2
+// The differences are taken in absolute value (4 limbs, no overflow) with their signs tracked.  The IMAD.WIDE that
+// does the products holds the multiplier pipe 4 cycles per warp instruction, the additions this costs (about 70
+// more than the schoolbook form) run on the ALU pipe at 2 — in the point formulas the ALU pipe has that room.
+// ---------------------------------------------------------------------------------------
+KB_FN void kb_cmul2(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b)
+{
+    const uint64_t p0 = (uint64_t)a0 * b, p1 = (uint64_t)a1 * b;
+    acc[0] = (uint32_t)p0; acc[1] = (uint32_t)(p0 >> 32);
+    acc[2] = (uint32_t)p1; acc[3] = (uint32_t)(p1 >> 32);
+}
+// acc[0..7) += x[0..7) (no carry out: callers guarantee it fits)
+KB_FN void kb_acc7(uint32_t* acc, const uint32_t* x)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t c = 0;
+    for (int i = 0; i < 7; i++) {
+        c += (uint64_t)acc[i] + x[i];
+        acc[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#else
+    asm("add.cc.u32 %0, %0, %7;\n\t"
+        "addc.cc.u32 %1, %1, %8;\n\t"
+        "addc.cc.u32 %2, %2, %9;\n\t"
+        "addc.cc.u32 %3, %3, %10;\n\t"
+        "addc.cc.u32 %4, %4, %11;\n\t"
+        "addc.cc.u32 %5, %5, %12;\n\t"
+        "addc.u32 %6, %6, %13;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]));
+#endif
+}
+// r[0..8) = a[0..4) * b[0..4): the even / odd column split of fe_mul_inl on 4 limbs (16 IMAD.WIDE, one 7-word merge)
+KB_FN void kb_mul4x4(uint32_t* r, const uint32_t* a, const uint32_t* b)
+{
+    uint32_t od[7];
+    kb_cmul2(&r[0], a[0], a[2], b[0]);                     // words 0..3
+    kb_cmul2(&od[0], a[1], a[3], b[0]);                    // words 1..4
+    r[4] = 0;
+    kb_cmad2_hi(&r[2], a[1], a[3], b[1]);                  // words 2..5
+    kb_cmad2_top(&od[0], a[0], a[2], b[1], od[4]);         // words 1..4, carry -> 5
+    kb_cmad2_top(&r[2], a[0], a[2], b[2], r[6]);           // words 2..5, carry -> 6
+    kb_cmad2_hi(&od[2], a[1], a[3], b[2]);                 // words 3..6
+    kb_cmad2_hi(&r[4], a[1], a[3], b[3]);                  // words 4..7
+    kb_cmad2_top(&od[2], a[0], a[2], b[3], od[6]);         // words 3..6, carry -> 7
+    kb_acc7(&r[1], &od[0]);
+}
+// d[0..4) = |x - y| on 4 limbs; returns 0xffffffff if x < y, else 0
+KB_FN uint32_t kb_absdiff4(uint32_t* d, const uint32_t* x, const uint32_t* y)
+{
+    uint32_t m;
+#if defined(KB_HOST_EMU)
+    uint64_t br = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint64_t t = (uint64_t)x[i] - y[i] - br;
+        d[i] = (uint32_t)t;
+        br = (t >> 32) & 1u;
+    }
+    m = 0u - (uint32_t)br;
+    uint64_t c = br;
+    for (int i = 0; i < 4; i++) {
+        c += (uint64_t)(d[i] ^ m);
+        d[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#else
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, 0, 0;"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(m)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+    d[0] ^= m; d[1] ^= m; d[2] ^= m; d[3] ^= m;
+    // (d ^ m) - m on 128 bits: + 1 when m is all ones
+    asm("sub.cc.u32 %0, %0, %4;\n\t"
+        "subc.cc.u32 %1, %1, %4;\n\t"
+        "subc.cc.u32 %2, %2, %4;\n\t"
+        "subc.u32 %3, %3, %4;"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(m));
+#endif
+    return m;
+}
+// t[0..16) = z0 + 2^128 (z0 + z2 -+ zm) + 2^256 z2 with z0 = t[0..8), z2 = t[8..16) on entry; nm = all ones to
+// SUBTRACT zm, 0 to add it
+KB_FN void kb_karatsuba_join(uint32_t* t, const uint32_t* zm, uint32_t nm)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t mid[9];
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)t[i] + t[8 + i];
+        mid[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    mid[8] = (uint32_t)c;
+    c = nm & 1u;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)mid[i] + (zm[i] ^ nm);
+        mid[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    mid[8] = (uint32_t)(mid[8] + nm + c);
+    c = 0;
+    for (int i = 0; i < 9; i++) {
+        c += (uint64_t)t[4 + i] + mid[i];
+        t[4 + i] = (uint32_t)c;
+        c >>= 32;
+    }
+    for (int i = 13; i < 16; i++) {
+        c += t[i];
+        t[i] = (uint32_t)c;
+        c >>= 32;
+    }
+#else
+    uint32_t m0, m1, m2, m3, m4, m5, m6, m7, m8;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(m0), "=&r"(m1), "=&r"(m2), "=&r"(m3), "=&r"(m4), "=&r"(m5), "=&r"(m6), "=&r"(m7), "=&r"(m8)
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]),
+          "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+    const uint32_t x0 = zm[0] ^ nm, x1 = zm[1] ^ nm, x2 = zm[2] ^ nm, x3 = zm[3] ^ nm, x4 = zm[4] ^ nm, x5 = zm[5] ^ nm, x6 = zm[6] ^ nm, x7 = zm[7] ^ nm;
+    uint32_t scratch;
+    // carry-in = nm & 1 (nm + 1 overflows exactly when nm is all ones); the ninth word takes the sign extension
+    asm("add.cc.u32 %9, %18, 1;\n\t"
+        "addc.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, %11;\n\t"
+        "addc.cc.u32 %2, %2, %12;\n\t"
+        "addc.cc.u32 %3, %3, %13;\n\t"
+        "addc.cc.u32 %4, %4, %14;\n\t"
+        "addc.cc.u32 %5, %5, %15;\n\t"
+        "addc.cc.u32 %6, %6, %16;\n\t"
+        "addc.cc.u32 %7, %7, %17;\n\t"
+        "addc.u32 %8, %8, %18;"
+        : "+r"(m0), "+r"(m1), "+r"(m2), "+r"(m3), "+r"(m4), "+r"(m5), "+r"(m6), "+r"(m7), "+r"(m8), "=&r"(scratch)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(x4), "r"(x5), "r"(x6), "r"(x7), "r"(nm));
+    asm("add.cc.u32 %0, %0, %12;\n\t"
+        "addc.cc.u32 %1, %1, %13;\n\t"
+        "addc.cc.u32 %2, %2, %14;\n\t"
+        "addc.cc.u32 %3, %3, %15;\n\t"
+        "addc.cc.u32 %4, %4, %16;\n\t"
+        "addc.cc.u32 %5, %5, %17;\n\t"
+        "addc.cc.u32 %6, %6, %18;\n\t"
+        "addc.cc.u32 %7, %7, %19;\n\t"
+        "addc.cc.u32 %8, %8, %20;\n\t"
+        "addc.cc.u32 %9, %9, 0;\n\t"
+        "addc.cc.u32 %10, %10, 0;\n\t"
+        "addc.u32 %11, %11, 0;"
+        : "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(m6), "r"(m7), "r"(m8));
+#endif
+}
+KB_FN void fe_mul_karatsuba(fe& h, const fe& f, const fe& g)
+{
+    uint32_t t[16], zm[8], da[4], db[4];
+    const uint32_t sa = kb_absdiff4(da, f.v, f.v + 4);
+    const uint32_t sb = kb_absdiff4(db, g.v, g.v + 4);
+    kb_mul4x4(&t[0], f.v, g.v);
+    kb_mul4x4(&t[8], f.v + 4, g.v + 4);
+    kb_mul4x4(zm, da, db);
+    // (a0 - a1)(b0 - b1) = +zm when the signs agree: the middle term is then z0 + z2 - zm
+    kb_karatsuba_join(t, zm, ~(sa ^ sb));
+    fe_reduce512(h, t);
+}
+
 // Code-size knob.  With every multiplication inlined, the verify kernel is ~29 k instructions and
 // its window loop alone (75 KB) overflows the 32 KB L1.5 instruction cache: ncu reports
 // "no_instruction" as the largest stall reason.  With KB_FE_CALLS the two big bodies exist ONCE per
@@ -631,6 +807,9 @@ __device__ __noinline__ fe fe_sq_call(fe f)
 }
 KB_FN void fe_mul(fe& h, const fe& f, const fe& g) { h = fe_mul_call(f, g); }
 KB_FN void fe_sq(fe& h, const fe& f) { h = fe_sq_call(f); }
+#elif defined(KB_FE_KARATSUBA)
+KB_FN void fe_mul(fe& h, const fe& f, const fe& g) { fe_mul_karatsuba(h, f, g); }
+KB_FN void fe_sq(fe& h, const fe& f) { fe_sq_inl(h, f); }
 #else
 KB_FN void fe_mul(fe& h, const fe& f, const fe& g) { fe_mul_inl(h, f, g); }
 KB_FN void fe_sq(fe& h, const fe& f) { fe_sq_inl(h, f); }

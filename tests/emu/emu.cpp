@@ -48,6 +48,8 @@ void emu_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b)
     case 3: fe_sub(r, x, y); break;
     case 4: fe_invert(r, x); break;
     case 5: fe_pow22523(r, x); break;
+    case 7: fe_mul_karatsuba(r, x, y); break;
+    case 8: fe_mul_inl(r, x, y); break;
     default: r = x; break;
     }
     uint32_t w[8];

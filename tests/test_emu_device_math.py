@@ -57,6 +57,19 @@ def test_field_ops(emu):
             assert feop(3, b32(x), b32(y)) == b32((x - y) % P)
         assert feop(1, b32(x)) == b32(x * x % P)
         assert feop(6, b32(x)) == b32(x % P)
+    # both multiplication bodies (schoolbook and one level of Karatsuba), incl. operands whose halves are equal,
+    # ordered either way, all ones / all zeros — the sign and borrow paths of the Karatsuba differences
+    M128 = 2**128
+    halves = [0, 1, M128 - 1, 2**127, 0x0123456789abcdef0123456789abcdef, 2**32 - 1, 2**96]
+    structured = [lo + M128 * hi for lo in halves for hi in halves]
+    for x in structured:
+        for y in rnd.sample(structured, 6) + rnd.sample(vals, 3):
+            want = b32(x * y % P)
+            assert feop(7, b32(x), b32(y)) == want, (hex(x), hex(y))
+            assert feop(8, b32(x), b32(y)) == want
+    for x in vals:
+        for y in rnd.sample(vals, 4):
+            assert feop(7, b32(x), b32(y)) == b32(x * y % P)
     for x in vals[:40]:
         assert feop(4, b32(x)) == b32(pow(x, P - 2, P))
         assert feop(5, b32(x)) == b32(pow(x, (P - 5) // 8, P))
