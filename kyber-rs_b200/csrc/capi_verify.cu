@@ -1,5 +1,13 @@
 // capi_verify.cu — eddsa::verify_with_checks / schnorr::verify_with_checks and EdDSA::sign entry points
 #define KB_K_SIGN
+// Field-arithmetic bodies of THIS translation unit (fe.cuh): the zero-free row order of fe_mul / fe_sq and the borrow-mask
+// wrap of fe_sub.  All bodies are bit-exact; which one is faster depends on the kernel (the balance ptxas strikes between
+// the ALU and the multiplier pipe).  Measured, round 2, one B200: the verify step gains 0.8 % with all three
+// (k_verify_half_main 16.54 -> 16.42 ms, k_verify_half_prep 4.96 -> 4.90 ms) while the MSM and DKG kernels lose 1-4 %,
+// so only the verifiers (and the signing kernels that share this unit) are built with them.
+#define KB_FE_MUL_RIP
+#define KB_FE_SQ_RIP
+#define KB_FE_SUBMASK
 #include "ctx.cuh"
 #include "kernels.cuh"
 // per-signature scratch of the verifiers: 304-byte records (half-size-scalar path) / 96-byte points (full-length path)

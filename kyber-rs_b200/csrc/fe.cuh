@@ -286,6 +286,215 @@ KB_FN void kb_cmul3(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32
     acc[4] = (uint32_t)p2; acc[5] = (uint32_t)(p2 >> 32);
 }
 
+// ---------------------------------------------------------------------------------------
+// Rows whose top pair is FRESH, and rows that ripple their carry into an EXISTING pair.
+// An IMAD.WIDE adds a 64-bit addend held in a register PAIR.  When a row ends on (a word holding a captured carry,
+// a fresh word), ptxas has to materialise the fresh half as a zeroed register — one IMAD.MOV per row, on the
+// multiplier pipe (ncu, round 2: 46 of the 78 register zeroings of the verify loop).  Ordering the rows so that the
+// row which CREATES a pair runs first (its top pair is completely fresh: addend RZ) and the row below it then
+// ripples its carry into that existing pair (two IADD3.X on the ALU pipe) needs no zeroed registers at all.
+// ---------------------------------------------------------------------------------------
+// acc[0..2(N-1)) += {a..} * b on existing pairs; the top pair (acc[2N-2], acc[2N-1]) is fresh: it takes the last
+// product plus the carry (cannot overflow)
+KB_FN void kb_cmad4_new(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[6] = acc[7] = 0;
+    kb_cmad4(acc, a0, a1, a2, a3, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, 0;\n\t"
+        "madc.hi.u32 %7, %11, %12, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#endif
+}
+KB_FN void kb_cmad3_new(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[4] = acc[5] = 0;
+    kb_cmad3(acc, a0, a1, a2, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %9, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %9, 0;\n\t"
+        "madc.hi.u32 %5, %8, %9, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(acc[4]), "=r"(acc[5])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#endif
+}
+KB_FN void kb_cmad2_new(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    acc[2] = acc[3] = 0;
+    kb_cmad2(acc, a0, a1, b, top);
+#else
+    asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+        "madc.lo.cc.u32 %2, %5, %6, 0;\n\t"
+        "madc.hi.u32 %3, %5, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
+        : "r"(a0), "r"(a1), "r"(b));
+#endif
+}
+// acc[0..2N) += {a..} * b on existing pairs; the carry out ripples into the existing pair (r0, r1) above them
+// (callers guarantee it cannot leave r1)
+KB_FN void kb_cmad4_rip(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b, uint32_t& r0, uint32_t& r1)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    kb_cmad4(acc, a0, a1, a2, a3, b, top);
+    const uint64_t c = (uint64_t)r0 + top;
+    r0 = (uint32_t)c;
+    r1 += (uint32_t)(c >> 32);
+#else
+    asm("mad.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.cc.u32 %8, %8, 0;\n\t"
+        "addc.u32 %9, %9, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(r0), "+r"(r1)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#endif
+}
+KB_FN void kb_cmad3_rip(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t& r0, uint32_t& r1)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    kb_cmad3(acc, a0, a1, a2, b, top);
+    const uint64_t c = (uint64_t)r0 + top;
+    r0 = (uint32_t)c;
+    r1 += (uint32_t)(c >> 32);
+#else
+    asm("mad.lo.cc.u32 %0, %8, %11, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %11, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %11, %5;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(r0), "+r"(r1)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+#endif
+}
+KB_FN void kb_cmad2_rip(uint32_t* acc, uint32_t a0, uint32_t a1, uint32_t b, uint32_t& r0, uint32_t& r1)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    kb_cmad2(acc, a0, a1, b, top);
+    const uint64_t c = (uint64_t)r0 + top;
+    r0 = (uint32_t)c;
+    r1 += (uint32_t)(c >> 32);
+#else
+    asm("mad.lo.cc.u32 %0, %6, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.u32 %5, %5, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(r0), "+r"(r1)
+        : "r"(a0), "r"(a1), "r"(b));
+#endif
+}
+KB_FN void kb_cmad1_rip(uint32_t* acc, uint32_t a0, uint32_t b, uint32_t& r0, uint32_t& r1)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t top = 0;
+    kb_cmad1(acc, a0, b, top);
+    const uint64_t c = (uint64_t)r0 + top;
+    r0 = (uint32_t)c;
+    r1 += (uint32_t)(c >> 32);
+#else
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.u32 %3, %3, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(r0), "+r"(r1)
+        : "r"(a0), "r"(b));
+#endif
+}
+KB_FN void kb_cmul1(uint32_t* acc, uint32_t a0, uint32_t b)
+{
+    const uint64_t p0 = (uint64_t)a0 * b;
+    acc[0] = (uint32_t)p0; acc[1] = (uint32_t)(p0 >> 32);
+}
+// The merge of the squaring's two column sets, doubled:  t[1..16) = 2 * (ev[1..16) + od[0..15))  where ev[0] = ev[1] =
+// ev[14] = ev[15] = od[14] = 0 are never materialised (t[1] = 2 od[0], t[14] = 2 (od[13] + carry), ...).  t[0] is not
+// written (it is 0).
+KB_FN void kb_sq_merge_dbl(uint32_t* t, const uint32_t* ev, const uint32_t* od)
+{
+#if defined(KB_HOST_EMU)
+    uint32_t m[16];
+    uint64_t c = 0;
+    m[1] = od[0];
+    for (int i = 2; i <= 13; i++) {
+        c += (uint64_t)ev[i] + od[i - 1];
+        m[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    c += od[13];
+    m[14] = (uint32_t)c;
+    m[15] = (uint32_t)(c >> 32);
+    uint32_t cy = 0;
+    for (int i = 1; i < 16; i++) {
+        const uint32_t n = m[i] >> 31;
+        t[i] = (m[i] << 1) | cy;
+        cy = n;
+    }
+#else
+    uint32_t m2, m3, m4, m5, m6, m7, m8, m9, m10, m11, m12, m13, m14, m15;
+    asm("add.cc.u32 %0, %14, %26;\n\t"
+        "addc.cc.u32 %1, %15, %27;\n\t"
+        "addc.cc.u32 %2, %16, %28;\n\t"
+        "addc.cc.u32 %3, %17, %29;\n\t"
+        "addc.cc.u32 %4, %18, %30;\n\t"
+        "addc.cc.u32 %5, %19, %31;\n\t"
+        "addc.cc.u32 %6, %20, %32;\n\t"
+        "addc.cc.u32 %7, %21, %33;\n\t"
+        "addc.cc.u32 %8, %22, %34;\n\t"
+        "addc.cc.u32 %9, %23, %35;\n\t"
+        "addc.cc.u32 %10, %24, %36;\n\t"
+        "addc.cc.u32 %11, %25, %37;\n\t"
+        "addc.cc.u32 %12, %38, 0;\n\t"
+        "addc.u32 %13, 0, 0;"
+        : "=&r"(m2), "=&r"(m3), "=&r"(m4), "=&r"(m5), "=&r"(m6), "=&r"(m7), "=&r"(m8), "=&r"(m9), "=&r"(m10), "=&r"(m11), "=&r"(m12), "=&r"(m13), "=&r"(m14), "=&r"(m15)
+        : "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]),
+          "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]));
+    asm("add.cc.u32 %0, %15, %15;\n\t"
+        "addc.cc.u32 %1, %16, %16;\n\t"
+        "addc.cc.u32 %2, %17, %17;\n\t"
+        "addc.cc.u32 %3, %18, %18;\n\t"
+        "addc.cc.u32 %4, %19, %19;\n\t"
+        "addc.cc.u32 %5, %20, %20;\n\t"
+        "addc.cc.u32 %6, %21, %21;\n\t"
+        "addc.cc.u32 %7, %22, %22;\n\t"
+        "addc.cc.u32 %8, %23, %23;\n\t"
+        "addc.cc.u32 %9, %24, %24;\n\t"
+        "addc.cc.u32 %10, %25, %25;\n\t"
+        "addc.cc.u32 %11, %26, %26;\n\t"
+        "addc.cc.u32 %12, %27, %27;\n\t"
+        "addc.cc.u32 %13, %28, %28;\n\t"
+        "addc.u32 %14, %29, %29;"
+        : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8]), "=&r"(t[9]), "=&r"(t[10]), "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]), "=&r"(t[15])
+        : "r"(od[0]), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(m6), "r"(m7), "r"(m8), "r"(m9), "r"(m10), "r"(m11), "r"(m12), "r"(m13), "r"(m14), "r"(m15));
+#endif
+}
 // acc[0..15) += x[0..15) (no carry out: callers guarantee it fits)
 KB_FN void kb_acc15(uint32_t* acc, const uint32_t* x)
 {
@@ -427,6 +636,30 @@ KB_FN uint32_t kb_sub8(uint32_t* r, const uint32_t* a, const uint32_t* b)
     return c & 1;
 #endif
 }
+// r = a - b over 8 words; returns the borrow as a MASK (0 / 0xffffffff): `mask & 38` is one ALU instruction where
+// `38 * borrow` is an IMAD on the multiplier pipe
+KB_FN uint32_t kb_sub8m(uint32_t* r, const uint32_t* a, const uint32_t* b)
+{
+#if defined(KB_HOST_EMU)
+    return 0u - kb_sub8(r, a, b);
+#else
+    uint32_t t[8], c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = t[i];
+    return c;
+#endif
+}
 // r[0..8) += k (a 32-bit value), returns the carry out.
 KB_FN uint32_t kb_add_small(uint32_t* r, uint32_t k)
 {
@@ -449,6 +682,33 @@ KB_FN uint32_t kb_add_small(uint32_t* r, uint32_t k)
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=&r"(c)
+        : "r"(k));
+    return c;
+#endif
+}
+// r[0..8) -= k, returns the borrow as a mask
+KB_FN uint32_t kb_sub_smallm(uint32_t* r, uint32_t k)
+{
+#if defined(KB_HOST_EMU)
+    uint64_t br = k;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)r[i] - br;
+        r[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return 0u - (uint32_t)br;
+#else
+    uint32_t c;
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.cc.u32 %5, %5, 0;\n\t"
+        "subc.cc.u32 %6, %6, 0;\n\t"
+        "subc.cc.u32 %7, %7, 0;\n\t"
+        "subc.u32 %8, 0, 0;"
         : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=&r"(c)
         : "r"(k));
     return c;
@@ -518,6 +778,38 @@ KB_FN void kb_sqr_acc8(uint32_t* t, const uint32_t* a)
 #endif
 }
 
+// t[0..16) = t[1..16) (t[0] absent = 0) + the squares a[i]^2 on word pairs (2i, 2i+1).  a[0]^2 is a plain product (its
+// low word IS t[0]); its high word opens the carry chain with one add, the other seven squares follow as IMAD.WIDE.X.
+KB_FN void kb_sqr_acc8_fresh0(uint32_t* t, const uint32_t* a)
+{
+#if defined(KB_HOST_EMU)
+    t[0] = 0;
+    kb_sqr_acc8(t, a);
+#else
+    const uint64_t p0 = (uint64_t)a[0] * a[0];
+    t[0] = (uint32_t)p0;
+    const uint32_t p0h = (uint32_t)(p0 >> 32);
+    asm("add.cc.u32 %0, %0, %15;\n\t"
+        "madc.lo.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.hi.cc.u32 %2, %16, %16, %2;\n\t"
+        "madc.lo.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.hi.cc.u32 %4, %17, %17, %4;\n\t"
+        "madc.lo.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.hi.cc.u32 %6, %18, %18, %6;\n\t"
+        "madc.lo.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.hi.cc.u32 %8, %19, %19, %8;\n\t"
+        "madc.lo.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.hi.cc.u32 %10, %20, %20, %10;\n\t"
+        "madc.lo.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.hi.cc.u32 %12, %21, %21, %12;\n\t"
+        "madc.lo.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.hi.u32 %14, %22, %22, %14;"
+        : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]),
+          "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+        : "r"(p0h), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // reduction of a 512-bit product: t[0..16) -> r[0..8), using 2^256 = 38 (mod p)
 // ---------------------------------------------------------------------------------------
@@ -548,8 +840,8 @@ KB_FN void fe_reduce512(fe& r, uint32_t* t)
     r.v[0] += 38u * c;
 }
 
-// h = f * g   (fe.rs:299 fe_mul)
-KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g)
+// h = f * g   (fe.rs:299 fe_mul), rows in natural order
+KB_FN void fe_mul_rows(fe& h, const fe& f, const fe& g)
 {
     uint32_t ev[17], od[16];
     const uint32_t* a = f.v;
@@ -581,8 +873,41 @@ KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g)
     fe_reduce512(h, ev);
 }
 
-// h = f^2   (fe.rs:544 fe_square): 28 cross products, doubled, plus 8 squares
-KB_FN void fe_sq_inl(fe& h, const fe& f)
+// h = f * g, rows ordered so that no register has to be zeroed (see kb_cmad4_new / kb_cmad4_rip)
+KB_FN void fe_mul_rip(fe& h, const fe& f, const fe& g)
+{
+    uint32_t ev[16], od[15];
+    const uint32_t* a = f.v;
+    const uint32_t* b = g.v;
+    // Operand scanning over b; products a[j]*b[i] with i+j even accumulate in ev (word i+j),
+    // those with i+j odd in od (od[k] is word k+1), so every IMAD.WIDE is pair-aligned.
+    // Row 0 lands on fresh words: plain products, nothing to zero and no carries.
+    kb_cmul4(&ev[0], a[0], a[2], a[4], a[6], b[0]);
+    kb_cmul4(&od[0], a[1], a[3], a[5], a[7], b[0]);
+    // Two consecutive rows touch the same four pairs of a column set and together open ONE new pair.  The row that
+    // opens it runs first (kb_cmad4_new: the new pair takes product + carry, addend RZ), the other one then ripples
+    // its carry into that pair (kb_cmad4_rip) — no zeroed registers, no captured carries (see the primitives).
+    // Bounds: after rows 0..r the partial sum of a column set is < 2^(256 + 32 (r+1)), so a ripple never leaves its pair.
+    kb_cmad4_new(&ev[2], a[1], a[3], a[5], a[7], b[1]);                   // words 2..9
+    kb_cmad4_new(&od[2], a[1], a[3], a[5], a[7], b[2]);                   // words 3..10
+    kb_cmad4_rip(&od[0], a[0], a[2], a[4], a[6], b[1], od[8], od[9]);     // words 1..8, carry -> 9, 10
+    kb_cmad4_new(&ev[4], a[1], a[3], a[5], a[7], b[3]);                   // words 4..11
+    kb_cmad4_rip(&ev[2], a[0], a[2], a[4], a[6], b[2], ev[10], ev[11]);   // words 2..9, carry -> 10, 11
+    kb_cmad4_new(&od[4], a[1], a[3], a[5], a[7], b[4]);                   // words 5..12
+    kb_cmad4_rip(&od[2], a[0], a[2], a[4], a[6], b[3], od[10], od[11]);
+    kb_cmad4_new(&ev[6], a[1], a[3], a[5], a[7], b[5]);                   // words 6..13
+    kb_cmad4_rip(&ev[4], a[0], a[2], a[4], a[6], b[4], ev[12], ev[13]);
+    kb_cmad4_new(&od[6], a[1], a[3], a[5], a[7], b[6]);                   // words 7..14
+    kb_cmad4_rip(&od[4], a[0], a[2], a[4], a[6], b[5], od[12], od[13]);
+    kb_cmad4_new(&ev[8], a[1], a[3], a[5], a[7], b[7]);                   // words 8..15
+    kb_cmad4_rip(&ev[6], a[0], a[2], a[4], a[6], b[6], ev[14], ev[15]);
+    kb_cmad4_top(&od[6], a[0], a[2], a[4], a[6], b[7], od[14]);           // words 7..14, carry -> word 15 (a plain word)
+    kb_acc15(&ev[1], &od[0]);
+    fe_reduce512(h, ev);
+}
+
+// h = f^2   (fe.rs:544 fe_square), rows in natural order: 28 cross products, doubled, plus 8 squares
+KB_FN void fe_sq_rows(fe& h, const fe& f)
 {
     uint32_t ev[17], od[16];
     const uint32_t* a = f.v;
@@ -609,6 +934,46 @@ KB_FN void fe_sq_inl(fe& h, const fe& f)
     kb_sqr_acc8(ev, a);  // add the squares a[i]^2 on word pairs (2i, 2i+1)
     fe_reduce512(h, ev);
 }
+
+// h = f^2, rows ordered so that no register has to be zeroed: 28 cross products, doubled, plus 8 squares
+KB_FN void fe_sq_rip(fe& h, const fe& f)
+{
+    uint32_t ev[16], od[14], t[16];
+    const uint32_t* a = f.v;
+    // row i: a[j]*a[i] for j > i, word i+j; the rows are ordered as in fe_mul_inl — the row that opens a pair first
+    // (or a plain product where nothing precedes it), the row below it ripples its carry in.  ev[0], ev[1], ev[14],
+    // ev[15] and od[14] hold no cross product and are never materialised (kb_sq_merge_dbl).
+    kb_cmul4(&od[0], a[1], a[3], a[5], a[7], a[0]);                  // words 1,3,5,7
+    kb_cmul3(&ev[2], a[2], a[4], a[6], a[0]);                        // words 2,4,6
+    kb_cmad3_new(&ev[4], a[3], a[5], a[7], a[1]);                    // words 4,6,8
+    kb_cmad3_new(&od[4], a[3], a[5], a[7], a[2]);                    // words 5,7,9
+    kb_cmad3_rip(&od[2], a[2], a[4], a[6], a[1], od[8], od[9]);      // words 3,5,7, carry -> 9, 10
+    kb_cmad2_new(&ev[8], a[5], a[7], a[3]);                          // words 8,10
+    kb_cmad2_rip(&ev[6], a[4], a[6], a[2], ev[10], ev[11]);          // words 6,8, carry -> 10, 11
+    kb_cmad2_new(&od[8], a[5], a[7], a[4]);                          // words 9,11
+    kb_cmad2_rip(&od[6], a[4], a[6], a[3], od[10], od[11]);          // words 7,9, carry -> 11, 12
+    kb_cmul1(&ev[12], a[7], a[5]);                                   // word 12
+    kb_cmad1_rip(&ev[10], a[6], a[4], ev[12], ev[13]);               // word 10, carry -> 12, 13
+    kb_cmul1(&od[12], a[7], a[6]);                                   // word 13
+    kb_cmad1_rip(&od[10], a[6], a[5], od[12], od[13]);               // word 11, carry -> 13, 14
+    kb_sq_merge_dbl(t, ev, od);   // t[1..16) = doubled cross terms (sum < 2^511: the top bit is clear)
+    kb_sqr_acc8_fresh0(t, a);     // add the squares a[i]^2 on word pairs (2i, 2i+1)
+    fe_reduce512(h, t);
+}
+
+// Which bodies a translation unit uses (all are bit-exact; tests/emu runs every one):  MEASURED, round 2 — the
+// zero-free row order (-DKB_FE_MUL_RIP / -DKB_FE_SQ_RIP) and the borrow-mask wrap of fe_sub (-DKB_FE_SUBMASK) shift the
+// balance ptxas strikes between the ALU and the multiplier pipe differently in every kernel, see DESIGN §7.1.
+#if defined(KB_FE_MUL_RIP)
+KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g) { fe_mul_rip(h, f, g); }
+#else
+KB_FN void fe_mul_inl(fe& h, const fe& f, const fe& g) { fe_mul_rows(h, f, g); }
+#endif
+#if defined(KB_FE_SQ_RIP)
+KB_FN void fe_sq_inl(fe& h, const fe& f) { fe_sq_rip(h, f); }
+#else
+KB_FN void fe_sq_inl(fe& h, const fe& f) { fe_sq_rows(h, f); }
+#endif
 
 // ---------------------------------------------------------------------------------------
 // One level of (subtractive) Karatsuba for h = f * g: three 4 x 4-limb products (48 IMAD.WIDE) instead of 64.
@@ -826,9 +1191,15 @@ KB_FN void fe_add(fe& h, const fe& f, const fe& g)
 }
 KB_FN void fe_sub(fe& h, const fe& f, const fe& g)
 {
+#if defined(KB_FE_SUBMASK)
+    uint32_t m = kb_sub8m(h.v, f.v, g.v);
+    m = kb_sub_smallm(h.v, m & 38u);  // -2^256 = -38
+    h.v[0] -= m & 38u;                // after a second wrap the value is >= 2^256-38: cannot borrow
+#else
     uint32_t b = kb_sub8(h.v, f.v, g.v);
     b = kb_sub_small(h.v, 38u * b);  // -2^256 = -38
     h.v[0] -= 38u * b;               // after a second wrap the value is >= 2^256-38: cannot borrow
+#endif
 }
 KB_FN void fe_set(fe& h, uint32_t x)
 {

@@ -529,34 +529,86 @@ static __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, c
 #ifndef KB_VERIFY_PREP_MINBLOCKS
 #define KB_VERIFY_PREP_MINBLOCKS 5
 #endif
+// The two phases of the preparation load different pipes: the decompressions are multiplier-bound (IMAD.WIDE), the
+// hash and the lattice step ALU-bound, and blocks that start together on an SM stay in step for the whole launch.
+// -DKB_PREP_ROLES=1 lets every block draw its phase order from a counter of the SM it runs on (half of an SM's blocks
+// decompress while the other half hash).  MEASURED (round 2, 2^20 signatures): 5.96 ms against 4.97 ms with one phase
+// order — warps on different code paths miss the instruction cache more than the idle pipe costs; kept as a build
+// option only.  Each phase writes its part of the record straight to memory; only the flags, sign(v) and the window
+// count stay in registers across phases (312 -> 180 bytes of spill stores).
+#ifndef KB_PREP_ROLES
+#define KB_PREP_ROLES 0
+#endif
+#if KB_PREP_ROLES
+static __device__ unsigned int kb_prep_role_counter[1024];
+#endif
 template <bool SCHNORR>
 static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k_verify_half_prep(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs)
 {
+    int role = 0;
+#if KB_PREP_ROLES
+    __shared__ unsigned int s_role;
+    if (threadIdx.x == 0) {
+        unsigned int smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_role = atomicAdd(&kb_prep_role_counter[smid & 1023u], 1u);
+    }
+    __syncthreads();
+    role = (int)(s_role & 1u);
+#endif
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t pw[8], sw[16];
     kb_load32(pw, pk, i);
     kb_load32(sw, sig, 2 * i);
     kb_load32(sw + 8, sig, 2 * i + 1);
-    // msg_off holds offsets into the caller's whole message array; `msg` points at byte msg_base of it
-    const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
-    kb_half_rec rec;
-    sig_half_prep<SCHNORR>(rec, pw, sw, msg + (lo - msg_base), hi - lo);
     uint32_t* o = recs + KB_HALF_REC_WORDS * i;
-    kb_store_fe_cs(o, rec.ax);
-    kb_store_fe_cs(o + 8, rec.ay);
-    kb_store_fe_cs(o + 16, rec.at);
-    kb_store_fe_cs(o + 24, rec.rx);
-    kb_store_fe_cs(o + 32, rec.ry);
-    kb_store_fe_cs(o + 40, rec.rt);
+    uint32_t dec = 0, f = 0, vneg = 0;
+    int nwin = 0;
+    KB_NOUNROLL
+    for (int pass = 0; pass < 2; pass++) {
+        if ((pass ^ role) == 0) {
+            // one copy of the decompression code for both points
+            KB_NOUNROLL
+            for (int k = 0; k < 2; k++) {
+                fe x, y, t;
+                dec |= sig_half_point(x, y, t, k ? sw : pw) << k;
+                kb_store_fe_cs(o + 24 * k, x);
+                kb_store_fe_cs(o + 24 * k + 8, y);
+                kb_store_fe_cs(o + 24 * k + 16, t);
+            }
+        } else {
+            // msg_off holds offsets into the caller's whole message array; `msg` points at byte msg_base of it
+            const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+            kb_half_sc sc;
+            sig_half_scalars<SCHNORR>(sc, pw, sw, msg + (lo - msg_base), hi - lo);
+            uint4* q = reinterpret_cast<uint4*>(o + 48);
+            __stcs(q + 0, make_uint4(sc.w[0], sc.w[1], sc.w[2], sc.w[3]));
+            __stcs(q + 1, make_uint4(sc.w[4], sc.w[5], sc.w[6], sc.w[7]));
+            __stcs(q + 2, make_uint4(sc.u[0], sc.u[1], sc.u[2], sc.u[3]));
+            __stcs(q + 3, make_uint4(sc.u[4], sc.u[5], sc.u[6], sc.u[7]));
+            __stcs(q + 4, make_uint4(sc.v[0], sc.v[1], sc.v[2], sc.v[3]));
+            __stcs(q + 5, make_uint4(sc.v[4], sc.v[5], sc.v[6], sc.v[7]));
+            f = sc.f;
+            vneg = sc.vneg;
+            nwin = sc.nwin;
+        }
+    }
+    f = sig_half_flags<SCHNORR>(f, dec);
     uint4* q = reinterpret_cast<uint4*>(o + 48);
-    __stcs(q + 0, make_uint4(rec.w[0], rec.w[1], rec.w[2], rec.w[3]));
-    __stcs(q + 1, make_uint4(rec.w[4], rec.w[5], rec.w[6], rec.w[7]));
-    __stcs(q + 2, make_uint4(rec.u[0], rec.u[1], rec.u[2], rec.u[3]));
-    __stcs(q + 3, make_uint4(rec.u[4], rec.u[5], rec.u[6], rec.u[7]));
-    __stcs(q + 4, make_uint4(rec.v[0], rec.v[1], rec.v[2], rec.v[3]));
-    __stcs(q + 5, make_uint4(rec.v[4], rec.v[5], rec.v[6], rec.v[7]));
-    __stcs(q + 6, make_uint4(rec.f | ((uint32_t)rec.nwin << 8), 0u, 0u, 0u));
+    if (!(f & KB_F_FAST)) {
+        // off the fast path (rare): neutral operands, no windows
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u), one = make_uint4(1u, 0u, 0u, 0u);
+        uint4* r = reinterpret_cast<uint4*>(o);
+        KB_UNROLL
+        for (int k = 0; k < 12; k++) __stcs(r + k, (k == 2 || k == 8) ? one : z);
+        KB_UNROLL
+        for (int k = 0; k < 6; k++) __stcs(q + k, z);
+        nwin = 0;
+        vneg = 0;
+    }
+    // word 72: flags | window count << 8 | sign(v) << 16 (the main kernel turns -A into A' = -sign(v) A)
+    __stcs(q + 6, make_uint4(f | ((uint32_t)nwin << 8) | (vneg << 16), 0u, 0u, 0u));
 }
 #ifndef KB_VERIFY_HALF_MINBLOCKS
 #define KB_VERIFY_HALF_MINBLOCKS 3
@@ -589,7 +641,8 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k
         a = __ldcs(q + 5); rec.v[4] = a.x; rec.v[5] = a.y; rec.v[6] = a.z; rec.v[7] = a.w;
         a = __ldcs(q + 6);
         rec.f = a.x & 0xffu;
-        rec.nwin = (int)(a.x >> 8);
+        rec.nwin = (int)((a.x >> 8) & 0xffu);
+        sig_half_apply_vneg(rec.ax, rec.at, (a.x >> 16) & 1u);
     }
     ge_cached tbl[16];
     int16_t dw[KB_COMB_POS];

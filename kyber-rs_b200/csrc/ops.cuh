@@ -397,9 +397,29 @@ struct kb_half_rec {
     uint32_t f;       // KB_F_* flags
     int nwin;         // windows this signature needs (0 when it is off the fast path)
 };
-// byte-level checks, both decompressions, challenge hash, lattice step
+// The preparation is two independent phases — the kernel runs them in either order (kernels.cuh):
+//   points   decompress A and R (multiplier-bound)          -> -A, -R and the two "decodes" bits
+//   scalars  byte-level checks, challenge hash, lattice step, u*s mod L (ALU-bound) -> w, u, |v|, sign(v), window count
+// -P for the encoding w (affine X, Y, T); returns 1 if w decodes
+KB_FN uint32_t sig_half_point(fe& x, fe& y, fe& t, const uint32_t* w)
+{
+    ge_p3 p;
+    const uint32_t ok = ge_decompress(p, w);
+    fe_neg(x, p.X);
+    y = p.Y;
+    fe_neg(t, p.T);
+    return ok;
+}
+struct kb_half_sc {
+    uint32_t w[8], u[8], v[8];
+    uint32_t f;      // byte-level flags (KB_F_SC, RC, RS, AC, AS)
+    uint32_t vneg;   // v < 0: A' = +A
+    int nwin;
+};
+// The hash and the lattice step run for every signature that passes the byte-level checks (whether A and R decode is not
+// known here; sig_half_flags decides).
 template <bool SCHNORR>
-KB_FN void sig_half_prep(kb_half_rec& rec, const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen)
+KB_FN void sig_half_scalars(kb_half_sc& sc, const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen)
 {
     const uint32_t* r_w = sig_w;
     const uint32_t* s_w = sig_w + 8;
@@ -409,50 +429,79 @@ KB_FN void sig_half_prep(kb_half_rec& rec, const uint32_t* pk_w, const uint32_t*
     f |= pt_is_small_order_bytes(r_w) ? KB_F_RS : 0u;
     f |= pt_is_canonical(pk_w) ? KB_F_AC : 0u;
     f |= pt_is_small_order_bytes(pk_w) ? KB_F_AS : 0u;
-    const uint32_t pre_ok = (f & (KB_F_SC | KB_F_RC | KB_F_RS)) == (KB_F_SC | KB_F_RC);
-    // one copy of the decompression code for both points (the kernel is instruction-cache bound)
-    uint32_t dec = 0;
-    KB_NOUNROLL
-    for (int k = 0; k < 2; k++) {
-        ge_p3 p;
-        dec |= ge_decompress(p, k ? r_w : pk_w) << k;
-        fe_neg(p.X, p.X);
-        fe_neg(p.T, p.T);
-        if (k) { rec.rx = p.X; rec.ry = p.Y; rec.rt = p.T; }
-        else { rec.ax = p.X; rec.ay = p.Y; rec.at = p.T; }
-    }
-    f |= (dec & 2u) ? KB_F_ROK : 0u;
-    // EdDSA never looks at A when an earlier check fails; Schnorr decodes A before is_canonical(A)
-    if (SCHNORR || (pre_ok && (f & KB_F_AC))) f |= (dec & 1u) ? KB_F_AOK : 0u;
-    const bool fast = pre_ok && (dec & 2u) && (f & (KB_F_AC | KB_F_AS | KB_F_AOK)) == (KB_F_AC | KB_F_AOK);
-    if (fast) {
+    sc.f = f;
+    sc.vneg = 0;
+    sc.nwin = 0;
+    if ((f & (KB_F_SC | KB_F_RC | KB_F_RS | KB_F_AC | KB_F_AS)) == (KB_F_SC | KB_F_RC | KB_F_AC)) {
         uint32_t digest[16], hk[8];
         const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         sha512_ram(digest, r_w, pk_w, msg, mlen);
         sc_reduce512(hk, digest);
         kb_halfsc hs;
         sc_half(hs, hk);
-        sc_muladd(rec.w, hs.u, s_w, zero);
+        sc_muladd(sc.w, hs.u, s_w, zero);
         KB_UNROLL
         for (int i = 0; i < 8; i++) {
-            rec.u[i] = hs.u[i];
-            rec.v[i] = hs.v[i];
+            sc.u[i] = hs.u[i];
+            sc.v[i] = hs.v[i];
         }
-        fe nx, nt;   // A' = +A when v is negative
-        fe_neg(nx, rec.ax);
-        fe_neg(nt, rec.at);
-        fe_cmov(rec.ax, nx, hs.vneg);
-        fe_cmov(rec.at, nt, hs.vneg);
-        rec.nwin = hs.bits / 4 + 1;
-        f |= KB_F_FAST;
+        sc.vneg = hs.vneg;
+        sc.nwin = hs.bits / 4 + 1;
     } else {
         KB_UNROLL
-        for (int i = 0; i < 8; i++) rec.w[i] = rec.u[i] = rec.v[i] = 0;
-        fe_set(rec.ax, 0); fe_set(rec.ay, 1); fe_set(rec.at, 0);
-        fe_set(rec.rx, 0); fe_set(rec.ry, 1); fe_set(rec.rt, 0);
-        rec.nwin = 0;
+        for (int i = 0; i < 8; i++) sc.w[i] = sc.u[i] = sc.v[i] = 0;
     }
-    rec.f = f;
+}
+// byte-level flags + the "decodes" bits (bit 0: A, bit 1: R) -> the flags the main loop and sig_classify read
+template <bool SCHNORR>
+KB_FN uint32_t sig_half_flags(uint32_t f, uint32_t dec)
+{
+    const uint32_t pre_ok = (f & (KB_F_SC | KB_F_RC | KB_F_RS)) == (KB_F_SC | KB_F_RC);
+    f |= (dec & 2u) ? KB_F_ROK : 0u;
+    // EdDSA never looks at A when an earlier check fails; Schnorr decodes A before is_canonical(A)
+    if (SCHNORR || (pre_ok && (f & KB_F_AC))) f |= (dec & 1u) ? KB_F_AOK : 0u;
+    const bool fast = pre_ok && (dec & 2u) && (f & (KB_F_AC | KB_F_AS | KB_F_AOK)) == (KB_F_AC | KB_F_AOK);
+    return fast ? (f | KB_F_FAST) : f;
+}
+// what a signature off the fast path hands to the main loop: neutral operands, no windows
+KB_FN void sig_half_rec_neutral(kb_half_rec& rec)
+{
+    KB_UNROLL
+    for (int i = 0; i < 8; i++) rec.w[i] = rec.u[i] = rec.v[i] = 0;
+    fe_set(rec.ax, 0); fe_set(rec.ay, 1); fe_set(rec.at, 0);
+    fe_set(rec.rx, 0); fe_set(rec.ry, 1); fe_set(rec.rt, 0);
+    rec.nwin = 0;
+}
+// A' = -sign(v) * A from -A
+KB_FN void sig_half_apply_vneg(fe& ax, fe& at, uint32_t vneg)
+{
+    fe nx, nt;
+    fe_neg(nx, ax);
+    fe_neg(nt, at);
+    fe_cmov(ax, nx, vneg);
+    fe_cmov(at, nt, vneg);
+}
+// both phases and the flags: the record of one signature
+template <bool SCHNORR>
+KB_FN void sig_half_prep(kb_half_rec& rec, const uint32_t* pk_w, const uint32_t* sig_w, const uint8_t* msg, uint64_t mlen)
+{
+    uint32_t dec = sig_half_point(rec.ax, rec.ay, rec.at, pk_w);
+    dec |= sig_half_point(rec.rx, rec.ry, rec.rt, sig_w) << 1;
+    kb_half_sc sc;
+    sig_half_scalars<SCHNORR>(sc, pk_w, sig_w, msg, mlen);
+    rec.f = sig_half_flags<SCHNORR>(sc.f, dec);
+    if (rec.f & KB_F_FAST) {
+        KB_UNROLL
+        for (int i = 0; i < 8; i++) {
+            rec.w[i] = sc.w[i];
+            rec.u[i] = sc.u[i];
+            rec.v[i] = sc.v[i];
+        }
+        sig_half_apply_vneg(rec.ax, rec.at, sc.vneg);
+        rec.nwin = sc.nwin;
+    } else {
+        sig_half_rec_neutral(rec);
+    }
 }
 // digit strings and the two per-signature tables: tbl[0..7] = 1..8 A', tbl[8..15] = 1..8 R'
 KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, const kb_half_rec& rec)

@@ -36,7 +36,7 @@ static void base_init()
 }
 
 extern "C" {
-// op: 0 mul, 1 sq, 2 add, 3 sub, 4 invert, 5 pow22523, 6 canon(a)
+// op: 0 mul, 1 sq, 2 add, 3 sub, 4 invert, 5 pow22523, 6 canon(a), 7 Karatsuba, 8/9 both row orders of mul, 10/11 of sq, 12 sub (mask wrap)
 void emu_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b)
 {
     fe x, y, r;
@@ -49,7 +49,16 @@ void emu_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b)
     case 4: fe_invert(r, x); break;
     case 5: fe_pow22523(r, x); break;
     case 7: fe_mul_karatsuba(r, x, y); break;
-    case 8: fe_mul_inl(r, x, y); break;
+    case 8: fe_mul_rows(r, x, y); break;
+    case 9: fe_mul_rip(r, x, y); break;
+    case 10: fe_sq_rows(r, x); break;
+    case 11: fe_sq_rip(r, x); break;
+    case 12: {   // fe_sub with the borrow-mask wrap (KB_FE_SUBMASK)
+        uint32_t m = kb_sub8m(r.v, x.v, y.v);
+        m = kb_sub_smallm(r.v, m & 38u);
+        r.v[0] -= m & 38u;
+        break;
+    }
     default: r = x; break;
     }
     uint32_t w[8];

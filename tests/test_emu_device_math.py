@@ -57,6 +57,11 @@ def test_field_ops(emu):
             assert feop(3, b32(x), b32(y)) == b32((x - y) % P)
         assert feop(1, b32(x)) == b32(x * x % P)
         assert feop(6, b32(x)) == b32(x % P)
+        # every selectable body (fe.cuh: natural and zero-free row order, borrow-mask wrap)
+        assert feop(10, b32(x)) == feop(11, b32(x)) == b32(x * x % P)
+        for y in edge + rnd.sample(vals, 4):
+            assert feop(8, b32(x), b32(y)) == feop(9, b32(x), b32(y)) == b32(x * y % P)
+            assert feop(12, b32(x), b32(y)) == b32((x - y) % P)
     # both multiplication bodies (schoolbook and one level of Karatsuba), incl. operands whose halves are equal,
     # ordered either way, all ones / all zeros — the sign and borrow paths of the Karatsuba differences
     M128 = 2**128
