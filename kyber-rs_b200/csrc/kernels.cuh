@@ -539,6 +539,9 @@ static __global__ void __launch_bounds__(KB_THREADS) k_verify_stage2(size_t n, c
 #ifndef KB_PREP_ROLES
 #define KB_PREP_ROLES 0
 #endif
+#ifndef KB_PREP_SYNC
+#define KB_PREP_SYNC 1
+#endif
 #if KB_PREP_ROLES
 static __device__ unsigned int kb_prep_role_counter[1024];
 #endif
@@ -556,8 +559,12 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k
     __syncthreads();
     role = (int)(s_role & 1u);
 #endif
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#if KB_PREP_SYNC
+    if (i >= n) i = n - 1;   // tail threads redo the last item (same values, same address) so that they reach the barriers
+#else
     if (i >= n) return;
+#endif
     uint32_t pw[8], sw[16];
     kb_load32(pw, pk, i);
     kb_load32(sw, sig, 2 * i);
@@ -567,10 +574,16 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k
     int nwin = 0;
     KB_NOUNROLL
     for (int pass = 0; pass < 2; pass++) {
+#if KB_PREP_SYNC
+        __syncthreads();
+#endif
         if ((pass ^ role) == 0) {
             // one copy of the decompression code for both points
             KB_NOUNROLL
             for (int k = 0; k < 2; k++) {
+#if KB_PREP_SYNC
+                __syncthreads();
+#endif
                 fe x, y, t;
                 dec |= sig_half_point(x, y, t, k ? sw : pw) << k;
                 kb_store_fe_cs(o + 24 * k, x);
@@ -613,6 +626,9 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k
 #ifndef KB_VERIFY_HALF_MINBLOCKS
 #define KB_VERIFY_HALF_MINBLOCKS 3
 #endif
+#ifndef KB_HALF_PREFETCH
+#define KB_HALF_PREFETCH 1   // operands of the additions fetched one step ahead (ops.cuh ge_triple_scalarmult_prefetch)
+#endif
 template <bool SCHNORR>
 static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb, int min_windows)
 {
@@ -654,7 +670,11 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k
     __syncthreads();
     nwin = s_nwin;
     ge_p3 W;
+#if KB_HALF_PREFETCH
+    ge_triple_scalarmult_prefetch(W, nwin, dw, eu, ev, tbl, comb);
+#else
     ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, comb);
+#endif
     if (live) status[i] = (uint8_t)sig_half_finish<SCHNORR>(rec.f, W);
 }
 

@@ -567,6 +567,76 @@ KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, c
         }
     }
 }
+// The same loop with the operand of every addition FETCHED ONE STEP AHEAD.  The per-thread tables live in local memory
+// (2 KB per thread: L1 holds a fraction of an SM's 768 KB, most entries come from L2), and in the loop above an addition
+// starts with two dependent loads (digit -> table entry) right in front of its first multiplication: ncu's source view
+// (round 2) charges 7 % of the kernel's stall samples to exactly those loads (long scoreboard).  Here the raw entry of
+// the NEXT addition is requested between the front end and the four closing products of the CURRENT step (about 800
+// instructions of cover); only the identity / negation selects wait for it, at the point of use.  While the closing
+// products run, 32 more registers are live than before — they fit under the kernel's 168.
+struct kb_operand {
+    ge_cached c;     // raw table / comb entry (for comb entries c.Z is not loaded)
+    uint32_t neg;    // negate it
+    uint32_t nz;     // digit != 0 (otherwise the operand is the identity and c is ignored)
+};
+// operand of addition `a` (0: A' with ev, 1: R' with eu) of window i >= 0, or of comb position -1 - i for i < 0
+KB_FN void kb_operand_fetch(kb_operand& o, int i, int a, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
+{
+    int d;
+    if (i >= 0) d = a ? eu[i] : ev[i];
+    else d = dw[-1 - i];
+    o.neg = (uint32_t)d >> 31;
+    const int babs = (d ^ -(int)o.neg) + (int)o.neg;
+    o.nz = (uint32_t)(babs != 0);
+    const int idx = babs != 0 ? babs - 1 : 0;   // always a valid entry: the loads are unconditional
+    if (i >= 0) o.c = tbl[8 * a + idx];
+    else kb_ld_precomp(o.c, comb + (size_t)(-1 - i) * KB_COMB_HALF + idx);
+}
+KB_FN void kb_operand_use(ge_cached& c, const kb_operand& o, bool is_comb)
+{
+    ge_cached id;
+    ge_cached_identity(id);
+    c = o.c;
+    if (is_comb) fe_set(c.Z, 1);
+    fe_cmov(c.YpX, id.YpX, o.nz ^ 1u);
+    fe_cmov(c.YmX, id.YmX, o.nz ^ 1u);
+    fe_cmov(c.T2d, id.T2d, o.nz ^ 1u);
+    fe_cmov(c.Z, id.Z, o.nz ^ 1u);
+    ge_cached_cneg(c, o.neg);
+}
+KB_FN void ge_triple_scalarmult_prefetch(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
+{
+    ge_identity(h);
+    kb_operand nx;
+    kb_operand_fetch(nx, nwin - 1, 0, dw, eu, ev, tbl, comb);   // the first window has no doublings in front of it
+    KB_NOUNROLL
+    for (int i = nwin - 1; i >= -KB_COMB_POS; i--) {
+        KB_LOCKSTEP();
+        const int ndbl = (i >= 0 && i != nwin - 1) ? 4 : 0;
+        const int nstep = ndbl + (i >= 0 ? 2 : 1);
+        KB_NOUNROLL
+        for (int step = 0; step < nstep; step++) {
+            fe e, f, g, hh;
+            bool with_t;
+            if (step < ndbl) {
+                ge_dbl_front(e, f, g, hh, h);
+                with_t = step == ndbl - 1;
+                if (with_t) kb_operand_fetch(nx, i, 0, dw, eu, ev, tbl, comb);   // the window's first addition follows
+            } else {
+                const int a = step - ndbl;
+                ge_cached c;
+                kb_operand_use(c, nx, i < 0);
+                ge_add_front(e, f, g, hh, h, c);
+                // T is dead when a doubling (or the end) follows
+                with_t = !((i > 0 && step + 1 == nstep) || i == -KB_COMB_POS);
+                // the next addition, unless doublings come first (then their last one fetches) or this is the end
+                if (i >= 0 && a == 0) kb_operand_fetch(nx, i, 1, dw, eu, ev, tbl, comb);
+                else if (i <= 0 && i > -KB_COMB_POS) kb_operand_fetch(nx, i - 1, 0, dw, eu, ev, tbl, comb);
+            }
+            ge_tail(h, e, f, g, hh, with_t);
+        }
+    }
+}
 // h = a * B for a PUBLIC scalar through the comb: 20 mixed additions instead of 64 (ge_scalarmult_base), no doublings.
 // Any 32-byte scalar gives the reference's result: sc_effective is the integer the reference's digit loop
 // multiplies by, and B has order L, so that integer may be reduced mod L first.
@@ -643,7 +713,7 @@ KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, cons
     sig_half_setup(dw, eu, ev, tbl, rec);
     const int nwin = rec.nwin < min_windows ? min_windows : rec.nwin;
     ge_p3 W;
-    ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, comb);
+    ge_triple_scalarmult_prefetch(W, nwin, dw, eu, ev, tbl, comb);
     return sig_half_finish<SCHNORR>(rec.f, W);
 }
 
