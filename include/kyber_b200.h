@@ -38,7 +38,11 @@ extern "C" {
 /* Environment switches read once by kb_ctx_create (tests, tuning and A/B measurements; none changes a result):
  *   KB_VERIFY_FULL=1          signature verifiers: the full-length (253-doubling) kernels instead of the half-size-scalar ones
  *   KB_VERIFY_MIN_WINDOWS=k   half-size-scalar verifier: lower bound on the block-uniform window count (tests)
- *   KB_VERIFY_CHUNK_LOG2=k    host-buffer verify calls: 2^k signatures per pipelined chunk (default: n/4 within 2^15..2^18)
+ *   KB_VERIFY_CHUNK=n         host-buffer verify calls: largest pipelined chunk in signatures (default: 16 waves of the main
+ *                             kernel = 16 x SMs x 384; the chunks grow x4 from a third of a wave up to this cap)
+ *   KB_VERIFY_CHUNK_LOG2=k    the same cap as a power of two
+ *   KB_VERIFY_PIPE=1          host-buffer verify calls: kernels of all chunks on one stream and copies on a second one
+ *                             (default 0: two alternating lanes, each copy in / kernels / copy out)
  *   KB_DKG_FD=0|1             kb_dkg_verify_round: never / always by forward differences (default: by cost)
  *   KB_FD_PARTS=p             forward-difference round: cut each polynomial into p coefficient blocks, 1..4 (default: by cost)
  *   KB_MSM_C=c                Pippenger window bits (default floor(log2 n) - 3 within 4..16) */
@@ -132,7 +136,7 @@ int kb_challenge_batch(kb_ctx* ctx, size_t n, const uint8_t* r32, const uint8_t*
  * Two independent kernel families return the reference's status: the default multiplies the reference's equation by
  * an odd u with u*h = v (mod 8L), |u|, |v| ~ 2^128 (128 doublings instead of 253; equivalent for every input because the
  * whole curve group has order 8L — csrc/half.cuh); KB_VERIFY_FULL=1 in the environment of kb_ctx_create selects the
- * full-length kernels.  KB_VERIFY_CHUNK_LOG2=k fixes the chunk size of the pipelined host-buffer calls to 2^k signatures. */
+ * full-length kernels.  KB_VERIFY_CHUNK=n / KB_VERIFY_CHUNK_LOG2=k cap the chunk size of the pipelined host-buffer calls. */
 int kb_eddsa_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);
 /* schnorr::verify_with_checks (sign/schnorr/schnorr_sig.rs:53-110) */
 int kb_schnorr_verify_batch(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status);

@@ -57,6 +57,10 @@ int kb_ctx_create(int device, kb_ctx** out)
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->fd_pw_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2; k++) {
+        ok = ok && cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->pipe_done[k], cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) == cudaSuccess;
     if (ctx->verify_full) ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->comb, sizeof(ge_precomp) * KB_COMB_POS * KB_COMB_HALF) == cudaSuccess;
@@ -73,6 +77,11 @@ int kb_ctx_create(int device, kb_ctx** out)
         const char* vc = getenv("KB_VERIFY_CHUNK_LOG2");
         const int vcl = vc ? atoi(vc) : 0;
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
+        const char* vp = getenv("KB_VERIFY_PIPE");
+        ctx->verify_pipe = vp ? atoi(vp) : 0;
+        const char* vn = getenv("KB_VERIFY_CHUNK");
+        const long long vnn = vn ? atoll(vn) : 0;
+        ctx->verify_chunk_n = (vnn >= 1024 && vnn <= (1ll << 24)) ? (size_t)vnn : 0;
         const char* fd = getenv("KB_DKG_FD");
         ctx->dkg_fd = fd ? atoi(fd) : -1;
         const char* fp = getenv("KB_FD_PARTS");
@@ -108,6 +117,10 @@ void kb_ctx_destroy(kb_ctx* ctx)
         if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
     if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
     if (ctx->fd_pw_ev) cudaEventDestroy(ctx->fd_pw_ev);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->pipe_ready[k]) cudaEventDestroy(ctx->pipe_ready[k]);
+        if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);

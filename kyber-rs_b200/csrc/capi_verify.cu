@@ -63,30 +63,47 @@ int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_m
     KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
     KB_DEV_RETURN(st, kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, 0, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, st));
 }
-// Host-buffer verification, pipelined: the batch is cut into chunks of KB_VERIFY_CHUNK signatures that
-// alternate between two streams, so the H2D copy of chunk k+1 and the D2H of chunk k-1 overlap the
-// kernels of chunk k (each stream owns its own staging and scratch buffers).
+// Host-buffer verification, pipelined: the batch is cut into chunks that alternate between two staging lanes, so the
+// H2D copy of chunk k+1 and the D2H of chunk k-1 overlap the kernels of chunk k (each lane owns its own staging and
+// scratch buffers).
+#define KB_VERIFY_MAX_CHUNKS 4096
 static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status, int schnorr)
 {
     KB_ENTER();
     if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     if (msg_off[n] && !msg) return KB_ERR_ARG;
-    // measured on a 2^20 batch (tools/e2e_sweep.py): 2^18-signature chunks give the best overlap of copies and kernels
-    size_t chunk = ctx->verify_chunk;
-    if (chunk == 0) {
-        chunk = (size_t)1 << 15;
-        while (chunk < KB_VERIFY_CHUNK && chunk * 4 < n) chunk <<= 1;
+    // Chunk sizes.  Measured on a 2^20 batch (tools/e2e_sweep.py, round 2): whole WAVES of the main kernel — 3 resident
+    // blocks of 128 signatures per SM, 56 832 signatures on 148 SMs — beat powers of two, and the chunks GROW: a third of
+    // a wave first (the kernels start after a copy of 3 MB), then four times the previous chunk each, up to the cap.  A
+    // chunk's copy (168 B per signature at PCIe speed) is shorter than the kernels of the chunk before it as long as the
+    // growth factor stays below about 6, so the device never waits for a copy after the first one, and a 2^20 batch is
+    // 4 chunks (8 launches) instead of 6.
+    const size_t wave = (size_t)ctx->sm_count * KB_VERIFY_HALF_MINBLOCKS * KB_THREADS;
+    size_t cap = ctx->verify_chunk_n ? ctx->verify_chunk_n : ctx->verify_chunk;
+    if (cap == 0) cap = 16 * wave;
+    // cut[k] .. cut[k+1]: signatures of chunk k
+    size_t cut[KB_VERIFY_MAX_CHUNKS + 1];
+    size_t nchunks = 0;
+    cut[0] = 0;
+    {
+        size_t lo = 0, step = wave / 3;
+        if (step > cap) step = cap;
+        while (lo < n) {
+            if (nchunks + 1 == KB_VERIFY_MAX_CHUNKS) step = n - lo;   // (never with the default sizes: 2^35 signatures)
+            lo = (lo + step < n) ? lo + step : n;
+            cut[++nchunks] = lo;
+            step = (step == wave / 3) ? wave : 4 * step;
+            if (step > cap) step = cap;
+        }
     }
-    const size_t first_chunk = (n > chunk && chunk >= 4096) ? chunk / 4 : chunk;
-    size_t max_mbytes = 0;
-    for (size_t lo = 0, step = first_chunk; lo < n; lo += step, step = chunk) {
-        const size_t hi = (lo + step < n) ? lo + step : n;
-        if (msg_off[hi] < msg_off[lo]) return KB_ERR_ARG;
-        const size_t mb = (size_t)(msg_off[hi] - msg_off[lo]);
+    size_t max_mbytes = 0, cn_max = 0;
+    for (size_t k = 0; k < nchunks; k++) {
+        if (msg_off[cut[k + 1]] < msg_off[cut[k]]) return KB_ERR_ARG;
+        const size_t mb = (size_t)(msg_off[cut[k + 1]] - msg_off[cut[k]]);
         if (mb > max_mbytes) max_mbytes = mb;
+        if (cut[k + 1] - cut[k] > cn_max) cn_max = cut[k + 1] - cut[k];
     }
-    const size_t cn_max = n < chunk ? n : chunk;
     cudaStream_t lane[2] = {ctx->stream, ctx->stream2};
     uint8_t *d_pk[2], *d_sig[2], *d_m[2], *d_st[2], *fl[2];
     uint64_t* d_off[2];
@@ -101,12 +118,17 @@ static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
         KB_SCRATCH(b + 5, KB_VERIFY_SCRATCH_BYTES * cn_max, xyz[l]);
         KB_SCRATCH(b + 6, cn_max, fl[l]);
     }
-    // The device idles while the FIRST chunk is copied in: when there are several chunks the first one is a quarter
-    // chunk, so that the kernels start after a quarter of that copy.
-    const size_t first = first_chunk;
-    int l = 0;
-    for (size_t lo = 0, step = first; lo < n; lo += step, step = chunk, l ^= 1) {
-        const size_t hi = (lo + step < n) ? lo + step : n, cn = hi - lo;
+    // Two schedules.  verify_pipe = 0 (default): two independent lanes (copy in, kernels, copy out each) that alternate;
+    // the device may run the kernels of consecutive chunks side by side, which fills the tail of every launch.
+    // verify_pipe = 1: the kernels of ALL chunks on one stream, in order, the copies on the other one, tied together by
+    // events per staging lane — the preparation of chunk k+1 then never shares an SM with the main loop of chunk k.
+    // Measured (tools/e2e_sweep.py): 47.1 M sigs/s at best against 47.7 M for the two lanes — the filled tails are worth
+    // more than the undisturbed instruction cache.
+    const bool pipe = ctx->verify_pipe != 0;
+    cudaStream_t compute = ctx->stream, copy = ctx->stream2;
+    for (size_t k = 0; k < nchunks; k++) {
+        const int l = (int)(k & 1);
+        const size_t lo = cut[k], hi = cut[k + 1], cn = hi - lo;
         // the offsets of a chunk are validated right before it is enqueued: the walk over the next chunk's offsets then
         // runs while the device works on this one (a kernel that met hi < lo would read out of bounds)
         if (!kb_msg_off_ok(cn, msg_off + lo)) {
@@ -115,15 +137,40 @@ static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
             return KB_ERR_ARG;
         }
         const size_t m0 = (size_t)msg_off[lo], mb = (size_t)msg_off[hi] - m0;
-        cudaStream_t st = lane[l];
+        cudaStream_t st = pipe ? copy : lane[l];
+        // lane l still holds chunk k-2: its kernels must have finished (its statuses were copied out behind the same event)
+        if (pipe && k >= 2) KB_CUDA(cudaStreamWaitEvent(copy, ctx->pipe_done[l], 0));
         KB_CUDA(cudaMemcpyAsync(d_pk[l], pk + 32 * lo, 32 * cn, cudaMemcpyHostToDevice, st));
         KB_CUDA(cudaMemcpyAsync(d_sig[l], sig + 64 * lo, 64 * cn, cudaMemcpyHostToDevice, st));
         if (mb) KB_CUDA(cudaMemcpyAsync(d_m[l], msg + m0, mb, cudaMemcpyHostToDevice, st));
         KB_CUDA(cudaMemcpyAsync(d_off[l], msg_off + lo, 8 * (cn + 1), cudaMemcpyHostToDevice, st));
+        if (pipe) {
+            KB_CUDA(cudaEventRecord(ctx->pipe_ready[l], copy));
+            KB_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ready[l], 0));
+        }
         // offsets stay absolute; the kernel is told that d_m[l] starts at byte m0 of the caller's array
-        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l], d_off[l], (uint64_t)m0, d_sig[l], d_st[l], schnorr, xyz[l], fl[l], st);
-        if (rc != KB_OK) return rc;
-        KB_CUDA(cudaMemcpyAsync(status + lo, d_st[l], cn, cudaMemcpyDeviceToHost, st));
+        int rc = kb_verify_launch(ctx, cn, d_pk[l], d_m[l], d_off[l], (uint64_t)m0, d_sig[l], d_st[l], schnorr, xyz[l], fl[l], pipe ? compute : st);
+        if (rc != KB_OK) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->stream2);
+            return rc;
+        }
+        if (pipe) {
+            KB_CUDA(cudaEventRecord(ctx->pipe_done[l], compute));
+            // the statuses of the PREVIOUS chunk leave behind this chunk's inputs: the copy stream never waits for kernels
+            // that were enqueued after the copies it still has to do
+            if (k >= 1) {
+                KB_CUDA(cudaStreamWaitEvent(copy, ctx->pipe_done[l ^ 1], 0));
+                KB_CUDA(cudaMemcpyAsync(status + cut[k - 1], d_st[l ^ 1], cut[k] - cut[k - 1], cudaMemcpyDeviceToHost, copy));
+            }
+        } else {
+            KB_CUDA(cudaMemcpyAsync(status + lo, d_st[l], cn, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (pipe) {
+        const int l = (int)((nchunks - 1) & 1);
+        KB_CUDA(cudaStreamWaitEvent(copy, ctx->pipe_done[l], 0));
+        KB_CUDA(cudaMemcpyAsync(status + cut[nchunks - 1], d_st[l], n - cut[nchunks - 1], cudaMemcpyDeviceToHost, copy));
     }
     KB_CUDA(cudaStreamSynchronize(ctx->stream));
     KB_CUDA(cudaStreamSynchronize(ctx->stream2));

@@ -10,7 +10,6 @@
 #include "ge.cuh"
 
 #define KB_NSLOTS 64
-#define KB_VERIFY_CHUNK (1u << 18)   // largest signatures-per-chunk of the pipelined host-buffer verify calls
 #define KB_SLOT_XYZ 28
 #define KB_SLOT_FLAGS 29
 
@@ -28,6 +27,9 @@ struct kb_ctx {
     int dkg_fd;              // KB_DKG_FD: 1 = always / 0 = never use the forward-difference DKG round (default: by cost)
     int fd_parts;            // KB_FD_PARTS: number of coefficient blocks of the forward-difference round (0 = by cost)
     int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
+    int verify_pipe;         // KB_VERIFY_PIPE: 0 = two independent lanes (default); 1 = kernels of all chunks on ONE stream, copies on the other
+    size_t verify_chunk_n;   // KB_VERIFY_CHUNK: signatures per chunk as a plain count (overrides KB_VERIFY_CHUNK_LOG2)
+    cudaEvent_t pipe_ready[2], pipe_done[2];   // per staging lane: inputs copied in / kernels finished
     int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
     int timing_valid;
     cudaEvent_t tev[3];
