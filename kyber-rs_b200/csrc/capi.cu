@@ -57,6 +57,8 @@ int kb_ctx_create(int device, kb_ctx** out)
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->order_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->fd_pw_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; k < 2; k++) {
         ok = ok && cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->pipe_done[k], cudaEventDisableTiming) == cudaSuccess;
@@ -89,6 +91,9 @@ int kb_ctx_create(int device, kb_ctx** out)
         const char* mc = getenv("KB_MSM_C");
         const int mcv = mc ? atoi(mc) : 0;
         ctx->msm_c = (mcv >= 4 && mcv <= 16) ? mcv : 0;
+        const char* mg = getenv("KB_MSM_GROUPS");
+        const int mgv = mg ? atoi(mg) : 0;
+        ctx->msm_groups = (mgv >= 32 && mgv <= 16384) ? mgv : 0;
         const char* vw = getenv("KB_VERIFY_MIN_WINDOWS");
         const int vwn = vw ? atoi(vw) : 0;
         ctx->verify_min_windows = (vwn > KB_HALF_MIN_WINDOWS && vwn <= 64) ? vwn : KB_HALF_MIN_WINDOWS;
@@ -117,6 +122,8 @@ void kb_ctx_destroy(kb_ctx* ctx)
         if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
     if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);
     if (ctx->fd_pw_ev) cudaEventDestroy(ctx->fd_pw_ev);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     for (int k = 0; k < 2; k++) {
         if (ctx->pipe_ready[k]) cudaEventDestroy(ctx->pipe_ready[k]);
         if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);

@@ -30,10 +30,15 @@ int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const void* d_po
         pl.half = 1u << (pl.c - 1);
         pl.nb = pl.windows * pl.half;
         pl.k = kb_msm_chunk_entries(cn, pl.half);
-        const uint32_t groups = pl.half < KB_MSM_GROUPS ? pl.half : KB_MSM_GROUPS;
+        // bucket groups per window: fewer groups = longer serial runs in k_msm_reduce but a shorter fold in k_msm_window_sums
+        // (one block per window).  Measured (round 2, KB_MSM_GROUPS): 2^17 points 1.40 / 1.32 / 1.27 / 1.29 ms for
+        // 4096 / 2048 / 1024 / 512 groups, 2^22 points 14.76 / 14.66 / 14.68 / 14.86 ms.
+        const uint32_t gmax = ctx->msm_groups ? (uint32_t)ctx->msm_groups : (pl.half <= 8192u ? 1024u : 2048u);
+        const uint32_t groups = pl.half < gmax ? pl.half : gmax;
         const size_t nthreads = (cn * pl.windows + pl.k - 1) / pl.k;
         uint32_t *pts, *mags, *counts, *offsets, *cursor, *sorted, *bucket_sum, *heads, *tails, *partial, *tile_sums, *long_list, *win_sum;
         uint8_t *negs, *flags;
+        uint32_t* tailb;
         KB_SCRATCH(12, 96 * cn, pts);
         KB_SCRATCH(13, 32 * cn, mags);
         KB_SCRATCH(14, cn, negs);
@@ -45,6 +50,7 @@ int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const void* d_po
         KB_SCRATCH(20, 128 * nthreads, heads);
         KB_SCRATCH(21, 128 * nthreads, tails);
         KB_SCRATCH(22, nthreads, flags);
+        KB_SCRATCH(53, 4 * nthreads, tailb);
         KB_SCRATCH(23, 2 * 128 * (size_t)pl.windows * groups, partial);
         uint32_t* part_tot = partial + 32 * (size_t)pl.windows * groups;
         KB_SCRATCH(24, 4 * 2048, tile_sums);
@@ -65,13 +71,22 @@ int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const void* d_po
         KB_LAUNCHED();
         k_msm_scatter<<<kb_blocks(cn, 256), 256, 0, st>>>(pl, mags, negs, offsets, cursor, sorted);
         KB_LAUNCHED();
-        k_msm_accum<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, sorted, pts, bucket_sum, heads, tails, flags);
+        k_msm_accum<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, sorted, pts, bucket_sum, heads, tails, flags, tailb);
         KB_LAUNCHED();
         KB_CUDA(cudaMemsetAsync(long_list, 0, 4, st));  // word 0 of the block is the queue length
-        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, long_list, long_list + 4, bucket_sum, heads, tails, flags);
+        // The long runs (few, summed by whole blocks) and the short ones (many, one thread each) touch different buckets:
+        // a first pass only queues the long ones, then the two kernels run side by side on two streams.
+        cudaStream_t side = (st == ctx->stream2) ? ctx->stream : ctx->stream2;
+        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, long_list, long_list + 4, bucket_sum, heads, tails, flags, tailb, 1);
         KB_LAUNCHED();
-        k_msm_merge_long<<<ctx->sm_count * 2, KB_MSM_LONG_THREADS, 0, st>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
+        KB_CUDA(cudaEventRecord(ctx->fork_ev, st));
+        KB_CUDA(cudaStreamWaitEvent(side, ctx->fork_ev, 0));
+        k_msm_merge_long<<<ctx->sm_count * 2, KB_MSM_LONG_THREADS, 0, side>>>(nthreads, long_list, long_list + 4, bucket_sum, heads, tails, flags);
         KB_LAUNCHED();
+        KB_CUDA(cudaEventRecord(ctx->join_ev, side));
+        k_msm_merge<<<kb_blocks(nthreads, KB_THREADS), KB_THREADS, 0, st>>>(pl, nthreads, offsets, long_list, long_list + 4, bucket_sum, heads, tails, flags, tailb, 2);
+        KB_LAUNCHED();
+        KB_CUDA(cudaStreamWaitEvent(st, ctx->join_ev, 0));
         k_msm_reduce<<<kb_blocks((size_t)pl.windows * groups, KB_THREADS), KB_THREADS, 0, st>>>(pl, groups, offsets, bucket_sum, partial, part_tot);
         KB_LAUNCHED();
         k_msm_window_sums<<<pl.windows, 256, 0, st>>>(pl, groups, partial, part_tot, win_sum);

@@ -24,11 +24,13 @@ struct kb_ctx {
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
     int msm_c;               // KB_MSM_C: Pippenger window bits override (0 = by size)
+    int msm_groups;          // KB_MSM_GROUPS: bucket groups per window in the Pippenger reduction (0 = default)
     int dkg_fd;              // KB_DKG_FD: 1 = always / 0 = never use the forward-difference DKG round (default: by cost)
     int fd_parts;            // KB_FD_PARTS: number of coefficient blocks of the forward-difference round (0 = by cost)
     int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
     int verify_pipe;         // KB_VERIFY_PIPE: 0 = two independent lanes (default); 1 = kernels of all chunks on ONE stream, copies on the other
     size_t verify_chunk_n;   // KB_VERIFY_CHUNK: signatures per chunk as a plain count (overrides KB_VERIFY_CHUNK_LOG2)
+    cudaEvent_t fork_ev, join_ev;              // a device entry point that runs two independent kernels side by side (Pippenger merge)
     cudaEvent_t pipe_ready[2], pipe_done[2];   // per staging lane: inputs copied in / kernels finished
     int timing;              // kb_verify_kernel_times: record events around the two launches of a device verify
     int timing_valid;
@@ -117,7 +119,7 @@ int kb_dev_end(kb_ctx* ctx, cudaStream_t st);
 // Scratch slot map (one owner per slot within a call chain):
 //   0..7    host-entry staging (inputs / outputs of kb_* calls)
 //   8, 9    committed polynomials in cached form + bad flags (kb_poly_run); forward-difference array A / dealer flags
-//   10..27  Pippenger (msm)
+//   10..26, 53  Pippenger (msm);  27: multiplier table of the forward-difference round (cached across calls)
 //   28, 29  KB_SLOT_XYZ / KB_SLOT_FLAGS: per-item intermediate points / flags
 //   30, 31  forward-difference arrays B / decoded commitments
 //   32..45  two lanes of the pipelined host-buffer verify

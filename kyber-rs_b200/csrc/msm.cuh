@@ -23,7 +23,7 @@
 #include "sc.cuh"
 
 #define KB_MSM_CHUNK (1u << 22)
-#define KB_MSM_GROUPS 4096  // bucket groups per window in the reduction
+#define KB_MSM_GROUPS 4096  // most bucket groups per window in the reduction (scratch sizing; the driver picks 1024 or 2048)
 
 #if defined(KB_HOST_EMU)
 KB_FN uint32_t kb_atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
@@ -152,8 +152,9 @@ KB_FN void kb_load_p3(ge_p3& p, const uint32_t* o)
 
 // ---- accum: thread t owns sorted entries [t*K, (t+1)*K)
 // flags[t]: bit0 = head partial valid, bit1 = tail partial valid
+// tailb[t]: the bucket of the tail partial (what k_msm_merge would otherwise have to search for)
 KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* offsets, const uint32_t* sorted, const uint32_t* pts, uint32_t* bucket_sum, uint32_t* heads,
-                             uint32_t* tails, uint8_t* flags)
+                             uint32_t* tails, uint8_t* flags, uint32_t* tailb)
 {
     const uint32_t total = offsets[pl.nb];
     const uint64_t s64 = (uint64_t)t * pl.k;
@@ -216,6 +217,7 @@ KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* of
                 fl |= 1u;
             } else if (ends_after) {
                 kb_store_p3(tails + 32 * t, acc);
+                tailb[t] = b;
                 fl |= 2u;
             } else {
                 kb_store_p3(bucket_sum + 32 * (size_t)b, acc);
@@ -233,28 +235,24 @@ KB_FN void kb_msm_accum_body(const kb_msm_plan& pl, size_t t, const uint32_t* of
 // ---- merge: thread t whose tail partial is valid owns that bucket: tail[t] + head[t+1] + ...
 // Runs that continue over more than max_serial following chunks (skewed scalars; the top window
 // of any reduced scalar set) are queued in long_list and summed by a whole warp (k_msm_merge_long).
+// mode 0: both in one pass; 1: only queue the long runs; 2: only the short ones (the queue was filled by a mode-1 pass,
+// so that the long and the short runs can be summed by two kernels side by side)
 KB_FN void kb_msm_merge_body(const kb_msm_plan& pl, size_t t, size_t nthreads, const uint32_t* offsets, uint32_t max_serial, uint32_t* long_count, uint32_t* long_list,
-                             uint32_t* bucket_sum, const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
+                             uint32_t* bucket_sum, const uint32_t* heads, const uint32_t* tails, const uint8_t* flags, const uint32_t* tailb, int mode = 0)
 {
     if (!(flags[t] & 2u)) return;
-    // the bucket of the last entry of chunk t
-    const uint32_t last = (uint32_t)((t + 1) * pl.k) - 1;
-    uint32_t lo = 0, hi = pl.nb;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (offsets[mid] <= last) lo = mid;
-        else hi = mid;
-    }
-    const uint32_t b = lo;
+    const uint32_t b = tailb[t];   // the bucket of the last entry of chunk t (recorded by the accumulation)
     const uint32_t bend = offsets[b + 1];
     const size_t u_end = ((size_t)bend + pl.k - 1) / pl.k;  // chunks t+1 .. u_end-1 start inside the bucket
     if (u_end - (t + 1) > max_serial) {
+        if (mode == 2) return;
         const uint32_t slot = kb_atomic_add(long_count, 1u);
         long_list[3 * slot] = (uint32_t)t;
         long_list[3 * slot + 1] = (uint32_t)u_end;
         long_list[3 * slot + 2] = b;
         return;
     }
+    if (mode == 1) return;
     ge_p3 acc, h;
     kb_load_p3(acc, tails + 32 * t);
     for (size_t u = t + 1; u < u_end && u < nthreads; u++) {
@@ -502,18 +500,18 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(kb_msm_plan pl, cons
     kb_msm_scatter_body(pl, i, mags, negs, offsets, cursor, sorted);
 }
 static __global__ void __launch_bounds__(KB_THREADS) k_msm_accum(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, const uint32_t* sorted, const uint32_t* pts, uint32_t* bucket_sum, uint32_t* heads,
-                                                          uint32_t* tails, uint8_t* flags)
+                                                          uint32_t* tails, uint8_t* flags, uint32_t* tailb)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    kb_msm_accum_body(pl, t, offsets, sorted, pts, bucket_sum, heads, tails, flags);
+    kb_msm_accum_body(pl, t, offsets, sorted, pts, bucket_sum, heads, tails, flags, tailb);
 }
 static __global__ void __launch_bounds__(KB_THREADS) k_msm_merge(kb_msm_plan pl, size_t nthreads, const uint32_t* offsets, uint32_t* long_count, uint32_t* long_list, uint32_t* bucket_sum,
-                                                          const uint32_t* heads, const uint32_t* tails, const uint8_t* flags)
+                                                          const uint32_t* heads, const uint32_t* tails, const uint8_t* flags, const uint32_t* tailb, int mode)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    kb_msm_merge_body(pl, t, nthreads, offsets, 8u, long_count, long_list, bucket_sum, heads, tails, flags);
+    kb_msm_merge_body(pl, t, nthreads, offsets, 8u, long_count, long_list, bucket_sum, heads, tails, flags, tailb, mode);
 }
 static __global__ void __launch_bounds__(KB_THREADS) k_msm_reduce(kb_msm_plan pl, uint32_t groups, const uint32_t* offsets, const uint32_t* bucket_sum, uint32_t* part_run, uint32_t* part_tot)
 {
@@ -539,6 +537,31 @@ __device__ __forceinline__ void kb_warp_sum_point(ge_p3& p)
         ge_cached qc;
         ge_to_cached(qc, q);
         ge_add<true>(p, p, qc);
+    }
+}
+// two independent butterflies in one loop: the additions of a level do not depend on each other, so a warp that runs
+// alone on its scheduler (the folds at the end of an MSM) overlaps their latencies
+__device__ __forceinline__ void kb_warp_sum_point2(ge_p3& p, ge_p3& r)
+{
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+        ge_p3 q, u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            q.X.v[k] = __shfl_xor_sync(0xffffffffu, p.X.v[k], off);
+            q.Y.v[k] = __shfl_xor_sync(0xffffffffu, p.Y.v[k], off);
+            q.Z.v[k] = __shfl_xor_sync(0xffffffffu, p.Z.v[k], off);
+            q.T.v[k] = __shfl_xor_sync(0xffffffffu, p.T.v[k], off);
+            u.X.v[k] = __shfl_xor_sync(0xffffffffu, r.X.v[k], off);
+            u.Y.v[k] = __shfl_xor_sync(0xffffffffu, r.Y.v[k], off);
+            u.Z.v[k] = __shfl_xor_sync(0xffffffffu, r.Z.v[k], off);
+            u.T.v[k] = __shfl_xor_sync(0xffffffffu, r.T.v[k], off);
+        }
+        ge_cached qc, uc;
+        ge_to_cached(qc, q);
+        ge_to_cached(uc, u);
+        ge_add<true>(p, p, qc);
+        ge_add<true>(r, r, uc);
     }
 }
 #if defined(KB_K_MSM)
@@ -600,8 +623,7 @@ static __global__ void __launch_bounds__(256) k_msm_window_sums(kb_msm_plan pl, 
     if (c1 > groups) c1 = groups;
     ge_p3 t1, t2;
     kb_msm_window_chunk(t1, t2, c0, c1, part_run + 32 * (size_t)w * groups, part_tot + 32 * (size_t)w * groups);
-    kb_warp_sum_point(t1);
-    kb_warp_sum_point(t2);
+    kb_warp_sum_point2(t1, t2);
     if (lane == 0) {
         kb_store_p3(wtot + 32 * warp, t1);
         kb_store_p3(wtot + 32 * (8 + warp), t2);
@@ -615,8 +637,7 @@ static __global__ void __launch_bounds__(256) k_msm_window_sums(kb_msm_plan pl, 
             kb_load_p3(a, wtot + 32 * lane);
             kb_load_p3(b, wtot + 32 * (8 + lane));
         }
-        kb_warp_sum_point(a);
-        kb_warp_sum_point(b);
+        kb_warp_sum_point2(a, b);
         if (lane == 0) {
             const uint32_t gs = (pl.half + groups - 1) / groups;
             ge_cached ac;

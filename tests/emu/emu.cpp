@@ -354,8 +354,9 @@ int emu_msm(uint8_t* out, size_t n, const uint8_t* scalars, const uint8_t* point
     for (uint32_t b = 0; b < pl.nb; b++) { offsets[b] = run; run += counts[b]; }
     offsets[pl.nb] = run;
     for (size_t i = 0; i < n; i++) kb_msm_scatter_body(pl, i, mags.data(), negs.data(), offsets.data(), cursor.data(), sorted.data());
-    for (size_t t = 0; t < nthreads; t++) kb_msm_accum_body(pl, t, offsets.data(), sorted.data(), pts.data(), bucket_sum.data(), heads.data(), tails.data(), flags.data());
-    for (size_t t = 0; t < nthreads; t++) kb_msm_merge_body(pl, t, nthreads, offsets.data(), 0xffffffffu, nullptr, nullptr, bucket_sum.data(), heads.data(), tails.data(), flags.data());
+    std::vector<uint32_t> tailb(nthreads);
+    for (size_t t = 0; t < nthreads; t++) kb_msm_accum_body(pl, t, offsets.data(), sorted.data(), pts.data(), bucket_sum.data(), heads.data(), tails.data(), flags.data(), tailb.data());
+    for (size_t t = 0; t < nthreads; t++) kb_msm_merge_body(pl, t, nthreads, offsets.data(), 0xffffffffu, nullptr, nullptr, bucket_sum.data(), heads.data(), tails.data(), flags.data(), tailb.data());
     std::vector<uint32_t> part_tot(32 * (size_t)pl.windows * groups);
     for (size_t t = 0; t < (size_t)pl.windows * groups; t++) kb_msm_reduce_body(pl, t, groups, offsets.data(), bucket_sum.data(), partial.data(), part_tot.data());
     // window sums as k_msm_window_sums forms them: 256 "threads" per window, chunked groups
