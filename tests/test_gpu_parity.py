@@ -374,6 +374,43 @@ def test_bad_message_offsets_are_refused(kb, ctx, golden_records):
     assert not ctx.verify_batch(pk, flat, off, sg).any()      # the context is still usable
 
 
+@pytest.mark.parametrize("pipe,chunk", [(0, None), (1, None), (0, 1024), (1, 1024), (1, 4999), (0, 30000)])
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_host_verify_pipeline_schedules(kb, ctx, coracle, golden_records, schnorr, pipe, chunk):
+    """The host-buffer verify calls cut a batch into chunks (a third of a wave, then growing) and run them on two
+    alternating lanes or, with KB_VERIFY_PIPE=1, with all kernels on one stream and the copies on a second one.  Every
+    schedule and chunk cap — including caps that leave a ragged last chunk and dozens of chunks — must return the
+    statuses of the single-launch device path, and a bad offset in a late chunk must be an argument error."""
+    env = {"KB_VERIFY_PIPE": str(pipe)}
+    if chunk is not None:
+        env["KB_VERIFY_CHUNK"] = str(chunk)
+    os.environ.update(env)
+    try:
+        c = kb.Context(0)
+    finally:
+        for k in env:
+            del os.environ[k]
+    try:
+        n = 70001
+        pks, msgs, sigs = make_sig_batch(golden_records[:256], n, bad_every=5)
+        pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+        want = ctx.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+        # the reference's verdict on a prefix (the whole oracle pass would take minutes); the mutation classes themselves
+        # are covered by test_verify_reject_classes
+        m = 3000
+        assert (want[:m] == coracle.verify_batch(pk[:m], flat, off[:m + 1], sg[:m], nthreads=8, schnorr=schnorr)).all()
+        got = c.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+        assert (got == want).all()
+        assert (c.verify_batch(pk[:1], flat, off[:2], sg[:1], schnorr=schnorr) == want[:1]).all()   # a single signature
+        bad = off.copy()
+        bad[n - 3] = bad[n - 2] + 1
+        with pytest.raises(kb.KBError):
+            c.verify_batch(pk, flat, bad, sg, schnorr=schnorr)
+        assert (c.verify_batch(pk, flat, off, sg, schnorr=schnorr) == want).all()   # still usable afterwards
+    finally:
+        c.close()
+
+
 def test_group_laws_host_mirror(kb, ctx):
     """util/test/group_test.rs:210-555 in miniature: 2G, -1*G + G = 0, DH commutativity, homomorphisms."""
     H = kb.host
