@@ -336,14 +336,20 @@ def main():
             die(what)
 
     def timed(fn, reps=3):
-        """seconds per call: CUDA events on the launch stream, barrier + synchronize on both sides, MAX over ranks"""
+        """seconds per call: CUDA events on the launch stream around EVERY repetition, barrier + synchronize on both sides,
+        the MEDIAN over the repetitions (a single 20 ms hiccup of the box would otherwise triple a 6 ms round), MAX over ranks"""
         fn(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier(); a.record()
-        for _ in range(reps):
+        reps = max(reps, 5)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        barrier()
+        for a, b in ev:
+            a.record()
             fn()
-        b.record(); barrier()
-        return max_over_ranks(a.elapsed_time(b) / reps) * 1e-3
+            b.record()
+        barrier()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ev)
+        return max_over_ranks(ms[len(ms) // 2]) * 1e-3
 
     # ---- integer-multiply roofline denominator ---------------------------------------------------------------------
     # The path's multiplier is IMAD.WIDE.U32 (32x32+64 -> 64); it issues on the "fmaheavy" pipe at 4 cycles per warp
@@ -517,6 +523,7 @@ def main():
         "cpu_baseline": cpu,
         "parity_checked": parity,
         "configs": configs,
+        "configs_timing": "every configs / stages entry: CUDA events on the launch stream around each repetition, median of >= 5 repetitions after one warm-up call, max over ranks",
         "stages": stages,
         "extras": extras,
     }

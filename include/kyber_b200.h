@@ -239,6 +239,9 @@ int kb_msm(kb_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points,
 int kb_point_sum(kb_ctx* ctx, size_t k, const uint8_t* partials128, uint8_t* out32);
 
 /* ---- device-pointer variants (inputs already resident in HBM) --------------------------- */
+/* d_msg_off: n+1 uint64 offsets in DEVICE memory.  The host-buffer calls validate the offsets (non-decreasing) and answer
+ * KB_ERR_ARG; here they cannot be read by the host, so the caller must guarantee msg_off[i] <= msg_off[i+1] and
+ * msg_off[n] <= the size of d_msg — a kernel that met a decreasing pair would read out of bounds. */
 int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_msg, const void* d_msg_off, const void* d_sig, void* d_status, int schnorr, void* stream);
 int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_out, uint32_t flags, void* stream);
 int kb_dev_point_mul(kb_ctx* ctx, size_t n, const void* d_scalars, const void* d_points, void* d_out, void* d_status, uint32_t flags, void* stream);
