@@ -71,13 +71,19 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     else k_fd_decode<<<kb_blocks(nd * t, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, (const uint8_t*)d_commits, dec, dbad);
     KB_LAUNCHED();
     const size_t hl = kb_fd_part_len(t, h, parts - 1);
+    static const long q4_env = getenv("KB_FD_Q4_MAX") ? atol(getenv("KB_FD_Q4_MAX")) : -1;   // cells up to which a conversion launch uses four lanes per cell (tuning / A-B switch)
+    const size_t q4_max = q4_env >= 0 ? (size_t)q4_env : 8192;
     for (size_t s = 1; s < h; s++) {
         const size_t sl = s + hl >= h ? s + hl - h : 0;
         const size_t cells = (parts - 1) * s + sl;
         if (cells == 0) continue;
         const uint32_t* src = (s & 1) ? rb : ra;
         uint32_t* dst = (s & 1) ? ra : rb;
-        k_fd_conv<<<kb_blocks(nd * cells, KB_FD_CONV_THREADS), KB_FD_CONV_THREADS, 0, st>>>(nd, t, h, parts, s, dec, src, dst);
+        // few cells: the launch lasts one cell's latency — four lanes per cell shorten it (dkgfd.cuh).  Measured (round 2,
+        // KB_FD_Q4_MAX sweep): the 32-dealer shard of config 3 (one rank of 8) 2.85 -> 2.33 ms with every launch on four lanes;
+        // no gain from 128 dealers on, a loss when launches of more than ~10^4 cells use it (config 3 on one GPU: 5.9 -> 6.5 ms)
+        if (q4_max && nd * cells <= q4_max) k_fd_conv_q4<<<kb_blocks(4 * nd * cells, KB_FD_CONV_THREADS), KB_FD_CONV_THREADS, 0, st>>>(nd, t, h, parts, s, dec, src, dst);
+        else k_fd_conv<<<kb_blocks(nd * cells, KB_FD_CONV_THREADS), KB_FD_CONV_THREADS, 0, st>>>(nd, t, h, parts, s, dec, src, dst);
         KB_LAUNCHED();
     }
     const uint32_t* diffs = ((h - 1) & 1) ? ra : rb;   // what the last iteration wrote

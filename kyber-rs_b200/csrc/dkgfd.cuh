@@ -294,6 +294,146 @@ static __global__ void __launch_bounds__(KB_FD_CONV_THREADS, KB_FD_CONV_MINBLOCK
     kb_fd_store(KB_FD_AT(dst, q * h + k, d, nd), v);
 }
 
+// ---- Stage A for SMALL rounds: one cell on FOUR lanes -----------------------------------------------------------------
+// With few dealers (the shard of one rank of 8, config 3) a conversion launch holds so few cells that it lasts exactly one
+// cell's latency: an addition and a multiplication by k, about 12 dependent point operations of ~1 us each on a lone warp
+// (a point operation is two or three levels of four independent field multiplications, and one warp cannot issue an
+// IMAD.WIDE more often than every 4 cycles: 4 x 73 x 4 cycles per level).  Here the four lanes of a quad hold the same
+// point and each does ONE of the four multiplications of a level; the products travel by warp shuffle.  Same formulas,
+// same results (every lane ends with the full point); 2.5x shorter latency for 4x the lanes — used only while the grid
+// leaves the GPU mostly idle (kb_dkg_fd_run).
+// (the shuffles name only the four lanes of the quad, so the quads of a warp — which may hold cells with different
+// multipliers — are free to diverge from each other)
+__device__ __forceinline__ void kb_q4_bcast(fe& out, const fe& in, int src_lane)
+{
+    const unsigned mask = 0xFu << (src_lane & 28);
+#pragma unroll
+    for (int w = 0; w < 8; w++) out.v[w] = __shfl_sync(mask, in.v[w], src_lane);
+}
+// the closing products of the addition / doubling formulas: X3 = E F, Y3 = G H, Z3 = F G, T3 = E H
+__device__ __forceinline__ void kb_q4_tail(ge_p3& p, const fe& e, const fe& f, const fe& g, const fe& h)
+{
+    const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+    fe l = e, r = f, prod;
+    fe_cmov(l, g, (uint32_t)(role == 1));
+    fe_cmov(l, f, (uint32_t)(role == 2));
+    fe_cmov(r, h, (uint32_t)(role == 1 || role == 3));
+    fe_cmov(r, g, (uint32_t)(role == 2));
+    fe_mul(prod, l, r);
+    kb_q4_bcast(p.X, prod, base + 0);
+    kb_q4_bcast(p.Y, prod, base + 1);
+    kb_q4_bcast(p.Z, prod, base + 2);
+    kb_q4_bcast(p.T, prod, base + 3);
+}
+__device__ __forceinline__ void kb_q4_dbl(ge_p3& p)
+{
+    const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+    fe in = p.X, t, sq;
+    fe_add(t, p.X, p.Y);
+    fe_cmov(in, p.Y, (uint32_t)(role == 1));
+    fe_cmov(in, p.Z, (uint32_t)(role == 2));
+    fe_cmov(in, t, (uint32_t)(role == 3));
+    fe_sq(sq, in);
+    fe a, b, c, d, e, f, g, h;
+    kb_q4_bcast(a, sq, base + 0);
+    kb_q4_bcast(b, sq, base + 1);
+    kb_q4_bcast(c, sq, base + 2);
+    kb_q4_bcast(d, sq, base + 3);
+    fe_dbl(c, c);
+    fe_add(h, a, b);
+    fe_sub(e, h, d);
+    fe_sub(g, a, b);
+    fe_add(f, c, g);
+    kb_q4_tail(p, e, f, g, h);
+}
+// p = p + q (sub = false) or p - q; `sub` is uniform over the quad
+__device__ __forceinline__ void kb_q4_addsub(ge_p3& p, const ge_cached& q, bool sub)
+{
+    const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
+    // role 0: (Y1 - X1) * (Y2 -+ X2)   1: (Y1 + X1) * (Y2 +- X2)   2: T1 * 2d T2   3: Z1 * Z2
+    fe l, r, t, prod;
+    fe_sub(l, p.Y, p.X);
+    fe_add(t, p.Y, p.X);
+    fe_cmov(l, t, (uint32_t)(role == 1));
+    fe_cmov(l, p.T, (uint32_t)(role == 2));
+    fe_cmov(l, p.Z, (uint32_t)(role == 3));
+    r = sub ? q.YpX : q.YmX;
+    t = sub ? q.YmX : q.YpX;
+    fe_cmov(r, t, (uint32_t)(role == 1));
+    fe_cmov(r, q.T2d, (uint32_t)(role == 2));
+    fe_cmov(r, q.Z, (uint32_t)(role == 3));
+    fe_mul(prod, l, r);
+    fe a, b, c, d, e, f, g, h;
+    kb_q4_bcast(a, prod, base + 0);
+    kb_q4_bcast(b, prod, base + 1);
+    kb_q4_bcast(c, prod, base + 2);
+    kb_q4_bcast(d, prod, base + 3);
+    fe_dbl(d, d);
+    fe_sub(e, b, a);
+    fe_add(h, b, a);
+    if (sub) {
+        fe_add(f, d, c);
+        fe_sub(g, d, c);
+    } else {
+        fe_sub(f, d, c);
+        fe_add(g, d, c);
+    }
+    kb_q4_tail(p, e, f, g, h);
+}
+// (the cached form of an operand costs one multiplication by 2d; doing it on one lane only would not shorten anything, so every lane does it)
+__device__ __forceinline__ void kb_q4_conv_cell(ge_p3& v, const ge_p3& lower, bool has_self, const kb_naf& k)
+{
+    if (has_self) {
+        ge_cached c;
+        ge_to_cached(c, lower);
+        kb_q4_addsub(v, c, false);
+    } else {
+        v = lower;
+    }
+    if (k.len <= 1) return;
+    ge_cached vc;
+    ge_to_cached(vc, v);
+#pragma unroll 1
+    for (int i = k.len - 2; i >= 0; i--) {
+        const int d = k.d[i];
+        kb_q4_dbl(v);
+        if (d != 0) kb_q4_addsub(v, vc, d < 0);
+    }
+}
+// k_fd_conv with four lanes per cell (same indexing; thread / 4 is the cell)
+static __global__ void __launch_bounds__(KB_FD_CONV_THREADS) k_fd_conv_q4(size_t nd, size_t t, size_t h, size_t parts, size_t s, const uint32_t* dec, const uint32_t* src, uint32_t* dst)
+{
+    size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t hl = kb_fd_part_len(t, h, parts - 1);
+    const size_t sl = s + hl >= h ? s + hl - h : 0;
+    const size_t cells = (parts - 1) * s + sl;
+    const bool live = idx < nd * cells;
+    if (!live) return;   // whole quads leave together (a quad is one cell)
+    const size_t c = idx / nd, d = idx % nd;
+    size_t q, k, sq, hq;
+    if (c < (parts - 1) * s) {
+        q = c % (parts - 1);
+        k = s - c / (parts - 1);
+        sq = s;
+        hq = h;
+    } else {
+        q = parts - 1;
+        k = sl - (c - (parts - 1) * s);
+        sq = sl;
+        hq = hl;
+    }
+    ge_p3 v, lower;
+    if (k == 1) kb_fd_load(lower, KB_FD_AT(dec, q * h + (hq - sq), d, nd));
+    else kb_fd_load(lower, KB_FD_AT(src, q * h + k - 1, d, nd));
+    const bool has_self = k < sq;
+    if (has_self) kb_fd_load(v, KB_FD_AT(src, q * h + k, d, nd));
+    else ge_identity(v);
+    kb_naf kn;
+    kb_naf_from(kn, (uint64_t)k);
+    kb_q4_conv_cell(v, lower, has_self, kn);
+    if ((threadIdx.x & 3) == 0) kb_fd_store(KB_FD_AT(dst, q * h + k, d, nd), v);
+}
+
 // Stage C.  Block = one (dealer, block q); thread = order k.  All n steps in one launch: per step every lane turns its
 // value into the operand form (1 M), hands it to the lane below (shuffle; the lowest lane of a warp through shared
 // memory), adds what it received (8 M), and lane 0 records the value E_q(i + 1) into evals[(q * n + i) * nd + d].  An order
