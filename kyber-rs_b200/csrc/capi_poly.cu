@@ -88,11 +88,19 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     }
     const uint32_t* diffs = ((h - 1) & 1) ? ra : rb;   // what the last iteration wrote
     const unsigned step_threads = 32u * (unsigned)((h + 31) / 32);
-    // up to 192 orders per block: 3 blocks (18 warps) per SM at 112 registers; up to 256: 2 blocks
+    // up to 192 orders per block: 3 blocks (18 warps) per SM at 96 registers, or 4 at 80; up to 256: 2 blocks.
+    // A whole round (thousands of blocks) runs equally fast with 2, 3 or 4 resident blocks per SM — the kernel is bound by the
+    // multiplier pipe — but a SHARD's grid is a few blocks per SM and the launch lasts whole waves: 512 blocks (the 128 dealers
+    // of one rank of 8) are 1.15 waves of 3 per SM and one wave of 4.  The variant whose waves cost less is launched.
     static const int wide = getenv("KB_FD_STEPS_WIDE") ? atoi(getenv("KB_FD_STEPS_WIDE")) : 0;   // A/B switch (tuning)
-    // (measured: 2, 3 or 4 resident blocks per SM give the same round time — the kernel is bound by the multiplier pipe)
-    if (step_threads <= 192 && !wide) k_fd_steps<192, 3><<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
-    else k_fd_steps<KB_FD_MAX_H, 2><<<(unsigned)(nd * parts), step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
+    static const int minb_env = getenv("KB_FD_STEPS_MINB") ? atoi(getenv("KB_FD_STEPS_MINB")) : 0;   // 3 / 4: force a variant
+    const size_t blocks = nd * parts, sms = (size_t)ctx->sm_count;
+    const size_t waves3 = (blocks + 3 * sms - 1) / (3 * sms), waves4 = (blocks + 4 * sms - 1) / (4 * sms);
+    const bool four = minb_env ? minb_env == 4 : (double)waves4 * 4.0 * 1.06 < (double)waves3 * 3.0;
+    if (step_threads <= 192 && !wide) {
+        if (four) k_fd_steps<192, 4><<<(unsigned)blocks, step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
+        else k_fd_steps<192, 3><<<(unsigned)blocks, step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
+    } else k_fd_steps<KB_FD_MAX_H, 2><<<(unsigned)blocks, step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
     KB_LAUNCHED();
     k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
     KB_LAUNCHED();
