@@ -118,6 +118,7 @@ void kb_ctx_destroy(kb_ctx* ctx)
     if (ctx->base128) cudaFree(ctx->base128);
     if (ctx->comb) cudaFree(ctx->comb);
     if (ctx->fd_pw_host) cudaFreeHost(ctx->fd_pw_host);
+    if (ctx->fd_graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)ctx->fd_graph_exec);
     for (int k = 0; k < 3; k++)
         if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
     if (ctx->order_ev) cudaEventDestroy(ctx->order_ev);

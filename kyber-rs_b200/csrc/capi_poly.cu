@@ -73,7 +73,62 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     const size_t hl = kb_fd_part_len(t, h, parts - 1);
     static const long q4_env = getenv("KB_FD_Q4_MAX") ? atol(getenv("KB_FD_Q4_MAX")) : -1;   // cells up to which a conversion launch uses four lanes per cell (tuning / A-B switch)
     const size_t q4_max = q4_env >= 0 ? (size_t)q4_env : 8192;
-    for (size_t s = 1; s < h; s++) {
+    // The h - 1 conversion launches form a chain in which every launch depends on the one before it and, for shards, lasts
+    // a few microseconds: launched one by one they sit 2 - 2.7 us apart, as the nodes of a CUDA graph 0.5 us (measured on a
+    // B200, tools/probe_graph.cu).  The chain only touches the context's scratch arrays, so it is built once per shape as an
+    // explicit graph (kernel nodes in a line, no stream capture on the caller's stream) and kept with the context.
+    static const int use_graph = getenv("KB_FD_GRAPH") ? atoi(getenv("KB_FD_GRAPH")) : 1;
+    const size_t gkey[8] = {nd, t, h, parts, q4_max, (size_t)dec, (size_t)ra, (size_t)rb};
+    bool graph_ok = false;
+    if (use_graph && h > 1) {
+        if (!ctx->fd_graph_exec || memcmp(gkey, ctx->fd_graph_key, sizeof(gkey)) != 0) {
+            if (ctx->fd_graph_exec) {
+                cudaGraphExecDestroy((cudaGraphExec_t)ctx->fd_graph_exec);
+                ctx->fd_graph_exec = nullptr;
+            }
+            cudaGraph_t g = nullptr;
+            cudaGraphNode_t prev = nullptr;
+            bool ok = cudaGraphCreate(&g, 0) == cudaSuccess;
+            size_t nodes = 0;
+            for (size_t s = 1; ok && s < h; s++) {
+                const size_t sl = s + hl >= h ? s + hl - h : 0;
+                const size_t cells = (parts - 1) * s + sl;
+                if (cells == 0) continue;
+                const uint32_t* src = (s & 1) ? rb : ra;
+                uint32_t* dst = (s & 1) ? ra : rb;
+                const bool q4 = q4_max && nd * cells <= q4_max;
+                size_t a_nd = nd, a_t = t, a_h = h, a_parts = parts, a_s = s;
+                const uint32_t* a_dec = dec;
+                void* args[8] = {&a_nd, &a_t, &a_h, &a_parts, &a_s, &a_dec, &src, &dst};
+                cudaKernelNodeParams kp;
+                memset(&kp, 0, sizeof(kp));
+                kp.func = q4 ? (void*)k_fd_conv_q4 : (void*)k_fd_conv;
+                kp.gridDim = dim3(kb_blocks((q4 ? 4 : 1) * nd * cells, KB_FD_CONV_THREADS));
+                kp.blockDim = dim3(KB_FD_CONV_THREADS);
+                kp.kernelParams = args;
+                cudaGraphNode_t node;
+                ok = cudaGraphAddKernelNode(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, &kp) == cudaSuccess;
+                prev = node;
+                nodes++;
+            }
+            cudaGraphExec_t ge = nullptr;
+            ok = ok && nodes > 0 && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (ok) {
+                ctx->fd_graph_exec = ge;
+                ctx->fd_graph_nodes = nodes;
+                memcpy(ctx->fd_graph_key, gkey, sizeof(gkey));
+            } else {
+                (void)cudaGetLastError();   // fall through to the plain launches below
+            }
+        }
+        if (ctx->fd_graph_exec && memcmp(gkey, ctx->fd_graph_key, sizeof(gkey)) == 0) {
+            KB_CUDA(cudaGraphLaunch((cudaGraphExec_t)ctx->fd_graph_exec, st));
+            ctx->launches += ctx->fd_graph_nodes;
+            graph_ok = true;
+        }
+    }
+    for (size_t s = 1; !graph_ok && s < h; s++) {
         const size_t sl = s + hl >= h ? s + hl - h : 0;
         const size_t cells = (parts - 1) * s + sl;
         if (cells == 0) continue;

@@ -44,6 +44,10 @@ struct kb_ctx {
     size_t fd_pw_host_words;
     size_t fd_pw_key[3];
     cudaEvent_t fd_pw_ev;    // end of the last upload from fd_pw_host
+    // the chain of conversion launches of the forward-difference round as an instantiated CUDA graph, per shape (capi_poly.cu)
+    void* fd_graph_exec;     // cudaGraphExec_t
+    size_t fd_graph_nodes;
+    size_t fd_graph_key[8];
     void* slot[KB_NSLOTS];
     size_t slot_bytes[KB_NSLOTS];
     uint64_t launches;
