@@ -157,7 +157,13 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
         else k_fd_steps<192, 3><<<(unsigned)blocks, step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
     } else k_fd_steps<KB_FD_MAX_H, 2><<<(unsigned)blocks, step_threads, 0, st>>>(nd, t, h, parts, n, dec, diffs, evals);
     KB_LAUNCHED();
-    k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
+    // a few thousand items leave the GPU idle while each warp walks its ~450 dependent point operations: four lanes per item.
+    // Measured (KB_FD_CHECK_Q4_MAX): a round of n = 64, t = 43 (4 096 items) 1.31 -> 1.08 ms; 8 192 items 2.24 -> 2.20 ms;
+    // 16 384 items 2.32 -> 2.74 ms (slower: the table scans and conversions every lane repeats outweigh the shorter chain)
+    static const long cq4_env = getenv("KB_FD_CHECK_Q4_MAX") ? atol(getenv("KB_FD_CHECK_Q4_MAX")) : -1;
+    const size_t cq4_max = cq4_env >= 0 ? (size_t)cq4_env : 8192;
+    if (nd * n <= cq4_max) k_fd_check_q4<<<kb_blocks(4 * nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
+    else k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
     KB_LAUNCHED();
     return KB_OK;
 }

@@ -561,4 +561,92 @@ static __global__ void __launch_bounds__(KB_THREADS) k_fd_check(size_t nd, size_
     same &= fe_is_zero(df);
     if (live) verdict[slot] = (uint8_t)(same & (dealer_bad[d] ? 0u : 1u));
 }
+// Stage D for SMALL shards: one item on four lanes.  With a few thousand (dealer, verifier) pairs — the 32 dealers of one
+// rank of 8 in config 3 — the check kernel is a handful of warps that each run ~450 dependent point operations; the same
+// quad-cooperative operations as in k_fd_conv_q4 shorten that chain 2.5x.  Every lane of a quad holds the whole item (its
+// own copy of the tables in local memory); the share still only meets the constant-time scan of the comb in shared memory.
+static __global__ void __launch_bounds__(KB_THREADS) k_fd_check_q4(size_t nd, size_t n, size_t parts, const uint32_t* evals, const uint32_t* pw, const uint8_t* shares, const uint32_t* dealer_bad,
+                                                                     const ge_precomp* table, uint8_t* verdict)
+{
+    extern __shared__ uint4 smem4[];
+    ge_precomp* base = reinterpret_cast<ge_precomp*>(smem4);
+    kb_stage(reinterpret_cast<uint32_t*>(base), reinterpret_cast<const uint32_t*>(table), 64 * 8 * 24);
+    size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = idx < nd * n;   // the loops hold block barriers: the quads past the end redo the last item
+    if (!live) idx = nd * n - 1;
+    const size_t i = idx / nd, d = idx % nd;
+    const size_t slot = d * n + i;
+    const int nt = (int)parts - 1;
+    ge_cached tbl[8 * (KB_FD_MAX_PARTS - 1)];
+    int8_t e[64 * (KB_FD_MAX_PARTS - 1)];
+    ge_p3 P, W;
+#pragma unroll 1
+    for (int q = 0; q < nt; q++) {
+        uint32_t pw9[9];
+        for (int w = 0; w < 9; w++) pw9[w] = pw[i * 9 * nt + 9 * q + w];
+        kb_fd_load(P, evals + (((size_t)(q + 1) * n + i) * nd + d) * 32);
+        if (pw9[8]) {
+            fe_neg(P.X, P.X);
+            fe_neg(P.T, P.T);
+        }
+        sc_recode16(e + 64 * q, pw9);
+        // tbl[8 q + j] = (j + 1) P
+        ge_p3 m = P;
+        ge_to_cached(tbl[8 * q], P);
+#pragma unroll 1
+        for (int j = 1; j < 8; j++) {
+            kb_q4_addsub(m, tbl[8 * q], false);
+            ge_to_cached(tbl[8 * q + j], m);
+        }
+    }
+    ge_identity(W);
+    if (nt > 0) {
+#pragma unroll 1
+        for (int w = 63; w >= 0; w--) {
+            KB_LOCKSTEP();
+            if (w != 63) {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) kb_q4_dbl(W);
+            }
+#pragma unroll 1
+            for (int q = 0; q < nt; q++) {
+                ge_cached c;
+                ge_select_cached<false>(c, tbl + 8 * q, e[64 * q + w]);   // public, warp-uniform digits
+                kb_q4_addsub(W, c, false);
+            }
+        }
+    }
+    kb_fd_load(P, evals + ((size_t)i * nd + d) * 32);
+    ge_cached c0;
+    ge_to_cached(c0, P);
+    kb_q4_addsub(W, c0, false);
+    // share * B through the constant-time comb: every lane scans the window itself, the addition runs on the quad
+    uint32_t sw[8];
+    int8_t es[64];
+    kb_load32(sw, shares, slot);
+    sc_recode16(es, sw);
+    ge_p3 hb;
+    ge_identity(hb);
+#pragma unroll 1
+    for (int w = 0; w < 64; w++) {
+        ge_precomp pc;
+        ge_select_precomp<true>(pc, base + 8 * w, es[w]);
+        ge_cached c;
+        c.YpX = pc.ypx;
+        c.YmX = pc.ymx;
+        c.T2d = pc.xy2d;
+        fe_set(c.Z, 1);
+        kb_q4_addsub(hb, c, false);
+    }
+    fe l, r, df;
+    fe_mul(l, W.X, hb.Z);
+    fe_mul(r, hb.X, W.Z);
+    fe_sub(df, l, r);
+    uint32_t same = fe_is_zero(df);
+    fe_mul(l, W.Y, hb.Z);
+    fe_mul(r, hb.Y, W.Z);
+    fe_sub(df, l, r);
+    same &= fe_is_zero(df);
+    if (live && (threadIdx.x & 3) == 0) verdict[slot] = (uint8_t)(same & (dealer_bad[d] ? 0u : 1u));
+}
 #endif  // !KB_HOST_EMU
