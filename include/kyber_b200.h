@@ -46,6 +46,7 @@ extern "C" {
  *   KB_DKG_FD=0|1             kb_dkg_verify_round: never / always by forward differences (default: by cost)
  *   KB_FD_PARTS=p             forward-difference round: cut each polynomial into p coefficient blocks, 1..4 (default: by cost)
  *   KB_FD_GRAPH=0             forward-difference round: launch the conversion chain kernel by kernel instead of as a CUDA graph
+ *   KB_FD_CHECK_Q4_MAX=c      forward-difference round: the final check uses four lanes per item up to c items (default 8192, 0 = never)
  *   KB_FD_Q4_MAX=c            forward-difference round: conversion launches of up to c cells use four lanes per cell (default 8192, 0 = never)
  *   KB_MSM_C=c                Pippenger window bits (default floor(log2 n) - 3 within 4..16) */
 typedef struct kb_ctx kb_ctx;
