@@ -204,17 +204,21 @@ def dkg_config(env, name, n, t, with_signatures):
     if rank == 0:
         mctx = env["mctx"]
         _, dc_all, ds_all, exp_all = build_round(env, ctx, n, t, 0, n, name)
-        commits_all, shares_all = dc_all.cpu().numpy(), ds_all.cpu().numpy()
+        # pinned host buffers, as for the headline's end-to-end number (pageable memory would add a staging copy)
+        commits_all, shares_all = dc_all.cpu().pin_memory().numpy(), ds_all.cpu().pin_memory().numpy()
         del dc_all, ds_all
-        v = np.zeros(n * n, dtype=np.uint8)
+        v = torch.zeros(n * n, dtype=torch.uint8).pin_memory().numpy()
         mctx.dkg_verify_round(n, t, commits_all, shares_all, verdict=v)
-        t0 = time.perf_counter()
-        mctx.dkg_verify_round(n, t, commits_all, shares_all, verdict=v)
-        e2e = time.perf_counter() - t0
+        samples = []
+        for _ in range(3):   # wall clock around the call; the median of three
+            t0 = time.perf_counter()
+            mctx.dkg_verify_round(n, t, commits_all, shares_all, verdict=v)
+            samples.append(time.perf_counter() - t0)
+        e2e = sorted(samples)[1]
         if not (v.reshape(n, n) == exp_all).all():
             env["die"](f"{name}: e2e verdicts (multi-device context) differ from the expected ones")
         out["e2e"] = {"round_ms": e2e * 1e3, "value": checks / e2e, "unit": "share checks/s", "h2d_bytes": int(commits_all.nbytes + shares_all.nbytes), "d2h_bytes": int(v.nbytes),
-                      "how": "kb_mctx_dkg_verify_round on host buffers, dealers split over all GPUs inside the library"}
+                      "how": "kb_mctx_dkg_verify_round on pinned host buffers, dealers split over all GPUs inside the library"}
         env["parity"].append({"what": f"{name}: e2e kb_mctx_dkg_verify_round verdicts vs expectation", "items": n * n, "devices": world})
         if world == 1:
             # CPU baseline: the reference's per-share evaluation on the host cores, a bounded sample of the checks
