@@ -88,6 +88,16 @@ int kb_ctx_create(int device, kb_ctx** out)
         ctx->dkg_fd = fd ? atoi(fd) : -1;
         const char* fp = getenv("KB_FD_PARTS");
         ctx->fd_parts = fp ? atoi(fp) : 0;
+        const char* fq = getenv("KB_FD_Q4_MAX");
+        ctx->fd_q4_max = (fq && atol(fq) >= 0) ? (size_t)atol(fq) : 8192;
+        const char* fc = getenv("KB_FD_CHECK_Q4_MAX");
+        ctx->fd_check_q4_max = (fc && atol(fc) >= 0) ? (size_t)atol(fc) : 8192;
+        const char* fg = getenv("KB_FD_GRAPH");
+        ctx->fd_graph = fg ? atoi(fg) : 1;
+        const char* fw = getenv("KB_FD_STEPS_WIDE");
+        ctx->fd_steps_wide = fw ? atoi(fw) : 0;
+        const char* fm = getenv("KB_FD_STEPS_MINB");
+        ctx->fd_steps_minb = fm ? atoi(fm) : 0;
         const char* mc = getenv("KB_MSM_C");
         const int mcv = mc ? atoi(mc) : 0;
         ctx->msm_c = (mcv >= 4 && mcv <= 16) ? mcv : 0;

@@ -71,13 +71,12 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     else k_fd_decode<<<kb_blocks(nd * t, KB_THREADS), KB_THREADS, 0, st>>>(nd, t, (const uint8_t*)d_commits, dec, dbad);
     KB_LAUNCHED();
     const size_t hl = kb_fd_part_len(t, h, parts - 1);
-    static const long q4_env = getenv("KB_FD_Q4_MAX") ? atol(getenv("KB_FD_Q4_MAX")) : -1;   // cells up to which a conversion launch uses four lanes per cell (tuning / A-B switch)
-    const size_t q4_max = q4_env >= 0 ? (size_t)q4_env : 8192;
+    const size_t q4_max = ctx->fd_q4_max;   // cells up to which a conversion launch uses four lanes per cell (KB_FD_Q4_MAX)
     // The h - 1 conversion launches form a chain in which every launch depends on the one before it and, for shards, lasts
     // a few microseconds: launched one by one they sit 2 - 2.7 us apart, as the nodes of a CUDA graph 0.5 us (measured on a
     // B200, tools/probe_graph.cu).  The chain only touches the context's scratch arrays, so it is built once per shape as an
     // explicit graph (kernel nodes in a line, no stream capture on the caller's stream) and kept with the context.
-    static const int use_graph = getenv("KB_FD_GRAPH") ? atoi(getenv("KB_FD_GRAPH")) : 1;
+    const int use_graph = ctx->fd_graph;   // KB_FD_GRAPH
     const size_t gkey[8] = {nd, t, h, parts, q4_max, (size_t)dec, (size_t)ra, (size_t)rb};
     bool graph_ok = false;
     if (use_graph && h > 1) {
@@ -147,8 +146,8 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     // A whole round (thousands of blocks) runs equally fast with 2, 3 or 4 resident blocks per SM — the kernel is bound by the
     // multiplier pipe — but a SHARD's grid is a few blocks per SM and the launch lasts whole waves: 512 blocks (the 128 dealers
     // of one rank of 8) are 1.15 waves of 3 per SM and one wave of 4.  The variant whose waves cost less is launched.
-    static const int wide = getenv("KB_FD_STEPS_WIDE") ? atoi(getenv("KB_FD_STEPS_WIDE")) : 0;   // A/B switch (tuning)
-    static const int minb_env = getenv("KB_FD_STEPS_MINB") ? atoi(getenv("KB_FD_STEPS_MINB")) : 0;   // 3 / 4: force a variant
+    const int wide = ctx->fd_steps_wide;      // KB_FD_STEPS_WIDE: A/B switch (tuning)
+    const int minb_env = ctx->fd_steps_minb;  // KB_FD_STEPS_MINB = 3 / 4: force a variant
     const size_t blocks = nd * parts, sms = (size_t)ctx->sm_count;
     const size_t waves3 = (blocks + 3 * sms - 1) / (3 * sms), waves4 = (blocks + 4 * sms - 1) / (4 * sms);
     const bool four = minb_env ? minb_env == 4 : (double)waves4 * 4.0 * 1.06 < (double)waves3 * 3.0;
@@ -160,8 +159,7 @@ static int kb_dkg_fd_run(kb_ctx* ctx, size_t n, size_t t, size_t nd, size_t h, c
     // a few thousand items leave the GPU idle while each warp walks its ~450 dependent point operations: four lanes per item.
     // Measured (KB_FD_CHECK_Q4_MAX): a round of n = 64, t = 43 (4 096 items) 1.31 -> 1.08 ms; 8 192 items 2.24 -> 2.20 ms;
     // 16 384 items 2.32 -> 2.74 ms (slower: the table scans and conversions every lane repeats outweigh the shorter chain)
-    static const long cq4_env = getenv("KB_FD_CHECK_Q4_MAX") ? atol(getenv("KB_FD_CHECK_Q4_MAX")) : -1;
-    const size_t cq4_max = cq4_env >= 0 ? (size_t)cq4_env : 8192;
+    const size_t cq4_max = ctx->fd_check_q4_max;   // KB_FD_CHECK_Q4_MAX
     if (nd * n <= cq4_max) k_fd_check_q4<<<kb_blocks(4 * nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
     else k_fd_check<<<kb_blocks(nd * n, KB_THREADS), KB_THREADS, 64 * 8 * 96, st>>>(nd, n, parts, evals, pw, d_shares, dbad, ctx->base_table, d_verdict);
     KB_LAUNCHED();

@@ -26,6 +26,10 @@ struct kb_ctx {
     int msm_c;               // KB_MSM_C: Pippenger window bits override (0 = by size)
     int msm_groups;          // KB_MSM_GROUPS: bucket groups per window in the Pippenger reduction (0 = default)
     int dkg_fd;              // KB_DKG_FD: 1 = always / 0 = never use the forward-difference DKG round (default: by cost)
+    size_t fd_q4_max;        // KB_FD_Q4_MAX: conversion launches of up to this many cells run on four lanes per cell (default 8192)
+    size_t fd_check_q4_max;  // KB_FD_CHECK_Q4_MAX: the same for the items of the final check (default 8192)
+    int fd_graph;            // KB_FD_GRAPH: 1 (default) = the conversion chain is launched as a CUDA graph
+    int fd_steps_wide, fd_steps_minb;   // KB_FD_STEPS_WIDE / KB_FD_STEPS_MINB: variants of the step kernel (tuning)
     int fd_parts;            // KB_FD_PARTS: number of coefficient blocks of the forward-difference round (0 = by cost)
     int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
     int verify_pipe;         // KB_VERIFY_PIPE: 0 = two independent lanes (default); 1 = kernels of all chunks on ONE stream, copies on the other

@@ -503,6 +503,18 @@ def ctx_fd(kb):
         finally:
             del os.environ["KB_DKG_FD"]
             os.environ.pop("KB_FD_PARTS", None)
+    # the variants small rounds would not reach by default: one lane per cell / item (instead of the four-lane kernels
+    # of small rounds), kernel-by-kernel launches (instead of the CUDA graph), every variant of the step kernel
+    for extra in ({"KB_FD_Q4_MAX": "0", "KB_FD_CHECK_Q4_MAX": "0", "KB_FD_GRAPH": "0", "KB_FD_STEPS_MINB": "3"},
+                  {"KB_FD_Q4_MAX": "100000000", "KB_FD_CHECK_Q4_MAX": "100000000", "KB_FD_STEPS_MINB": "4"},
+                  {"KB_FD_Q4_MAX": "0", "KB_FD_STEPS_WIDE": "1", "KB_FD_PARTS": "2"}):
+        env = dict(extra, KB_DKG_FD="1")
+        os.environ.update(env)
+        try:
+            cs.append(kb.Context(0))
+        finally:
+            for k in env:
+                del os.environ[k]
     yield cs
     for c in cs:
         c.close()
