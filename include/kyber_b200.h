@@ -43,6 +43,10 @@ extern "C" {
  *   KB_VERIFY_CHUNK_LOG2=k    the same cap as a power of two
  *   KB_VERIFY_PIPE=1          host-buffer verify calls: kernels of all chunks on one stream and copies on a second one
  *                             (default 0: two alternating lanes, each copy in / kernels / copy out)
+ *   KB_VERIFY_SPLIT=1|2       half-size-scalar verifier: the preparation as two kernels side by side — a persistent "scalars"
+ *                             kernel of KB_VERIFY_SPLIT_BLOCKS (1..8, default 1) blocks per SM on a side stream beside the "points"
+ *                             grid — for batches of at least one block per SM (1) or every batch (2); default 0: one kernel with
+ *                             both phases (faster)
  *   KB_DKG_FD=0|1             kb_dkg_verify_round: never / always by forward differences (default: by cost)
  *   KB_FD_PARTS=p             forward-difference round: cut each polynomial into p coefficient blocks, 1..4 (default: by cost)
  *   KB_FD_GRAPH=0             forward-difference round: launch the conversion chain kernel by kernel instead of as a CUDA graph

@@ -63,6 +63,12 @@ int kb_ctx_create(int device, kb_ctx** out)
         ok = ok && cudaEventCreateWithFlags(&ctx->pipe_ready[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->pipe_done[k], cudaEventDisableTiming) == cudaSuccess;
     }
+    for (int k = 0; k < 2; k++) {
+        ok = ok && cudaStreamCreateWithFlags(&ctx->vs_side[k], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->vs_fork[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->vs_join[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&ctx->vs_counter, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->base_table, sizeof(ge_precomp) * 64 * 8) == cudaSuccess;
     if (ctx->verify_full) ok = ok && cudaMalloc(&ctx->base128, sizeof(ge_precomp) * 128) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->comb, sizeof(ge_precomp) * KB_COMB_POS * KB_COMB_HALF) == cudaSuccess;
@@ -79,6 +85,13 @@ int kb_ctx_create(int device, kb_ctx** out)
         const char* vc = getenv("KB_VERIFY_CHUNK_LOG2");
         const int vcl = vc ? atoi(vc) : 0;
         ctx->verify_chunk = (vcl >= 10 && vcl <= 24) ? ((size_t)1 << vcl) : 0;   // 0: a quarter of the batch, 2^15..2^18
+        const char* vsp = getenv("KB_VERIFY_SPLIT");
+        ctx->verify_split = vsp ? atoi(vsp) : 0;
+        const char* vsb = getenv("KB_VERIFY_SPLIT_BLOCKS");
+        const int vsbn = vsb ? atoi(vsb) : 0;
+        ctx->vs_blocks = (vsbn >= 1 && vsbn <= 8) ? vsbn : 1;
+        const char* vpb = getenv("KB_VERIFY_SPLIT_PBOUND");
+        ctx->vs_pbound = vpb ? atoi(vpb) : 0;
         const char* vp = getenv("KB_VERIFY_PIPE");
         ctx->verify_pipe = vp ? atoi(vp) : 0;
         const char* vn = getenv("KB_VERIFY_CHUNK");
@@ -139,6 +152,12 @@ void kb_ctx_destroy(kb_ctx* ctx)
         if (ctx->pipe_ready[k]) cudaEventDestroy(ctx->pipe_ready[k]);
         if (ctx->pipe_done[k]) cudaEventDestroy(ctx->pipe_done[k]);
     }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->vs_fork[k]) cudaEventDestroy(ctx->vs_fork[k]);
+        if (ctx->vs_join[k]) cudaEventDestroy(ctx->vs_join[k]);
+        if (ctx->vs_side[k]) cudaStreamDestroy(ctx->vs_side[k]);
+    }
+    if (ctx->vs_counter) cudaFree(ctx->vs_counter);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     free(ctx);

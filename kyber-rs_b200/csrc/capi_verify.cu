@@ -22,9 +22,32 @@ int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* 
         // the 96-byte-per-item xyz scratch of the full-length path is not needed; `xyz` carries the 304-byte records
         const unsigned gp = kb_blocks(n, KB_THREADS);
         if (tm) cudaEventRecord(ctx->tev[0], st);
-        if (schnorr) k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
-        else k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
-        KB_LAUNCHED();
+        if (ctx->verify_split == 2 || (ctx->verify_split && n >= (size_t)ctx->sm_count * KB_THREADS)) {   // 2: every batch size (tests)
+            // two kernels side by side (kernels.cuh): the persistent scalars kernel first, on the side stream of this lane
+            const int lane = (st == ctx->stream2) ? 1 : 0;
+            cudaStream_t side = ctx->vs_side[lane];
+            unsigned long long* counter = ctx->vs_counter + lane;
+            const unsigned gs = (unsigned)(ctx->sm_count * ctx->vs_blocks);
+            KB_CUDA(cudaEventRecord(ctx->vs_fork[lane], st));
+            KB_CUDA(cudaStreamWaitEvent(side, ctx->vs_fork[lane], 0));
+            KB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), side));
+            if (schnorr) k_verify_half_scalars<true><<<gs, KB_THREADS, 0, side>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, counter);
+            else k_verify_half_scalars<false><<<gs, KB_THREADS, 0, side>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz, counter);
+            KB_LAUNCHED();
+            KB_CUDA(cudaEventRecord(ctx->vs_join[lane], side));
+            if (ctx->vs_pbound == 4) k_verify_half_points<4><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_sig, xyz);
+            else if (ctx->vs_pbound == 6) k_verify_half_points<6><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_sig, xyz);
+            else k_verify_half_points<5><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_sig, xyz);
+            KB_LAUNCHED();
+            KB_CUDA(cudaStreamWaitEvent(st, ctx->vs_join[lane], 0));
+            if (schnorr) k_verify_half_fix<true><<<kb_blocks(n, 256), 256, 0, st>>>(n, xyz);
+            else k_verify_half_fix<false><<<kb_blocks(n, 256), 256, 0, st>>>(n, xyz);
+            KB_LAUNCHED();
+        } else {
+            if (schnorr) k_verify_half_prep<true><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+            else k_verify_half_prep<false><<<gp, KB_THREADS, 0, st>>>(n, d_pk, d_msg, d_msg_off, msg_base, d_sig, xyz);
+            KB_LAUNCHED();
+        }
         if (tm) cudaEventRecord(ctx->tev[1], st);
         if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
         else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);

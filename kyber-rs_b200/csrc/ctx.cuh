@@ -32,6 +32,12 @@ struct kb_ctx {
     int fd_steps_wide, fd_steps_minb;   // KB_FD_STEPS_WIDE / KB_FD_STEPS_MINB: variants of the step kernel (tuning)
     int fd_parts;            // KB_FD_PARTS: number of coefficient blocks of the forward-difference round (0 = by cost)
     int verify_min_windows;  // KB_VERIFY_MIN_WINDOWS (tests): lower bound on the block-uniform window count of k_verify_half_main
+    // KB_VERIFY_SPLIT: the preparation of the half-size-scalar verifiers as TWO kernels that share the SMs (capi_verify.cu):
+    // a persistent ALU-bound "scalars" kernel (vs_blocks blocks per SM) beside the multiplier-bound "points" kernel
+    int verify_split, vs_blocks, vs_pbound;
+    cudaStream_t vs_side[2];                   // side stream per launch stream (the two lanes of the host-buffer pipeline)
+    cudaEvent_t vs_fork[2], vs_join[2];
+    unsigned long long* vs_counter;            // work counters of the persistent kernel, one per side stream
     int verify_pipe;         // KB_VERIFY_PIPE: 0 = two independent lanes (default); 1 = kernels of all chunks on ONE stream, copies on the other
     size_t verify_chunk_n;   // KB_VERIFY_CHUNK: signatures per chunk as a plain count (overrides KB_VERIFY_CHUNK_LOG2)
     cudaEvent_t fork_ev, join_ev;              // a device entry point that runs two independent kernels side by side (Pippenger merge)

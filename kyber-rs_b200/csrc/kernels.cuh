@@ -623,6 +623,87 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_PREP_MINBLOCKS) k
     // word 72: flags | window count << 8 | sign(v) << 16 (the main kernel turns -A into A' = -sign(v) A)
     __stcs(q + 6, make_uint4(f | ((uint32_t)nwin << 8) | (vneg << 16), 0u, 0u, 0u));
 }
+// ---- the preparation as TWO kernels that share the SMs (KB_VERIFY_SPLIT=1, capi_verify.cu).  The phases of
+// k_verify_half_prep load different pipes and run one after the other in every block; here the "scalars" phase is a
+// PERSISTENT kernel of a few blocks per SM (work drawn from a counter) that is launched first on a side stream, and the
+// "points" phase an ordinary grid that fills what is left of every SM: warps of both kinds are resident at all times, the
+// ALU-bound ones issue into the slots the multiplier-bound ones leave empty.  The verdict bits of both meet in
+// k_verify_half_fix (word 72 / 73 of the record), which also neutralises the records that are off the fast path — the
+// main kernel reads the same record layout from either preparation.
+template <int MINB>
+static __global__ void __launch_bounds__(KB_THREADS, MINB) k_verify_half_points(size_t n, const uint8_t* pk, const uint8_t* sig, uint32_t* recs)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) i = n - 1;   // tail threads redo the last item (same values, same address) so that they reach the barriers
+    uint32_t* o = recs + KB_HALF_REC_WORDS * i;
+    uint32_t dec = 0;
+    KB_NOUNROLL
+    for (int k = 0; k < 2; k++) {
+        __syncthreads();
+        uint32_t w[8];
+        if (k) kb_load32(w, sig, 2 * i);
+        else kb_load32(w, pk, i);
+        fe x, y, t;
+        dec |= sig_half_point(x, y, t, w) << k;
+        kb_store_fe_cs(o + 24 * k, x);
+        kb_store_fe_cs(o + 24 * k + 8, y);
+        kb_store_fe_cs(o + 24 * k + 16, t);
+    }
+    __stcs(o + 73, dec);
+}
+template <bool SCHNORR>
+static __global__ void __launch_bounds__(KB_THREADS, 4) k_verify_half_scalars(size_t n, const uint8_t* pk, const uint8_t* msg, const uint64_t* msg_off, uint64_t msg_base, const uint8_t* sig, uint32_t* recs,
+                                                                              unsigned long long* counter)
+{
+    __shared__ unsigned long long s_base;
+    for (;;) {
+        if (threadIdx.x == 0) s_base = atomicAdd(counter, (unsigned long long)blockDim.x);
+        __syncthreads();
+        const size_t base = (size_t)s_base;
+        __syncthreads();
+        if (base >= n) return;
+        const size_t i = base + threadIdx.x;
+        if (i >= n) continue;
+        uint32_t pw[8], sw[16];
+        kb_load32(pw, pk, i);
+        kb_load32(sw, sig, 2 * i);
+        kb_load32(sw + 8, sig, 2 * i + 1);
+        const uint64_t lo = msg_off[i], hi = msg_off[i + 1];
+        kb_half_sc sc;
+        sig_half_scalars<SCHNORR>(sc, pw, sw, msg + (lo - msg_base), hi - lo);
+        uint32_t* o = recs + KB_HALF_REC_WORDS * i;
+        uint4* q = reinterpret_cast<uint4*>(o + 48);
+        __stcs(q + 0, make_uint4(sc.w[0], sc.w[1], sc.w[2], sc.w[3]));
+        __stcs(q + 1, make_uint4(sc.w[4], sc.w[5], sc.w[6], sc.w[7]));
+        __stcs(q + 2, make_uint4(sc.u[0], sc.u[1], sc.u[2], sc.u[3]));
+        __stcs(q + 3, make_uint4(sc.u[4], sc.u[5], sc.u[6], sc.u[7]));
+        __stcs(q + 4, make_uint4(sc.v[0], sc.v[1], sc.v[2], sc.v[3]));
+        __stcs(q + 5, make_uint4(sc.v[4], sc.v[5], sc.v[6], sc.v[7]));
+        __stcs(o + 72, sc.f | ((uint32_t)sc.nwin << 8) | (sc.vneg << 16));
+    }
+}
+template <bool SCHNORR>
+static __global__ void __launch_bounds__(256) k_verify_half_fix(size_t n, uint32_t* recs)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t* o = recs + KB_HALF_REC_WORDS * i;
+    uint4* q = reinterpret_cast<uint4*>(o + 48);
+    const uint4 a = __ldcs(q + 6);
+    const uint32_t f = sig_half_flags<SCHNORR>(a.x & 0xffu, a.y);
+    uint32_t rest = a.x & 0x1ff00u;   // window count, sign(v)
+    if (!(f & KB_F_FAST)) {
+        // off the fast path (rare): neutral operands, no windows
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u), one = make_uint4(1u, 0u, 0u, 0u);
+        uint4* r = reinterpret_cast<uint4*>(o);
+        KB_UNROLL
+        for (int k = 0; k < 12; k++) __stcs(r + k, (k == 2 || k == 8) ? one : z);
+        KB_UNROLL
+        for (int k = 0; k < 6; k++) __stcs(q + k, z);
+        rest = 0;
+    }
+    __stcs(q + 6, make_uint4(f | rest, 0u, 0u, 0u));
+}
 #ifndef KB_VERIFY_HALF_MINBLOCKS
 #define KB_VERIFY_HALF_MINBLOCKS 3
 #endif

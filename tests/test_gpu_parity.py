@@ -52,6 +52,21 @@ def ctx_long(kb):
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_split(kb):
+    """The preparation of the half-size-scalar verifiers as two kernels side by side (a persistent "scalars" kernel on a
+    side stream beside the "points" grid, joined by k_verify_half_fix), forced for every batch size."""
+    os.environ["KB_VERIFY_SPLIT"] = "2"
+    os.environ["KB_VERIFY_SPLIT_BLOCKS"] = "2"
+    try:
+        c = kb.Context(0)
+    finally:
+        del os.environ["KB_VERIFY_SPLIT"]
+        del os.environ["KB_VERIFY_SPLIT_BLOCKS"]
+    yield c
+    c.close()
+
+
 def _golden_pks(records, n):
     return np.frombuffer(b"".join(r[1] for r in records[:n]), dtype=np.uint8).reshape(-1, 32).copy()
 
@@ -252,6 +267,23 @@ def test_verify_long_window_loops(ctx_long, coracle, golden_records, schnorr):
     got = ctx_long.verify_batch(pk, flat, off, sg, schnorr=schnorr)
     want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
     assert (got == want).all(), np.nonzero(got != want)[0][:10]
+
+
+@pytest.mark.parametrize("schnorr", [False, True])
+def test_verify_split_preparation(ctx, ctx_split, coracle, golden_records, schnorr):
+    """The two-kernel preparation (KB_VERIFY_SPLIT) writes the same records: every mutation class and the mixed-order
+    keys get the oracle's statuses, device-resident and through the pipelined host-buffer call."""
+    good, bad = make_mixed_order_sigs(32, seed=7)
+    pks, msgs, sigs = make_sig_batch(golden_records, 4096, bad_every=2)
+    pks += [x[0] for x in good + bad]
+    msgs += [x[1] for x in good + bad]
+    sigs += [x[2] for x in good + bad]
+    pk, flat, off, sg = pack_batch(pks, msgs, sigs)
+    want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
+    got = ctx_split.verify_batch(pk, flat, off, sg, schnorr=schnorr)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    assert (ctx.verify_batch(pk, flat, off, sg, schnorr=schnorr) == want).all()
+    assert set(np.unique(want)) == {0, 2, 3, 4, 5, 6, 7, 8}
 
 
 def test_verify_paths_agree_on_random_batch(kb, ctx, ctx_full, coracle):
