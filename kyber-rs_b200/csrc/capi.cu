@@ -193,7 +193,7 @@ int kb_dev_point_mul_base(kb_ctx* ctx, size_t n, const void* d_scalars, void* d_
     const int split = 1;
     const unsigned blocks = kb_blocks(n * split, KB_THREADS);
     if (flags & KB_FLAG_VARTIME) {
-        // public scalars: the shared 20-position comb (ops.cuh ge_scalarmult_base_comb), 3x fewer additions
+        // public scalars: the shared 15-position comb (ops.cuh ge_scalarmult_base_comb), 4x fewer additions
         const unsigned th = kb_item_threads(ctx, n);
         k_mul_base_comb<<<kb_blocks(n, th), th, 0, st>>>(n, (const uint8_t*)d_scalars, xyz, ctx->comb);
     } else

@@ -20,7 +20,7 @@ struct kb_ctx {
     cudaStream_t stream2;    // second copy/compute lane of the pipelined host entry points
     ge_precomp* base_table;  // 64 x 8 entries: (j+1) * 16^w * B
     ge_precomp* base128;     // 128 entries: (j+1) * B (built only for the full-length verifiers, KB_VERIFY_FULL=1)
-    ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(13 p) * B (7.9 MB)
+    ge_precomp* comb;        // KB_COMB_POS x KB_COMB_HALF entries: (j+1) * 2^(17 p) * B (94 MB)
     int verify_full;         // KB_VERIFY_FULL=1 in the environment: the full-length (253-doubling) verify kernels
     size_t verify_chunk;     // signatures per pipelined chunk of the host-buffer verify calls (KB_VERIFY_CHUNK_LOG2 overrides)
     int msm_c;               // KB_MSM_C: Pippenger window bits override (0 = by size)

@@ -85,7 +85,7 @@ static __global__ void k_base128_init(ge_precomp* table)
     fe_set(pos.Z, 1);
     kb_base_window(table, pos, 128);
 }
-// comb[p][j] = (j+1) * 2^(13 p) * B: the fixed-base comb of the half-size-scalar verifiers (ops.cuh)
+// comb[p][j] = (j+1) * 2^(KB_COMB_BITS p) * B: the fixed-base comb of the half-size-scalar verifiers (ops.cuh)
 static __global__ void __launch_bounds__(KB_THREADS) k_comb_init(ge_precomp* comb, const ge_precomp* base_table)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,7 +231,7 @@ static __global__ void __launch_bounds__(KB_THREADS) k_mul_base(size_t n, const 
     if (live && part == 0) kb_store_xyz(xyz, i, h);
 }
 
-// public scalars (KB_FLAG_VARTIME): the shared comb, 20 mixed additions per scalar, nothing staged in shared memory
+// public scalars (KB_FLAG_VARTIME): the shared comb, KB_COMB_POS (15) mixed additions per scalar, nothing staged in shared memory
 static __global__ void __launch_bounds__(KB_THREADS) k_mul_base_comb(size_t n, const uint8_t* scalars, uint32_t* xyz, const ge_precomp* comb)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -742,7 +742,7 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k
         sig_half_apply_vneg(rec.ax, rec.at, (a.x >> 16) & 1u);
     }
     ge_cached tbl[16];
-    int16_t dw[KB_COMB_POS];
+    kb_comb_digit dw[KB_COMB_POS];
     int8_t eu[64], ev[64];
     sig_half_setup(dw, eu, ev, tbl, rec);
     // the window count of the block = the longest any of its signatures needs

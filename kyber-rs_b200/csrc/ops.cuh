@@ -345,18 +345,30 @@ KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uin
 //   W = (u*s mod L)*B + |v|*A' + u*R',   A' = -sign(v)*A,  R' = -R,   accept <=> W is the identity
 // with (u, v) = sc_half(h).  One signed radix-16 table each for A' and R' (tbl[0..7], tbl[8..15]) inside the
 // doubling loop.  The multiple of B needs no doublings at all: it is a comb over a table that is computed once
-// per context and shared by every signature, comb[p][j] = (j+1) * 2^(13 p) * B, p = 0..19, j = 0..4095 (7.9 MB,
-// L2-resident): 20 additions after the loop instead of 32 inside it.  The number of windows is BLOCK-uniform
+// per context and shared by every signature, comb[p][j] = (j+1) * 2^(17 p) * B, p = 0..14, j = 0..65535 (94 MB;
+// the first version had 13-bit windows: 20 positions, 7.9 MB): 15 additions after the loop instead of 32 inside it.  The number of windows is BLOCK-uniform
 // (the loop holds a block barrier): the kernel takes the maximum over its threads, 33 for almost every block
 // of honest input.
 #define KB_F_ROK 128u  // R decodes            (ge.rs:124)
 #define KB_HALF_MIN_WINDOWS 1
-#define KB_COMB_BITS 13
-#define KB_COMB_POS 20
+// Window width of the comb.  Every position less is one addition less per signature (0.08 ms per 2^20 signatures); the
+// operands are fetched one step ahead, so it does not matter that a wider table no longer fits the L2.  Measured on one
+// B200 (profiles/r2_ab_comb*.txt), k_verify_half_main for 2^20 signatures: 13 bits x 20 positions (7.9 MB) 16.35 ms,
+// 14 x 19 16.28, 15 x 17 (27 MB) 16.10, 16 x 16 (50 MB) 16.03, 17 x 15 (94 MB) 15.95.  19 x 14 would take 352 MB for one more.
+#ifndef KB_COMB_BITS
+#define KB_COMB_BITS 17
+#define KB_COMB_POS 15
+#endif
+static_assert(KB_COMB_BITS * KB_COMB_POS >= 254 && KB_COMB_BITS <= 20, "the comb must cover 253 bits and the recoding carry");
 #define KB_COMB_HALF (1 << (KB_COMB_BITS - 1))
+#if KB_COMB_BITS > 15
+typedef int32_t kb_comb_digit;
+#else
+typedef int16_t kb_comb_digit;
+#endif
 
-// signed radix-2^13 digits of a scalar < 2^253: d[0..19] in (-4096, 4096]
-KB_FN void sc_recode_comb(int16_t* d, const uint32_t* s)
+// signed radix-2^KB_COMB_BITS digits of a scalar < 2^253: d[0..KB_COMB_POS) in (-KB_COMB_HALF, KB_COMB_HALF]
+KB_FN void sc_recode_comb(kb_comb_digit* d, const uint32_t* s)
 {
     int carry = 0;
     KB_UNROLL
@@ -366,7 +378,7 @@ KB_FN void sc_recode_comb(int16_t* d, const uint32_t* s)
         if (sh + KB_COMB_BITS > 32 && wi + 1 < 8) x |= s[wi + 1] << (32 - sh);
         int v = (int)(x & ((1u << KB_COMB_BITS) - 1u)) + carry;
         carry = v > KB_COMB_HALF;
-        d[p] = (int16_t)(v - (carry << KB_COMB_BITS));
+        d[p] = (kb_comb_digit)(v - (carry << KB_COMB_BITS));
     }
 }
 KB_FN void kb_ld_precomp(ge_cached& c, const ge_precomp* e)
@@ -504,7 +516,7 @@ KB_FN void sig_half_prep(kb_half_rec& rec, const uint32_t* pk_w, const uint32_t*
     }
 }
 // digit strings and the two per-signature tables: tbl[0..7] = 1..8 A', tbl[8..15] = 1..8 R'
-KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, const kb_half_rec& rec)
+KB_FN void sig_half_setup(kb_comb_digit* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, const kb_half_rec& rec)
 {
     sc_recode_comb(dw, rec.w);
     sc_recode16(eu, rec.u);
@@ -529,7 +541,7 @@ KB_FN void sig_half_setup(int16_t* dw, int8_t* eu, int8_t* ev, ge_cached* tbl, c
 // W = |v|*A' + u*R' by `nwin` shared windows of four doublings, then the comb for the multiple of B.  Every thread
 // of the block runs the same trip count; one addition body serves all three operands (the comb entries are widened
 // to the cached form, Z = 1).
-KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
+KB_FN void ge_triple_scalarmult_vartime(ge_p3& h, int nwin, const kb_comb_digit* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
 {
     ge_identity(h);
     KB_NOUNROLL
@@ -580,7 +592,7 @@ struct kb_operand {
     uint32_t nz;     // digit != 0 (otherwise the operand is the identity and c is ignored)
 };
 // operand of addition `a` (0: A' with ev, 1: R' with eu) of window i >= 0, or of comb position -1 - i for i < 0
-KB_FN void kb_operand_fetch(kb_operand& o, int i, int a, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
+KB_FN void kb_operand_fetch(kb_operand& o, int i, int a, const kb_comb_digit* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
 {
     int d;
     if (i >= 0) d = a ? eu[i] : ev[i];
@@ -604,7 +616,7 @@ KB_FN void kb_operand_use(ge_cached& c, const kb_operand& o, bool is_comb)
     fe_cmov(c.Z, id.Z, o.nz ^ 1u);
     ge_cached_cneg(c, o.neg);
 }
-KB_FN void ge_triple_scalarmult_prefetch(ge_p3& h, int nwin, const int16_t* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
+KB_FN void ge_triple_scalarmult_prefetch(ge_p3& h, int nwin, const kb_comb_digit* dw, const int8_t* eu, const int8_t* ev, const ge_cached* tbl, const ge_precomp* comb)
 {
     ge_identity(h);
     kb_operand nx;
@@ -637,7 +649,7 @@ KB_FN void ge_triple_scalarmult_prefetch(ge_p3& h, int nwin, const int16_t* dw, 
         }
     }
 }
-// h = a * B for a PUBLIC scalar through the comb: 20 mixed additions instead of 64 (ge_scalarmult_base), no doublings.
+// h = a * B for a PUBLIC scalar through the comb: KB_COMB_POS (15) mixed additions instead of 64 (ge_scalarmult_base), no doublings.
 // Any 32-byte scalar gives the reference's result: sc_effective is the integer the reference's digit loop
 // multiplies by, and B has order L, so that integer may be reduced mod L first.
 KB_FN void ge_scalarmult_base_comb(ge_p3& h, const uint32_t* s, const ge_precomp* comb)
@@ -647,7 +659,7 @@ KB_FN void ge_scalarmult_base_comb(ge_p3& h, const uint32_t* s, const ge_precomp
     KB_UNROLL
     for (int i = 8; i < 16; i++) x[i] = 0;
     sc_reduce512(r, x);
-    int16_t dw[KB_COMB_POS];
+    kb_comb_digit dw[KB_COMB_POS];
     sc_recode_comb(dw, r);
     ge_identity(h);
     KB_NOUNROLL
@@ -666,7 +678,7 @@ KB_FN void ge_scalarmult_base_comb(ge_p3& h, const uint32_t* s, const ge_precomp
         ge_madd<true>(h, h, q);
     }
 }
-// comb[p][j] = (j+1) * 2^(13 p) * B in affine (y+x, y-x, 2dxy) form; entries whose multiplier does not fit 255 bits are
+// comb[p][j] = (j+1) * 2^(KB_COMB_BITS p) * B in affine (y+x, y-x, 2dxy) form; entries whose multiplier does not fit 255 bits are
 // never addressed by a scalar below 2^253 and hold the identity.  `base` = the 64 x 8 fixed-base table (kb_base_window).
 KB_FN void kb_comb_entry(ge_precomp& out, int p, int j, const ge_precomp* base)
 {
@@ -708,7 +720,7 @@ KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, cons
 {
     kb_half_rec rec;
     sig_half_prep<SCHNORR>(rec, pk_w, sig_w, msg, mlen);
-    int16_t dw[KB_COMB_POS];
+    kb_comb_digit dw[KB_COMB_POS];
     int8_t eu[64], ev[64];
     sig_half_setup(dw, eu, ev, tbl, rec);
     const int nwin = rec.nwin < min_windows ? min_windows : rec.nwin;

@@ -6,6 +6,8 @@
 // no GPU.  It is never linked into libkyber_b200.so and is not a CPU fallback: the product
 // library has no host compute path.
 #define KB_HOST_EMU 1
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <utility>
 #include <vector>
@@ -123,7 +125,57 @@ static void comb_init()
     base_init();
     if (!g_comb.empty()) return;
     g_comb.resize((size_t)KB_COMB_POS * KB_COMB_HALF);
-    for (int k = 0; k < KB_COMB_POS * KB_COMB_HALF; k++) kb_comb_entry(g_comb[k], k / KB_COMB_HALF, k % KB_COMB_HALF, g_base);
+    // The device computes every entry on its own (k_comb_init: one scalar multiplication and one inversion per thread);
+    // a host core would need minutes for the 15 x 65536 entries, so here a position is built by repeated addition of its
+    // first entry and ONE inversion (Montgomery's trick).  Same points; a sample of them is checked against kb_comb_entry.
+    const fe d2 = KB_FE_D2;
+    std::vector<ge_p3> run(KB_COMB_HALF);
+    std::vector<fe> pre(KB_COMB_HALF);
+    for (int p = 0; p < KB_COMB_POS; p++) {
+        ge_precomp first;
+        kb_comb_entry(first, p, 0, g_base);
+        ge_identity(run[0]);
+        ge_madd<true>(run[0], run[0], first);
+        for (int j = 1; j < KB_COMB_HALF; j++) ge_madd<true>(run[j], run[j - 1], first);
+        fe acc;
+        fe_set(acc, 1);
+        for (int j = 0; j < KB_COMB_HALF; j++) {
+            pre[j] = acc;
+            fe_mul(acc, acc, run[j].Z);
+        }
+        fe inv;
+        fe_invert(inv, acc);
+        for (int j = KB_COMB_HALF - 1; j >= 0; j--) {
+            fe zinv, x, y, xy;
+            fe_mul(zinv, inv, pre[j]);
+            fe_mul(inv, inv, run[j].Z);
+            ge_precomp& out = g_comb[(size_t)p * KB_COMB_HALF + j];
+            const int bit = KB_COMB_BITS * p;
+            if (bit + KB_COMB_BITS + 1 > 255 && ((uint64_t)(j + 1) >> (255 - bit)) != 0) {   // never addressed (kb_comb_entry)
+                ge_precomp_identity(out);
+                continue;
+            }
+            fe_mul(x, run[j].X, zinv);
+            fe_mul(y, run[j].Y, zinv);
+            fe_add(out.ypx, y, x);
+            fe_sub(out.ymx, y, x);
+            fe_mul(xy, x, y);
+            fe_mul(out.xy2d, xy, d2);
+        }
+        for (int j : {1, 2, KB_COMB_HALF / 3, KB_COMB_HALF - 1}) {
+            ge_precomp want;
+            kb_comb_entry(want, p, j, g_base);
+            const ge_precomp& got = g_comb[(size_t)p * KB_COMB_HALF + j];
+            uint32_t a[8], b[8];
+            fe_to_words(a, got.ypx); fe_to_words(b, want.ypx);
+            bool same = memcmp(a, b, 32) == 0;
+            fe_to_words(a, got.ymx); fe_to_words(b, want.ymx);
+            same = same && memcmp(a, b, 32) == 0;
+            fe_to_words(a, got.xy2d); fe_to_words(b, want.xy2d);
+            same = same && memcmp(a, b, 32) == 0;
+            if (!same) { fprintf(stderr, "emu comb: entry (%d, %d) differs from kb_comb_entry\n", p, j); abort(); }
+        }
+    }
 }
 // Point::mul(s, None) for public scalars through the shared comb
 void emu_mul_base_comb(uint8_t* out, const uint8_t* scalar)
