@@ -741,17 +741,25 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k
         rec.nwin = (int)((a.x >> 8) & 0xffu);
         sig_half_apply_vneg(rec.ax, rec.at, (a.x >> 16) & 1u);
     }
-    ge_cached tbl[16];
     kb_comb_digit dw[KB_COMB_POS];
+#if KB_HALF_JOINT
+    ge_cached tbl[KB_JOINT_SLOTS];
+    uint32_t uk[8], vk[8];
+    sig_half_setup_joint(dw, uk, vk, tbl, rec);
+#else
+    ge_cached tbl[16];
     int8_t eu[64], ev[64];
     sig_half_setup(dw, eu, ev, tbl, rec);
+#endif
     // the window count of the block = the longest any of its signatures needs
     int nwin = __reduce_max_sync(0xffffffffu, rec.nwin);
     if ((threadIdx.x & 31) == 0) atomicMax(&s_nwin, nwin);
     __syncthreads();
     nwin = s_nwin;
     ge_p3 W;
-#if KB_HALF_PREFETCH
+#if KB_HALF_JOINT
+    ge_triple_scalarmult_joint(W, nwin, dw, uk, vk, tbl, comb);
+#elif KB_HALF_PREFETCH
     ge_triple_scalarmult_prefetch(W, nwin, dw, eu, ev, tbl, comb);
 #else
     ge_triple_scalarmult_vartime(W, nwin, dw, eu, ev, tbl, comb);

@@ -355,6 +355,9 @@ KB_FN uint32_t sig_verify(const uint32_t* pk_w, const uint32_t* sig_w, const uin
 // operands are fetched one step ahead, so it does not matter that a wider table no longer fits the L2.  Measured on one
 // B200 (profiles/r2_ab_comb*.txt), k_verify_half_main for 2^20 signatures: 13 bits x 20 positions (7.9 MB) 16.35 ms,
 // 14 x 19 16.28, 15 x 17 (27 MB) 16.10, 16 x 16 (50 MB) 16.03, 17 x 15 (94 MB) 15.95.  19 x 14 would take 352 MB for one more.
+#ifndef KB_HALF_JOINT
+#define KB_HALF_JOINT 1   // one joint radix-4 table for A' and R' instead of two radix-16 tables (below)
+#endif
 #ifndef KB_COMB_BITS
 #define KB_COMB_BITS 17
 #define KB_COMB_POS 15
@@ -649,6 +652,128 @@ KB_FN void ge_triple_scalarmult_prefetch(ge_p3& h, int nwin, const kb_comb_digit
         }
     }
 }
+// ---- JOINT windows for the two variable points (KB_HALF_JOINT, default).  Instead of one signed radix-16 table each for
+// A' and R' (16 entries, two additions per four doublings) the loop uses ONE table of the combinations i R' + j A' of
+// signed radix-4 digits, i in {0, 1, 2}, j in {-2 .. 2} (the sign of a digit pair is pulled out: 11 entries), and adds
+// once per TWO doublings: 9 additions instead of 14 to build the tables, 65 instead of 66 additions in the loop of a
+// 128-bit pair, 1.4 KB instead of 2 KB of per-thread table.  A digit pair is turned into one signed code:
+// |code| - 1 = table slot, 0 = both digits zero, sign = negate the entry.
+//   slot: 0 A'   1 2A'   2 R'-2A'   3 R'-A'   4 R'   5 R'+A'   6 R'+2A'   (7 unused)   8 2R'-A'   9 2R'   10 2R'+A'   11 2R'+2A'
+#define KB_JOINT_SLOTS 12
+// Signed radix-4 digits in [-1, 2] without a carry loop: digit_i = value_i + carry_i - 4 carry_(i+1), and a carry leaves
+// digit i exactly when value_i + carry_i + 1 >= 4 — which is the carry of the plain 256-bit addition x + 0x55..55 out
+// of its i-th pair of bits.  So with xk = x + 0x55..55 the digit is (pair i of xk) - 1, for every i at once.
+KB_FN void sc_joint4_bias(uint32_t* xk, const uint32_t* x)
+{
+    const uint32_t k[8] = {0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u};
+    kb_add8(xk, x, k);   // x < 2^253: no carry leaves the top pair
+}
+// code of digit pair `idx` (0..127) of (u, v), from the biased words
+KB_FN int sc_joint4_code(const uint32_t* uk, const uint32_t* vk, int idx)
+{
+    const int sh = 2 * (idx & 15);
+    int du = (int)((uk[idx >> 4] >> sh) & 3u) - 1;
+    int dv = (int)((vk[idx >> 4] >> sh) & 3u) - 1;
+    const int neg = (du < 0) | ((du == 0) & (dv < 0));
+    du = neg ? -du : du;
+    dv = neg ? -dv : dv;
+    const int code = du * 5 + dv;   // (0, 0) -> 0, (0, 1) -> 1 ... (2, 2) -> 12: slot + 1
+    return neg ? -code : code;
+}
+// the joint table from A' and R' (affine): nine additions through ONE addition body.  Start points are A', R', the
+// previous sum or -A'; operands are entries already written (A', R', 2R'), possibly negated.
+KB_FN void ge_build_joint_table(ge_cached* tbl, const kb_half_rec& rec)
+{
+    ge_p3 m;
+    m.X = rec.ax; m.Y = rec.ay; m.T = rec.at; fe_set(m.Z, 1);
+    ge_to_cached(tbl[0], m);
+    m.X = rec.rx; m.Y = rec.ry; m.T = rec.rt;
+    ge_to_cached(tbl[4], m);
+    ge_cached_identity(tbl[7]);
+    //  step        0     1     2     3      4     5      6      7       8
+    //  sum        2A'   2R'   R'+A' R'+2A' R'-A' R'-2A' 2R'+A' 2R'+2A' 2R'-A'
+    //  start      A'    R'    R'    prev   R'    prev   A'     prev    -A'
+    //  operand    A'    R'    A'    A'     -A'   -A'    2R'    A'      2R'
+    KB_NOUNROLL
+    for (int st = 0; st < 9; st++) {
+        const uint32_t from = (uint32_t)(0x320212110ull >> (4 * st)) & 15u;   // 0 A', 1 R', 2 previous sum, 3 -A'
+        const uint32_t opnd = (uint32_t)(0x909000040ull >> (4 * st)) & 15u;   // slot of the operand
+        const uint32_t neg = (0x030u >> st) & 1u;
+        const uint32_t dst = (uint32_t)(0x8BA236591ull >> (4 * st)) & 15u;
+        ge_p3 b = m;
+        if (from != 2) {
+            const uint32_t isr = (uint32_t)(from == 1);
+            b.X = rec.ax; b.Y = rec.ay; b.T = rec.at;
+            fe_cmov(b.X, rec.rx, isr);
+            fe_cmov(b.Y, rec.ry, isr);
+            fe_cmov(b.T, rec.rt, isr);
+            fe_set(b.Z, 1);
+            if (from == 3) { fe_neg(b.X, b.X); fe_neg(b.T, b.T); }
+        }
+        ge_cached c = tbl[opnd];
+        ge_cached_cneg(c, neg);
+        ge_add<true>(m, b, c);
+        ge_to_cached(tbl[dst], m);
+    }
+}
+KB_FN void sig_half_setup_joint(kb_comb_digit* dw, uint32_t* uk, uint32_t* vk, ge_cached* tbl, const kb_half_rec& rec)
+{
+    sc_recode_comb(dw, rec.w);
+    sc_joint4_bias(uk, rec.u);
+    sc_joint4_bias(vk, rec.v);
+    ge_build_joint_table(tbl, rec);
+}
+// operand of an addition, one step ahead: a joint-table entry by its code, or comb position p
+KB_FN void kb_operand_fetch_code(kb_operand& o, int d, const ge_cached* tbl)
+{
+    o.neg = (uint32_t)d >> 31;
+    const int babs = (d ^ -(int)o.neg) + (int)o.neg;
+    o.nz = (uint32_t)(babs != 0);
+    o.c = tbl[babs != 0 ? babs - 1 : 0];   // code = slot + 1; always a valid entry: the load is unconditional
+}
+KB_FN void kb_operand_fetch_comb(kb_operand& o, int p, const kb_comb_digit* dw, const ge_precomp* comb)
+{
+    const int d = dw[p];
+    o.neg = (uint32_t)d >> 31;
+    const int babs = (d ^ -(int)o.neg) + (int)o.neg;
+    o.nz = (uint32_t)(babs != 0);
+    kb_ld_precomp(o.c, comb + (size_t)p * KB_COMB_HALF + (babs != 0 ? babs - 1 : 0));
+}
+// W = |v|*A' + u*R' + w*B: `nwin` windows of FOUR bits = (two doublings, one joint addition) twice, then the comb.  The
+// first window starts at its first addition.  Operands are fetched one step ahead as in ge_triple_scalarmult_prefetch.
+KB_FN void ge_triple_scalarmult_joint(ge_p3& h, int nwin, const kb_comb_digit* dw, const uint32_t* uk, const uint32_t* vk, const ge_cached* tbl, const ge_precomp* comb)
+{
+    ge_identity(h);
+    kb_operand nx;
+    kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, 2 * (nwin - 1) + 1), tbl);
+    KB_NOUNROLL
+    for (int i = nwin - 1; i >= -KB_COMB_POS; i--) {
+        KB_LOCKSTEP();
+        const int lead = (i >= 0 && i != nwin - 1) ? 2 : 0;
+        const int nstep = i >= 0 ? lead + 4 : 1;
+        KB_NOUNROLL
+        for (int step = 0; step < nstep; step++) {
+            const int q = step - lead;   // i >= 0:  < 0 leading doublings, 0 addition (high pair), 1, 2 doublings, 3 addition (low pair)
+            const bool is_add = i < 0 || q == 0 || q == 3;
+            fe e, f, g, hh;
+            bool with_t;
+            if (!is_add) {
+                ge_dbl_front(e, f, g, hh, h);
+                with_t = q == -1 || q == 2;   // an addition follows
+                if (q == -1) kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, 2 * i + 1), tbl);
+                else if (q == 2) kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, 2 * i), tbl);
+            } else {
+                ge_cached c;
+                kb_operand_use(c, nx, i < 0);
+                ge_add_front(e, f, g, hh, h, c);
+                // T is dead when a doubling (or the end) follows: it is needed in front of the comb additions only
+                with_t = (i == 0 && q == 3) || (i < 0 && i != -KB_COMB_POS);
+                if (with_t) kb_operand_fetch_comb(nx, -i, dw, comb);   // position -1 - (i - 1)
+            }
+            ge_tail(h, e, f, g, hh, with_t);
+        }
+    }
+}
 // h = a * B for a PUBLIC scalar through the comb: KB_COMB_POS (15) mixed additions instead of 64 (ge_scalarmult_base), no doublings.
 // Any 32-byte scalar gives the reference's result: sc_effective is the integer the reference's digit loop
 // multiplies by, and B has order L, so that integer may be reduced mod L first.
@@ -721,11 +846,17 @@ KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, cons
     kb_half_rec rec;
     sig_half_prep<SCHNORR>(rec, pk_w, sig_w, msg, mlen);
     kb_comb_digit dw[KB_COMB_POS];
-    int8_t eu[64], ev[64];
-    sig_half_setup(dw, eu, ev, tbl, rec);
     const int nwin = rec.nwin < min_windows ? min_windows : rec.nwin;
     ge_p3 W;
+#if KB_HALF_JOINT
+    uint32_t uk[8], vk[8];
+    sig_half_setup_joint(dw, uk, vk, tbl, rec);
+    ge_triple_scalarmult_joint(W, nwin, dw, uk, vk, tbl, comb);
+#else
+    int8_t eu[64], ev[64];
+    sig_half_setup(dw, eu, ev, tbl, rec);
     ge_triple_scalarmult_prefetch(W, nwin, dw, eu, ev, tbl, comb);
+#endif
     return sig_half_finish<SCHNORR>(rec.f, W);
 }
 
