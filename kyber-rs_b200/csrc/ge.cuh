@@ -186,6 +186,23 @@ KB_FN void ge_add_front(fe& e, fe& f, fe& g, fe& h, const ge_p3& p, const ge_cac
     fe_add(g, d, c);
     fe_add(h, b, a);
 }
+// the same when the operand is known to have Z = 1 in some calls (q_z_one, uniform over the warp): 2 Z1 needs no product
+KB_FN void ge_add_front_z(fe& e, fe& f, fe& g, fe& h, const ge_p3& p, const ge_cached& q, bool q_z_one)
+{
+    fe a, b, c, d;
+    fe_sub(a, p.Y, p.X);
+    fe_add(b, p.Y, p.X);
+    fe_mul(a, a, q.YmX);
+    fe_mul(b, b, q.YpX);
+    fe_mul(c, p.T, q.T2d);
+    if (q_z_one) d = p.Z;
+    else fe_mul(d, p.Z, q.Z);
+    fe_dbl(d, d);
+    fe_sub(e, b, a);
+    fe_sub(f, d, c);
+    fe_add(g, d, c);
+    fe_add(h, b, a);
+}
 KB_FN void ge_dbl_front(fe& e, fe& f, fe& g, fe& h, const ge_p3& p)
 {
     fe a, b, c;

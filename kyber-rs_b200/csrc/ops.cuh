@@ -765,7 +765,7 @@ KB_FN void ge_triple_scalarmult_joint(ge_p3& h, int nwin, const kb_comb_digit* d
             } else {
                 ge_cached c;
                 kb_operand_use(c, nx, i < 0);
-                ge_add_front(e, f, g, hh, h, c);
+                ge_add_front_z(e, f, g, hh, h, c, i < 0);   // comb entries are affine
                 // T is dead when a doubling (or the end) follows: it is needed in front of the comb additions only
                 with_t = (i == 0 && q == 3) || (i < 0 && i != -KB_COMB_POS);
                 if (with_t) kb_operand_fetch_comb(nx, -i, dw, comb);   // position -1 - (i - 1)
