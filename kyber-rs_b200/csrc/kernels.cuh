@@ -714,7 +714,11 @@ template <bool SCHNORR>
 static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k_verify_half_main(size_t n, const uint32_t* recs, uint8_t* status, const ge_precomp* comb, int min_windows)
 {
     __shared__ int s_nwin;
+#if KB_HALF_JOINT
+    if (threadIdx.x == 0) s_nwin = 2 * min_windows;   // the joint loop counts radix-4 digit pairs
+#else
     if (threadIdx.x == 0) s_nwin = min_windows;   // KB_HALF_MIN_WINDOWS, or more when a test forces long loops
+#endif
     __syncthreads();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;   // tail threads redo the last item so that they reach the block barriers
@@ -752,7 +756,11 @@ static __global__ void __launch_bounds__(KB_THREADS, KB_VERIFY_HALF_MINBLOCKS) k
     sig_half_setup(dw, eu, ev, tbl, rec);
 #endif
     // the window count of the block = the longest any of its signatures needs
+#if KB_HALF_JOINT
+    int nwin = __reduce_max_sync(0xffffffffu, sc_joint4_pairs(rec.u, rec.v));
+#else
     int nwin = __reduce_max_sync(0xffffffffu, rec.nwin);
+#endif
     if ((threadIdx.x & 31) == 0) atomicMax(&s_nwin, nwin);
     __syncthreads();
     nwin = s_nwin;

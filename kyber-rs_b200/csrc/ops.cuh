@@ -739,35 +739,39 @@ KB_FN void kb_operand_fetch_comb(kb_operand& o, int p, const kb_comb_digit* dw, 
     o.nz = (uint32_t)(babs != 0);
     kb_ld_precomp(o.c, comb + (size_t)p * KB_COMB_HALF + (babs != 0 ? babs - 1 : 0));
 }
-// W = |v|*A' + u*R' + w*B: `nwin` windows of FOUR bits = (two doublings, one joint addition) twice, then the comb.  The
-// first window starts at its first addition.  Operands are fetched one step ahead as in ge_triple_scalarmult_prefetch.
-KB_FN void ge_triple_scalarmult_joint(ge_p3& h, int nwin, const kb_comb_digit* dw, const uint32_t* uk, const uint32_t* vk, const ge_cached* tbl, const ge_precomp* comb)
+// number of radix-4 digit pairs the joint loop needs for (u, v): digits lie in [-1, 2], so n pairs represent every
+// magnitude up to 2 (4^n - 1) / 3 and 2 n >= bits + 1 is enough
+KB_FN int sc_joint4_pairs(const uint32_t* u, const uint32_t* v)
+{
+    const int bu = kb_bitlen8(u), bv = kb_bitlen8(v);
+    return (bu > bv ? bu : bv) / 2 + 1;
+}
+// W = |v|*A' + u*R' + w*B: `npair` steps of (two doublings, one joint addition) — the first one starts at its addition —
+// then the comb.  The trip count is uniform over the block (the loop holds the lockstep barrier, every second pair).
+// Operands are fetched one step ahead as in ge_triple_scalarmult_prefetch.
+KB_FN void ge_triple_scalarmult_joint(ge_p3& h, int npair, const kb_comb_digit* dw, const uint32_t* uk, const uint32_t* vk, const ge_cached* tbl, const ge_precomp* comb)
 {
     ge_identity(h);
     kb_operand nx;
-    kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, 2 * (nwin - 1) + 1), tbl);
+    kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, npair - 1), tbl);
     KB_NOUNROLL
-    for (int i = nwin - 1; i >= -KB_COMB_POS; i--) {
-        KB_LOCKSTEP();
-        const int lead = (i >= 0 && i != nwin - 1) ? 2 : 0;
-        const int nstep = i >= 0 ? lead + 4 : 1;
+    for (int i = npair - 1; i >= -KB_COMB_POS; i--) {
+        if (i < 0 || (i & 1)) KB_LOCKSTEP();
+        const int lead = (i >= 0 && i != npair - 1) ? 2 : 0;
         KB_NOUNROLL
-        for (int step = 0; step < nstep; step++) {
-            const int q = step - lead;   // i >= 0:  < 0 leading doublings, 0 addition (high pair), 1, 2 doublings, 3 addition (low pair)
-            const bool is_add = i < 0 || q == 0 || q == 3;
+        for (int step = 0; step <= lead; step++) {
             fe e, f, g, hh;
             bool with_t;
-            if (!is_add) {
+            if (step < lead) {
                 ge_dbl_front(e, f, g, hh, h);
-                with_t = q == -1 || q == 2;   // an addition follows
-                if (q == -1) kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, 2 * i + 1), tbl);
-                else if (q == 2) kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, 2 * i), tbl);
+                with_t = step == lead - 1;   // the addition follows
+                if (with_t) kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, i), tbl);
             } else {
                 ge_cached c;
                 kb_operand_use(c, nx, i < 0);
                 ge_add_front_z(e, f, g, hh, h, c, i < 0);   // comb entries are affine
                 // T is dead when a doubling (or the end) follows: it is needed in front of the comb additions only
-                with_t = (i == 0 && q == 3) || (i < 0 && i != -KB_COMB_POS);
+                with_t = i <= 0 && i != -KB_COMB_POS;
                 if (with_t) kb_operand_fetch_comb(nx, -i, dw, comb);   // position -1 - (i - 1)
             }
             ge_tail(h, e, f, g, hh, with_t);
@@ -851,7 +855,8 @@ KB_FN uint32_t sig_verify_half(const uint32_t* pk_w, const uint32_t* sig_w, cons
 #if KB_HALF_JOINT
     uint32_t uk[8], vk[8];
     sig_half_setup_joint(dw, uk, vk, tbl, rec);
-    ge_triple_scalarmult_joint(W, nwin, dw, uk, vk, tbl, comb);
+    const int np = sc_joint4_pairs(rec.u, rec.v);
+    ge_triple_scalarmult_joint(W, np < 2 * min_windows ? 2 * min_windows : np, dw, uk, vk, tbl, comb);
 #else
     int8_t eu[64], ev[64];
     sig_half_setup(dw, eu, ev, tbl, rec);
