@@ -92,6 +92,8 @@ int kb_ctx_create(int device, kb_ctx** out)
         ctx->vs_blocks = (vsbn >= 1 && vsbn <= 8) ? vsbn : 1;
         const char* vpb = getenv("KB_VERIFY_SPLIT_PBOUND");
         ctx->vs_pbound = vpb ? atoi(vpb) : 0;
+        const char* vso = getenv("KB_VERIFY_SORT");
+        ctx->verify_sort = vso ? atoi(vso) : 1;
         const char* vp = getenv("KB_VERIFY_PIPE");
         ctx->verify_pipe = vp ? atoi(vp) : 0;
         const char* vn = getenv("KB_VERIFY_CHUNK");

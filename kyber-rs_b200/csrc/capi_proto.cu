@@ -91,7 +91,7 @@ int kb_dev_dkg_process_round(kb_ctx* ctx, size_t n, size_t t, size_t ndealers, i
     uint32_t* xyz;
     uint8_t* fl;
     KB_SCRATCH(KB_SLOT_XYZ, (size_t)KB_VERIFY_SCRATCH_BYTES * m, xyz);
-    KB_SCRATCH(KB_SLOT_FLAGS, m, fl);
+    KB_SCRATCH(KB_SLOT_FLAGS, KB_VERIFY_FLAG_BYTES(m), fl);
     if (d_deal_sig) {
         rc = kb_verify_launch(ctx, m, (const uint8_t*)d_deal_pk, (const uint8_t*)d_deal_msg, (const uint64_t*)d_deal_msg_off, 0, (const uint8_t*)d_deal_sig, (uint8_t*)d_deal_status, 1, xyz, fl, st);
         if (rc != KB_OK) return rc;

@@ -49,8 +49,26 @@ int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* 
             KB_LAUNCHED();
         }
         if (tm) cudaEventRecord(ctx->tev[1], st);
-        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
-        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, d_status, ctx->comb, ctx->verify_min_windows);
+        // Records sorted by the length of their loop (kernels.cuh k_half_sort_*): the trip count of the main kernel is
+        // uniform over a block, so a block of like records stops at ITS length instead of the longest of 128 random ones.
+        const uint32_t* perm = nullptr;
+#if KB_HALF_JOINT
+        if (ctx->verify_sort && (n >= 16384 || ctx->verify_sort == 2) && n < ((size_t)1 << 32)) {   // 2: every batch size (tests)
+            uint32_t* pm = reinterpret_cast<uint32_t*>(fl);
+            uint8_t* keys = fl + 4 * n;
+            uint32_t* hist = reinterpret_cast<uint32_t*>(fl + ((5 * n + 255) & ~(size_t)255));
+            KB_CUDA(cudaMemsetAsync(hist, 0, 4 * KB_SORT_BINS, st));
+            k_half_sort_count<<<kb_blocks(n, 256), 256, 0, st>>>(n, xyz, keys, hist);
+            KB_LAUNCHED();
+            k_half_sort_scan<<<1, 32, 0, st>>>(hist, hist + KB_SORT_BINS);
+            KB_LAUNCHED();
+            k_half_sort_scatter<<<kb_blocks(n, 256), 256, 0, st>>>(n, keys, hist + KB_SORT_BINS, pm);
+            KB_LAUNCHED();
+            perm = pm;
+        }
+#endif
+        if (schnorr) k_verify_half_main<true><<<g1, th, 0, st>>>(n, xyz, perm, d_status, ctx->comb, ctx->verify_min_windows);
+        else k_verify_half_main<false><<<g1, th, 0, st>>>(n, xyz, perm, d_status, ctx->comb, ctx->verify_min_windows);
         KB_LAUNCHED();
         if (tm) {
             cudaEventRecord(ctx->tev[2], st);
@@ -83,7 +101,7 @@ int kb_dev_eddsa_verify(kb_ctx* ctx, size_t n, const void* d_pk, const void* d_m
     uint32_t* xyz;
     uint8_t* fl;
     KB_SCRATCH(KB_SLOT_XYZ, KB_VERIFY_SCRATCH_BYTES * n, xyz);
-    KB_SCRATCH(KB_SLOT_FLAGS, n, fl);
+    KB_SCRATCH(KB_SLOT_FLAGS, KB_VERIFY_FLAG_BYTES(n), fl);
     KB_DEV_RETURN(st, kb_verify_launch(ctx, n, (const uint8_t*)d_pk, (const uint8_t*)d_msg, (const uint64_t*)d_msg_off, 0, (const uint8_t*)d_sig, (uint8_t*)d_status, schnorr, xyz, fl, st));
 }
 // Host-buffer verification, pipelined: the batch is cut into chunks that alternate between two staging lanes, so the
@@ -139,7 +157,7 @@ static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
         KB_SCRATCH(b + 3, 8 * (cn_max + 1), d_off[l]);
         KB_SCRATCH(b + 4, cn_max, d_st[l]);
         KB_SCRATCH(b + 5, KB_VERIFY_SCRATCH_BYTES * cn_max, xyz[l]);
-        KB_SCRATCH(b + 6, cn_max, fl[l]);
+        KB_SCRATCH(b + 6, KB_VERIFY_FLAG_BYTES(cn_max), fl[l]);
     }
     // Two schedules.  verify_pipe = 0 (default): two independent lanes (copy in, kernels, copy out each) that alternate;
     // the device may run the kernels of consecutive chunks side by side, which fills the tail of every launch.

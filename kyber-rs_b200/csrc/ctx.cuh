@@ -38,6 +38,7 @@ struct kb_ctx {
     cudaStream_t vs_side[2];                   // side stream per launch stream (the two lanes of the host-buffer pipeline)
     cudaEvent_t vs_fork[2], vs_join[2];
     unsigned long long* vs_counter;            // work counters of the persistent kernel, one per side stream
+    int verify_sort;         // KB_VERIFY_SORT (default 1): the main kernel walks the records in the order of their loop lengths
     int verify_pipe;         // KB_VERIFY_PIPE: 0 = two independent lanes (default); 1 = kernels of all chunks on ONE stream, copies on the other
     size_t verify_chunk_n;   // KB_VERIFY_CHUNK: signatures per chunk as a plain count (overrides KB_VERIFY_CHUNK_LOG2)
     cudaEvent_t fork_ev, join_ev;              // a device entry point that runs two independent kernels side by side (Pippenger merge)
@@ -144,6 +145,9 @@ int kb_dev_end(kb_ctx* ctx, cudaStream_t st);
 int kb_verify_launch(kb_ctx* ctx, size_t n, const uint8_t* d_pk, const uint8_t* d_msg, const uint64_t* d_msg_off, uint64_t msg_base, const uint8_t* d_sig, uint8_t* d_status, int schnorr,
                      uint32_t* xyz, uint8_t* fl, cudaStream_t st);
 #define KB_VERIFY_SCRATCH_BYTES 304   // per signature in `xyz` (4 * KB_HALF_REC_WORDS)
+// bytes of the `fl` scratch of kb_verify_launch: one flag byte per signature (full-length path) or, for the half-size-scalar
+// path, the order in which the main kernel walks the records — uint32 perm[n], uint8 keys[n], 2 x 129 counters
+#define KB_VERIFY_FLAG_BYTES(n) (5 * (size_t)(n) + 4096)
 // capi_msm.cu: Pippenger on device buffers
 // (ext != 0: the points are already decoded, 128 bytes each as X, Y, Z, T words)
 int kb_msm_run(kb_ctx* ctx, size_t n, const uint8_t* d_scalars, const void* d_points, int ext, uint8_t* d_out32, uint32_t* d_partial128, unsigned long long* d_bad, cudaStream_t st);

@@ -58,11 +58,13 @@ def ctx_split(kb):
     side stream beside the "points" grid, joined by k_verify_half_fix), forced for every batch size."""
     os.environ["KB_VERIFY_SPLIT"] = "2"
     os.environ["KB_VERIFY_SPLIT_BLOCKS"] = "2"
+    os.environ["KB_VERIFY_SORT"] = "2"   # and the records sorted by loop length for every batch size (default: from 16384 on)
     try:
         c = kb.Context(0)
     finally:
         del os.environ["KB_VERIFY_SPLIT"]
         del os.environ["KB_VERIFY_SPLIT_BLOCKS"]
+        del os.environ["KB_VERIFY_SORT"]
     yield c
     c.close()
 
@@ -282,6 +284,8 @@ def test_verify_split_preparation(ctx, ctx_split, coracle, golden_records, schno
     want = coracle.verify_batch(pk, flat, off, sg, nthreads=8, schnorr=schnorr)
     got = ctx_split.verify_batch(pk, flat, off, sg, schnorr=schnorr)
     assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    for m in (1, 2, 127, 129, 1000):   # ragged sizes through the sorted order
+        assert (ctx_split.verify_batch(pk[:m], flat[: int(off[m])], off[: m + 1], sg[:m], schnorr=schnorr) == want[:m]).all()
     assert (ctx.verify_batch(pk, flat, off, sg, schnorr=schnorr) == want).all()
     assert set(np.unique(want)) == {0, 2, 3, 4, 5, 6, 7, 8}
 
