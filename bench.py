@@ -49,7 +49,7 @@ IMAD_EQ_PER_MSM_POINT = 20_700
 IMAD_EQ_PER_DECOMPRESS = 20 * 72 + 255 * 44
 # what the half-size-scalar kernels execute per signature (IMAD.WIDE, M = 73, S = 44):
 EXEC_PREP_PER_VERIFY = 25_600
-EXEC_MAIN_PER_VERIFY = 103_600   # 130 doublings x 413 + 66 joint-table additions x 555 + 15 comb additions x 482 (affine operands) + 6.1 k for the joint table
+EXEC_MAIN_PER_VERIFY = 101_800   # 127.3 doublings x 413 + 64.6 joint-table additions x 555 (records sorted by length) + 15 comb additions x 482 (affine operands) + 6.1 k for the joint table
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")
@@ -510,7 +510,7 @@ def main():
                      "note": "integer-multiply roofline (north_star): 154k 32x32->64 MAC-equivalents CHARGED per signature (SURVEY 8d: decompress A + 253-doubling Straus + compress) / CUDA-event step time; "
                              f"peak = ARCHITECTURAL IMAD.WIDE.U32 rate, 32 lanes/clk/SM x {ctx.sm_count} SMs x {sm_max_mhz:.0f} MHz (the fmaheavy pipe issues one warp instruction per 4 cycles). "
                              "The kernels EXECUTE fewer multiplies than charged (half-size scalars: 128 doublings, csrc/half.cuh): see `executed`",
-                     "kernel": "one step = k_verify_half_prep (checks, decompress A and R, SHA-512, lattice step) + k_verify_half_main (tables, 33-window loop, comb, verdict)",
+                     "kernel": "one step = k_verify_half_prep (checks, decompress A and R, SHA-512, lattice step) + k_half_sort_count/scan/scatter (records ordered by loop length; timed with the main kernel) + k_verify_half_main (joint radix-4 table of A and R, ~65 steps of two doublings and one addition, 15-position comb, verdict)",
                      "kernels_ms": {"k_verify_half_prep": prep_s * 1e3, "k_verify_half_main": main_s * 1e3, "timed_steps": len(k_main_ms),
                                     "how": "cudaEventRecord on the launch stream around each launch (kb_verify_kernel_times), averaged over a second pass of the same steps"},
                      "executed": {"imad_wide_per_sig": {"k_verify_half_prep": EXEC_PREP_PER_VERIFY, "k_verify_half_main": EXEC_MAIN_PER_VERIFY},
