@@ -49,7 +49,7 @@ IMAD_EQ_PER_MSM_POINT = 20_700
 IMAD_EQ_PER_DECOMPRESS = 20 * 72 + 255 * 44
 # what the half-size-scalar kernels execute per signature (IMAD.WIDE, M = 73, S = 44):
 EXEC_PREP_PER_VERIFY = 25_600
-EXEC_MAIN_PER_VERIFY = 101_800   # 127.3 doublings x 413 + 64.6 joint-table additions x 555 (records sorted by length) + 15 comb additions x 482 (affine operands) + 6.1 k for the joint table
+EXEC_MAIN_PER_VERIFY = 101_200   # 127.3 doublings x 413 + 63.6 joint-table additions x 555 (records sorted by length; the first operand is taken as it is) + 15 comb additions x 482 (affine operands) + 6.1 k for the joint table
 ALG_BYTES_PER_SIG = 161           # 32 pk + 64 sig + 64 msg + 1 status
 L_ORDER = 2**252 + 27742317777372353535851937790883648493
 WEAK_R = bytes.fromhex("c7176a703d4dd84fba3c0b760d10670f2a2053fa2c39ccc64ec7fd7792ac037a")

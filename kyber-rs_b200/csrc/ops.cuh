@@ -746,18 +746,31 @@ KB_FN int sc_joint4_pairs(const uint32_t* u, const uint32_t* v)
     const int bu = kb_bitlen8(u), bv = kb_bitlen8(v);
     return (bu > bv ? bu : bv) / 2 + 1;
 }
-// W = |v|*A' + u*R' + w*B: `npair` steps of (two doublings, one joint addition) — the first one starts at its addition —
+// W = |v|*A' + u*R' + w*B: `npair` steps of (two doublings, one joint addition) — the first one IS its operand —
 // then the comb.  The trip count is uniform over the block (the loop holds the lockstep barrier, every second pair).
 // Operands are fetched one step ahead as in ge_triple_scalarmult_prefetch.
+#ifndef KB_JOINT_SYNC
+#define KB_JOINT_SYNC 1   // lockstep barrier when (pair index & KB_JOINT_SYNC) == KB_JOINT_SYNC: every second pair
+#endif
 KB_FN void ge_triple_scalarmult_joint(ge_p3& h, int npair, const kb_comb_digit* dw, const uint32_t* uk, const uint32_t* vk, const ge_cached* tbl, const ge_precomp* comb)
 {
-    ge_identity(h);
+    if (npair < 2) npair = 2;   // a leading zero pair costs nothing wrong; it lets the first step below drop T
     kb_operand nx;
     kb_operand_fetch_code(nx, sc_joint4_code(uk, vk, npair - 1), tbl);
+    {
+        // the first addition would add to the identity: take the operand itself, (2X : 2Y : 2Z) from (Y+X, Y-X, Z);
+        // doublings follow, so T is not needed
+        ge_cached c;
+        kb_operand_use(c, nx, false);
+        fe_sub(h.X, c.YpX, c.YmX);
+        fe_add(h.Y, c.YpX, c.YmX);
+        fe_dbl(h.Z, c.Z);
+        fe_set(h.T, 0);
+    }
     KB_NOUNROLL
-    for (int i = npair - 1; i >= -KB_COMB_POS; i--) {
-        if (i < 0 || (i & 1)) KB_LOCKSTEP();
-        const int lead = (i >= 0 && i != npair - 1) ? 2 : 0;
+    for (int i = npair - 2; i >= -KB_COMB_POS; i--) {
+        if (i < 0 || (i & KB_JOINT_SYNC) == KB_JOINT_SYNC) KB_LOCKSTEP();
+        const int lead = i >= 0 ? 2 : 0;
         KB_NOUNROLL
         for (int step = 0; step <= lead; step++) {
             fe e, f, g, hh;
