@@ -39,7 +39,7 @@ extern "C" {
  *   KB_VERIFY_FULL=1          signature verifiers: the full-length (253-doubling) kernels instead of the half-size-scalar ones
  *   KB_VERIFY_MIN_WINDOWS=k   half-size-scalar verifier: lower bound on the block-uniform window count (tests)
  *   KB_VERIFY_CHUNK=n         host-buffer verify calls: largest pipelined chunk in signatures (default: 16 waves of the main
- *                             kernel = 16 x SMs x 384; the chunks grow x4 from a third of a wave up to this cap)
+ *                             kernel = 16 x SMs x 512; the chunks grow x4 from a third of a wave up to this cap)
  *   KB_VERIFY_CHUNK_LOG2=k    the same cap as a power of two
  *   KB_VERIFY_PIPE=1          host-buffer verify calls: kernels of all chunks on one stream and copies on a second one
  *                             (default 0: two alternating lanes, each copy in / kernels / copy out)

@@ -759,8 +759,11 @@ static __global__ void __launch_bounds__(256) k_half_sort_scatter(size_t n, cons
     if (i < n) perm[s_base[key] + rank] = (uint32_t)i;
 }
 #endif
+// Resident blocks per SM of the main kernel.  3 (168 registers, no spills) was the best setting while two radix-16 tables
+// sat in local memory (2 blocks: +5 %, 4: slower in round 1); with the joint table (1.7 KB per thread, a third of the DRAM
+// traffic) 4 blocks (128 registers, 208 bytes of spills) win: 14.82 -> 14.51 ms for 2^20 signatures (profiles/r2_ab_sync1_mb4.txt).
 #ifndef KB_VERIFY_HALF_MINBLOCKS
-#define KB_VERIFY_HALF_MINBLOCKS 3
+#define KB_VERIFY_HALF_MINBLOCKS 4
 #endif
 #ifndef KB_HALF_PREFETCH
 #define KB_HALF_PREFETCH 1   // operands of the additions fetched one step ahead (ops.cuh ge_triple_scalarmult_prefetch)
