@@ -108,6 +108,35 @@ int emu_mul(uint8_t* out, const uint8_t* scalar, const uint8_t* point, int ct)
     st(out, o, 8);
     return (int)ok;
 }
+// the joint radix-4 machinery of the half-size-scalar verifier (ops.cuh): codes[i] = sc_joint4_code of digit pair i of
+// (u, v), i < 128; table[12 x 32] = encodings of the joint table built from the points a and r (slot 7 is unused)
+void emu_joint4(int8_t* codes, uint8_t* table, const uint8_t* u, const uint8_t* v, const uint8_t* a, const uint8_t* r)
+{
+    uint32_t uw[8], vw[8], uk[8], vk[8], aw[8], rw[8];
+    ld(uw, u, 8); ld(vw, v, 8); ld(aw, a, 8); ld(rw, r, 8);
+    sc_joint4_bias(uk, uw);
+    sc_joint4_bias(vk, vw);
+    for (int i = 0; i < 128; i++) codes[i] = (int8_t)sc_joint4_code(uk, vk, i);
+    ge_p3 pa, pr;
+    ge_decompress(pa, aw);
+    ge_decompress(pr, rw);
+    kb_half_rec rec;
+    rec.ax = pa.X; rec.ay = pa.Y; rec.at = pa.T;
+    rec.rx = pr.X; rec.ry = pr.Y; rec.rt = pr.T;
+    ge_cached tbl[KB_JOINT_SLOTS];
+    ge_build_joint_table(tbl, rec);
+    for (int k = 0; k < KB_JOINT_SLOTS; k++) {
+        // cached (Y+X, Y-X, 2dT, Z) -> (2X : 2Y : 2Z)
+        ge_p3 q;
+        uint32_t o[8];
+        fe_sub(q.X, tbl[k].YpX, tbl[k].YmX);
+        fe_add(q.Y, tbl[k].YpX, tbl[k].YmX);
+        fe_dbl(q.Z, tbl[k].Z);
+        fe_set(q.T, 0);
+        ge_compress(o, q);
+        st(table + 32 * k, o, 8);
+    }
+}
 void emu_mul_base(uint8_t* out, const uint8_t* scalar, int ct)
 {
     uint32_t s[8], o[8];

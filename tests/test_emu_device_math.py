@@ -27,6 +27,7 @@ def emu():
     E = ctypes.CDLL(so)
     E.emu_sha512_ram.argtypes = [ctypes.c_char_p] * 4 + [ctypes.c_uint64]
     E.emu_sig_verify.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    E.emu_joint4.argtypes = [ctypes.c_char_p] * 6
     E.emu_sig_verify_half.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_int]
     E.emu_sc_half.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
     E.emu_eddsa_sign.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64]
@@ -189,6 +190,39 @@ def test_half_size_lattice_step(emu):
         if k >= len(special):
             worst = max(worst, bits)
     assert worst <= 140   # 33 or 34 radix-16 windows for honest challenges
+
+
+def test_joint_radix4_digits_and_table(emu, golden_records):
+    """The joint loop of the half-size-scalar verifier: the digit pairs read from x + 0x55..55 are signed radix-4 digits
+    in [-1, 2] of u and v (sign of the pair pulled out, one code per pair), and the 11 table entries are i*R + j*A."""
+    import random
+    rng = random.Random(7)
+    # code -> (du, dv): code = du * 5 + dv with du in {0, 1, 2}, dv in {-2 .. 2}
+    pairs = {du * 5 + dv: (du, dv) for du in range(3) for dv in range(-2, 3)}
+    pk, rb = golden_records[3][1], golden_records[4][2][:32]
+    A, R = O.point_decode(pk), O.point_decode(rb)
+    codes = ctypes.create_string_buffer(128)
+    table = ctypes.create_string_buffer(12 * 32)
+    for bits in (1, 2, 64, 127, 128, 129, 200, 253):
+        for _ in range(4):
+            u, v = rng.getrandbits(bits) | (1 << (bits - 1)), rng.getrandbits(bits)
+            emu.emu_joint4(codes, table, u.to_bytes(32, "little"), v.to_bytes(32, "little"), pk, rb)
+            su = sv = 0
+            for i, c in enumerate(codes.raw):
+                c = c - 256 if c > 127 else c
+                du, dv = pairs[abs(c)]
+                assert (du, dv) != (2, -2) and -1 <= du <= 2 and -2 <= dv <= 2
+                sgn = -1 if c < 0 else 1
+                assert -1 <= sgn * du <= 2 and -1 <= sgn * dv <= 2
+                su += sgn * du * 4**i
+                sv += sgn * dv * 4**i
+            assert (su, sv) == (u, v)
+            top = max(u.bit_length(), v.bit_length()) // 2 + 1   # sc_joint4_pairs: no digit at or above it
+            assert not any(codes.raw[top:])
+    want = {1: (0, 1), 2: (0, 2), 3: (1, -2), 4: (1, -1), 5: (1, 0), 6: (1, 1), 7: (1, 2), 9: (2, -1), 10: (2, 0), 11: (2, 1), 12: (2, 2)}
+    for code, (i, j) in want.items():
+        Q = O.point_add(O._mul_int(i, R), O._mul_int(j % (8 * O.L), A))
+        assert table.raw[32 * (code - 1): 32 * code] == O.point_encode(Q), code
 
 
 def test_verify_half_state_machine(emu, coracle, golden_records):
