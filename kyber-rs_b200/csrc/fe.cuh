@@ -813,6 +813,42 @@ KB_FN void kb_sqr_acc8_fresh0(uint32_t* t, const uint32_t* a)
 // ---------------------------------------------------------------------------------------
 // reduction of a 512-bit product: t[0..16) -> r[0..8), using 2^256 = 38 (mod p)
 // ---------------------------------------------------------------------------------------
+// upper word of (hi:lo) << s, 0 < s < 32 — a funnel shift (ALU pipe; a plain shift may become IMAD.SHL on the multiplier pipe)
+KB_FN uint32_t kb_fshl(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#if defined(KB_HOST_EMU)
+    return (hi << s) | (lo >> (32 - s));
+#else
+    return __funnelshift_l(lo, hi, s);
+#endif
+}
+#if defined(KB_FE_FOLD_SHIFT)
+// The same reduction WITHOUT multiplications: 38 H = 2 (H + 2H + 16H) by funnel shifts and carry chains, so that the eight
+// IMAD.WIDE of the fold leave the multiplier pipe (about 50 ALU instructions instead).  Experimental (-DKB_FE_FOLD_SHIFT).
+KB_FN void fe_reduce512(fe& r, uint32_t* t)
+{
+    const uint32_t* H = t + 8;
+    uint32_t s1[8], s4[8], u[8];
+    s1[0] = kb_fshl(0u, H[0], 1);
+    s4[0] = kb_fshl(0u, H[0], 4);
+    KB_UNROLL
+    for (int k = 1; k < 8; k++) {
+        s1[k] = kb_fshl(H[k - 1], H[k], 1);
+        s4[k] = kb_fshl(H[k - 1], H[k], 4);
+    }
+    uint32_t top = kb_fshl(H[7], 0u, 1) + kb_fshl(H[7], 0u, 4);   // H[7] >> 31, H[7] >> 28
+    top += kb_add8(u, H, s1);
+    top += kb_add8(u, u, s4);      // (top : u) = 19 H < 2^261
+    uint32_t S[8];
+    S[0] = kb_fshl(0u, u[0], 1);
+    KB_UNROLL
+    for (int k = 1; k < 8; k++) S[k] = kb_fshl(u[k - 1], u[k], 1);
+    uint32_t w8 = kb_fshl(u[7], top, 1);   // word 8 of 38 H, < 2^6
+    w8 += kb_add8(r.v, t, S);
+    uint32_t c = kb_add_small(r.v, w8 * 38u);
+    r.v[0] += 38u * c;
+}
+#else
 KB_FN void fe_reduce512(fe& r, uint32_t* t)
 {
     // even high words: (t0..t7) += 38 * {t8,t10,t12,t14}, carry into r8
@@ -839,6 +875,7 @@ KB_FN void fe_reduce512(fe& r, uint32_t* t)
     // a second wrap leaves a value < 38*2^7, so adding 38 once more cannot carry
     r.v[0] += 38u * c;
 }
+#endif
 
 // h = f * g   (fe.rs:299 fe_mul), rows in natural order
 KB_FN void fe_mul_rows(fe& h, const fe& f, const fe& g)
