@@ -38,7 +38,7 @@ static void base_init()
 }
 
 extern "C" {
-// op: 0 mul, 1 sq, 2 add, 3 sub, 4 invert, 5 pow22523, 6 canon(a), 7 Karatsuba, 8/9 both row orders of mul, 10/11 of sq, 12 sub (mask wrap)
+// op: 0 mul, 1 sq, 2 add, 3 sub, 4 invert, 5 pow22523, 6 canon(a), 7 Karatsuba, 8/9 both row orders of mul, 10/11 of sq, 12 sub (mask wrap), 13/14 both reductions of (b : a)
 void emu_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b)
 {
     fe x, y, r;
@@ -55,6 +55,13 @@ void emu_fe_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b)
     case 9: fe_mul_rip(r, x, y); break;
     case 10: fe_sq_rows(r, x); break;
     case 11: fe_sq_rip(r, x); break;
+    case 13:
+    case 14: {   // both reductions of the 512-bit value (b : a): with the multiplications by 38 / by shifts (KB_FE_FOLD_SHIFT)
+        uint32_t t[16];
+        for (int i = 0; i < 8; i++) { t[i] = x.v[i]; t[8 + i] = y.v[i]; }
+        if (op == 13) fe_reduce512_mul(r, t); else fe_reduce512_shift(r, t);
+        break;
+    }
     case 12: {   // fe_sub with the borrow-mask wrap (KB_FE_SUBMASK)
         uint32_t m = kb_sub8m(r.v, x.v, y.v);
         m = kb_sub_smallm(r.v, m & 38u);

@@ -63,6 +63,10 @@ def test_field_ops(emu):
         for y in edge + rnd.sample(vals, 4):
             assert feop(8, b32(x), b32(y)) == feop(9, b32(x), b32(y)) == b32(x * y % P)
             assert feop(12, b32(x), b32(y)) == b32((x - y) % P)
+    # both reductions of a 512-bit value (hi : lo): the multiplications by 38 and the shift form (-DKB_FE_FOLD_SHIFT)
+    for lo in vals[:60]:
+        for hi in edge + rnd.sample(vals, 4):
+            assert feop(13, b32(lo), b32(hi)) == feop(14, b32(lo), b32(hi)) == b32((lo + (hi << 256)) % P)
     # both multiplication bodies (schoolbook and one level of Karatsuba), incl. operands whose halves are equal,
     # ordered either way, all ones / all zeros — the sign and borrow paths of the Karatsuba differences
     M128 = 2**128
