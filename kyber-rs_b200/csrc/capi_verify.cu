@@ -114,8 +114,9 @@ static int kb_verify_host(kb_ctx* ctx, size_t n, const uint8_t* pk, const uint8_
     if (n && (!pk || !msg_off || !sig || !status)) return KB_ERR_ARG;
     if (n == 0) return KB_OK;
     if (msg_off[n] && !msg) return KB_ERR_ARG;
-    // Chunk sizes.  Measured on a 2^20 batch (tools/e2e_sweep.py, round 2): whole WAVES of the main kernel — 3 resident
-    // blocks of 128 signatures per SM, 56 832 signatures on 148 SMs — beat powers of two, and the chunks GROW: a third of
+    // Chunk sizes.  Measured on a 2^20 batch (tools/e2e_sweep.py, round 2): whole WAVES of the main kernel — its resident
+    // blocks of 128 signatures per SM: 56 832 signatures on 148 SMs at the 3 blocks of that measurement, 75 776 at today's 4 —
+    // beat powers of two, and the chunks GROW: a third of
     // a wave first (the kernels start after a copy of 3 MB), then four times the previous chunk each, up to the cap.  A
     // chunk's copy (168 B per signature at PCIe speed) is shorter than the kernels of the chunk before it as long as the
     // growth factor stays below about 6, so the device never waits for a copy after the first one, and a 2^20 batch is

@@ -23,7 +23,7 @@ h_pk, h_msg, h_off, h_sig = [x.numpy() for x in hp]
 h_off = h_off.view(np.uint64)
 h_out = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
 # (pipeline schedule, chunk size): KB_VERIFY_PIPE = 1 one compute stream + one copy stream, 0 two independent lanes;
-# chunk sizes as powers of two and as whole waves of the main kernel (148 SMs x 3 blocks x 128 signatures = 56832)
+# chunk sizes as powers of two and as multiples of 56832 (a wave of the main kernel when it ran 3 blocks per SM; 75776 at 4)
 cases = [(None, None)] + [(p, c) for p in (0, 1) for c in (227328, 454656, 909312, 1 << 20)] + [(None, None)]
 for pipe, chunk in cases:
     for key, val in (("KB_VERIFY_PIPE", pipe), ("KB_VERIFY_CHUNK", chunk)):
